@@ -1,0 +1,146 @@
+/* pcreid.h -- C ABI of libpcreid_sm100.so, the B200 (sm_100a) replacement for the data-parallel hot
+ * path of bentherien/point-cloud-reid.  Plain pointers and sizes only; every pointer is a DEVICE
+ * pointer unless stated; `stream` is a cudaStream_t passed as void*.  Every function is asynchronous
+ * on `stream`, allocates nothing, keeps no global state and returns PCREID_OK (0) or an error code
+ * (the reference launchers fprintf + exit(-1) instead, e.g. knn_cuda.cu:110-114).
+ *
+ * Citations are into the reference tree (mmdet3d/...).  Section A is the op-level boundary: each entry
+ * point takes exactly the arguments of the reference's `*_kernel_launcher` it replaces, so the
+ * reference's pybind wrapper (ops/<op>/src/<op>.cpp) can call it unchanged.
+ * Section B is the model-level boundary: the kernels the Python modules in
+ * point-cloud-reid_b200/models call from ReIDNet.forward / backbone.forward / match_forward_inference.
+ */
+#ifndef PCREID_H_
+#define PCREID_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCREID_OK 0
+#define PCREID_ERR_ARG 1          /* null pointer / bad size */
+#define PCREID_ERR_LAUNCH 2       /* cudaGetLastError() != cudaSuccess after the launch */
+#define PCREID_ERR_UNSUPPORTED 3  /* shape outside what the kernels were built for */
+
+int pcreid_abi_version(void);
+
+/* ------------------------------------------------------------------ A. mmdet3d point ops ------- */
+
+/* replaces furthest_point_sampling_kernel_launcher(b,n,m,dataset,temp,idxs,stream)
+ * (ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:143-211; python
+ * furthest_point_sample.py:7-44).  xyz (b,n,3) f32, temp (b,n) f32 scratch pre-filled with 1e10 by
+ * the caller (may be NULL: treated as 1e10), idx (b,m) i32.  First index is 0; ties follow the
+ * reference's shared-memory tree: min (bitreverse(k mod bs), k), bs = pcreid_fps_block_size(n). */
+int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, void* stream);
+/* replaces furthest_point_sampling_with_dist_kernel_launcher (same file :333-400): dist (b,n,n). */
+int pcreid_fps_with_dist(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
+int pcreid_fps_block_size(int n); /* host helper: opt_n_threads(n), same file :11-15 */
+
+/* replaces knn_kernel_launcher(b,n,m,nsample,xyz,new_xyz,idx,dist2,stream) (ops/knn/src/knn_cuda.cu:97-116;
+ * python knn.py:7-71).  xyz (b,n,3), new_xyz (b,m,3), idx/dist2 (b,m,nsample); nsample <= 100.
+ * Ascending distance; exact ties resolved exactly as the reference's max-heap does. */
+int pcreid_knn(int b, int n, int m, int nsample, const float* xyz, const float* new_xyz, int* idx, float* dist2, void* stream);
+/* same search, idx/dist2 written as (b,nsample,m): the layout knn.py:62 returns */
+int pcreid_knn_t(int b, int n, int m, int nsample, const float* xyz, const float* new_xyz, int* idx, float* dist2, void* stream);
+
+/* replaces ball_query_kernel_launcher(b,n,m,min_radius,max_radius,nsample,new_xyz,xyz,idx,stream)
+ * (ops/ball_query/src/ball_query_cuda.cu:56-82; python ball_query.py:7-54).  idx (b,m,nsample) must be
+ * zero-filled by the caller (ball_query.py:41); rows without a hit are left untouched. */
+int pcreid_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
+                      const float* new_xyz, const float* xyz, int* idx, void* stream);
+
+/* replaces group_points_kernel_launcher(b,c,n,npoints,nsample,points,idx,out,stream)
+ * (ops/group_points/src/group_points_cuda.cu:81-100): out[b,c,s,j] = points[b,c,idx[b,s,j]]. */
+int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out, void* stream);
+/* replaces gather_points_kernel_launcher(b,c,n,npoints,points,idx,out,stream)
+ * (ops/gather_points/src/gather_points_cuda.cu:28-49): out[b,c,m] = points[b,c,idx[b,m]]. */
+int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream);
+
+/* ------------------------------------------------------------------ B. encoder / match path ---- */
+/* All feature tensors are channel-major per object, exactly the reference's (B, C, N) layout:
+ * element (b, c, n) at  base + map(b)*bs + c*ld + n.  `map` (optional) is an int32 object-gather map,
+ * used to score pairs without materialising `feat[pairs[:,0]]` (tracking_point_reid.py:110).        */
+
+/* torch-path kNN of the ReID backbones (models/pointnet2_utils.py:169-216 square_distance + argsort):
+ * expansion-form distance, canonical ascending (d, idx) order.  idx (b,m,k) i32. */
+int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream);
+/* DGCNN kNN (models/dgcnn_orig.py:22-28): x (b,c,n) channel-major, k largest of
+ * pd = -|xi|^2 + 2 xi.xj - |xj|^2, lower index first on ties.  idx (b,n,k) i32. */
+int pcreid_knn_feature(int b, int c, int n, int k, const float* x, int* idx, void* stream);
+
+enum { PCREID_ACT_NONE = 0, PCREID_ACT_RELU = 1, PCREID_ACT_LEAKY02 = 2, PCREID_ACT_ELU1 = 3 };
+
+/* Y[b,co,n] = act( sum_k W1[k,co] X1[b,k,n] + sum_k W2[k,co] X2[b,k,n] + bias[co] (+R) ) (+R)
+ * = every nn.Linear / 1x1 Conv1d / Conv2d(+folded eval BatchNorm) on the path.  Weights are k-major
+ * [K, CO] (the transpose of torch's [CO, K]); per-object weights via w*_bs / w1_map. */
+typedef struct pcreid_linear_args {
+  int B, rows, CO, K1, K2;
+  const float* X1; long long x1_bs; int ldx1; int x1_pm; const int* x1_map;   /* x*_pm=1: point-major (rows,K) */
+  const float* X2; long long x2_bs; int ldx2; int x2_pm; const int* x2_map;
+  const float* W1; long long w1_bs; const int* w1_map;
+  const float* W2; long long w2_bs;
+  const float* bias;
+  const float* R; long long r_bs; int ldr; const int* r_map; int res_after_act;
+  int act;
+  float* Y; long long y_bs; int ldy;
+} pcreid_linear_args;
+int pcreid_cn_linear(const pcreid_linear_args* args, void* stream);
+
+/* GroupNorm over channel groups per (object, point) -- LayerNorm is G=1 (eps 1e-5, torch default):
+ * Y = act( GN(X)*gamma + beta (+R) ).  Used for nn.LayerNorm (pointnet2_utils.py:87-88, attention.py:187-188)
+ * and LinearRes' GroupNorm (lanegcn_nets.py:206-221). */
+typedef struct pcreid_norm_args {
+  int B, rows, C, G;
+  const float* X; long long x_bs; int ldx;
+  const float* gamma; const float* beta;
+  const float* R; long long r_bs; int ldr; const int* r_map;
+  int act;
+  float* Y; long long y_bs; int ldy;
+} pcreid_norm_args;
+int pcreid_cn_groupnorm(const pcreid_norm_args* args, void* stream);
+
+/* LinearAttention (pointnet2_utils.py:14-47, attention.py:19-54), split in two kernels:
+ * kv:    Wkv[b] (d x d, k-major, block diagonal per head) = sum_s (elu(k_s)+1) (x) (v_s / S);  ksum[b] (d)
+ * scale: Qs[b,c,n] = (elu(q)+1) * S / ( (elu(q_h)+1) . ksum_h + 1e-6 )
+ * so that message = cn_linear(X1=Qs, W1=Wkv (per object)). */
+int pcreid_linattn_kv(int B, int S, int d, int H, const float* K, long long k_bs, int ldk,
+                      const float* V, long long v_bs, int ldv, float* Wkv, float* ksum, void* stream);
+int pcreid_linattn_scale(int B, int rows, int d, int H, int S, const float* Q, long long q_bs, int ldq, const int* q_map,
+                         const float* ksum, const int* ksum_map, float* Qs, long long qs_bs, int ldqs, void* stream);
+
+/* pooling over points (ReIDNet.get_pooled_feats, ReIDNet.py:526-534; PointNet max-pool pointnet.py:31,70).
+ * mode 0: out[b, c] = max_n, out[b, C + c] = mean_n over the rows of X1 (and X2 if given: 'point-cat');
+ * mode 1: max only.  Output element (b, c) at out + b*ob + c*oc. */
+int pcreid_cn_pool(int B, int C, int rows1, const float* X1, long long x1_bs, int ldx1,
+                   int rows2, const float* X2, long long x2_bs, int ldx2,
+                   int mode, float* out, long long ob, long long oc, void* stream);
+/* 'max' pool_type of the reference: MaxPool1d over the CHANNEL axis (ReIDNet.py:527-528, 455-456):
+ * out[b, n] = max_c X[b, c, n]; element (b, n) at out + b*ob + n*on. */
+int pcreid_cn_chanmax(int B, int C, int rows, const float* X, long long x_bs, int ldx, float* out, long long ob, long long on, void* stream);
+
+/* Fused set-abstraction edge MLP (PointNetSetAbstractionEdgeSA.forward, pointnet2_utils.py:333-357) after the
+ * first 1x1 conv has been factorised into a per-point term P1 and a per-centre term Cc:
+ *   out[b,c,s] = max_j relu(W3 relu(W2 relu(P1[b,:,idx[b,s,j]] + Cc[b,:,s]) + b2) + b3)[c]
+ * P1 (b,C,n), Cc (b,C,S), idx (b,S,k) i32, W2/W3 k-major (C,C) with eval BatchNorm folded, out (b,C,S). */
+int pcreid_sa_edge_mlp(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
+                       const float* W2, const float* b2, const float* W3, const float* b3, float* out, void* stream);
+
+/* EdgeConv gather-max (dgcnn_orig.py:31-54,129-147 with the bias-free conv factorised):
+ *   out[b,c,i] = act( max_j P[b,c,idx[b,i,j]] + Q[b,c,i] ),  element (b,c,i) at out + b*o_bs + c*ldo + i */
+int pcreid_edge_gather_max(int B, int C, int N, int k, const float* P, const float* Q, const int* idx, int act,
+                           float* out, long long o_bs, int ldo, void* stream);
+
+/* Fused 'concat' match head over ALL pairs (ReIDNet.py:415-419,455-458 + LinearRes/Linear,
+ * lanegcn_nets.py:228-241) without materialising the T x D x 2E pair tensor:
+ *   logit[t,d] = w . relu( GN2(W2 relu(GN1(A[t] + Bv[d]))) + [e_t ; e_d] ) + b0
+ * A (T,Hd) = W1[:, :E] e_t, Bv (D,Hd) = W1[:, E:] e_d (row-major, from cn_linear), E_t (T,E), E_d (D,E),
+ * Hd = 2E <= 256, G groups.  mask (T,D) u8 optional: 0 -> logit 0 (class gating,
+ * tracking_point_reid.py:15-33).  out (T,D) f32 row-major. */
+int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const float* Bv, const float* Et, const float* Ed,
+                            const float* W2, const float* g1, const float* be1, const float* g2, const float* be2,
+                            const float* w, float b0, const unsigned char* mask, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCREID_H_ */

@@ -1,0 +1,542 @@
+// Point ops for sm_100a: kNN, furthest point sampling, ball query, group / gather.
+//
+// These replace the reference's scalar SIMT kernels (one thread per query, heap in local memory,
+// FPS distances in global memory) with warp-cooperative kernels:
+//   knn          one warp per query, distances staged in shared memory as order-preserving keys,
+//                k rounds of warp arg-min (two REDUX per round), canonical (d, idx) ascending order;
+//                exact-tie queries of the mmdet3d op fall back to an in-warp emulation of the
+//                reference heap so indices stay bit-identical   (ref: ops/knn/src/knn_cuda.cu:58-94)
+//   fps          one CTA (or one warp) per object, coordinates and running min-distances in
+//                registers, block arg-max with the reference's tie rule
+//                                                  (ref: ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:25-141)
+//   ball_query   one warp per query, ballot + prefix popcount keeps index order
+//                                                  (ref: ops/ball_query/src/ball_query_cuda.cu:11-54)
+//   group/gather indices read once per position (not once per channel), 128-bit streaming stores
+//                                                  (ref: ops/group_points/src/group_points_cuda.cu:56-79,
+//                                                        ops/gather_points/src/gather_points_cuda.cu:8-26)
+#include "common.cuh"
+#include <math.h>
+
+// ------------------------------------------------------------------------------------------------
+// distance arithmetic (must match the reference bit for bit; never let nvcc re-contract)
+// ------------------------------------------------------------------------------------------------
+// mode 0: mmdet3d CUDA ops.  nvcc -fmad=true contracts dx*dx+dy*dy+dz*dz to fma(dz,dz,fma(dx,dx,dy*dy)).
+__device__ __forceinline__ float dist_direct(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  float t = __fmul_rn(dy, dy);
+  t = __fmaf_rn(dx, dx, t);
+  return __fmaf_rn(dz, dz, t);
+}
+// mode 1: torch path square_distance (models/pointnet2_utils.py:169-188):
+//   m = q.p as a sequential fma chain, |v|^2 = (x*x + y*y) + z*z, d = (-2*m + |q|^2) + |p|^2
+__device__ __forceinline__ float sqnorm3(float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+__device__ __forceinline__ float dist_expand(float qx, float qy, float qz, float qn, float px, float py, float pz) {
+  float m = __fmul_rn(qx, px);
+  m = __fmaf_rn(qy, py, m);
+  m = __fmaf_rn(qz, pz, m);
+  float pn = sqnorm3(px, py, pz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(-2.f, m), qn), pn);
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN
+// ------------------------------------------------------------------------------------------------
+__device__ void heap_reheap(float* dist, int* idx, int k) {
+  int root = 0, child = 1;
+  while (child < k) {
+    if (child + 1 < k && dist[child + 1] > dist[child]) child++;
+    if (dist[root] > dist[child]) return;
+    float tf = dist[root]; dist[root] = dist[child]; dist[child] = tf;
+    int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
+    root = child;
+    child = root * 2 + 1;
+  }
+}
+
+// MODE 0: direct-form distance, MODE 1: expansion-form distance.
+// idx/dist2 element (b, q, j) lives at  b*M*k + q*sq + j*sk   (sq=k, sk=1 -> [B,M,k]; sq=1, sk=M -> [B,k,M]).
+template <int MODE>
+__global__ void __launch_bounds__(256) knn_kernel(int N, int M, int k, const float* __restrict__ xyz,
+                                                  const float* __restrict__ qxyz, int* __restrict__ idx,
+                                                  float* __restrict__ dist2, long long sq, long long sk,
+                                                  int heap_ties, int npad) {
+  extern __shared__ uint32_t smem_u32[];
+  const int warps = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * warps + warp;
+  const int b = blockIdx.y;
+  if (q >= M) return;   // warp-uniform; only warp-level sync below
+
+  uint32_t* keys = smem_u32 + (size_t)warp * npad;
+  const float* P = xyz + (size_t)b * N * 3;
+  const float* Q = qxyz + ((size_t)b * M + q) * 3;
+  const float qx = Q[0], qy = Q[1], qz = Q[2];
+  const float qn = sqnorm3(qx, qy, qz);
+  int* oi = idx + (size_t)b * M * k + (size_t)q * sq;
+  float* od = dist2 ? dist2 + (size_t)b * M * k + (size_t)q * sq : nullptr;
+
+  uint32_t lmin = 0xffffffffu;
+  int lidx = lane;
+  for (int i = lane; i < N; i += 32) {
+    float px = __ldg(P + i * 3), py = __ldg(P + i * 3 + 1), pz = __ldg(P + i * 3 + 2);
+    float d = MODE == 0 ? dist_direct(qx, qy, qz, px, py, pz) : dist_expand(qx, qy, qz, qn, px, py, pz);
+    uint32_t key = f32_to_ordered(d);
+    keys[i] = key;
+    if (key < lmin) { lmin = key; lidx = i; }
+  }
+  __syncwarp();
+
+  const int nsel = k < N ? k : N;
+  const int rounds = (heap_ties && N > k) ? k + 1 : nsel;
+  bool slow = false;
+  uint32_t prev = 0;
+  for (int r = 0; r < rounds; ++r) {
+    uint32_t dmin = warp_min_u32(lmin);
+    uint32_t win = warp_min_u32(lmin == dmin ? (uint32_t)lidx : 0xffffffffu);
+    if (r > 0 && dmin == prev) slow = true;
+    prev = dmin;
+    if (r < nsel) {
+      float dv = ordered_to_f32(dmin);
+      if (heap_ties && !(dv < 1e10f)) slow = true;   // reference heap never admits d2 >= 1e10
+      if (lane == 0) {
+        oi[(size_t)r * sk] = (int)win;
+        if (od) od[(size_t)r * sk] = dv;
+      }
+    }
+    if (lane == (int)(win & 31u)) {
+      keys[win] = 0xffffffffu;
+      lmin = 0xffffffffu;
+      lidx = lane;
+      for (int i = lane; i < N; i += 32) {
+        uint32_t key = keys[i];
+        if (key < lmin) { lmin = key; lidx = i; }
+      }
+    }
+    __syncwarp();
+  }
+  if (heap_ties) {
+    // unfilled slots of the reference heap: (idx 0, dist 1e10) at the tail (knn_cuda.cu:74-77)
+    for (int r = nsel + lane; r < k; r += 32) {
+      oi[(size_t)r * sk] = 0;
+      if (od) od[(size_t)r * sk] = 1e10f;
+    }
+    __syncwarp();
+    if (slow) {
+      // exact tie among the selected k / at the k-th boundary: which tied candidates survive and their
+      // order depend on the heap's internal structure -> replay the reference heap (one lane).
+      float* hd = reinterpret_cast<float*>(smem_u32 + (size_t)warps * npad) + (size_t)warp * 2 * k;
+      int* hi = reinterpret_cast<int*>(hd + k);
+      if (lane == 0) {
+        for (int i = 0; i < k; ++i) { hd[i] = 1e10f; hi[i] = 0; }
+        for (int i = 0; i < N; ++i) {
+          float px = __ldg(P + i * 3), py = __ldg(P + i * 3 + 1), pz = __ldg(P + i * 3 + 2);
+          float d = MODE == 0 ? dist_direct(qx, qy, qz, px, py, pz) : dist_expand(qx, qy, qz, qn, px, py, pz);
+          if (d < hd[0]) { hd[0] = d; hi[0] = i; heap_reheap(hd, hi, k); }
+        }
+        for (int i = k - 1; i > 0; --i) {   // heap_sort (knn_cuda.cu:45-54)
+          float tf = hd[0]; hd[0] = hd[i]; hd[i] = tf;
+          int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
+          heap_reheap(hd, hi, i);
+        }
+        for (int i = 0; i < k; ++i) {
+          oi[(size_t)i * sk] = hi[i];
+          if (od) od[(size_t)i * sk] = hd[i];
+        }
+      }
+    }
+  }
+}
+
+static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, const float* qxyz, int* idx,
+                      float* dist2, long long sq, long long sk, int heap_ties, cudaStream_t st) {
+  if (b <= 0 || m <= 0 || k <= 0) return PCREID_OK;
+  if (n <= 0 || !xyz || !qxyz || !idx) return PCREID_ERR_ARG;
+  if (heap_ties && k > 100) return PCREID_ERR_ARG;   // reference limit (knn.py:30)
+  if (!heap_ties && k > n) return PCREID_ERR_ARG;
+  int npad = (n + 31) & ~31;
+  int warps = 8;
+  const size_t budget = 200 * 1024;
+  auto need = [&](int w) { return (size_t)w * npad * 4 + (heap_ties ? (size_t)w * 2 * k * 4 : 0); };
+  while (warps > 1 && need(warps) > budget) warps >>= 1;
+  if (need(warps) > budget) return PCREID_ERR_UNSUPPORTED;
+  if (m < warps) { while (warps > 1 && warps / 2 >= m) warps >>= 1; }
+  size_t smem = need(warps);
+  dim3 grid(ceil_div(m, warps), b);
+  if (mode == 0) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(knn_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    knn_kernel<0><<<grid, warps * 32, smem, st>>>(n, m, k, xyz, qxyz, idx, dist2, sq, sk, heap_ties, npad);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(knn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    knn_kernel<1><<<grid, warps * 32, smem, st>>>(n, m, k, xyz, qxyz, idx, dist2, sq, sk, heap_ties, npad);
+  }
+  return pcreid_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// DGCNN kNN in feature space (models/dgcnn_orig.py:22-28)
+//   m_ij  = sequential fma chain over channels (what torch.matmul does on the CPU oracle)
+//   xx_i  = sum_c x_ci^2, ATen cascade: sequential inside blocks of 16 channels, block sums added in order
+//   pd_ij = ((-xx_i) - (-2 m_ij)) - xx_j ; k largest, lower index first on ties
+// CTA = 8 warps x QPW queries; the object's features stream through shared memory in 128-point tiles.
+// ------------------------------------------------------------------------------------------------
+constexpr int KF_JT = 128;
+template <int QPW>
+__global__ void __launch_bounds__(256) knn_feature_kernel(int C, int N, int k, const float* __restrict__ x,
+                                                          int* __restrict__ idx, int npad) {
+  extern __shared__ uint32_t smem_u32[];
+  constexpr int QPC = 8 * QPW;
+  float* xs = reinterpret_cast<float*>(smem_u32);              // [C][KF_JT]
+  float* xx = xs + (size_t)C * KF_JT;                          // [npad]
+  float* qv = xx + npad;                                       // [QPC][C]
+  uint32_t* keys = reinterpret_cast<uint32_t*>(qv + (size_t)QPC * C);   // [QPC][npad]
+  const int b = blockIdx.y, q0 = blockIdx.x * QPC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* xb = x + (size_t)b * C * N;
+
+  for (int j = threadIdx.x; j < N; j += 256) {
+    float tot = 0.f;
+    for (int c0 = 0; c0 < C; c0 += 16) {
+      float blk = 0.f;
+      const int ce = min(c0 + 16, C);
+      for (int c = c0; c < ce; ++c) { float v = xb[(size_t)c * N + j]; blk = __fadd_rn(blk, __fmul_rn(v, v)); }
+      tot = c0 == 0 ? blk : __fadd_rn(tot, blk);
+    }
+    xx[j] = tot;
+  }
+  for (int t = threadIdx.x; t < QPC * C; t += 256) {
+    int ql = t / C, c = t % C;
+    qv[t] = (q0 + ql < N) ? xb[(size_t)c * N + q0 + ql] : 0.f;
+  }
+  for (int j0 = 0; j0 < N; j0 += KF_JT) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < C * KF_JT; t += 256) {
+      int c = t / KF_JT, j = t % KF_JT;
+      xs[t] = (j0 + j < N) ? xb[(size_t)c * N + j0 + j] : 0.f;
+    }
+    __syncthreads();
+    float acc[QPW][4];
+#pragma unroll
+    for (int a = 0; a < QPW; ++a)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) acc[a][t] = 0.f;
+    for (int c = 0; c < C; ++c) {
+      float pv[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) pv[t] = xs[c * KF_JT + lane + 32 * t];
+#pragma unroll
+      for (int a = 0; a < QPW; ++a) {
+        const float qc = qv[(warp * QPW + a) * C + c];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) acc[a][t] = __fmaf_rn(qc, pv[t], acc[a][t]);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < QPW; ++a) {
+      const int ql = warp * QPW + a;
+      if (q0 + ql >= N) continue;
+      const float xi = xx[q0 + ql];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int j = j0 + lane + 32 * t;
+        if (j < N) {
+          float inner = __fmul_rn(-2.f, acc[a][t]);
+          float pd = __fsub_rn(__fsub_rn(-xi, inner), xx[j]);
+          keys[(size_t)ql * npad + j] = f32_to_ordered(-pd);
+        }
+      }
+    }
+  }
+  __syncwarp();
+  for (int a = 0; a < QPW; ++a) {
+    const int ql = warp * QPW + a, q = q0 + ql;
+    if (q >= N) continue;
+    uint32_t* kq = keys + (size_t)ql * npad;
+    uint32_t lmin = 0xffffffffu;
+    int lidx = lane;
+    for (int i = lane; i < N; i += 32) { uint32_t key = kq[i]; if (key < lmin) { lmin = key; lidx = i; } }
+    int* oi = idx + ((size_t)b * N + q) * k;
+    for (int r = 0; r < k; ++r) {
+      uint32_t dmin = warp_min_u32(lmin);
+      uint32_t win = warp_min_u32(lmin == dmin ? (uint32_t)lidx : 0xffffffffu);
+      if (lane == 0) oi[r] = (int)win;
+      if (lane == (int)(win & 31u)) {
+        kq[win] = 0xffffffffu;
+        lmin = 0xffffffffu;
+        lidx = lane;
+        for (int i = lane; i < N; i += 32) { uint32_t key = kq[i]; if (key < lmin) { lmin = key; lidx = i; } }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// furthest point sampling
+// ------------------------------------------------------------------------------------------------
+// Tie rule of the reference (first strict '>' per thread over k = tid, tid+bs, ..; shared-memory tree that
+// keeps the lower slot on equal values): among tied maxima the winner minimises (bitreverse(k mod bs), k).
+__device__ __forceinline__ uint32_t fps_tie32(int k, int log2bs) {
+  if (log2bs == 0) return (uint32_t)k;
+  uint32_t kmod = (uint32_t)k & ((1u << log2bs) - 1u);
+  uint32_t rev = __brev(kmod) >> (32 - log2bs);
+  return (rev << (32 - log2bs)) | ((uint32_t)k >> log2bs);
+}
+__device__ __forceinline__ int fps_untie32(uint32_t t, int log2bs) {
+  if (log2bs == 0) return (int)t;
+  uint32_t rev = t >> (32 - log2bs);
+  uint32_t kmod = __brev(rev) >> (32 - log2bs);
+  uint32_t hi = t & ((1u << (32 - log2bs)) - 1u);
+  return (int)((hi << log2bs) | kmod);
+}
+
+template <int PPT, int MAXT>
+__global__ void __launch_bounds__(MAXT) fps_kernel(int N, int M, int log2bs, const float* __restrict__ data,
+                                                   float* __restrict__ temp, int* __restrict__ idxs, int with_dist) {
+  if (M <= 0) return;
+  __shared__ uint32_t s_hi[2][32], s_lo[2][32];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+  const int b = blockIdx.x;
+  const float* ds = data + (size_t)b * N * (with_dist ? (size_t)N : 3);
+  float* tp = temp ? temp + (size_t)b * N : nullptr;
+  int* out = idxs + (size_t)b * M;
+
+  float x[PPT], y[PPT], z[PPT], t[PPT];
+  uint32_t tie[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT; ++j) {
+    int k = tid + T * j;
+    x[j] = y[j] = z[j] = 0.f;
+    t[j] = 1e10f;
+    tie[j] = 0;
+    if (k < N) {
+      if (!with_dist) { x[j] = ds[k * 3]; y[j] = ds[k * 3 + 1]; z[j] = ds[k * 3 + 2]; }
+      if (tp) t[j] = tp[k];
+      tie[j] = ~fps_tie32(k, log2bs);
+    }
+  }
+  int old = 0;
+  if (tid == 0) out[0] = 0;
+  for (int s = 1; s < M; ++s) {
+    float x1 = 0.f, y1 = 0.f, z1 = 0.f;
+    if (!with_dist) { x1 = __ldg(ds + old * 3); y1 = __ldg(ds + old * 3 + 1); z1 = __ldg(ds + old * 3 + 2); }
+    uint32_t bhi = 0, blo = 0;
+    bool have = false;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      int k = tid + T * j;
+      if (k < N) {
+        float d = with_dist ? __ldg(ds + (size_t)old * N + k) : dist_direct(x[j], y[j], z[j], x1, y1, z1);
+        float d2 = fminf(d, t[j]);
+        t[j] = d2;
+        uint32_t hi = f32_to_ordered(d2);
+        if (!have || hi > bhi || (hi == bhi && tie[j] > blo)) { bhi = hi; blo = tie[j]; have = true; }
+      }
+    }
+    uint32_t whi = warp_max_u32(bhi);
+    uint32_t wlo = warp_max_u32((have && bhi == whi) ? blo : 0u);
+    if (nwarp > 1) {
+      const int buf = s & 1;
+      if (lane == 0) { s_hi[buf][warp] = whi; s_lo[buf][warp] = wlo; }
+      __syncthreads();
+      uint32_t h = lane < nwarp ? s_hi[buf][lane] : 0u;
+      uint32_t l = lane < nwarp ? s_lo[buf][lane] : 0u;
+      whi = warp_max_u32(h);
+      wlo = warp_max_u32((lane < nwarp && h == whi) ? l : 0u);
+    }
+    old = fps_untie32(~wlo, log2bs);
+    if (tid == 0) out[s] = old;
+  }
+  if (tp) {
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+      int k = tid + T * j;
+      if (k < N) tp[k] = t[j];
+    }
+  }
+}
+
+static int fps_block_size_ref(int n) {   // opt_n_threads, furthest_point_sample_cuda.cu:11-15
+  int pow_2 = (int)(std::log(static_cast<double>(n)) / std::log(2.0));
+  int t = 1 << pow_2;
+  if (t > 1024) t = 1024;
+  if (t < 1) t = 1;
+  return t;
+}
+
+static int fps_launch(int b, int n, int m, const float* data, float* temp, int* idxs, int with_dist, cudaStream_t st) {
+  if (b <= 0 || m <= 0) return PCREID_OK;
+  if (n <= 0 || !data || !idxs) return PCREID_ERR_ARG;
+  int bs = fps_block_size_ref(n), log2bs = 0;
+  while ((1 << log2bs) < bs) ++log2bs;
+  int T;
+  if (b >= 592 && n <= 1024 && !with_dist) T = 32;          // many small objects: one warp each, no barriers
+  else {
+    T = 32;
+    while (T < 1024 && T * 4 < n) T <<= 1;                  // ~4 points per thread, latency bound otherwise
+  }
+  int ppt = ceil_div(n, T);
+  int p2 = 1;
+  while (p2 < ppt) p2 <<= 1;
+  if (p2 > 32) return PCREID_ERR_UNSUPPORTED;               // n > 32768
+#define FPS_CASE(P)                                                                              \
+  case P:                                                                                        \
+    if (T == 32) fps_kernel<P, 32><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist);   \
+    else fps_kernel<P, 1024><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist);         \
+    break;
+  switch (p2) {
+    FPS_CASE(1) FPS_CASE(2) FPS_CASE(4) FPS_CASE(8) FPS_CASE(16) FPS_CASE(32)
+  }
+#undef FPS_CASE
+  return pcreid_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// ball query
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ball_query_kernel(int N, int M, int k, float min_r2, float max_r2,
+                                                         const float* __restrict__ qxyz, const float* __restrict__ xyz,
+                                                         int* __restrict__ idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp, b = blockIdx.y;
+  if (q >= M) return;
+  const float* P = xyz + (size_t)b * N * 3;
+  const float* Q = qxyz + ((size_t)b * M + q) * 3;
+  const float qx = Q[0], qy = Q[1], qz = Q[2];
+  int* o = idx + ((size_t)b * M + q) * k;
+  int cnt = 0;
+  for (int base = 0; base < N && cnt < k; base += 32) {
+    int i = base + lane;
+    bool hit = false;
+    if (i < N) {
+      float d2 = dist_direct(qx, qy, qz, __ldg(P + i * 3), __ldg(P + i * 3 + 1), __ldg(P + i * 3 + 2));
+      hit = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+    }
+    uint32_t mask = __ballot_sync(FULL_MASK, hit);
+    if (mask == 0) continue;
+    if (cnt == 0) {   // first hit is broadcast to every slot (ball_query_cuda.cu:44-48)
+      int first = base + __ffs(mask) - 1;
+      for (int l = lane; l < k; l += 32) o[l] = first;
+      __syncwarp();
+    }
+    int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+    if (hit && pos < k) o[pos] = i;
+    cnt += __popc(mask);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// group_points / gather_points:  out[b, c, p] = points[b, c, idx[b, p]],  p in [0, P)  (P = S*k or M)
+// ------------------------------------------------------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(256) group_kernel(int C, int N, int P, const float* __restrict__ points,
+                                                    const int* __restrict__ idx, float* __restrict__ out) {
+  const int b = blockIdx.y;
+  const int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+  if (p0 >= P) return;
+  const int* ib = idx + (size_t)b * P + p0;
+  int id[VEC];
+  if (VEC == 4) {
+    int4 v = *reinterpret_cast<const int4*>(ib);
+    id[0] = v.x; id[1 % VEC] = v.y; id[2 % VEC] = v.z; id[3 % VEC] = v.w;
+  } else {
+    id[0] = ib[0];
+  }
+  const float* pb = points + (size_t)b * C * N;
+  float* ob = out + (size_t)b * C * P + p0;
+#pragma unroll 4
+  for (int c = 0; c < C; ++c) {
+    const float* row = pb + (size_t)c * N;
+    if (VEC == 4) {
+      float4 v = make_float4(__ldg(row + id[0]), __ldg(row + id[1 % VEC]), __ldg(row + id[2 % VEC]), __ldg(row + id[3 % VEC]));
+      st_cs_f4(ob + (size_t)c * P, v);
+    } else {
+      ob[(size_t)c * P] = __ldg(row + id[0]);
+    }
+  }
+}
+
+static int group_launch(int b, int c, int n, int p, const float* points, const int* idx, float* out, cudaStream_t st) {
+  if (b <= 0 || c <= 0 || p <= 0) return PCREID_OK;
+  if (!points || !idx || !out || n <= 0) return PCREID_ERR_ARG;
+  bool vec = (p % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (vec) {
+    dim3 grid(ceil_div(p / 4, 256), b);
+    group_kernel<4><<<grid, 256, 0, st>>>(c, n, p, points, idx, out);
+  } else {
+    dim3 grid(ceil_div(p, 256), b);
+    group_kernel<1><<<grid, 256, 0, st>>>(c, n, p, points, idx, out);
+  }
+  return pcreid_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI (declared in include/pcreid.h)
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, void* stream) {
+  return fps_launch(b, n, m, xyz, temp, idx, 0, (cudaStream_t)stream);
+}
+int pcreid_fps_with_dist(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream) {
+  return fps_launch(b, n, m, dist, temp, idx, 1, (cudaStream_t)stream);
+}
+int pcreid_fps_block_size(int n) { return n > 0 ? fps_block_size_ref(n) : 1; }
+
+// mmdet3d op: idx/dist2 laid out [b, m, k] exactly like knn_kernel_launcher's outputs.
+int pcreid_knn(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, float* dist2, void* stream) {
+  return knn_launch(0, b, n, m, k, xyz, new_xyz, idx, dist2, k, 1, 1, (cudaStream_t)stream);
+}
+// same search, output already transposed to [b, k, m] (what knn.py:62 returns after .transpose(2,1).contiguous())
+int pcreid_knn_t(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, float* dist2, void* stream) {
+  return knn_launch(0, b, n, m, k, xyz, new_xyz, idx, dist2, 1, m, 1, (cudaStream_t)stream);
+}
+// torch-path kNN of the ReID backbones (pointnet2_utils.py:205-216): expansion-form distance, canonical
+// (d, idx) order, idx [b, m, k] int32.
+int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream) {
+  return knn_launch(1, b, n, m, k, xyz, new_xyz, idx, nullptr, k, 1, 0, (cudaStream_t)stream);
+}
+
+int pcreid_knn_feature(int b, int c, int n, int k, const float* x, int* idx, void* stream) {
+  if (b <= 0 || n <= 0 || k <= 0) return PCREID_OK;
+  if (!x || !idx || c <= 0 || k > n) return PCREID_ERR_ARG;
+  if (b > 65535) return PCREID_ERR_UNSUPPORTED;
+  const int npad = (n + 31) & ~31;
+  auto need = [&](int qpc) { return ((size_t)c * KF_JT + npad + (size_t)qpc * c + (size_t)qpc * npad) * 4; };
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t budget = 200 * 1024;
+  if (need(32) <= budget) {
+    cudaFuncSetAttribute(knn_feature_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(32));
+    knn_feature_kernel<4><<<dim3(ceil_div(n, 32), b), 256, need(32), st>>>(c, n, k, x, idx, npad);
+  } else if (need(16) <= budget) {
+    cudaFuncSetAttribute(knn_feature_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(16));
+    knn_feature_kernel<2><<<dim3(ceil_div(n, 16), b), 256, need(16), st>>>(c, n, k, x, idx, npad);
+  } else if (need(8) <= budget) {
+    cudaFuncSetAttribute(knn_feature_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(8));
+    knn_feature_kernel<1><<<dim3(ceil_div(n, 8), b), 256, need(8), st>>>(c, n, k, x, idx, npad);
+  } else {
+    return PCREID_ERR_UNSUPPORTED;
+  }
+  return pcreid_launch_status();
+}
+
+int pcreid_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample, const float* new_xyz,
+                      const float* xyz, int* idx, void* stream) {
+  if (b <= 0 || m <= 0 || nsample <= 0) return PCREID_OK;
+  if (n <= 0 || !new_xyz || !xyz || !idx) return PCREID_ERR_ARG;
+  dim3 grid(ceil_div(m, 8), b);
+  ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, nsample, min_radius * min_radius,
+                                                            max_radius * max_radius, new_xyz, xyz, idx);
+  return pcreid_launch_status();
+}
+
+int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out,
+                        void* stream) {
+  return group_launch(b, c, n, npoints * nsample, points, idx, out, (cudaStream_t)stream);
+}
+int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream) {
+  return group_launch(b, c, n, npoints, points, idx, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

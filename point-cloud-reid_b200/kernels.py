@@ -1,0 +1,232 @@
+"""Thin torch-facing layer over the C ABI: allocates outputs with torch, passes raw device pointers and
+the current CUDA stream.  No arithmetic happens here.
+
+Feature tensors are channel-major ``(B, C, N)`` (the reference's layout) with unit stride along N;
+arbitrary object / channel strides are passed through, so views such as ``qkv[:, :C]`` cost nothing.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_ELU1 = 0, 1, 2, 3
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("pcreid_b200 kernels need CUDA tensors (there is no CPU fallback)")
+
+
+def _cn(t, name):
+    """validates a channel-major tensor view and returns (object stride, channel stride)."""
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32")
+    if t.dim() != 3:
+        raise ValueError(f"{name} must be (B, C, N)")
+    if t.shape[2] > 1 and t.stride(2) != 1:
+        raise ValueError(f"{name} must have unit stride along points; got strides {t.stride()}")
+    return t.stride(0), t.stride(1)
+
+
+def _map(m):
+    if m is None:
+        return None
+    if m.dtype != torch.int32 or not m.is_contiguous():
+        raise TypeError("object maps must be contiguous int32")
+    return m
+
+
+def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_after_act=False, rows=None,
+              x1_map=None, x2_map=None, w1_map=None, r_map=None, x1_pm=False, x2_pm=False, out=None, B=None):
+    """Y[b,:,n] = act(W1^T X1[b,:,n] + W2^T X2[b,:,n] + bias (+res)) (+res).  w*: k-major (K, CO) or (Bw, K, CO)."""
+    _need_cuda(x1, w1, x2, w2, bias, res, out)
+    a = _lib.LinearArgs()
+    K1, CO = w1.shape[-2], w1.shape[-1]
+    if x1_pm:
+        if not x1.is_contiguous() or x1.shape[2] != K1:
+            raise ValueError("point-major x1 must be contiguous (B, N, K)")
+        n_in, a.x1_bs, a.ldx1 = x1.shape[1], x1.shape[1] * x1.shape[2], x1.shape[2]
+    else:
+        if x1.shape[1] != K1:
+            raise ValueError(f"x1 has {x1.shape[1]} channels, weight expects {K1}")
+        a.x1_bs, a.ldx1 = _cn(x1, "x1")
+        n_in = x1.shape[2]
+    rows = n_in if rows is None else rows
+    if B is None:
+        B = x1_map.numel() if x1_map is not None else x1.shape[0]
+    a.B, a.rows, a.CO, a.K1 = B, rows, CO, K1
+    a.X1, a.x1_pm, a.x1_map = _p(x1), int(x1_pm), _p(_map(x1_map))
+    if not w1.is_contiguous() or w1.dtype != torch.float32:
+        raise ValueError("weights must be contiguous float32")
+    a.W1, a.w1_bs, a.w1_map = _p(w1), (w1.shape[-2] * w1.shape[-1] if w1.dim() == 3 else 0), _p(_map(w1_map))
+    if x2 is not None:
+        K2 = w2.shape[-2]
+        if w2.shape[-1] != CO or not w2.is_contiguous():
+            raise ValueError("w2 must be contiguous (K2, CO)")
+        if x2_pm:
+            if not x2.is_contiguous() or x2.shape[2] != K2:
+                raise ValueError("point-major x2 must be contiguous (B, N, K)")
+            a.x2_bs, a.ldx2 = x2.shape[1] * x2.shape[2], x2.shape[2]
+        else:
+            if x2.shape[1] != K2:
+                raise ValueError(f"x2 has {x2.shape[1]} channels, weight expects {K2}")
+            a.x2_bs, a.ldx2 = _cn(x2, "x2")
+        a.K2, a.X2, a.x2_pm, a.x2_map = K2, _p(x2), int(x2_pm), _p(_map(x2_map))
+        a.W2, a.w2_bs = _p(w2), (w2.shape[-2] * w2.shape[-1] if w2.dim() == 3 else 0)
+    else:
+        a.K2 = 0
+    a.bias = _p(bias)
+    if res is not None:
+        a.r_bs, a.ldr = _cn(res, "res")
+        a.R, a.r_map, a.res_after_act = _p(res), _p(_map(r_map)), int(res_after_act)
+    a.act = act
+    if out is None:
+        out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
+    a.y_bs, a.ldy = _cn(out, "out")
+    a.Y = _p(out)
+    _lib.check(_lib.lib().pcreid_cn_linear(ctypes.byref(a), _stream()), "pcreid_cn_linear")
+    return out
+
+
+def cn_groupnorm(x, gamma, beta, groups=1, res=None, r_map=None, act=ACT_NONE, out=None):
+    """Y = act(GroupNorm_G(X) * gamma + beta (+res)) per (object, point); LayerNorm is groups=1."""
+    _need_cuda(x, gamma, beta, res)
+    a = _lib.NormArgs()
+    a.B, a.C, a.rows, a.G = x.shape[0], x.shape[1], x.shape[2], groups
+    a.x_bs, a.ldx = _cn(x, "x")
+    a.X, a.gamma, a.beta = _p(x), _p(gamma), _p(beta)
+    if res is not None:
+        a.r_bs, a.ldr = _cn(res, "res")
+        a.R, a.r_map = _p(res), _p(_map(r_map))
+    a.act = act
+    if out is None:
+        out = torch.empty(tuple(x.shape), device=x.device, dtype=torch.float32)
+    a.y_bs, a.ldy = _cn(out, "out")
+    a.Y = _p(out)
+    _lib.check(_lib.lib().pcreid_cn_groupnorm(ctypes.byref(a), _stream()), "pcreid_cn_groupnorm")
+    return out
+
+
+def linattn_kv(k, v, nhead):
+    """-> (Wkv (B, d, d) k-major block-diagonal, ksum (B, d)) from pre-activation keys / values (B, d, S)."""
+    _need_cuda(k, v)
+    B, d, S = k.shape
+    k_bs, ldk = _cn(k, "k")
+    v_bs, ldv = _cn(v, "v")
+    wkv = torch.empty((B, d, d), device=k.device, dtype=torch.float32)
+    ksum = torch.empty((B, d), device=k.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_linattn_kv(B, S, d, nhead, _p(k), k_bs, ldk, _p(v), v_bs, ldv, _p(wkv), _p(ksum), _stream()),
+               "pcreid_linattn_kv")
+    return wkv, ksum
+
+
+def linattn_scale(q, ksum, nhead, s_len, q_map=None, ksum_map=None, B=None):
+    """Qs = (elu(q)+1) * S / ((elu(q_h)+1).ksum_h + 1e-6)."""
+    _need_cuda(q, ksum)
+    q_bs, ldq = _cn(q, "q")
+    d, rows = q.shape[1], q.shape[2]
+    if B is None:
+        B = q_map.numel() if q_map is not None else (ksum_map.numel() if ksum_map is not None else q.shape[0])
+    out = torch.empty((B, d, rows), device=q.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_linattn_scale(B, rows, d, nhead, s_len, _p(q), q_bs, ldq, _p(_map(q_map)), _p(ksum),
+                                               _p(_map(ksum_map)), _p(out), d * rows, rows, _stream()), "pcreid_linattn_scale")
+    return out
+
+
+def cn_pool(x1, x2=None, mode=0, out=None, transposed=False):
+    """mode 0: cat(max, mean) over points of x1 (and x2); mode 1: max.  -> (B, C') or, transposed, (1, C', B)."""
+    _need_cuda(x1, x2)
+    B, C, r1 = x1.shape
+    bs1, ld1 = _cn(x1, "x1")
+    bs2 = ld2 = r2 = 0
+    if x2 is not None:
+        bs2, ld2 = _cn(x2, "x2")
+        r2 = x2.shape[2]
+    Co = 2 * C if mode == 0 else C
+    if out is None:
+        out = torch.empty((1, Co, B) if transposed else (B, Co), device=x1.device, dtype=torch.float32)
+    ob, oc = (1, B) if transposed else (Co, 1)
+    _lib.check(_lib.lib().pcreid_cn_pool(B, C, r1, _p(x1), bs1, ld1, r2, _p(x2), bs2, ld2, mode, _p(out), ob, oc, _stream()),
+               "pcreid_cn_pool")
+    return out
+
+
+def cn_chanmax(x, out=None, transposed=False):
+    """max over the channel axis: (B, C, N) -> (B, N) or, transposed, (1, N, B)."""
+    _need_cuda(x)
+    B, C, rows = x.shape
+    bs, ld = _cn(x, "x")
+    if out is None:
+        out = torch.empty((1, rows, B) if transposed else (B, rows), device=x.device, dtype=torch.float32)
+    ob, on = (1, B) if transposed else (rows, 1)
+    _lib.check(_lib.lib().pcreid_cn_chanmax(B, C, rows, _p(x), bs, ld, _p(out), ob, on, _stream()), "pcreid_cn_chanmax")
+    return out
+
+
+def knn_point(k, xyz, new_xyz):
+    """torch-path kNN of the backbones: int32 (B, S, k), canonical (d, idx) order."""
+    _need_cuda(xyz, new_xyz)
+    if not (xyz.is_contiguous() and new_xyz.is_contiguous()):
+        raise ValueError("xyz / new_xyz must be contiguous")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    idx = torch.empty((B, S, k), device=xyz.device, dtype=torch.int32)
+    _lib.check(_lib.lib().pcreid_knn_point(B, N, S, k, _p(xyz), _p(new_xyz), _p(idx), _stream()), "pcreid_knn_point")
+    return idx
+
+
+def knn_feature(x, k):
+    """DGCNN kNN in feature space: x (B, C, N) contiguous -> int32 (B, N, k)."""
+    _need_cuda(x)
+    if not x.is_contiguous():
+        raise ValueError("x must be contiguous (B, C, N)")
+    B, C, N = x.shape
+    idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
+    _lib.check(_lib.lib().pcreid_knn_feature(B, C, N, k, _p(x), _p(idx), _stream()), "pcreid_knn_feature")
+    return idx
+
+
+def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
+    _need_cuda(p1, cc, idx)
+    B, C, N = p1.shape
+    S, k = idx.shape[1], idx.shape[2]
+    if not (p1.is_contiguous() and cc.is_contiguous() and idx.is_contiguous()):
+        raise ValueError("sa_edge_mlp inputs must be contiguous")
+    out = torch.empty((B, C, S), device=p1.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_sa_edge_mlp(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2), _p(b2), _p(w3), _p(b3), _p(out),
+                                             _stream()), "pcreid_sa_edge_mlp")
+    return out
+
+
+def edge_gather_max(p, q, idx, act, out=None):
+    _need_cuda(p, q, idx)
+    B, C, N = p.shape
+    k = idx.shape[2]
+    if not (p.is_contiguous() and q.is_contiguous() and idx.is_contiguous()):
+        raise ValueError("edge_gather_max inputs must be contiguous")
+    if out is None:
+        out = torch.empty((B, C, N), device=p.device, dtype=torch.float32)
+    o_bs, ldo = _cn(out, "out")
+    _lib.check(_lib.lib().pcreid_edge_gather_max(B, C, N, k, _p(p), _p(q), _p(idx), act, _p(out), o_bs, ldo, _stream()),
+               "pcreid_edge_gather_max")
+    return out
+
+
+def pair_concat_head(a, bv, et, ed, w2, g1, be1, g2, be2, w, b0, groups, mask=None):
+    _need_cuda(a, bv, et, ed)
+    T, D, E = a.shape[0], bv.shape[0], et.shape[1]
+    out = torch.empty((T, D), device=a.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_pair_concat_head(T, D, E, groups, _p(a), _p(bv), _p(et), _p(ed), _p(w2), _p(g1), _p(be1),
+                                                  _p(g2), _p(be2), _p(w), float(b0), _p(mask), _p(out), _stream()),
+               "pcreid_pair_concat_head")
+    return out

@@ -1,0 +1,25 @@
+"""ball_query(min_radius, max_radius, sample_num, xyz, center_xyz) -> int32 (B, npoint, sample_num).
+Reference: mmdet3d/ops/ball_query/ball_query.py:7-54."""
+import torch
+
+from ._common import check, lib, ptr, require, stream
+
+
+class BallQuery:
+    @staticmethod
+    def apply(min_radius, max_radius, sample_num, xyz, center_xyz):
+        require(center_xyz, "center_xyz")
+        require(xyz, "xyz")
+        assert min_radius < max_radius
+        B, N, _ = xyz.shape
+        npoint = center_xyz.shape[1]
+        with torch.cuda.device(xyz.device):
+            idx = torch.zeros((B, npoint, sample_num), dtype=torch.int32, device=xyz.device)
+            check(lib().pcreid_ball_query(B, N, npoint, float(min_radius), float(max_radius), sample_num, ptr(center_xyz),
+                                          ptr(xyz), ptr(idx), stream()), "pcreid_ball_query")
+        return idx
+
+    forward = apply
+
+
+ball_query = BallQuery.apply
