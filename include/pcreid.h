@@ -64,9 +64,9 @@ int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, 
 /* torch-path kNN of the ReID backbones (models/pointnet2_utils.py:169-216 square_distance + argsort):
  * expansion-form distance, canonical ascending (d, idx) order.  idx (b,m,k) i32. */
 int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream);
-/* DGCNN kNN (models/dgcnn_orig.py:22-28): x (b,c,n) channel-major, k largest of
+/* DGCNN kNN (models/dgcnn_orig.py:22-28): x (b,c,n) channel-major with object stride x_bs, k largest of
  * pd = -|xi|^2 + 2 xi.xj - |xj|^2, lower index first on ties.  idx (b,n,k) i32. */
-int pcreid_knn_feature(int b, int c, int n, int k, const float* x, int* idx, void* stream);
+int pcreid_knn_feature(int b, int c, int n, int k, const float* x, long long x_bs, int* idx, void* stream);
 
 enum { PCREID_ACT_NONE = 0, PCREID_ACT_RELU = 1, PCREID_ACT_LEAKY02 = 2, PCREID_ACT_ELU1 = 3 };
 
@@ -82,7 +82,7 @@ typedef struct pcreid_linear_args {
   const float* bias;
   const float* R; long long r_bs; int ldr; const int* r_map; int res_after_act;
   int act;
-  float* Y; long long y_bs; int ldy;
+  float* Y; long long y_bs; int ldy; int y_pm;   /* y_pm=1: Y written point-major (rows, CO), ldy = row stride */
 } pcreid_linear_args;
 int pcreid_cn_linear(const pcreid_linear_args* args, void* stream);
 

@@ -1,0 +1,108 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference modules
+(imported by path from /root/reference through oracle/ref_loader.py) on seeded synthetic inputs.
+
+    python oracle/make_golden.py          # only works where /root/reference exists
+
+The reference ships no golden vectors; these fixtures are what pins the oracle and
+the CUDA path on machines where the reference tree is absent (the GPU box).  Weights are the reference
+modules' default init under torch.manual_seed(66) (reference `seed`, reidentification_runtime.py:16)
+followed by oracle.reid_oracle.perturb_norm_state (deterministic de-trivialisation of norm statistics);
+the product's modules reproduce them bit-for-bit from the same seed (asserted by a checksum).
+The only non-reference code on the path is the ReIDNet glue (ReIDNet.py:311-332, 231-247, 526-534,
+444-462), which cannot be imported (mmcv / mmdet / pytorch3d absent) and is restated below on top of
+the reference's own corss_attention / LinearRes / nn.Linear modules.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader, reid_oracle as O   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def checksum(sd):
+    return float(sum(v.double().abs().sum() for k, v in sorted(sd.items()) if v.dtype.is_floating_point))
+
+
+def build_reference(R, kind):
+    """Reference modules in ReIDNet.__init__ construction order (backbone, match_head, downsample, cross_stage1/2)."""
+    torch.manual_seed(66)
+    mods = {}
+    if kind == "pt":
+        mods["backbone"] = R.Pointnet_Backbone(input_channels=0, use_xyz=True, conv_out=64)
+        ng = 8
+    elif kind == "dgcnn":
+        mods["backbone"] = R.DGCNN(dropout=0.5, emb_dims=1024, k=20, output_channels=40)
+        ng = 16
+    else:
+        mods["backbone"] = R.PointNet(k=40, normal_channel=False)
+        ng = 8
+    mods["match_head"] = torch.nn.Sequential(R.LinearRes(128, 128, norm='GN', ng=ng), torch.nn.Linear(128, 1))
+    if kind != "pt":
+        mods["downsample"] = torch.nn.Sequential(R.LinearRes(1024, 512, norm='GN', ng=64), R.LinearRes(512, 128, norm='GN', ng=16),
+                                                 torch.nn.Linear(128, 64))
+    mods["cross_stage1"] = R.corss_attention(d_model=64, nhead=2, attention='linear')
+    mods["cross_stage2"] = R.corss_attention(d_model=64, nhead=2, attention='linear')
+    net = torch.nn.ModuleDict(mods).eval()
+    sd = O.perturb_norm_state(net.state_dict())
+    net.load_state_dict(sd)
+    return net, sd
+
+
+@torch.no_grad()
+def ref_encode(net, kind, pts, blist):
+    if kind == "pt":
+        return net["backbone"](pts, blist)
+    _, h = net["backbone"](pts.permute(0, 2, 1), blist)
+    B, C, N = h.shape
+    h = net["downsample"](h.permute(0, 2, 1).reshape(-1, C)).reshape(B, N, -1).permute(0, 2, 1)
+    return pts, h
+
+
+@torch.no_grad()
+def ref_match(net, h1, h2, xyz1, xyz2):
+    a = net["cross_stage1"](h1, xyz1, h2, xyz2)
+    b = net["cross_stage1"](h2, xyz2, h1, xyz1)
+    o1 = net["cross_stage2"](a, xyz1, b, xyz2)
+    o2 = net["cross_stage2"](b, xyz2, a, xyz1)
+    out = torch.cat([o1, o2], dim=2)
+    pooled = torch.cat((F.adaptive_max_pool1d(out, 1).view(out.size(0), -1), F.adaptive_avg_pool1d(out, 1).view(out.size(0), -1)), 1)
+    return net["match_head"](pooled).squeeze(1)
+
+
+def main():
+    R = ref_loader.load()
+    os.makedirs(OUT, exist_ok=True)
+    for kind, N, blist, T, D in (("pt", 128, [128, 64, 32], 4, 5), ("pt256", 256, [256, 128, 64], 2, 3),
+                                 ("dgcnn", 128, [128, 64, 32], 3, 4), ("pointnet", 128, [128, 64, 32], 4, 4)):
+        base = "pt" if kind.startswith("pt") else kind
+        net, sd = build_reference(R, base)
+        t = O.synth_objects(T, N, 0)
+        d = O.synth_objects(D, N, 1)
+        xt, ht = ref_encode(net, base, t, blist)
+        xd, hd = ref_encode(net, base, d, blist)
+        pairs = torch.cartesian_prod(torch.arange(T), torch.arange(D))
+        logits = ref_match(net, ht[pairs[:, 0]], hd[pairs[:, 1]], xt[pairs[:, 0]], xd[pairs[:, 1]]).reshape(T, D)
+        np.savez_compressed(os.path.join(OUT, f"reid_{kind}.npz"), tracks=t.numpy(), dets=d.numpy(), h_t=ht.numpy(),
+                            h_d=hd.numpy(), logits=logits.numpy(), weight_checksum=np.float64(checksum(sd)),
+                            backbone_list=np.array(blist))
+        print(kind, "h", tuple(ht.shape), "logits std", float(logits.std()), "checksum", checksum(sd))
+    # kNN index golden from the reference's own knn_point / dgcnn knn on tie-free input
+    p2 = R.pointnet2_utils
+    x = O.synth_objects(3, 160, 5)
+    idx = p2.knn_point(48, x, x[:, :80])
+    xf = torch.randn(2, 64, 96, generator=torch.Generator().manual_seed(3))
+    idx_f = R.dgcnn_orig.knn(xf, 20)
+    np.savez_compressed(os.path.join(OUT, "knn_torch_path.npz"), xyz=x.numpy(), idx=idx.numpy().astype(np.int32),
+                        feat=xf.numpy(), idx_feat=idx_f.numpy().astype(np.int32))
+    print("knn golden written")
+
+
+if __name__ == "__main__":
+    main()

@@ -172,3 +172,49 @@ void oracle_gather_points(int b, int c, int n, int m, const float *points, const
       for (int s = 0; s < m; ++s)
         out[((size_t)bi * c + ci) * m + s] = points[((size_t)bi * c + ci) * n + idx[(size_t)bi * m + s]];
 }
+
+/* ---- canonical arithmetic of the torch-path distances (what the CUDA kNN kernels reproduce) ----
+ * square_distance (models/pointnet2_utils.py:169-188) as torch/MKL evaluates it on the CPU oracle:
+ *   m = fma chain over (x,y,z); |v|^2 = (x*x + y*y) + z*z; d = (-2*m + |q|^2) + |p|^2             */
+void oracle_sqdist_expand(int b, int n, int m, const float *xyz, const float *new_xyz, float *out) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int q = 0; q < m; ++q) {
+      const float *c = new_xyz + ((size_t)bi * m + q) * 3;
+      float qn = (c[0] * c[0] + c[1] * c[1]) + c[2] * c[2];
+      for (int i = 0; i < n; ++i) {
+        const float *p = xyz + ((size_t)bi * n + i) * 3;
+        float mm = c[0] * p[0];
+        mm = fmaf(c[1], p[1], mm);
+        mm = fmaf(c[2], p[2], mm);
+        float pn = (p[0] * p[0] + p[1] * p[1]) + p[2] * p[2];
+        out[((size_t)bi * m + q) * n + i] = (-2.f * mm + qn) + pn;
+      }
+    }
+}
+
+/* DGCNN pairwise "distance" (models/dgcnn_orig.py:22-25): x (b,c,n);
+ *   m_ij sequential fma chain over channels; xx_i = cascade sum (blocks of 16 channels, block sums in order);
+ *   pd_ij = ((-xx_j) - (-2 m_ij)) - xx_i                                                           */
+void oracle_dgcnn_pd(int b, int c, int n, const float *x, float *out) {
+  float *xx = (float *)malloc(sizeof(float) * n);
+  for (int bi = 0; bi < b; ++bi) {
+    const float *xb = x + (size_t)bi * c * n;
+    for (int j = 0; j < n; ++j) {
+      float tot = 0.f;
+      for (int c0 = 0; c0 < c; c0 += 16) {
+        float blk = 0.f;
+        for (int cc = c0; cc < c0 + 16 && cc < c; ++cc) { float v = xb[(size_t)cc * n + j]; blk = blk + v * v; }
+        tot = c0 == 0 ? blk : tot + blk;
+      }
+      xx[j] = tot;
+    }
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        float acc = 0.f;
+        for (int cc = 0; cc < c; ++cc) acc = fmaf(xb[(size_t)cc * n + i], xb[(size_t)cc * n + j], acc);
+        float inner = -2.f * acc;
+        out[((size_t)bi * n + i) * n + j] = ((-xx[j]) - inner) - xx[i];   /* xx is (B,1,N): broadcasts over rows first */
+      }
+  }
+  free(xx);
+}

@@ -185,3 +185,24 @@ def ref_gather_points(features, indices):
     out = torch.zeros(B, C, M, device=features.device)
     _ref().ref_gather_points(B, C, N, M, _p(features), _p(indices), _p(out), _s())
     return out
+
+
+# ---------------------------------------------------------------- canonical distance arithmetic (CPU)
+def sqdist_expand(new_xyz, xyz):
+    """C restatement of square_distance(new_xyz, xyz) -> (B, S, N); must equal torch bit for bit."""
+    x = _c(xyz, np.float32)
+    c = _c(new_xyz, np.float32)
+    B, N, _ = x.shape
+    S = c.shape[1]
+    out = np.zeros((B, S, N), np.float32)
+    _cpu().oracle_sqdist_expand(B, N, S, _fp(x), _fp(c), _fp(out))
+    return torch.from_numpy(out)
+
+
+def dgcnn_pd(x):
+    """C restatement of dgcnn_orig.knn's pairwise_distance for x (B, C, N) -> (B, N, N)."""
+    a = _c(x, np.float32)
+    B, C, N = a.shape
+    out = np.zeros((B, N, N), np.float32)
+    _cpu().oracle_dgcnn_pd(B, C, N, _fp(a), _fp(out))
+    return torch.from_numpy(out)

@@ -24,7 +24,7 @@ class LinearArgs(ctypes.Structure):
         ("bias", c_vp),
         ("R", c_vp), ("r_bs", c_ll), ("ldr", c_int), ("r_map", c_vp), ("res_after_act", c_int),
         ("act", c_int),
-        ("Y", c_vp), ("y_bs", c_ll), ("ldy", c_int),
+        ("Y", c_vp), ("y_bs", c_ll), ("ldy", c_int), ("y_pm", c_int),
     ]
 
 
@@ -48,7 +48,7 @@ _SIGS = {
     "pcreid_knn": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_t": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_point": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
-    "pcreid_knn_feature": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp],
+    "pcreid_knn_feature": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_vp],
     "pcreid_ball_query": [c_int, c_int, c_int, c_float, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
@@ -91,6 +91,11 @@ def lib():
     return L
 
 
+ABI_CALLS = 0   # number of C-ABI compute calls made by this process (each launches >= 1 kernel)
+
+
 def check(rc, what):
+    global ABI_CALLS
+    ABI_CALLS += 1
     if rc != 0:
         raise RuntimeError(f"{what} failed: {ERRORS.get(rc, rc)}")

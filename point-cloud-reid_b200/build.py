@@ -43,7 +43,7 @@ def build_library(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed for {src}:\n{out}")
         if verbose and out:
             print(out)
-    subprocess.run([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart"], check=True)
+    subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"], check=True)
     return LIB
 
 

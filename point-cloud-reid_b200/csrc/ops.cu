@@ -178,13 +178,13 @@ static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, co
 // DGCNN kNN in feature space (models/dgcnn_orig.py:22-28)
 //   m_ij  = sequential fma chain over channels (what torch.matmul does on the CPU oracle)
 //   xx_i  = sum_c x_ci^2, ATen cascade: sequential inside blocks of 16 channels, block sums added in order
-//   pd_ij = ((-xx_i) - (-2 m_ij)) - xx_j ; k largest, lower index first on ties
+//   pd_ij = ((-xx_j) - (-2 m_ij)) - xx_i ; k largest, lower index first on ties
 // CTA = 8 warps x QPW queries; the object's features stream through shared memory in 128-point tiles.
 // ------------------------------------------------------------------------------------------------
 constexpr int KF_JT = 128;
 template <int QPW>
 __global__ void __launch_bounds__(256) knn_feature_kernel(int C, int N, int k, const float* __restrict__ x,
-                                                          int* __restrict__ idx, int npad) {
+                                                          long long x_bs, int* __restrict__ idx, int npad) {
   extern __shared__ uint32_t smem_u32[];
   constexpr int QPC = 8 * QPW;
   float* xs = reinterpret_cast<float*>(smem_u32);              // [C][KF_JT]
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(256) knn_feature_kernel(int C, int N, int k, c
   uint32_t* keys = reinterpret_cast<uint32_t*>(qv + (size_t)QPC * C);   // [QPC][npad]
   const int b = blockIdx.y, q0 = blockIdx.x * QPC;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* xb = x + (size_t)b * C * N;
+  const float* xb = x + (size_t)b * x_bs;
 
   for (int j = threadIdx.x; j < N; j += 256) {
     float tot = 0.f;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) knn_feature_kernel(int C, int N, int k, c
         const int j = j0 + lane + 32 * t;
         if (j < N) {
           float inner = __fmul_rn(-2.f, acc[a][t]);
-          float pd = __fsub_rn(__fsub_rn(-xi, inner), xx[j]);
+          float pd = __fsub_rn(__fsub_rn(-xx[j], inner), xi);   // (-xx (B,1,N)) - inner - xx^T
           keys[(size_t)ql * npad + j] = f32_to_ordered(-pd);
         }
       }
@@ -498,7 +498,7 @@ int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* 
   return knn_launch(1, b, n, m, k, xyz, new_xyz, idx, nullptr, k, 1, 0, (cudaStream_t)stream);
 }
 
-int pcreid_knn_feature(int b, int c, int n, int k, const float* x, int* idx, void* stream) {
+int pcreid_knn_feature(int b, int c, int n, int k, const float* x, long long x_bs, int* idx, void* stream) {
   if (b <= 0 || n <= 0 || k <= 0) return PCREID_OK;
   if (!x || !idx || c <= 0 || k > n) return PCREID_ERR_ARG;
   if (b > 65535) return PCREID_ERR_UNSUPPORTED;
@@ -508,13 +508,13 @@ int pcreid_knn_feature(int b, int c, int n, int k, const float* x, int* idx, voi
   const size_t budget = 200 * 1024;
   if (need(32) <= budget) {
     cudaFuncSetAttribute(knn_feature_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(32));
-    knn_feature_kernel<4><<<dim3(ceil_div(n, 32), b), 256, need(32), st>>>(c, n, k, x, idx, npad);
+    knn_feature_kernel<4><<<dim3(ceil_div(n, 32), b), 256, need(32), st>>>(c, n, k, x, x_bs, idx, npad);
   } else if (need(16) <= budget) {
     cudaFuncSetAttribute(knn_feature_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(16));
-    knn_feature_kernel<2><<<dim3(ceil_div(n, 16), b), 256, need(16), st>>>(c, n, k, x, idx, npad);
+    knn_feature_kernel<2><<<dim3(ceil_div(n, 16), b), 256, need(16), st>>>(c, n, k, x, x_bs, idx, npad);
   } else if (need(8) <= budget) {
     cudaFuncSetAttribute(knn_feature_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need(8));
-    knn_feature_kernel<1><<<dim3(ceil_div(n, 8), b), 256, need(8), st>>>(c, n, k, x, idx, npad);
+    knn_feature_kernel<1><<<dim3(ceil_div(n, 8), b), 256, need(8), st>>>(c, n, k, x, x_bs, idx, npad);
   } else {
     return PCREID_ERR_UNSUPPORTED;
   }

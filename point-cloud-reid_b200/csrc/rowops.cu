@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_arg
   float* Y = a.Y + (size_t)b * a.y_bs;
   const float* R = nullptr;
   if (a.R) R = a.R + (size_t)(a.r_map ? a.r_map[b] : b) * a.r_bs;
-  const bool vy = (a.ldy % 4 == 0) && (a.rows % 4 == 0) && aligned16(Y) && (!R || ((a.ldr % 4 == 0) && aligned16(R)));
+  const bool vy = !a.y_pm && (a.ldy % 4 == 0) && (a.rows % 4 == 0) && aligned16(Y) && (!R || ((a.ldr % 4 == 0) && aligned16(R)));
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     const int co = co0 + col_of<TN>(ty, j);
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_arg
           if (R && !a.res_after_act) x += r;
           x = apply_act(x, a.act);
           if (R && a.res_after_act) x += r;
-          Y[(size_t)co * a.ldy + n + i] = x;
+          if (a.y_pm) Y[(size_t)(n + i) * a.ldy + co] = x;
+          else Y[(size_t)co * a.ldy + n + i] = x;
         }
       }
     }

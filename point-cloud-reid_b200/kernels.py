@@ -47,7 +47,8 @@ def _map(m):
 
 
 def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_after_act=False, rows=None,
-              x1_map=None, x2_map=None, w1_map=None, r_map=None, x1_pm=False, x2_pm=False, out=None, B=None):
+              x1_map=None, x2_map=None, w1_map=None, r_map=None, x1_pm=False, x2_pm=False, out=None, B=None,
+              y_pm=False):
     """Y[b,:,n] = act(W1^T X1[b,:,n] + W2^T X2[b,:,n] + bias (+res)) (+res).  w*: k-major (K, CO) or (Bw, K, CO)."""
     _need_cuda(x1, w1, x2, w2, bias, res, out)
     a = _lib.LinearArgs()
@@ -90,9 +91,16 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
         a.r_bs, a.ldr = _cn(res, "res")
         a.R, a.r_map, a.res_after_act = _p(res), _p(_map(r_map)), int(res_after_act)
     a.act = act
-    if out is None:
-        out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
-    a.y_bs, a.ldy = _cn(out, "out")
+    if y_pm:
+        if out is None:
+            out = torch.empty((B, rows, CO), device=x1.device, dtype=torch.float32)
+        if not out.is_contiguous():
+            raise ValueError("point-major out must be contiguous (B, rows, CO)")
+        a.y_bs, a.ldy, a.y_pm = rows * CO, CO, 1
+    else:
+        if out is None:
+            out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
+        a.y_bs, a.ldy = _cn(out, "out")
     a.Y = _p(out)
     _lib.check(_lib.lib().pcreid_cn_linear(ctypes.byref(a), _stream()), "pcreid_cn_linear")
     return out
@@ -188,11 +196,12 @@ def knn_point(k, xyz, new_xyz):
 def knn_feature(x, k):
     """DGCNN kNN in feature space: x (B, C, N) contiguous -> int32 (B, N, k)."""
     _need_cuda(x)
-    if not x.is_contiguous():
-        raise ValueError("x must be contiguous (B, C, N)")
     B, C, N = x.shape
+    x_bs, ld = _cn(x, "x")
+    if C > 1 and ld != N:
+        raise ValueError("x must be dense in (C, N) per object")
     idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_knn_feature(B, C, N, k, _p(x), _p(idx), _stream()), "pcreid_knn_feature")
+    _lib.check(_lib.lib().pcreid_knn_feature(B, C, N, k, _p(x), x_bs, _p(idx), _stream()), "pcreid_knn_feature")
     return idx
 
 

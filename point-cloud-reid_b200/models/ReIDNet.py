@@ -1,0 +1,321 @@
+"""ReIDNet -- siamese point-set encoder + match head (mmdet3d/models/ReIDNet.py:111-167 ctor, 189-212
+forward / forward_inference, 231-247 xcorr_eff, 311-332 siamese_forward, 444-462 match_forward_inference,
+526-534 get_pooled_feats, 637-689 forward_test), inference path only, on the pcreid CUDA kernels.
+
+New relative to the reference: ``match_all_pairs`` scores the whole track x detection matrix the way the
+deprecated tracker did (trackers/deprecated/tracking_point_reid.py:95-116) but without materialising
+``feat[pairs[:, 0]]`` / ``feat[pairs[:, 1]]``: everything that depends on one object only (stage-1 queries,
+key/value summaries, position codes) is computed once per object and gathered through index maps.
+"""
+import copy
+
+import torch
+from torch import nn
+
+from .. import kernels as K
+from .attention import corss_attention
+from .backbone_net import Pointnet_Backbone
+from .builder import FUSIONMODELS
+from .dgcnn_orig import DGCNN
+from .lanegcn_nets import LinearRes
+from .pointnet import PointNet
+
+module_obj = {
+    'Linear': nn.Linear, 'ReLU': nn.ReLU, 'LSTM': nn.LSTM, 'GroupNorm': nn.GroupNorm, 'Embedding': nn.Embedding,
+    'LayerNorm': nn.LayerNorm, 'LinearRes': LinearRes, 'Pointnet_Backbone': Pointnet_Backbone,
+    'corss_attention': corss_attention, 'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d, 'BatchNorm1d': nn.BatchNorm1d,
+    'Sigmoid': nn.Sigmoid, 'dgcnn': DGCNN, 'PointNet': PointNet,
+}
+_OUT_OF_SCOPE = ('PostRes', 'local_self_attention', 'cross_lin_attn')   # image / 'xcorr' matchers
+
+
+def build_module(cfg):
+    """ReIDNet.py:78-87 (without mutating the caller's cfg)."""
+    if cfg is None or cfg == {}:
+        return None
+    if isinstance(cfg, list):
+        return build_sequential(cfg)
+    cfg = dict(cfg)
+    typ = cfg.pop('type')
+    if typ in _OUT_OF_SCOPE:
+        raise NotImplementedError(f"module type '{typ}' is outside the accelerated hot path")
+    return module_obj[typ](**cfg)
+
+
+def build_sequential(module_list):
+    if module_list is None or module_list == {}:
+        return None
+    return nn.Sequential(*[build_module(c) for c in module_list])
+
+
+def _i32(t):
+    return t.to(torch.int32).contiguous()
+
+
+@FUSIONMODELS.register_module()
+class ReIDNet(nn.Module):
+    def __init__(self, hidden_size, backbone, cls_head, match_head, shape_head, fp_head, downsample,
+                 cross_stage1, local_stage1, cross_stage2, local_stage2, match_type='xcorr', pool_type='max', combine='cat',
+                 compute_summary=True, train_cfg=None, test_cfg=None, backbone_list=[512, 256, 128], use_dgcnn=False,
+                 losses_to_use=dict(kl=True, match=True, cls=True, shape=True, fp=True, dense=False), output_sequence_size=32,
+                 alpha=dict(kl=1, match=1, cls=1, shape=1, fp=1, triplet=1, dense=1), triplet_sample_num=5,
+                 triplet_loss=dict(margin=0.2, p=2), eval_only=False, use_o=False, eval_flip=False):
+        super().__init__()
+        self.eval_only = eval_only
+        self.hidden_size = hidden_size
+        self.match_type = match_type
+        self.backbone = build_module(backbone)
+        self.cls_head = build_module(cls_head)
+        self.match_head = build_module(match_head)
+        self.shape_head = build_module(shape_head)
+        self.fp_head = build_module(fp_head)
+        self.downsample = build_module(downsample)
+        self.cross_stage1 = build_module(cross_stage1)
+        self.local_stage1 = build_module(local_stage1)
+        self.cross_stage2 = build_module(cross_stage2)
+        self.local_stage2 = build_module(local_stage2)
+        self.losses_to_use = dict(kl=False, match=True, cls=False, shape=False, fp=False, dense=False)
+        self.losses_to_use.update(losses_to_use)
+        self.backbone_list = backbone_list
+        self.output_sequence_size = output_sequence_size
+        self.pool_type = pool_type
+        self.maxpool = nn.MaxPool1d(self.output_sequence_size)
+        self.bce = nn.BCEWithLogitsLoss()
+        self.alpha = alpha
+        self.use_o = use_o
+        self.eval_flip = eval_flip
+        self.verbose = False
+        self.sampling = None
+        self.compute_summary = compute_summary
+        self.use_dgcnn = use_dgcnn
+        self.combine = combine
+        if self.match_type not in ('xcorr_eff', 'concat'):
+            raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
+                                      "(shipped point configs use 'xcorr_eff'; the baseline uses 'concat')")
+
+    # ------------------------------------------------------------------ encoders
+    def _encode(self, pts):
+        """pts (B, N, 3) -> (xyz (B, N, 3), h (B, C, N)); applies the per-point `downsample` for DGCNN / PointNet
+        exactly as siamese_forward does (ReIDNet.py:316-324)."""
+        pts = pts.float().contiguous()
+        if self.use_dgcnn or isinstance(self.backbone, (DGCNN, PointNet)):
+            _, h = self.backbone(pts.permute(0, 2, 1).contiguous(), self.backbone_list)
+            if self.downsample is not None:
+                for m in self.downsample:
+                    if isinstance(m, LinearRes):
+                        h = m.forward_cn(h)
+                    elif isinstance(m, nn.Linear):
+                        h = K.cn_linear(h, _kmajor_cached(m), bias=_bias_cached(m))
+                    else:
+                        raise NotImplementedError(type(m))
+            return pts, h
+        return self.backbone(pts, self.backbone_list)
+
+    def encode(self, pts):
+        """public inference entry: pts (B, N, 3) -> (xyz (B, N, 3), per-point embedding (B, C, N))."""
+        with torch.no_grad():
+            return self._encode(pts)
+
+    def forward_inference(self, pts_batched):
+        with torch.no_grad():
+            return self.backbone(pts_batched, self.backbone_list)
+
+    def siamese_forward(self, sparse_1, sparse_2):
+        assert sparse_1.shape == sparse_2.shape
+        b = sparse_1.shape[0]
+        with torch.no_grad():
+            xyz, h = self._encode(torch.cat([sparse_1, sparse_2], dim=0))
+        return xyz[:b], xyz[b:], h[:b], h[b:]
+
+    # ------------------------------------------------------------------ pooling / heads
+    def get_pooled_feats(self, h_cat):
+        if self.pool_type == 'max':      # MaxPool1d over the channel axis of h.permute(0,2,1) (ReIDNet.py:527-528)
+            if h_cat.shape[1] != self.output_sequence_size:
+                raise NotImplementedError("pool_type='max' with channels != output_sequence_size")
+            return K.cn_chanmax(_cn(h_cat))
+        if self.pool_type == 'both':
+            return K.cn_pool(_cn(h_cat), mode=0)
+        raise NotImplementedError
+
+    def _head_cn(self, pooled_cn):
+        """match_head on channel-major pooled features (1, C, P) -> logits (P,)."""
+        x = pooled_cn
+        for m in self.match_head:
+            if isinstance(m, LinearRes):
+                x = m.forward_cn(x)
+            elif isinstance(m, nn.Linear):
+                x = K.cn_linear(x, _kmajor_cached(m), bias=_bias_cached(m))
+            else:
+                raise NotImplementedError(type(m))
+        return x.reshape(-1)
+
+    def xcorr_eff(self, o1, xyz1, o2, xyz2, combine='add'):
+        o1__ = self.cross_stage1(o1, xyz1, o2, xyz2)
+        o2__ = self.cross_stage1(o2, xyz2, o1, xyz1)
+        o1 = self.cross_stage2(o1__, xyz1, o2__, xyz2)
+        o2 = self.cross_stage2(o2__, xyz2, o1__, xyz1)
+        if self.combine == 'add':
+            out = o1 + o2
+        elif self.combine == 'minus':
+            out = o1 - o2
+        elif self.combine == 'cat':
+            out = torch.cat([o1, o2], dim=1)
+        elif self.combine == 'point-cat':
+            out = torch.cat([o1, o2], dim=2)
+        else:
+            raise NotImplementedError(self.combine)
+        return out, o1, o2
+
+    def match_forward_inference(self, h1, h2, xyz1, xyz2):
+        """aligned pairs: h1/h2 (P, C, N), xyz1/xyz2 (P, N, 3) -> logits (P,)."""
+        with torch.no_grad():
+            P = h1.shape[0]
+            if self.match_type == 'xcorr_eff':
+                ar = torch.arange(P, device=h1.device, dtype=torch.int32)
+                return self._xcorr_pairs(_cn(h1), xyz1.float().contiguous(), _cn(h2), xyz2.float().contiguous(), ar, ar)
+            if self.match_type == 'concat':
+                e1 = K.cn_chanmax(_cn(h1))
+                e2 = K.cn_chanmax(_cn(h2))
+                cat = torch.cat([e1, e2], dim=1).t().contiguous().unsqueeze(0)
+                return self._head_cn(cat)
+            raise NotImplementedError
+
+    # ------------------------------------------------------------------ all-pairs driver
+    def _xcorr_pairs(self, h_t, xyz_t, h_d, xyz_d, ti, dj):
+        """xcorr_eff + pooling + head for the pairs (ti[p], dj[p]) -> logits (P,), fp32 parity path."""
+        X1, X2 = self.cross_stage1, self.cross_stage2
+        N_t, N_d = h_t.shape[2], h_d.shape[2]
+        # ---- per-object work (stage 1): queries, template summaries
+        q_t, q_d = X1.search_query(h_t), X1.search_query(h_d)
+        wkv_t, ks_t = X1.template_summary(h_t, X1.position_code(xyz_t))
+        wkv_d, ks_d = X1.template_summary(h_d, X1.position_code(xyz_d))
+        pos2_t, pos2_d = X2.position_code(xyz_t), X2.position_code(xyz_d)
+        # ---- per-pair work
+        a = X1.attend(h_t, q_t, wkv_d, ks_d, N_d, s_map=ti, t_map=dj)       # o1__ = X1(o1 <- o2)
+        b = X1.attend(h_d, q_d, wkv_t, ks_t, N_t, s_map=dj, t_map=ti)       # o2__ = X1(o2 <- o1)
+        wkv_b, ks_b = X2.template_summary(b, pos2_d, pos_map=dj)
+        wkv_a, ks_a = X2.template_summary(a, pos2_t, pos_map=ti)
+        o1 = X2.attend(a, X2.search_query(a), wkv_b, ks_b, N_d)
+        o2 = X2.attend(b, X2.search_query(b), wkv_a, ks_a, N_t)
+        return self._pairs_head(o1, o2)
+
+    def _pairs_head(self, o1, o2):
+        if self.pool_type == 'both' and self.combine == 'point-cat':
+            return self._head_cn(K.cn_pool(o1, o2, mode=0, transposed=True))
+        out = {'add': lambda: o1 + o2, 'minus': lambda: o1 - o2, 'cat': lambda: torch.cat([o1, o2], 1),
+               'point-cat': lambda: torch.cat([o1, o2], 2)}[self.combine]()
+        return self._head_cn(self.get_pooled_feats(out).t().contiguous().unsqueeze(0))
+
+    def match_all_pairs(self, h_t, xyz_t, h_d, xyz_d, pair_mask=None, chunk=8192):
+        """Dense (T, D) logit matrix; entries where ``pair_mask`` (bool (T, D), e.g. the tracker's class gate,
+        tracking_point_reid.py:15-33) is False are 0, as in the reference cost matrix."""
+        with torch.no_grad():
+            h_t, h_d = _cn(h_t), _cn(h_d)
+            xyz_t, xyz_d = xyz_t.float().contiguous(), xyz_d.float().contiguous()
+            T, D = h_t.shape[0], h_d.shape[0]
+            dev = h_t.device
+            if self.match_type == 'concat':
+                return self._concat_all_pairs(h_t, h_d, pair_mask)
+            out = torch.zeros((T, D), device=dev, dtype=torch.float32)
+            if pair_mask is None:
+                pairs = None
+                total = T * D
+            else:
+                pairs = pair_mask.nonzero()
+                total = pairs.shape[0]
+            flat = out.view(-1)
+            for s in range(0, total, chunk):
+                e = min(total, s + chunk)
+                if pairs is None:
+                    lin = torch.arange(s, e, device=dev)
+                    ti, dj = lin // D, lin % D
+                else:
+                    ti, dj = pairs[s:e, 0], pairs[s:e, 1]
+                    lin = ti * D + dj
+                flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
+            return out
+
+    def _concat_all_pairs(self, h_t, h_d, pair_mask):
+        """'concat' head over all pairs, first Linear hoisted per object (W1 [e_t; e_d] = W1a e_t + W1b e_d)."""
+        lr, fin = self.match_head[0], self.match_head[1]
+        e_t, e_d = K.cn_chanmax(h_t), K.cn_chanmax(h_d)                      # (T, E), (D, E)
+        E = e_t.shape[1]
+        pk = lr.packed()
+        if lr.transform is not None or pk["w1"].shape[0] != 2 * E:
+            raise NotImplementedError("concat head expects LinearRes(2E, 2E)")
+        w1a, w1b = _half_cached(lr, pk, E)
+        A = K.cn_linear(e_t.unsqueeze(0), w1a, x1_pm=True, y_pm=True)[0]     # (T, 2E)
+        Bv = K.cn_linear(e_d.unsqueeze(0), w1b, x1_pm=True, y_pm=True)[0]    # (D, 2E)
+        mask = None if pair_mask is None else pair_mask.to(torch.uint8).contiguous()
+        return K.pair_concat_head(A, Bv, e_t, e_d, pk["w2"], pk["g1"], pk["b1"], pk["g2"], pk["b2"],
+                                  fin.weight.detach().float().reshape(-1).contiguous(), float(fin.bias.detach()[0]),
+                                  lr.groups, mask)
+
+    # ------------------------------------------------------------------ mmdet BaseDetector surface
+    def forward(self, return_loss=True, **kwargs):
+        if return_loss:
+            return self.forward_train(**kwargs)
+        return self.forward_test(**kwargs)
+
+    def forward_train(self, *args, **kwargs):
+        raise NotImplementedError("pcreid_b200 implements the inference hot path; train with the reference")
+
+    def preprocess_inputs_size_vis(self, sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2, size_1, size_2,
+                                   vis_1, vis_2):
+        st, ct = torch.stack, torch.cat
+        return (st(sparse_1, 0), st(sparse_2, 0), st(dense_1, 0), st(dense_2, 0), ct(label_1, 0), ct(label_2, 0),
+                ct(id_1, 0), ct(id_2, 0), ct(size_1, 0), ct(size_2, 0), ct(vis_1, 0), ct(vis_2, 0))
+
+    def get_match_supervision(self, h1, h2, xyz1, xyz2, id_1, id_2):
+        return h1, h2, xyz1, xyz2, (id_1 == id_2).float()
+
+    def forward_test(self, sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2, size_1, size_2, vis_1, vis_2,
+                     *args, **kwargs):
+        """Same result dict as ReIDNet.forward_test (ReIDNet.py:637-689) for configs whose auxiliary heads are None."""
+        (sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2, size_1, size_2, vis_1, vis_2) = \
+            self.preprocess_inputs_size_vis(sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2,
+                                            size_1, size_2, vis_1, vis_2)
+        xyz1, xyz2, h1, h2 = self.siamese_forward(sparse_1, sparse_2)
+        h1, h2, xyz1, xyz2, match = self.get_match_supervision(h1, h2, xyz1, xyz2, id_1, id_2)
+        match_preds = self.match_forward_inference(h1, h2, xyz1, xyz2)
+        match_loss = self.bce(match_preds, match) * self.alpha['match']
+        zero = torch.tensor([0.])
+        labels = torch.cat([label_1, label_2], dim=0)
+        results = {
+            'val_dense_loss': zero, 'val_fp_loss': zero, 'val_match_loss': torch.tensor([match_loss]),
+            'val_shape_loss': zero, 'val_cls_loss': zero, 'val_kl_loss': zero,
+            'val_match_preds': match_preds, 'val_match_gt': match, 'val_cls_preds': None, 'val_cls_gt': labels,
+            'val_fp_preds': None, 'val_fp_gt': (labels > 9).float(),
+            'match_classes': torch.cat([label_1.unsqueeze(1), label_2.unsqueeze(1)], dim=1),
+            'is_fp': torch.logical_or(label_1 > 9, label_2 > 9),
+            'num_points': torch.cat([size_1.unsqueeze(1), size_2.unsqueeze(1)], dim=1),
+            'val_vis_gt_all': torch.cat([vis_1.unsqueeze(1), vis_2.unsqueeze(1)], dim=1),
+        }
+        return [results]
+
+
+# ---------------------------------------------------------------------- small caches for plain nn.Linear heads
+def _cn(t):
+    t = t.float()
+    return t if (t.dim() == 3 and (t.stride(2) == 1 or t.shape[2] == 1)) else t.contiguous()
+
+
+def _kmajor_cached(m):
+    key = (m.weight.data_ptr(), m.weight._version)
+    if getattr(m, "_pcreid_key", None) != key:
+        m._pcreid_w = m.weight.detach().float().t().contiguous()
+        m._pcreid_b = None if m.bias is None else m.bias.detach().float().contiguous()
+        m._pcreid_key = key
+    return m._pcreid_w
+
+
+def _bias_cached(m):
+    _kmajor_cached(m)
+    return m._pcreid_b
+
+
+def _half_cached(lr, pk, E):
+    if "w1a" not in pk:
+        pk["w1a"] = pk["w1"][:E].contiguous()
+        pk["w1b"] = pk["w1"][E:].contiguous()
+    return pk["w1a"], pk["w1b"]

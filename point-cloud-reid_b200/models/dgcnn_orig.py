@@ -1,0 +1,63 @@
+"""DGCNN backbone (mmdet3d/models/dgcnn_orig.py:84-152): 4 dynamic kNN-graph EdgeConv layers + conv5.
+
+Each bias-free 1x1 conv on cat(x_j - x_i, x_i) is factorised into a per-point GEMM
+  W [x_j - x_i ; x_i] = Wd x_j + (Wc - Wd) x_i
+so the GEMM runs over N rows instead of N*k, and (eval BatchNorm folded, LeakyReLU monotonic)
+  max_j act(bn(conv(edge_ij))) = act( max_j P[idx_ij] + Q_i ).
+"""
+import torch
+from torch import nn
+
+from .. import kernels as K
+from ._packing import PackedModule, bn_scale_shift
+
+
+class DGCNN(PackedModule):
+    def __init__(self, dropout=0.5, emb_dims=1024, k=20, output_channels=40):
+        super().__init__()
+        self.k = k
+        self.bn1 = nn.BatchNorm2d(64)
+        self.bn2 = nn.BatchNorm2d(64)
+        self.bn3 = nn.BatchNorm2d(128)
+        self.bn4 = nn.BatchNorm2d(256)
+        self.bn5 = nn.BatchNorm1d(emb_dims)
+        self.conv1 = nn.Sequential(nn.Conv2d(6, 64, kernel_size=1, bias=False), self.bn1, nn.LeakyReLU(negative_slope=0.2))
+        self.conv2 = nn.Sequential(nn.Conv2d(64 * 2, 64, kernel_size=1, bias=False), self.bn2, nn.LeakyReLU(negative_slope=0.2))
+        self.conv3 = nn.Sequential(nn.Conv2d(64 * 2, 128, kernel_size=1, bias=False), self.bn3, nn.LeakyReLU(negative_slope=0.2))
+        self.conv4 = nn.Sequential(nn.Conv2d(128 * 2, 256, kernel_size=1, bias=False), self.bn4, nn.LeakyReLU(negative_slope=0.2))
+        self.conv5 = nn.Sequential(nn.Conv1d(512, emb_dims, kernel_size=1, bias=False), self.bn5, nn.LeakyReLU(negative_slope=0.2))
+
+    def _pack(self):
+        pk = {}
+        for i, (conv, bn) in enumerate(((self.conv1, self.bn1), (self.conv2, self.bn2), (self.conv3, self.bn3),
+                                        (self.conv4, self.bn4)), 1):
+            w = conv[0].weight.detach().reshape(conv[0].weight.shape[0], -1).float()
+            c = w.shape[1] // 2
+            s, t = bn_scale_shift(bn)
+            wd, wc = w[:, :c] * s[:, None], w[:, c:] * s[:, None]
+            pk[f"p{i}"] = wd.t().contiguous()
+            pk[f"q{i}"] = (wc - wd).t().contiguous()
+            pk[f"t{i}"] = t.contiguous()
+        s, t = bn_scale_shift(self.bn5)
+        w5 = self.conv5[0].weight.detach().reshape(self.conv5[0].weight.shape[0], -1).float() * s[:, None]
+        pk["w5"] = w5.t().contiguous()
+        pk["t5"] = t.contiguous()
+        return pk
+
+    def forward(self, xyz, backbone_list=None):
+        """xyz (B, 3, N) -> (xyz, features (B, emb_dims, N))."""
+        self._inference_only()
+        pk = self.packed()
+        x = xyz.float().contiguous()
+        B, _, N = x.shape
+        widths = (64, 64, 128, 256)
+        cat = torch.empty((B, sum(widths), N), device=x.device, dtype=torch.float32)
+        cur, off = x, 0
+        for i, co in enumerate(widths, 1):
+            idx = K.knn_feature(cur, self.k)
+            p = K.cn_linear(cur, pk[f"p{i}"])
+            q = K.cn_linear(cur, pk[f"q{i}"], bias=pk[f"t{i}"])
+            cur = K.edge_gather_max(p, q, idx, K.ACT_LEAKY02, out=cat[:, off:off + co])
+            off += co
+        feats = K.cn_linear(cat, pk["w5"], bias=pk["t5"], act=K.ACT_LEAKY02)
+        return xyz, feats

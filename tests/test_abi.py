@@ -1,0 +1,50 @@
+"""The C-ABI shared library loads and exports every symbol include/pcreid.h declares (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pcreid.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\bint\s+(pcreid_\w+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pcreid_b200 import _lib
+    L = _lib.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/pcreid.h but not exported"
+    assert sorted(_lib.exported_symbols()) == names
+    assert L.pcreid_abi_version() >= 1
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of pcreid_linear_args / pcreid_norm_args have the header's field order."""
+    from pcreid_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "pcreid.h")).read()
+    for struct, cls in (("pcreid_linear_args", _lib.LinearArgs), ("pcreid_norm_args", _lib.NormArgs)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            names = decl.replace("*", " ").split(",")
+            fields.append(names[0].split()[-1])
+            fields += [n.strip() for n in names[1:]]
+        assert fields == [f[0] for f in cls._fields_], struct
+
+
+def test_host_helpers_without_gpu():
+    from pcreid_b200 import _lib
+    L = _lib.lib()
+    assert [L.pcreid_fps_block_size(n) for n in (1, 2, 160, 256, 1000, 2048, 5000)] == [1, 2, 128, 256, 512, 1024, 1024]
+    # argument validation happens before any CUDA call
+    assert L.pcreid_knn(1, 8, 4, 101, None, None, None, None, None) == 1
+    assert L.pcreid_cn_linear(None, None) == 1

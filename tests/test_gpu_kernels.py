@@ -1,0 +1,116 @@
+"""-m gpu: every fp32 row-op kernel against the torch emulation of its specification (tests/fake_kernels.py)."""
+import pytest
+import torch
+
+import fake_kernels as F
+import pcreid_b200.kernels as K
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def close(a, b, tol=2e-5):
+    a, b = a.cpu(), b.cpu()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    err = (a - b).abs().max().item()
+    scale = max(1.0, b.abs().max().item())
+    assert err <= tol * scale, f"max err {err} (scale {scale})"
+
+
+@pytest.mark.parametrize("B,K1,CO,N", [(3, 64, 64, 256), (2, 3, 32, 160), (2, 128, 192, 130), (1, 1024, 512, 77), (5, 67, 9, 33)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_cn_linear_basic(B, K1, CO, N, act):
+    x, w, b = rnd(B, K1, N, seed=1), rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
+    close(K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act), F.cn_linear(x, w, bias=b, act=act))
+
+
+def test_cn_linear_two_inputs_residual_maps_strides():
+    B, N = 6, 200
+    x1, x2 = rnd(4, 64, N, seed=1), rnd(3, N, 3, seed=2)
+    w1, w2 = rnd(64, 128, seed=3) / 8, rnd(3, 128, seed=4)
+    res = rnd(5, 128, N, seed=5)
+    m1 = torch.tensor([0, 3, 1, 1, 2, 0], dtype=torch.int32)
+    m2 = torch.tensor([2, 2, 0, 1, 1, 0], dtype=torch.int32)
+    mr = torch.tensor([4, 0, 1, 2, 3, 3], dtype=torch.int32)
+    for after in (False, True):
+        got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), x2_pm=True, act=1, res=res.to(DEV),
+                          res_after_act=after, x1_map=m1.to(DEV), x2_map=m2.to(DEV), r_map=mr.to(DEV), B=B)
+        close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, x2_pm=True, act=1, res=res, res_after_act=after, x1_map=m1, x2_map=m2,
+                               r_map=mr, B=B))
+    # strided views (qkv slices), rows < N, per-object weights with a map, point-major output
+    qkv = rnd(3, 192, N, seed=6)
+    wk = rnd(4, 64, 64, seed=7) / 8
+    wm = torch.tensor([3, 0, 2], dtype=torch.int32)
+    qd = qkv.to(DEV)
+    close(K.cn_linear(qd[:, 64:128], wk.to(DEV), w1_map=wm.to(DEV), rows=96), F.cn_linear(qkv[:, 64:128], wk, w1_map=wm, rows=96))
+    close(K.cn_linear(qd[:, 128:], wk[0].contiguous().to(DEV), y_pm=True), F.cn_linear(qkv[:, 128:], wk[0], y_pm=True))
+    out = torch.zeros(3, 256, N, device=DEV)
+    K.cn_linear(qd[:, :64], wk[1].contiguous().to(DEV), out=out[:, 64:128])
+    close(out[:, 64:128], F.cn_linear(qkv[:, :64], wk[1]))
+    assert float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
+
+
+@pytest.mark.parametrize("C,G,N", [(64, 1, 256), (128, 8, 100), (512, 64, 33), (32, 1, 7)])
+def test_cn_groupnorm(C, G, N):
+    x, g, b, r = rnd(3, C, N, seed=1) * 3 + 1, rnd(C, seed=2), rnd(C, seed=3), rnd(2, C, N, seed=4)
+    rm = torch.tensor([1, 0, 1], dtype=torch.int32)
+    close(K.cn_groupnorm(x.to(DEV), g.to(DEV), b.to(DEV), G), F.cn_groupnorm(x, g, b, G), 1e-4)
+    close(K.cn_groupnorm(x.to(DEV), g.to(DEV), b.to(DEV), G, res=r.to(DEV), r_map=rm.to(DEV), act=1),
+          F.cn_groupnorm(x, g, b, G, res=r, r_map=rm, act=1), 1e-4)
+
+
+@pytest.mark.parametrize("d,H,S", [(64, 2, 256), (32, 2, 100), (128, 2, 300), (64, 2, 37)])
+def test_linear_attention_pieces(d, H, S):
+    k, v, q = rnd(3, d, S, seed=1), rnd(3, d, S, seed=2), rnd(3, d, 150, seed=3)
+    wkv, ks = K.linattn_kv(k.to(DEV), v.to(DEV), H)
+    wkv_r, ks_r = F.linattn_kv(k, v, H)
+    close(wkv, wkv_r, 1e-5)
+    close(ks, ks_r, 1e-5)
+    qm = torch.tensor([2, 0, 0, 1], dtype=torch.int32)
+    km = torch.tensor([1, 1, 2, 0], dtype=torch.int32)
+    close(K.linattn_scale(q.to(DEV), ks, H, S, q_map=qm.to(DEV), ksum_map=km.to(DEV)),
+          F.linattn_scale(q, ks_r, H, S, q_map=qm, ksum_map=km), 1e-4)
+
+
+def test_pooling():
+    a, b = rnd(5, 64, 256, seed=1), rnd(5, 64, 200, seed=2)
+    close(K.cn_pool(a.to(DEV), b.to(DEV), mode=0), F.cn_pool(a, b, mode=0))
+    close(K.cn_pool(a.to(DEV), mode=1, transposed=True), F.cn_pool(a, mode=1, transposed=True))
+    close(K.cn_chanmax(a.to(DEV)), F.cn_chanmax(a))
+    close(K.cn_chanmax(a.to(DEV), transposed=True), F.cn_chanmax(a, transposed=True))
+
+
+@pytest.mark.parametrize("C,N,S,k", [(32, 256, 256, 32), (64, 256, 128, 48), (128, 128, 64, 48), (64, 160, 80, 48), (32, 40, 37, 20)])
+def test_sa_edge_mlp(C, N, S, k):
+    g = torch.Generator().manual_seed(C + k)
+    p1, cc = rnd(3, C, N, seed=1), rnd(3, C, S, seed=2)
+    idx = torch.randint(0, N, (3, S, k), generator=g, dtype=torch.int32)
+    w2, w3 = rnd(C, C, seed=3) / C ** 0.5, rnd(C, C, seed=4) / C ** 0.5
+    b2, b3 = rnd(C, seed=5) * 0.1, rnd(C, seed=6) * 0.1
+    got = K.sa_edge_mlp(p1.to(DEV), cc.to(DEV), idx.to(DEV), w2.to(DEV), b2.to(DEV), w3.to(DEV), b3.to(DEV))
+    close(got, F.sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3))
+
+
+def test_edge_gather_max_into_strided_output():
+    g = torch.Generator().manual_seed(3)
+    p, q = rnd(2, 64, 300, seed=1), rnd(2, 64, 300, seed=2)
+    idx = torch.randint(0, 300, (2, 300, 20), generator=g, dtype=torch.int32)
+    cat = torch.zeros(2, 512, 300, device=DEV)
+    K.edge_gather_max(p.to(DEV), q.to(DEV), idx.to(DEV), 2, out=cat[:, 64:128])
+    close(cat[:, 64:128], F.edge_gather_max(p, q, idx, 2))
+
+
+@pytest.mark.parametrize("T,D", [(5, 70), (33, 32)])
+def test_pair_concat_head(T, D):
+    E, G = 128, 32
+    a, bv, et, ed = rnd(T, 2 * E, seed=1), rnd(D, 2 * E, seed=2), rnd(T, E, seed=3), rnd(D, E, seed=4)
+    w2 = rnd(2 * E, 2 * E, seed=5) / 16
+    g1, b1, g2, b2, w = rnd(2 * E, seed=6), rnd(2 * E, seed=7), rnd(2 * E, seed=8), rnd(2 * E, seed=9), rnd(2 * E, seed=10) / 16
+    mask = (torch.rand(T, D, generator=torch.Generator().manual_seed(1)) > 0.3).to(torch.uint8)
+    dv = lambda *ts: [t.to(DEV) for t in ts]
+    got = K.pair_concat_head(*dv(a, bv, et, ed, w2, g1, b1, g2, b2, w), 0.25, G, mask.to(DEV))
+    close(got, F.pair_concat_head(a, bv, et, ed, w2, g1, b1, g2, b2, w, 0.25, G, mask), 1e-4)

@@ -1,0 +1,107 @@
+"""-m gpu: the encoders and match heads through the reference-facing model API on cuda:0, against the oracle on
+the same seeded inputs and against the committed golden vectors (tests/golden, made from the reference modules).
+
+Tolerances (fp32 parity mode): features 1e-4 absolute (values are O(1)), logits 1e-4, top-1 ReID
+decision unchanged on every row whose oracle top-1/top-2 gap exceeds 2x the tolerance."""
+import pytest
+import torch
+
+import helpers
+from oracle import reid_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = 1e-4
+
+
+@pytest.mark.parametrize("name,kind", [("reid_pt", "pt"), ("reid_pt256", "pt"), ("reid_dgcnn", "dgcnn"), ("reid_pointnet", "pointnet")])
+def test_golden_vectors(name, kind):
+    g = helpers.golden(name)
+    m, _ = helpers.build_pair(kind, tuple(int(v) for v in g["backbone_list"]), device=DEV)
+    assert abs(helpers.weight_checksum(m.state_dict()) - float(g["weight_checksum"])) < 1e-6 * float(g["weight_checksum"])
+    t, d = torch.from_numpy(g["tracks"]).to(DEV), torch.from_numpy(g["dets"]).to(DEV)
+    with torch.no_grad():
+        xt, ht = m._encode(t)
+        xd, hd = m._encode(d)
+    assert (ht.cpu() - torch.from_numpy(g["h_t"])).abs().max() < TOL
+    assert (hd.cpu() - torch.from_numpy(g["h_d"])).abs().max() < TOL
+    L = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    ref = torch.from_numpy(g["logits"])
+    assert (L - ref).abs().max() < TOL
+    ok, agree, n = helpers.margin_aware_top1(ref, L, TOL)
+    assert ok, f"top-1 changed on a decisive row (raw agreement {agree}, {n} decisive rows)"
+
+
+@pytest.mark.parametrize("kind,N,blist", [("pt", 128, (128, 64, 32)), ("pt", 256, (256, 128, 64)), ("pt", 160, (160, 80, 40)),
+                                          ("concat", 128, (128, 64, 32)), ("dgcnn", 256, (128, 64, 32)),
+                                          ("pointnet", 128, (128, 64, 32))])
+@pytest.mark.parametrize("dup", [False, True])
+def test_model_vs_oracle(kind, N, blist, dup):
+    m, orc = helpers.build_pair(kind, blist, device=DEV)
+    t, d = O.synth_objects(6, N, 0, dup=dup), O.synth_objects(7, N, 1, dup=dup)
+    with torch.no_grad():
+        xt, ht = m._encode(t.to(DEV))
+        xd, hd = m._encode(d.to(DEV))
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    assert ht.shape == oht.shape and ht.is_contiguous()
+    assert (ht.cpu() - oht).abs().max() < TOL and (hd.cpu() - ohd).abs().max() < TOL
+    L = m.match_all_pairs(ht, xt, hd, xd, chunk=16).cpu()
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    assert (L - Lo).abs().max() < TOL
+    ok, agree, n = helpers.margin_aware_top1(Lo, L, TOL)
+    assert ok, f"top-1 changed on a decisive row (raw agreement {agree}, {n} decisive rows)"
+    mask = torch.rand(6, 7, generator=torch.Generator().manual_seed(5)) > 0.5
+    Lm = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.to(DEV)).cpu()
+    assert (Lm - Lo * mask).abs().max() < TOL
+
+
+def test_degenerate_clouds_all_points_identical():
+    """all-zero / single-point clouds (empty crops, pc_utils.py:84-89): every kNN distance ties; features must still
+    match because tied neighbours are identical points."""
+    m, orc = helpers.build_pair("pt", device=DEV)
+    t = torch.zeros(2, 128, 3)
+    t[1] = O.synth_objects(1, 1, 3)[0, 0]
+    d = O.synth_objects(3, 128, 1, dup=True)
+    with torch.no_grad():
+        xt, ht = m._encode(t.to(DEV))
+        xd, hd = m._encode(d.to(DEV))
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    assert (ht.cpu() - oht).abs().max() < TOL
+    assert (m.match_all_pairs(ht, xt, hd, xd).cpu() - orc.match_all_pairs(oht, oxt, ohd, oxd)).abs().max() < TOL
+
+
+def test_reference_api_on_gpu():
+    m, orc = helpers.build_pair("pt", device=DEV)
+    s1, s2 = O.synth_objects(4, 128, 2), O.synth_objects(4, 128, 3)
+    x1, x2, h1, h2 = m.siamese_forward(s1.to(DEV), s2.to(DEV))
+    o = orc.siamese_forward(s1, s2)
+    lg = m.match_forward_inference(h1, h2, x1, x2)
+    assert (lg.cpu() - orc.match_forward_inference(o[2], o[3], o[0], o[1])).abs().max() < TOL
+    out, o1, o2 = m.xcorr_eff(h1, x1, h2, x2)
+    ro, _, _ = O.xcorr_eff(orc.sd, o[2], o[0], o[3], o[1])
+    assert (out.cpu() - ro).abs().max() < TOL
+    assert (m.get_pooled_feats(out).cpu() - O.pooled_feats(ro, "both")).abs().max() < TOL
+    xyz, feat = m.forward_inference(s1.to(DEV))
+    assert (feat.cpu() - o[2]).abs().max() < TOL
+
+
+def test_all_pairs_symmetry_property():
+    """point-cat + max/avg pooling makes the logit symmetric under swapping the two objects."""
+    m, _ = helpers.build_pair("pt", device=DEV)
+    a = O.synth_objects(9, 128, 4).to(DEV)
+    with torch.no_grad():
+        xa, ha = m._encode(a)
+    L = m.match_all_pairs(ha, xa, ha, xa)
+    assert (L - L.t()).abs().max() < 1e-4
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from pcreid_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libpcreid_sm100.so")
+    import pcreid_b200.build as bld
+    monkeypatch.setattr(bld, "build_library", lambda *a, **k: None)
+    with pytest.raises((RuntimeError, OSError)):
+        _lib.lib()

@@ -1,0 +1,184 @@
+"""-m gpu: the five mmdet3d point ops + the torch-path kNNs, through the C ABI, bit-exact against
+  (a) the C restatement of the reference kernels (oracle/ops_oracle.c) and
+  (b) the reference's own .cu files compiled unmodified for sm_100a (oracle/_ref), when that library travelled."""
+import pytest
+import torch
+
+from oracle import ops_oracle as P
+from oracle import reid_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def clouds(B, N, seed, kind):
+    if kind == "free":
+        return O.synth_objects(B, N, seed)
+    if kind == "dup":
+        return O.synth_objects(B, N, seed, dup=True)
+    if kind == "same":            # all points identical (subsamplePC of a <=2 point object, datasets/utils.py:610-619)
+        return O.synth_objects(B, 1, seed).expand(B, N, 3).contiguous()
+    if kind == "zero":
+        return torch.zeros(B, N, 3)
+    if kind == "u3":              # three unique points
+        base = O.synth_objects(B, 3, seed)
+        pick = torch.randint(0, 3, (B, N), generator=torch.Generator().manual_seed(seed))
+        return torch.gather(base, 1, pick.unsqueeze(-1).expand(B, N, 3)).contiguous()
+    raise ValueError(kind)
+
+
+KINDS = ["free", "dup", "same", "zero", "u3"]
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,M", [(256, 128), (160, 80), (1000, 64), (37, 37), (2048, 16), (5000, 8)])
+def test_fps_bit_exact(kind, N, M):
+    from pcreid_b200.ops import furthest_point_sample
+    x = clouds(3, N, 1, kind)
+    got = furthest_point_sample(x.to(DEV), M).cpu()
+    assert got.dtype == torch.int32 and got.shape == (3, M)
+    assert torch.equal(got, P.furthest_point_sample(x, M))
+    if P.ref_available():
+        assert torch.equal(got, P.ref_furthest_point_sample(x.to(DEV), M).cpu())
+
+
+def test_fps_many_small_objects_warp_path():
+    from pcreid_b200.ops import furthest_point_sample
+    x = O.synth_objects(700, 256, 5, dup=True)
+    assert torch.equal(furthest_point_sample(x.to(DEV), 64).cpu(), P.furthest_point_sample(x, 64))
+
+
+@pytest.mark.parametrize("N,M", [(128, 32), (100, 100)])
+def test_fps_with_dist_bit_exact(N, M):
+    from pcreid_b200.ops import furthest_point_sample_with_dist
+    x = O.synth_objects(2, N, 2, dup=True)
+    d = ((x[:, :, None, :] - x[:, None, :, :]) ** 2).sum(-1).contiguous()
+    got = furthest_point_sample_with_dist(d.to(DEV), M).cpu()
+    assert torch.equal(got, P.furthest_point_sample_with_dist(d, M))
+    if P.ref_available():
+        assert torch.equal(got, P.ref_furthest_point_sample_with_dist(d.to(DEV), M).cpu())
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,S,k", [(256, 256, 32), (256, 128, 48), (160, 80, 48), (1024, 64, 32), (12, 12, 16), (3000, 40, 100)])
+def test_knn_op_bit_exact_including_heap_ties(kind, N, S, k):
+    from pcreid_b200.ops import knn
+    x = clouds(2, N, 3, kind)
+    c = x[:, :S].contiguous()
+    got = knn(k, x.to(DEV), c.to(DEV), False).cpu()
+    assert got.dtype == torch.int32 and got.shape == (2, k, S)
+    assert torch.equal(got, P.knn(k, x, c))
+    if P.ref_available():
+        assert torch.equal(got, P.ref_knn(k, x.to(DEV), c.to(DEV)).cpu())
+
+
+def test_knn_transposed_and_default_center():
+    from pcreid_b200.ops import knn
+    x = O.synth_objects(2, 64, 9)
+    a = knn(8, x.to(DEV)).cpu()
+    b = knn(8, x.permute(0, 2, 1).contiguous().to(DEV), None, True).cpu()
+    assert torch.equal(a, P.knn(8, x)) and torch.equal(a, b)
+    with pytest.raises(AssertionError):
+        knn(101, x.to(DEV))
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,S,k,rmin,rmax", [(256, 64, 16, 0.0, 0.8), (300, 33, 32, 0.3, 1.5), (64, 64, 64, 0.0, 100.0)])
+def test_ball_query_bit_exact(kind, N, S, k, rmin, rmax):
+    from pcreid_b200.ops import ball_query
+    x = clouds(2, N, 4, kind)
+    c = (x[:, :S] + (0.0 if kind != "free" else 0.01)).contiguous()
+    got = ball_query(rmin, rmax, k, x.to(DEV), c.to(DEV)).cpu()
+    assert torch.equal(got, P.ball_query(rmin, rmax, k, x, c))
+    if P.ref_available():
+        assert torch.equal(got, P.ref_ball_query(rmin, rmax, k, x.to(DEV), c.to(DEV)).cpu())
+
+
+@pytest.mark.parametrize("C,N,S,k", [(64, 256, 128, 48), (3, 100, 7, 5), (131, 128, 64, 48)])
+def test_group_and_gather_exact(C, N, S, k):
+    from pcreid_b200.ops import gather_points, grouping_operation
+    g = torch.Generator().manual_seed(0)
+    f = torch.randn(2, C, N, generator=g)
+    idx = torch.randint(0, N, (2, S, k), generator=g, dtype=torch.int32)
+    got = grouping_operation(f.to(DEV), idx.to(DEV)).cpu()
+    assert torch.equal(got, P.grouping_operation(f, idx))
+    i2 = torch.randint(0, N, (2, S), generator=g, dtype=torch.int32)
+    got2 = gather_points(f.to(DEV), i2.to(DEV)).cpu()
+    assert torch.equal(got2, P.gather_points(f, i2))
+    if P.ref_available():
+        assert torch.equal(got, P.ref_grouping_operation(f.to(DEV), idx.to(DEV)).cpu())
+        assert torch.equal(got2, P.ref_gather_points(f.to(DEV), i2.to(DEV)).cpu())
+
+
+def test_query_and_group_and_sampler_modules():
+    from pcreid_b200.ops import Points_Sampler, QueryAndGroup
+    x = O.synth_objects(2, 128, 6)
+    f = torch.randn(2, 16, 128, generator=torch.Generator().manual_seed(1))
+    sampler = Points_Sampler([32], ["D-FPS"], [-1])
+    fi = sampler(x.to(DEV), f.to(DEV))
+    assert torch.equal(fi.cpu(), P.furthest_point_sample(x, 32))
+    centers = torch.gather(x, 1, fi.cpu().long().unsqueeze(-1).expand(2, 32, 3)).contiguous()
+    for max_r in (None, 0.9):
+        qg = QueryAndGroup(max_r, 8, use_xyz=True, return_grouped_idx=True)
+        nf, idx = qg(x.to(DEV), centers.to(DEV), f.to(DEV))
+        ref_idx = P.knn(8, x, centers).transpose(1, 2).contiguous() if max_r is None else P.ball_query(0, max_r, 8, x, centers)
+        assert torch.equal(idx.cpu(), ref_idx)
+        gx = P.grouping_operation(x.transpose(1, 2).contiguous(), ref_idx) - centers.transpose(1, 2).unsqueeze(-1)
+        ref_nf = torch.cat([gx, P.grouping_operation(f, ref_idx)], dim=1)
+        assert torch.equal(nf.cpu(), ref_nf)
+
+
+@pytest.mark.parametrize("kind", ["free", "dup", "same", "u3"])
+@pytest.mark.parametrize("N,S,k", [(256, 256, 32), (256, 128, 48), (128, 64, 48), (160, 80, 48), (1024, 512, 48)])
+def test_knn_point_torch_path_canonical(kind, N, S, k):
+    """torch-path kNN of the backbones: index-exact vs the oracle's canonical (d, idx) order, whose distances are
+    torch's own square_distance (bit-exact restatement checked in test_ops_oracle.py)."""
+    import pcreid_b200.kernels as K
+    x = clouds(3, N, 7, kind)
+    q = x[:, :S].contiguous()
+    got = K.knn_point(k, x.to(DEV), q.to(DEV)).cpu().long()
+    d = P.sqdist_expand(q, x)
+    ref = torch.sort(d, dim=-1, stable=True)[1][..., :k]
+    assert torch.equal(got, ref)
+    if kind == "free":
+        assert torch.equal(got.sort(-1)[0], O.knn_point(k, x, q, canonical=False).sort(-1)[0])
+
+
+@pytest.mark.parametrize("C,N,k", [(3, 256, 20), (64, 256, 20), (128, 160, 20), (64, 1024, 20)])
+def test_knn_feature_canonical(C, N, k):
+    import pcreid_b200.kernels as K
+    x = torch.randn(2, C, N, generator=torch.Generator().manual_seed(C + N))
+    x[:, :, 5] = x[:, :, 9]          # exact duplicate columns -> ties
+    got = K.knn_feature(x.to(DEV), k).cpu().long()
+    ref = torch.sort(P.dgcnn_pd(x), dim=-1, descending=True, stable=True)[1][..., :k]
+    assert torch.equal(got, ref)
+
+
+def test_golden_knn_vectors():
+    import numpy as np
+    import helpers
+    import pcreid_b200.kernels as K
+    g = helpers.golden("knn_torch_path")
+    x = torch.from_numpy(g["xyz"])
+    got = K.knn_point(48, x.to(DEV), x[:, :80].contiguous().to(DEV)).cpu().long()
+    assert torch.equal(got.sort(-1)[0], torch.from_numpy(g["idx"]).long().sort(-1)[0])
+    xf = torch.from_numpy(g["feat"])
+    gotf = K.knn_feature(xf.to(DEV), 20).cpu().long()
+    assert torch.equal(gotf.sort(-1)[0], torch.from_numpy(g["idx_feat"]).long().sort(-1)[0])
+
+
+def test_empty_inputs_are_noops():
+    from pcreid_b200.ops import furthest_point_sample, knn
+    x = torch.zeros(0, 16, 3, device=DEV)
+    assert furthest_point_sample(x, 4).shape == (0, 4)
+    assert knn(3, x).shape == (0, 3, 16)
+
+
+def test_large_scene_scale_sortedness_property():
+    """full-size property check (no oracle needed): distances ascending, self is nearest, indices in range."""
+    from pcreid_b200.ops import knn
+    x = O.synth_objects(8, 4096, 12).to(DEV)
+    idx, d2 = knn(32, x, x[:, :1024].contiguous(), False, True)
+    assert (d2[:, 1:, :] >= d2[:, :-1, :]).all()
+    assert (idx[:, 0, :] == torch.arange(1024, device=DEV, dtype=torch.int32)).all()
+    assert int(idx.min()) >= 0 and int(idx.max()) < 4096

@@ -1,0 +1,80 @@
+"""Host-side logic of the product modules (weight packing, eval-BatchNorm folding, first-conv
+factorisation, EdgeConv factorisation, object index maps, layouts) checked on CPU against the oracle by
+substituting the C-ABI kernels with a torch emulation of their *specification* (tests/fake_kernels.py)."""
+import pytest
+import torch
+
+import fake_kernels
+import helpers
+from oracle import reid_oracle as O
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    fake_kernels.install(monkeypatch)
+
+
+@pytest.mark.parametrize("kind", ["pt", "concat", "dgcnn", "pointnet"])
+def test_model_vs_oracle_with_spec_kernels(fake, kind):
+    m, orc = helpers.build_pair(kind)
+    t, d = O.synth_objects(3, 128, 0), O.synth_objects(4, 128, 1)
+    with torch.no_grad():
+        xt, ht = m._encode(t)
+        xd, hd = m._encode(d)
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    assert (ht - oht).abs().max() < 2e-5 and (hd - ohd).abs().max() < 2e-5
+    L = m.match_all_pairs(ht, xt, hd, xd, chunk=5)
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    assert (L - Lo).abs().max() < 2e-5
+    mask = torch.rand(3, 4, generator=torch.Generator().manual_seed(0)) > 0.4
+    Lm = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask, chunk=5)
+    assert (Lm - orc.match_all_pairs(oht, oxt, ohd, oxd, pair_mask=mask)).abs().max() < 2e-5
+    assert (Lm[~mask] == 0).all()
+
+
+def test_reference_api_surface(fake):
+    m, orc = helpers.build_pair("pt")
+    s1, s2 = O.synth_objects(3, 128, 2), O.synth_objects(3, 128, 3)
+    x1, x2, h1, h2 = m.siamese_forward(s1, s2)
+    assert h1.shape == (3, 64, 128) and x1.shape == (3, 128, 3)
+    lg = m.match_forward_inference(h1, h2, x1, x2)
+    o = orc.siamese_forward(s1, s2)
+    assert (lg - orc.match_forward_inference(o[2], o[3], o[0], o[1])).abs().max() < 2e-5
+    out, o1, o2 = m.xcorr_eff(h1, x1, h2, x2)
+    assert out.shape == (3, 64, 256)
+    assert m.get_pooled_feats(out).shape == (3, 128)
+    ids = [torch.tensor([i]) for i in range(3)]
+    lab = [torch.tensor([1]) for _ in range(3)]
+    res = m(return_loss=False, sparse_1=list(s1), sparse_2=list(s2), dense_1=list(s1), dense_2=list(s2), label_1=lab, label_2=lab,
+            id_1=ids, id_2=ids, size_1=lab, size_2=lab, vis_1=lab, vis_2=lab)
+    assert isinstance(res, list) and res[0]['val_match_preds'].shape == (3,) and res[0]['val_match_gt'].tolist() == [1., 1., 1.]
+    with pytest.raises(NotImplementedError):
+        m(return_loss=True)
+
+
+def test_registry_and_state_dict_roundtrip():
+    from pcreid_b200.models import FUSIONMODELS, build_model
+    assert "ReIDNet" in FUSIONMODELS
+    cfg = helpers.model_cfg("pt")
+    m = build_model(cfg)
+    assert cfg["backbone"]["type"] == "Pointnet_Backbone"          # cfg not mutated (the reference deletes 'type')
+    m2 = build_model(helpers.model_cfg("pt"))
+    m2.load_state_dict(m.state_dict(), strict=True)
+    assert any(k.startswith("backbone.FP_modules.0.mlp_convs") for k in m.state_dict())   # dead reference weights kept
+
+
+def test_train_mode_is_rejected(fake):
+    m, _ = helpers.build_pair("pt")
+    m.train()
+    with pytest.raises(RuntimeError):
+        m._encode(O.synth_objects(1, 128, 0))
+
+
+def test_kernels_refuse_cpu_tensors():
+    import pcreid_b200.kernels as K
+    with pytest.raises(RuntimeError):
+        K.cn_linear(torch.zeros(1, 4, 8), torch.zeros(4, 4))
+    from pcreid_b200.ops import knn
+    with pytest.raises(RuntimeError):
+        knn(3, torch.zeros(1, 8, 3))

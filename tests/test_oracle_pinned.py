@@ -1,0 +1,116 @@
+"""Pins the oracle (oracle/reid_oracle.py): (1) bit-exact against the unmodified reference modules where
+/root/reference exists, (2) against the committed golden vectors everywhere."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from oracle import ref_loader, reid_oracle as O
+
+needs_ref = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present on this machine")
+
+
+def _load_ref_sd(mod, prefix, sd):
+    mod.load_state_dict({k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)})
+
+
+@needs_ref
+@pytest.mark.parametrize("canonical", [False, True])
+def test_pt_backbone_bit_exact_vs_reference(canonical):
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    bb = R.Pointnet_Backbone(input_channels=0, use_xyz=True, conv_out=64).eval()
+    sd = O.perturb_norm_state({"backbone." + k: v for k, v in bb.state_dict().items()})
+    _load_ref_sd(bb, "backbone.", sd)
+    x = O.synth_objects(3, 160, 0)
+    with torch.no_grad():
+        _, h_r = bb(x, [160, 80, 40])
+        _, h_o = O.pt_backbone(sd, "backbone", x, [160, 80, 40], canonical=canonical)
+    assert torch.equal(h_r, h_o)      # tie-free input: canonical (d, idx) order == reference argsort
+
+
+@needs_ref
+def test_dgcnn_pointnet_heads_bit_exact_vs_reference():
+    R = ref_loader.load()
+    x = O.synth_objects(2, 128, 1).permute(0, 2, 1).contiguous()
+    torch.manual_seed(66)
+    dg = R.DGCNN().eval()
+    sd = O.perturb_norm_state({"backbone." + k: v for k, v in dg.state_dict().items()})
+    _load_ref_sd(dg, "backbone.", sd)
+    pn = R.PointNet(k=40, normal_channel=False).eval()
+    sdp = O.perturb_norm_state({"backbone." + k: v for k, v in pn.state_dict().items()})
+    _load_ref_sd(pn, "backbone.", sdp)
+    ca = R.corss_attention(d_model=64, nhead=2).eval()
+    sdc = O.perturb_norm_state({"cross_stage1." + k: v for k, v in ca.state_dict().items()})
+    _load_ref_sd(ca, "cross_stage1.", sdc)
+    lr = R.LinearRes(1024, 512, norm='GN', ng=64).eval()
+    sdl = O.perturb_norm_state({"d." + k: v for k, v in lr.state_dict().items()})
+    _load_ref_sd(lr, "d.", sdl)
+    s, t = torch.randn(3, 64, 128), torch.randn(3, 64, 96)
+    sx, tx = torch.randn(3, 128, 3), torch.randn(3, 96, 3)
+    r = torch.randn(10, 1024)
+    with torch.no_grad():
+        assert torch.equal(dg(x, None)[1], O.dgcnn_backbone(sd, "backbone", x, 20, canonical=True)[1])
+        assert torch.equal(pn(x, None)[1], O.pointnet_backbone(sdp, "backbone", x)[1])
+        assert torch.equal(ca(s, sx, t, tx), O.cross_attention(sdc, "cross_stage1", s, sx, t, tx))
+        assert torch.equal(lr(r), O.linear_res(sdl, "d", r, 64))
+
+
+@needs_ref
+def test_product_modules_reproduce_reference_init_and_keys():
+    """seed-66 default init of the product's modules == the reference's, key for key (so goldens travel)."""
+    R = ref_loader.load()
+    from pcreid_b200.models import DGCNN, LinearRes, PointNet, Pointnet_Backbone, corss_attention
+    for mine, ref in ((lambda: Pointnet_Backbone(input_channels=0, use_xyz=True, conv_out=64),
+                       lambda: R.Pointnet_Backbone(input_channels=0, use_xyz=True, conv_out=64)),
+                      (DGCNN, R.DGCNN), (lambda: PointNet(k=40, normal_channel=False), lambda: R.PointNet(k=40, normal_channel=False)),
+                      (lambda: corss_attention(64, 2), lambda: R.corss_attention(64, 2)),
+                      (lambda: LinearRes(1024, 512, ng=64), lambda: R.LinearRes(1024, 512, ng=64))):
+        torch.manual_seed(66)
+        a = mine().state_dict()
+        torch.manual_seed(66)
+        b = ref().state_dict()
+        assert list(a.keys()) == list(b.keys())
+        assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+@pytest.mark.parametrize("name,kind,tol", [("reid_pt", "pt", 2e-5), ("reid_pt256", "pt", 2e-5), ("reid_dgcnn", "dgcnn", 2e-5),
+                                           ("reid_pointnet", "pointnet", 2e-5)])
+def test_oracle_matches_golden(name, kind, tol):
+    """Goldens were produced by the reference modules (oracle/make_golden.py); tolerance covers BLAS/CPU differences
+    between the generating machine and this one (bit-exact on the generating machine)."""
+    g = helpers.golden(name)
+    _, orc = helpers.build_pair(kind, tuple(int(v) for v in g["backbone_list"]))
+    assert abs(helpers.weight_checksum(orc.sd) - float(g["weight_checksum"])) < 1e-6 * float(g["weight_checksum"])
+    t, d = torch.from_numpy(g["tracks"]), torch.from_numpy(g["dets"])
+    xt, ht = orc.encode(t)
+    xd, hd = orc.encode(d)
+    assert (ht - torch.from_numpy(g["h_t"])).abs().max() < tol
+    assert (hd - torch.from_numpy(g["h_d"])).abs().max() < tol
+    L = orc.match_all_pairs(ht, xt, hd, xd)
+    assert (L - torch.from_numpy(g["logits"])).abs().max() < tol
+
+
+def test_knn_golden_and_canonical_order():
+    g = helpers.golden("knn_torch_path")
+    """golden = the reference's own knn_point (unstable argsort) / dgcnn knn (topk) output.  The canonical (d, idx)
+    order must select the same neighbour set with the same ordered distance list; positions may differ only inside
+    exact-distance ties (continuous random input still has a few: 1 tied pair in 11520 entries here)."""
+    x = torch.from_numpy(g["xyz"])
+    ref, can = torch.from_numpy(g["idx"]).long(), O.knn_point(48, x, x[:, :80], canonical=True)
+    d = O.square_distance(x[:, :80], x)
+    assert torch.equal(torch.gather(d, 2, ref), torch.gather(d, 2, can))
+    assert torch.equal(ref.sort(-1)[0], can.sort(-1)[0])
+    assert (ref != can).float().mean() < 1e-3
+    xf = torch.from_numpy(g["feat"])
+    reff, canf = torch.from_numpy(g["idx_feat"]).long(), O.dgcnn_knn(xf, 20, canonical=True)
+    pd = O.dgcnn_pairwise(xf)
+    assert torch.equal(torch.gather(pd, 2, reff), torch.gather(pd, 2, canf))
+    assert torch.equal(reff.sort(-1)[0], canf.sort(-1)[0])
+
+
+def test_class_gate_matches_tracker_semantics():
+    lt = torch.tensor([0, 1, 1, 9, 3]); nt = torch.tensor([5, 1, 7, 9, 2])
+    ld = torch.tensor([1, 1, 3, 9]); nd = torch.tensor([4, 0, 2, 8])
+    m = O.class_gated_pairs(lt, nt, ld, nd)
+    assert m.tolist() == [[False] * 4, [False] * 4, [True, False, False, False], [False] * 4, [False, False, True, False]]
