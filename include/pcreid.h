@@ -140,6 +140,12 @@ int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const fl
                             const float* W2, const float* g1, const float* be1, const float* g2, const float* be2,
                             const float* w, float b0, const unsigned char* mask, float* out, void* stream);
 
+/* ------------------------------------------------------------------ C. tcgen05 self-test ------- */
+/* One 128 x n x k GEMM on the 5th-gen tensor cores in each operand configuration the fused kernels use
+ * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM);
+ * d (128, n) f32 = a (128, k) * b (n, k)^T.  Modes 0/2/3 take row-major a, b; mode 1 takes a^T (k,128), b^T (k,n). */
+int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

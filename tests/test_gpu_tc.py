@@ -1,0 +1,44 @@
+"""-m gpu: tcgen05 / TMEM primitives (csrc/tc_common.cuh) validated on hardware, one GEMM per operand configuration."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _probe(mode, N, K, seed=0):
+    from pcreid_b200 import _lib
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(128, K, generator=g)
+    b = torch.randn(N, K, generator=g)
+    if mode == 2:
+        ad, bd = a.to(DEV), b.to(DEV)
+        # tf32 keeps 10 mantissa bits: compare against operands truncated the same way with a loose bound
+        ref = a @ b.t()
+        tol = 8e-3 * K ** 0.5
+    else:
+        a, b = a.bfloat16(), b.bfloat16()
+        ref = a.float() @ b.float().t()
+        tol = 1e-4 * K ** 0.5
+        if mode == 1:
+            ad, bd = a.t().contiguous().to(DEV), b.t().contiguous().to(DEV)
+        else:
+            ad, bd = a.to(DEV), b.to(DEV)
+    d = torch.full((128, N), float("nan"), device=DEV)
+    rc = _lib.lib().pcreid_tc_probe(mode, N, K, ctypes.c_void_p(ad.data_ptr()), ctypes.c_void_p(bd.data_ptr()),
+                                    ctypes.c_void_p(d.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if rc == 3:
+        pytest.skip("operands exceed the probe's shared-memory budget")
+    assert rc == 0
+    torch.cuda.synchronize()
+    err = (d.cpu() - ref).abs().max().item()
+    return err, tol
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (192, 64), (64, 128), (16, 16), (256, 256), (80, 32)])
+def test_tc_probe(mode, N, K):
+    err, tol = _probe(mode, N, K)
+    assert err < tol, f"mode {mode} N={N} K={K}: max err {err} (tol {tol})"
