@@ -140,6 +140,24 @@ int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const fl
                             const float* W2, const float* g1, const float* be1, const float* g2, const float* be2,
                             const float* w, float b0, const unsigned char* mask, float* out, void* stream);
 
+/* ------------------------------------------------------------------ B'. fused tensor-core match path --- */
+/* "fast" mode of the xcorr_eff head (csrc/pair_tc.cu): bf16 tcgen05 GEMMs, fp32 accumulation / norms.
+ * Operand "images" are bf16 [k/8][row][8] tiles of 128 points x 64 channels (16 KB); d_model = 64, 2 heads,
+ * points per object a multiple of 128.  See point-cloud-reid_b200/models/fused_pairs.py for the host side. */
+int pcreid_pair_tc_smem_bytes(int phase);
+/* (B, C, N) channel-major fp32 -> [B][N/128][C/8][128][8] bf16 (act: PCREID_ACT_NONE or PCREID_ACT_ELU1) */
+int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, void* dst, void* stream);
+/* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 18432 bytes) */
+int pcreid_pack_b7(int B, const float* M, const float* ksum, void* dst, void* stream);
+/* phase 1: cross_stage1 both ways + stage-2 key/value summaries; phase 2: cross_stage2 + pooling partials */
+int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
+                   const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out, void* B7_out,
+                   int n_ctas, void* stream);
+int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
+                   float* pool_part, int n_ctas, void* stream);
+/* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor */
+int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream);
+
 /* ------------------------------------------------------------------ C. tcgen05 self-test ------- */
 /* One 128 x n x k GEMM on the 5th-gen tensor cores in each operand configuration the fused kernels use
  * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM);

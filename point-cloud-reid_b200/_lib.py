@@ -60,6 +60,12 @@ _SIGS = {
     "pcreid_cn_chanmax": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_ll, c_vp],
     "pcreid_sa_edge_mlp": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_edge_gather_max": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_ll, c_int, c_vp],
+    "pcreid_pair_tc_smem_bytes": [c_int],
+    "pcreid_pack_image": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_vp],
+    "pcreid_pack_b7": [c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_pair_p1": [c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],
+    "pcreid_pair_p2": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
+    "pcreid_pool_finish": [c_int, c_int, c_vp, c_vp, c_vp],
     "pcreid_tc_probe": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_concat_head": [c_int, c_int, c_int, c_int] + [c_vp] * 10 + [c_float, c_vp, c_vp, c_vp],
 }

@@ -1,0 +1,596 @@
+// Fused all-pairs `xcorr_eff` match on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 operands, fp32
+// accumulation, fp32 LayerNorm / linear-attention normalisation.  "fast" mode of the match head.
+//
+// Reference arithmetic: ReIDNet.xcorr_eff (mmdet3d/models/ReIDNet.py:231-247) = 2 x corss_attention each way
+// (mmdet3d/models/attention.py:192-219) + get_pooled_feats (ReIDNet.py:526-534).  The reference gathers
+// feat[pairs[:,0]] / feat[pairs[:,1]] and runs ~40 torch ops per pair batch; here a pair never leaves the chip
+// between layers:
+//
+//   phase 1 (pair_p1_kernel), unit = (pair, direction), per 128-point tile of the search object:
+//     G1  [Qf1_i | .] x MK1_j      -> per-head Q.KV.merge and the two Q.Ksum dots in ONE N=144 GEMM
+//         epilogue: z = 1/(dot+eps), merged = z0 D0 + z1 D1, LayerNorm1 -> X (bf16, smem operand image)
+//     G2  X x W0b^T (+ U_i = W0a h_i, precomputed per object) , ReLU -> Hd
+//     G3  Hd x W2^T, LayerNorm2, + h_i  -> a   (stage-1 output, kept on chip as the next A operand, also spilled
+//                                              once as bf16 for phase 2)
+//     G4  a x [Wk2;Wv2]^T -> Kf = elu+1, V (+ Wv2 pos_j)                -> operand image
+//     G5  [Kf|V]^T x [V|1]  accumulated over the tiles in TMEM          -> KV (64x64) and Ksum of the template
+//     G6  blockdiag(KV) x Wm2^T                                         -> B7 = stage-2 attention operand (global)
+//   phase 2 (pair_p2_kernel), unit = (pair, direction), per tile:
+//     G4' a x Wq2^T -> Qf2 ; G7 Qf2 x B7 (as G1) ; G8 [a|X] x W0^T, ReLU ; G9 Hd x W2^T, LayerNorm2, + a
+//     epilogue: per-channel max / sum over the points (smem transpose), accumulated over the tiles
+//   pool_finish: combine the two directions -> pooled (128) -> match head.
+//
+// Every GEMM is a tcgen05.mma (M=128, K=16 per instruction) issued by one thread per 128-thread group, operands in
+// shared memory in the no-swizzle canonical layouts validated by tc_probe.cu, accumulators in TMEM, epilogues by the
+// row-owning threads via tcgen05.ld.  A CTA holds two independent groups that share one copy of the weights, so the
+// tensor pipe of one group overlaps the epilogue of the other.
+#include "../../include/pcreid.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int GT = 128;                 // threads per group
+constexpr int IMG = 16384;              // bytes of a 128 x 64 bf16 operand image  [k/8][row][8]
+constexpr int NB7 = 144;                // columns of the attention operand: 64 (head 0) | 64 (head 1) | 16 (2 dots + pad)
+constexpr int B7_BYTES = (NB7 / 8) * 64 * 16;   // [n/8][k][8] bf16 = 18432
+constexpr int ONES_BYTES = 2 * 2048;    // two extra 8-column chunks appended to V: column 64 == 1 (Ksum), rest 0
+constexpr int KV_COL = 144;             // TMEM columns [144, 224) of a group: KV / Ksum accumulator
+constexpr float LN_EPS = 1e-5f, ATT_EPS = 1e-6f;
+
+// weights blob of phase 1 (bytes)
+constexpr int P1_W0B = 0, P1_W2 = 16384, P1_WKV = 32768, P1_WM = 49152, P1_LN = 57344, P1_WBYTES = 57344 + 1024;
+// weights blob of phase 2
+constexpr int P2_WQ = 0, P2_W0 = 8192, P2_W2 = 40960, P2_LN = 57344, P2_WBYTES = 57344 + 1024;
+// per-group shared memory of phase 1: QXa (16K) | HdKV (32K) + ones (4K) | MK1 (18K)
+constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ONES + ONES_BYTES, P1_GBYTES = P1_MK1 + B7_BYTES;
+// per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 (18K)
+constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_GBYTES = P2_B7 + B7_BYTES;
+
+struct P1Args {
+  int n_units, NT, role;
+  const int *u_search, *u_templ, *u_slot;
+  const uint8_t *QF1, *U, *H, *PV;      // search-side per-object images: [obj][NT][IMG] (U: [obj][NT][2*IMG])
+  const uint8_t* MK1;                    // template-side per-object stage-1 attention operand [obj][B7_BYTES]
+  const uint8_t* W;                      // P1 weights blob
+  uint8_t* A_out;                        // [slot][2][NT][IMG]   stage-1 outputs (bf16 operand images)
+  uint8_t* B7_out;                       // [slot][2][B7_BYTES]  stage-2 attention operands
+};
+struct P2Args {
+  int n_units, NT, role;
+  const int* u_slot;
+  const uint8_t* A_in;                   // == A_out of phase 1
+  const uint8_t* B7_in;                  // == B7_out of phase 1
+  const uint8_t* W;                      // P2 weights blob
+  float* pool_part;                      // [slot][2][128]: max (64) | sum (64) over the search object's points
+};
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+__device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, int bytes, int t, int nthr) {
+  for (int i = t * 16; i < bytes; i += nthr * 16) cp_async16(dst + i, src + i);
+}
+
+// one thread: D[tmem_d] (+)= A x B^T over `ksteps` K=16 steps
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
+                                           uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, uint32_t idesc,
+                                           int ksteps, bool accumulate) {
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t ad = tc::smem_desc(a_addr + ks * a_kstep, a_lbo, a_sbo, tc::LAYOUT_NONE);
+    const uint64_t bd = tc::smem_desc(b_addr + ks * b_kstep, b_lbo, b_sbo, tc::LAYOUT_NONE);
+    tc::umma_f16(tmem_d, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
+  }
+}
+// operand geometry (bytes): K-major activation image (128 rows), K-major weight image (N rows), MN-major attention operand
+#define A_IMG(addr) (addr), 2048u, 128u, 4096u
+#define W_IMG(addr, N) (addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16)
+#define B7_IMG(addr) (addr), 128u, 1024u, 256u
+
+struct Group {
+  int t, warp, gid;          // thread in group, warp in group, group in CTA
+  uint32_t tmem;             // TMEM base of the group (lane 0, first column)
+  uint32_t tlane;            // tmem + (lane base of this warp << 16)
+  uint64_t* bar;
+  uint64_t* bar2;
+  uint32_t par, par2;
+  __device__ __forceinline__ void sync() { tc::bar_sync(1 + gid, GT); }
+  // smem operands written by the group -> visible to the tensor core; returns after the group barrier
+  __device__ __forceinline__ void publish() {
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    sync();
+    tc::tc_fence_after();
+  }
+  __device__ __forceinline__ void wait() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); }
+  __device__ __forceinline__ void wait2() { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }
+};
+
+// ---- epilogues (thread == row of the 128-point tile) ---------------------------------------------------------
+
+// attention GEMM (N=144) -> z-normalised, head-merged message -> LayerNorm -> bf16 operand image
+__device__ __forceinline__ void epi_attn_ln(const Group& g, const float* __restrict__ ln, uint8_t* dst) {
+  float m[64];
+  uint32_t d8[8];
+  tc::tmem_ld8(g.tlane + 128, d8);
+  tc::tmem_ld_wait();
+  const float z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS), z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t r0[16], r1[16];
+    tc::tmem_ld16(g.tlane + c0, r0);
+    tc::tmem_ld16(g.tlane + 64 + c0, r1);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) m[c0 + j] = z0 * __uint_as_float(r0[j]) + z1 * __uint_as_float(r1[j]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) s += m[j];
+  const float mean = s * (1.f / 64.f);
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) { const float d = m[j] - mean; v = fmaf(d, d, v); }
+  const float rstd = rsqrtf(v * (1.f / 64.f) + LN_EPS);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = c * 8 + 2 * j;
+      const float y0 = (m[k] - mean) * rstd * ln[k] + ln[64 + k];
+      const float y1 = (m[k + 1] - mean) * rstd * ln[k + 1] + ln[64 + k + 1];
+      w[j] = tc::pack_bf16(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(dst + c * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// acc[ncols] (+ side image from global) -> ReLU -> bf16 operand image with ncols/8 chunks
+template <int NCOLS, bool HAS_SIDE>
+__device__ __forceinline__ void epi_relu(const Group& g, const uint8_t* __restrict__ side, uint8_t* dst) {
+#pragma unroll
+  for (int c0 = 0; c0 < NCOLS; c0 += 16) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + c0, r);
+    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+    if (HAS_SIDE) {
+      s0 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8) * 2048 + g.t * 16));
+      s1 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8 + 1) * 2048 + g.t * 16));
+    }
+    tc::tmem_ld_wait();
+    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+      if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
+      w[j] = tc::pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    }
+    *reinterpret_cast<uint4*>(dst + (c0 / 8) * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * 2048 + g.t * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// acc[64] -> LayerNorm -> + residual image (global, bf16) -> out[64] fp32
+__device__ __forceinline__ void epi_ln_res(const Group& g, const float* __restrict__ ln, const uint8_t* __restrict__ res,
+                                           float (&o)[64]) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + c0, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[c0 + j] = __uint_as_float(r[j]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) s += o[j];
+  const float mean = s * (1.f / 64.f);
+  float v = 0.f;
+#pragma unroll
+  for (int j = 0; j < 64; ++j) { const float d = o[j] - mean; v = fmaf(d, d, v); }
+  const float rstd = rsqrtf(v * (1.f / 64.f) + LN_EPS);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res + c * 2048 + g.t * 16));
+    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = c * 8 + 2 * j;
+      o[k] = (o[k] - mean) * rstd * ln[k] + ln[64 + k] + bf_lo(rw[j]);
+      o[k + 1] = (o[k + 1] - mean) * rstd * ln[k + 1] + ln[64 + k + 1] + bf_hi(rw[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void store_image64(const float (&o)[64], uint8_t* dst, int row) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(o[c * 8 + 2 * j], o[c * 8 + 2 * j + 1]);
+    *reinterpret_cast<uint4*>(dst + c * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// acc[cols c_base .. c_base+64) -> elu+1 (or + side image) -> bf16 chunks [chunk0, chunk0+8) of dst
+template <bool ELU, bool HAS_SIDE>
+__device__ __forceinline__ void epi_feat64(const Group& g, int c_base, const uint8_t* __restrict__ side, uint8_t* dst, int chunk0) {
+#pragma unroll
+  for (int c0 = 0; c0 < 64; c0 += 16) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + c_base + c0, r);
+    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
+    if (HAS_SIDE) {
+      s0 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8) * 2048 + g.t * 16));
+      s1 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8 + 1) * 2048 + g.t * 16));
+    }
+    tc::tmem_ld_wait();
+    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+      if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
+      if (ELU) { a = elu1(a); b = elu1(b); }
+      w[j] = tc::pack_bf16(a, b);
+    }
+    *reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8) * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8 + 1) * 2048 + g.t * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]  (MN-major image [n/8][k=d][8])
+__device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
+  const int h = d >> 5;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(M[c * 8 + 2 * j], M[c * 8 + 2 * j + 1]);
+    const uint4 val = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + c * 1024 + d * 16) = h == 0 ? val : zero;
+    *reinterpret_cast<uint4*>(dst + (8 + c) * 1024 + d * 16) = h == 1 ? val : zero;
+  }
+  *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) = make_uint4(h == 0 ? tc::pack_bf16(ksum, 0.f) : tc::pack_bf16(0.f, ksum), 0, 0, 0);
+  *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
+}
+
+__device__ __forceinline__ void group_setup(Group& g, uint64_t* bars, uint32_t tmem_base) {
+  g.gid = threadIdx.x / GT;
+  g.t = threadIdx.x % GT;
+  g.warp = g.t >> 5;
+  g.tmem = tmem_base + g.gid * 256;
+  g.tlane = g.tmem + ((uint32_t)(g.warp * 32) << 16);
+  g.bar = bars + 2 * g.gid;
+  g.bar2 = bars + 2 * g.gid + 1;
+  g.par = 0;
+  g.par2 = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// phase 1
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* Wsm = smem;
+  const float* ln1 = reinterpret_cast<const float*>(Wsm + P1_LN);         // gamma[64] | beta[64] of cross_stage1.norm1
+  const float* ln2 = ln1 + 128;                                           // cross_stage1.norm2
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P1_WBYTES, threadIdx.x, 2 * GT);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  Group g;
+  group_setup(g, bars, tmem_base_s);
+  uint8_t* G = smem + P1_WBYTES + g.gid * P1_GBYTES;
+  uint8_t* QXa = G + P1_QXA;
+  uint8_t* HdKV = G + P1_HDKV;
+  uint8_t* MK1 = G + P1_MK1;
+  {   // the two constant chunks appended to V: column 64 of B == 1 for every point
+    uint4* ones = reinterpret_cast<uint4*>(G + P1_ONES);
+    ones[g.t] = make_uint4(0x00003f80u, 0, 0, 0);      // bf16 1.0 in element 0 of the chunk
+    ones[GT + g.t] = make_uint4(0, 0, 0, 0);
+  }
+  const uint32_t sQXa = tc::smem_u32(QXa), sHd = tc::smem_u32(HdKV), sMK1 = tc::smem_u32(MK1), sW = tc::smem_u32(Wsm);
+  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t idkv = tc::instr_desc(128, 80, tc::FMT_BF16, tc::MAJOR_MN, tc::MAJOR_MN);
+
+  const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  int cur_templ = -1;
+  for (int u = u0; u < u1; ++u) {
+    const int so = a.u_search[u], te = a.u_templ[u], slot = a.u_slot[u];
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const size_t ti = (size_t)so * a.NT + tile;
+      if (tile > 0) g.wait2();                                            // previous tile's KV GEMM still reads HdKV
+      // ---- stage operands of G1
+      copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GT);
+      if (te != cur_templ) copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GT);
+      cur_templ = te;
+      cp_async_commit();
+      cp_async_wait<0>();
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), B7_IMG(sMK1), id144, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_attn_ln(g, ln1, QXa);                                           // X
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_W0B, 128), id128, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_relu<128, true>(g, a.U + ti * 2 * IMG, HdKV);                   // Hd = relu(X W0b^T + W0a h)
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sHd), W_IMG(sW + P1_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      g.wait();
+      {
+        float o[64];
+        epi_ln_res(g, ln2, a.H + ti * IMG, o);                            // a = h + LN2(.)
+        store_image64(o, QXa, g.t);
+        store_image64(o, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, g.t);
+      }
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WKV, 128), id128, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_feat64<true, false>(g, 0, nullptr, HdKV, 0);                    // Kf = elu(k)+1      -> chunks 0..7
+      epi_feat64<false, true>(g, 64, a.PV + ti * IMG, HdKV, 8);           // V = v + Wv pos     -> chunks 8..15
+      g.publish();
+      if (g.t == 0) {   // KV += [Kf|V]^T [V|1]   (M = 128 channels, N = 80, K = 128 points)
+        issue_gemm(g.tmem + KV_COL, sHd, 128u, 2048u, 256u, sHd + 8 * 2048, 128u, 2048u, 256u, idkv, 8, tile > 0);
+        tc::umma_commit(g.bar2);
+      }
+    }
+    g.wait2();
+    // ---- B7 = stage-2 attention operand of this (pair, direction) as template
+    {
+      float kv[64];
+      float ksum = 0.f;
+      if (g.t < 64) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + KV_COL + c0, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[c0 + j] = __uint_as_float(r[j]);
+        }
+        uint32_t r8[8];
+        tc::tmem_ld8(g.tlane + KV_COL + 64, r8);
+        tc::tmem_ld_wait();
+        ksum = __uint_as_float(r8[0]);
+        const int h = g.t >> 5;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) if ((j >> 5) != h) kv[j] = 0.f;     // block diagonal: head h keeps its own values
+        store_image64(kv, QXa, g.t);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(QXa + c * 2048 + g.t * 16) = make_uint4(0, 0, 0, 0);
+      }
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WM, 64), id64, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      if (g.t < 64) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 16) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + c0, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[c0 + j] = __uint_as_float(r[j]);
+        }
+        write_b7_row(kv, ksum, g.t, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
+      }
+      tc::tc_fence_before();
+      g.sync();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// phase 2
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float comb[2][2][128];
+  uint8_t* Wsm = smem;
+  const float* ln1 = reinterpret_cast<const float*>(Wsm + P2_LN);         // cross_stage2.norm1
+  const float* ln2 = ln1 + 128;                                           // cross_stage2.norm2
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P2_WBYTES, threadIdx.x, 2 * GT);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  Group g;
+  group_setup(g, bars, tmem_base_s);
+  uint8_t* G = smem + P2_WBYTES + g.gid * P2_GBYTES;
+  uint8_t* R1 = G + P2_R1;
+  uint8_t* B7 = G + P2_B7;
+  float* R1f = reinterpret_cast<float*>(R1);
+  const uint32_t sR1 = tc::smem_u32(R1), sB7 = tc::smem_u32(B7), sW = tc::smem_u32(Wsm);
+  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+
+  const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  const int pc = g.t & 63, phalf = g.t >> 6;                              // pooling: channel, row half
+  for (int u = u0; u < u1; ++u) {
+    const int slot = a.u_slot[u];
+    copy_to_smem(B7, a.B7_in + ((size_t)slot * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GT);
+    float pmax = -INFINITY, psum = 0.f;
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
+      copy_to_smem(R1, a_img, IMG, g.t, GT);
+      cp_async_commit();
+      cp_async_wait<0>();
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_WQ, 64), id64, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_feat64<true, false>(g, 0, nullptr, R1 + IMG, 0);                // Qf = elu(q)+1
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1 + IMG), B7_IMG(sB7), id144, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_attn_ln(g, ln1, R1 + IMG);                                      // X next to a: [a | X] is the K=128 operand
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W0, 128), id128, 8, false); tc::umma_commit(g.bar); }
+      g.wait();
+      epi_relu<128, false>(g, nullptr, R1);                               // Hd over [a | X]
+      g.publish();
+      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      g.wait();
+      {
+        float o[64];
+        epi_ln_res(g, ln2, a_img, o);                                     // o = a + LN2(.)
+        // transpose through shared memory (R1 is free: G9 has completed) with a rotation that keeps both the
+        // row-wise writes and the channel-wise reads bank-conflict free
+#pragma unroll
+        for (int c = 0; c < 64; ++c) R1f[c * 128 + ((g.t + c) & 127)] = o[c];
+      }
+      g.sync();
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const float v = R1f[pc * 128 + ((phalf * 64 + i + pc) & 127)];
+        pmax = fmaxf(pmax, v);
+        psum += v;
+      }
+      g.sync();                                                           // R1 is overwritten by the next tile
+    }
+    comb[g.gid][0][g.t] = pmax;
+    comb[g.gid][1][g.t] = psum;
+    g.sync();
+    if (g.t < 64) {
+      float* out = a.pool_part + ((size_t)slot * 2 + a.role) * 128;
+      out[g.t] = fmaxf(comb[g.gid][0][g.t], comb[g.gid][0][g.t + 64]);
+      out[64 + g.t] = comb[g.gid][1][g.t] + comb[g.gid][1][g.t + 64];
+    }
+    g.sync();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// packing kernels (fp32 per-object tensors of the parity path -> bf16 operand images)
+// ---------------------------------------------------------------------------------------------------------------
+// src (B, C, N) channel-major fp32 -> dst [B][N/128][C/8][128][8] bf16, optional elu+1
+__global__ void __launch_bounds__(256) pack_image_kernel(int B, int C, int N, const float* __restrict__ src, long long s_bs,
+                                                         int lds, int act, uint8_t* __restrict__ dst) {
+  const int nt = N / 128, nch = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = (int)(idx % 128);
+  const int chunk = (int)((idx / 128) % nch);
+  const int tile = (int)((idx / (128LL * nch)) % nt);
+  const long long b = idx / (128LL * nch * nt);
+  if (b >= B) return;
+  const float* s = src + b * s_bs + (size_t)(chunk * 8) * lds + tile * 128 + row;
+  uint32_t w[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float x0 = s[(size_t)(2 * j) * lds], x1 = s[(size_t)(2 * j + 1) * lds];
+    if (act == ACT_ELU1) { x0 = x0 > 0.f ? x0 + 1.f : expf(x0); x1 = x1 > 0.f ? x1 + 1.f : expf(x1); }
+    w[j] = tc::pack_bf16(x0, x1);
+  }
+  *reinterpret_cast<uint4*>(dst + (((size_t)b * nt + tile) * nch + chunk) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// M (B, 64 d, 64 out) fp32 [= blockdiag(KV) Wm^T rows, before head masking] + ksum (B, 64) -> attention operand images
+__global__ void __launch_bounds__(64) pack_b7_kernel(const float* __restrict__ M, const float* __restrict__ ksum,
+                                                     uint8_t* __restrict__ dst) {
+  const int b = blockIdx.x, d = threadIdx.x;
+  float m[64];
+#pragma unroll
+  for (int j = 0; j < 64; ++j) m[j] = M[((size_t)b * 64 + d) * 64 + j];
+  write_b7_row(m, ksum[(size_t)b * 64 + d], d, dst + (size_t)b * B7_BYTES);
+}
+
+// pool_part (P, 2, 128) -> pooled^T (128, P): max over both directions | mean over the 2*npts points
+__global__ void __launch_bounds__(256) pool_finish_kernel(int P, int npts, const float* __restrict__ part, float* __restrict__ out) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128LL * P) return;
+  const int c = (int)(idx / P), p = (int)(idx % P);
+  const float x0 = part[((size_t)p * 2) * 128 + c], x1 = part[((size_t)p * 2 + 1) * 128 + c];
+  out[idx] = c < 64 ? fmaxf(x0, x1) : (x0 + x1) / (float)(2 * npts);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcreid_pair_tc_smem_bytes(int phase) { return phase == 1 ? P1_WBYTES + 2 * P1_GBYTES : P2_WBYTES + 2 * P2_GBYTES; }
+
+int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, void* dst, void* stream) {
+  if (B <= 0) return PCREID_OK;
+  if (!src || !dst || C % 8 || N % 128) return PCREID_ERR_ARG;
+  const long long per = 128LL * (C / 8) * (N / 128);
+  pack_image_kernel<<<(unsigned)((per * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, act, (uint8_t*)dst);
+  return pcreid_launch_status();
+}
+
+int pcreid_pack_b7(int B, const float* M, const float* ksum, void* dst, void* stream) {
+  if (B <= 0) return PCREID_OK;
+  if (!M || !ksum || !dst) return PCREID_ERR_ARG;
+  pack_b7_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(M, ksum, (uint8_t*)dst);
+  return pcreid_launch_status();
+}
+
+int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream) {
+  if (P <= 0) return PCREID_OK;
+  if (!part || !out) return PCREID_ERR_ARG;
+  pool_finish_kernel<<<(unsigned)((128LL * P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, npts, part, out);
+  return pcreid_launch_status();
+}
+
+int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
+                   const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out, void* B7_out,
+                   int n_ctas, void* stream) {
+  if (n_units <= 0) return PCREID_OK;
+  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !PV || !MK1 || !W || !A_out || !B7_out || NT <= 0) return PCREID_ERR_ARG;
+  P1Args a{n_units, NT, role, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+           (const uint8_t*)PV, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
+  const int smem = P1_WBYTES + 2 * P1_GBYTES;
+  cudaFuncSetAttribute(pair_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid * 2 > n_units) grid = (n_units + 1) / 2;
+  pair_p1_kernel<<<grid, 2 * GT, smem, (cudaStream_t)stream>>>(a);
+  return pcreid_launch_status();
+}
+
+int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
+                   float* pool_part, int n_ctas, void* stream) {
+  if (n_units <= 0) return PCREID_OK;
+  if (!u_slot || !A_in || !B7_in || !W || !pool_part || NT <= 0) return PCREID_ERR_ARG;
+  P2Args a{n_units, NT, role, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
+  const int smem = P2_WBYTES + 2 * P2_GBYTES;
+  cudaFuncSetAttribute(pair_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid * 2 > n_units) grid = (n_units + 1) / 2;
+  pair_p2_kernel<<<grid, 2 * GT, smem, (cudaStream_t)stream>>>(a);
+  return pcreid_launch_status();
+}
+
+}  // extern "C"

@@ -89,6 +89,10 @@ class ReIDNet(nn.Module):
         self.compute_summary = compute_summary
         self.use_dgcnn = use_dgcnn
         self.combine = combine
+        # 'parity': fp32 kernels (logits within 1e-4 of the reference); 'fast': fused bf16 tcgen05 matcher where the
+        # configuration allows it (d_model 64, 2 heads, point-cat + both pooling, points a multiple of 128)
+        self.match_mode = 'parity'
+        self._fused = None
         if self.match_type not in ('xcorr_eff', 'concat'):
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
                                       "(shipped point configs use 'xcorr_eff'; the baseline uses 'concat')")
@@ -217,6 +221,15 @@ class ReIDNet(nn.Module):
             if self.match_type == 'concat':
                 return self._concat_all_pairs(h_t, h_d, pair_mask)
             out = torch.zeros((T, D), device=dev, dtype=torch.float32)
+            fused = None
+            if self.match_mode == 'fast':
+                from . import fused_pairs
+                if fused_pairs.supported(self, h_t.shape[2]) and h_t.shape[2] == h_d.shape[2]:
+                    if self._fused is None:
+                        self._fused = fused_pairs.FusedXcorr(self)
+                    fused = self._fused
+                    pk_t, pk_d = fused.prepare(h_t, xyz_t), fused.prepare(h_d, xyz_d)
+                    chunk = max(chunk, 65536 * 256 // h_t.shape[2])
             if pair_mask is None:
                 pairs = None
                 total = T * D
@@ -232,7 +245,10 @@ class ReIDNet(nn.Module):
                 else:
                     ti, dj = pairs[s:e, 0], pairs[s:e, 1]
                     lin = ti * D + dj
-                flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
+                if fused is not None:
+                    flat[lin] = fused.match(pk_t, pk_d, ti, dj)
+                else:
+                    flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
             return out
 
     def _concat_all_pairs(self, h_t, h_d, pair_mask):

@@ -1,0 +1,139 @@
+"""Host side of the fused tensor-core `xcorr_eff` matcher (csrc/pair_tc.cu) -- the "fast" mode of
+ReIDNet.match_all_pairs / match_forward_inference.
+
+Everything that depends on one object only is computed once per object with the fp32 kernels and packed to
+bf16 operand images (stage-1 queries elu(Wq1 h)+1, U = W0a1 h, h, Wv2 pos2(xyz), and the stage-1 attention
+operand MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the two fused kernels then score pairs without
+writing any per-pair activation except the bf16 stage-1 outputs (64 KB / pair at 256 points) and the stage-2
+attention operands (36 KB / pair).
+Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
+"""
+import ctypes
+
+import torch
+
+from .. import _lib
+from .. import kernels as K
+
+IMG = 16384
+B7_BYTES = 18432
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _w_image(w):
+    """torch weight (N, K) -> bf16 K-major operand image [K/8][N][8] as bytes."""
+    N, Kd = w.shape
+    return w.detach().to(torch.bfloat16).view(N, Kd // 8, 8).permute(1, 0, 2).contiguous().view(torch.uint8).flatten()
+
+
+def _f32_bytes(*ts):
+    return torch.cat([t.detach().float().flatten() for t in ts]).contiguous().view(torch.uint8)
+
+
+def supported(model, n_points):
+    X1, X2 = model.cross_stage1, model.cross_stage2
+    ok = (model.match_type == 'xcorr_eff' and model.combine == 'point-cat' and model.pool_type == 'both'
+          and X1 is not None and X2 is not None and X1.q_proj.weight.shape == (64, 64) and X1.nhead == 2
+          and X2.q_proj.weight.shape == (64, 64) and X2.nhead == 2 and n_points % 128 == 0)
+    return ok
+
+
+class ObjectPack:
+    """per-object operand images of a set of objects (tracks or detections)."""
+    __slots__ = ("n", "npts", "QF1", "U", "H", "PV", "MK1")
+
+
+class FusedXcorr:
+    def __init__(self, model):
+        self.model = model
+        self._key = None
+        self._w1 = self._w2 = None
+        self.n_ctas = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+    def _weights(self):
+        X1, X2 = self.model.cross_stage1, self.model.cross_stage2
+        key = tuple((t.data_ptr(), t._version) for t in list(X1.parameters()) + list(X2.parameters()))
+        if key != self._key:
+            with torch.no_grad():
+                d = 64
+                self._w1 = torch.cat([
+                    _w_image(X1.mlp[0].weight[:, d:]), _w_image(X1.mlp[2].weight),
+                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)), _w_image(X2.merge.weight),
+                    _f32_bytes(X1.norm1.weight, X1.norm1.bias, X1.norm2.weight, X1.norm2.bias)]).contiguous()
+                self._w2 = torch.cat([
+                    _w_image(X2.q_proj.weight), _w_image(X2.mlp[0].weight), _w_image(X2.mlp[2].weight),
+                    _f32_bytes(X2.norm1.weight, X2.norm1.bias, X2.norm2.weight, X2.norm2.bias)]).contiguous()
+                assert self._w1.numel() == 58368 and self._w2.numel() == 58368
+            self._key = key
+        return self._w1, self._w2
+
+    @staticmethod
+    def _pack_image(x, act=K.ACT_NONE):
+        B, C, N = x.shape
+        out = torch.empty((B, N // 128, C // 8, 128, 16), device=x.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().pcreid_pack_image(B, C, N, _p(x), x.stride(0), x.stride(1), act, _p(out), _stream()),
+                   "pcreid_pack_image")
+        return out
+
+    def prepare(self, h, xyz):
+        """h (B, 64, N) fp32 channel-major, xyz (B, N, 3) -> ObjectPack."""
+        X1, X2 = self.model.cross_stage1, self.model.cross_stage2
+        pk1, pk2 = X1.packed(), X2.packed()
+        B, C, N = h.shape
+        o = ObjectPack()
+        o.n, o.npts = B, N
+        o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
+        o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"]))
+        o.H = self._pack_image(h)
+        o.PV = self._pack_image(K.cn_linear(X2.position_code(xyz), pk2["v"]))
+        wkv, ksum = X1.template_summary(h, X1.position_code(xyz))          # (B, 64, 64) [d][v] block diagonal, (B, 64)
+        M = K.cn_linear(wkv, pk1["merge"], x1_pm=True, y_pm=True)           # (B, d, out) = blockdiag(KV) Wm^T
+        M.mul_(float(N))                                                    # undo the reference's values / S (attention.py:47)
+        o.MK1 = torch.empty((B, B7_BYTES), device=h.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), _p(o.MK1), _stream()), "pcreid_pack_b7")
+        return o
+
+    def match(self, pt, pd, ti, dj, debug=None):
+        """logits (P,) for the pairs (ti[p], dj[p]); ti / dj int64 or int32 index tensors on the device."""
+        assert pt.npts == pd.npts, "fused matcher expects equal point counts on both sides"
+        w1, w2 = self._weights()
+        dev = pt.H.device
+        P, NT, N = ti.numel(), pt.npts // 128, pt.npts
+        ti, dj = ti.long(), dj.long()
+        A = torch.empty((P, 2, NT, IMG), device=dev, dtype=torch.uint8)
+        B7 = torch.empty((P, 2, B7_BYTES), device=dev, dtype=torch.uint8)
+        part = torch.empty((P, 2, 128), device=dev, dtype=torch.float32)
+        L = _lib.lib()
+        for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
+            order = torch.argsort(tmpl, stable=True)                        # runs of units share the template operand
+            us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+            _lib.check(L.pcreid_pair_p1(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(ps.PV),
+                                        _p(pm.MK1), _p(w1), _p(A), _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1")
+        slots = torch.arange(P, device=dev, dtype=torch.int32)
+        for role in (0, 1):
+            _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part), self.n_ctas, _stream()),
+                       "pcreid_pair_p2")
+        pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
+        _lib.check(L.pcreid_pool_finish(P, N, _p(part), _p(pooled), _stream()), "pcreid_pool_finish")
+        if debug is not None:
+            debug.update(A=A, B7=B7, part=part, pooled=pooled)
+        return self.model._head_cn(pooled)
+
+
+def decode_image(img):
+    """(..., C/8, 128, 16) uint8 operand image -> (..., C, 128) fp32 (debug / tests)."""
+    x = img.contiguous().view(torch.bfloat16).float().transpose(-1, -2)     # (..., C/8, 8, 128)
+    return x.reshape(*x.shape[:-3], x.shape[-3] * 8, 128)
+
+
+def decode_b7(img):
+    """(..., 18432) uint8 attention operand -> (..., 64 k, 144 n) fp32 (debug / tests)."""
+    x = img.contiguous().view(torch.bfloat16).float().reshape(*img.shape[:-1], 18, 64, 8)   # [n/8][k][8]
+    return x.permute(*range(x.dim() - 3), x.dim() - 2, x.dim() - 3, x.dim() - 1).reshape(*img.shape[:-1], 64, 144)

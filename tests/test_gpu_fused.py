@@ -1,0 +1,53 @@
+"""-m gpu: fused tcgen05 matcher ("fast" mode) against the fp32 parity path and the oracle.
+Tolerance (bf16 operands, fp32 accumulate/norms; SURVEY.md 7 pre-study): |dlogit| <= 3e-2; the top-1 decision must
+be unchanged on rows whose oracle gap exceeds 2x the measured error."""
+import pytest
+import torch
+
+import helpers
+from oracle import reid_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL_FAST = 3e-2
+
+
+@pytest.mark.parametrize("N,T,D", [(256, 5, 7), (128, 6, 4), (512, 2, 3)])
+def test_fused_matches_parity_and_oracle(N, T, D):
+    m, orc = helpers.build_pair("pt", (N, N // 2, N // 4), device=DEV)
+    t, d = O.synth_objects(T, N, 0), O.synth_objects(D, N, 1)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    Lp = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    m.match_mode = 'fast'
+    Lf = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu())
+    err = (Lf - Lo).abs().max().item()
+    assert (Lp - Lo).abs().max() < 1e-4
+    assert err < TOL_FAST, f"fast-mode logits off by {err}"
+    ok, agree, n = helpers.margin_aware_top1(Lo, Lf, err)
+    assert ok, f"top-1 changed on a decisive row (agreement {agree}, {n} decisive rows)"
+
+
+def test_fused_with_pair_mask_and_unsorted_pairs():
+    m, orc = helpers.build_pair("pt", (256, 128, 64), device=DEV)
+    t, d = O.synth_objects(9, 256, 2), O.synth_objects(11, 256, 3)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    mask = torch.rand(9, 11, generator=torch.Generator().manual_seed(0)) > 0.5
+    m.match_mode = 'fast'
+    Lf = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.to(DEV)).cpu()
+    Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu(), pair_mask=mask)
+    assert (Lf - Lo).abs().max() < TOL_FAST
+    assert (Lf[~mask] == 0).all()
+
+
+def test_fused_symmetry_and_determinism():
+    m, _ = helpers.build_pair("pt", (256, 128, 64), device=DEV)
+    a = O.synth_objects(8, 256, 4).to(DEV)
+    xa, ha = m.encode(a)
+    m.match_mode = 'fast'
+    L1 = m.match_all_pairs(ha, xa, ha, xa)
+    L2 = m.match_all_pairs(ha, xa, ha, xa)
+    assert torch.equal(L1, L2)
+    assert (L1 - L1.t()).abs().max() < TOL_FAST
