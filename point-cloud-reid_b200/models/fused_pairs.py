@@ -56,6 +56,7 @@ class FusedXcorr:
         self._key = None
         self._w1 = self._w2 = None
         self.n_ctas = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
@@ -73,6 +74,19 @@ class FusedXcorr:
                 assert self._w1.numel() == 58368 and self._w2.numel() == 58368
             self._key = key
         return self._w1, self._w2
+
+    def _tick(self):
+        if self.timing is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def _tock(self, name, e0, units):
+        if e0 is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            self.timing.append((name, e0, e1, units))
 
     @staticmethod
     def _pack_image(x, act=K.ACT_NONE):
@@ -114,12 +128,16 @@ class FusedXcorr:
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             order = torch.argsort(tmpl, stable=True)                        # runs of units share the template operand
             us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+            e0 = self._tick()
             _lib.check(L.pcreid_pair_p1(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(ps.PV),
                                         _p(pm.MK1), _p(w1), _p(A), _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1")
+            self._tock("pair_p1_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         for role in (0, 1):
+            e0 = self._tick()
             _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part), self.n_ctas, _stream()),
                        "pcreid_pair_p2")
+            self._tock("pair_p2_kernel", e0, P)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
         _lib.check(L.pcreid_pool_finish(P, N, _p(part), _p(pooled), _stream()), "pcreid_pool_finish")
         if debug is not None:
