@@ -30,7 +30,7 @@
 
 namespace {
 
-constexpr int GT = 128;                 // threads per group
+constexpr int GT = 256;                 // threads per group: 8 warps = 4 TMEM lane quadrants x 2 column halves
 constexpr int IMG = 16384;              // bytes of a 128 x 64 bf16 operand image  [k/8][row][8]
 constexpr int NB7 = 144;                // columns of the attention operand: 64 (head 0) | 64 (head 1) | 16 (2 dots + pad)
 constexpr int B7_BYTES = (NB7 / 8) * 64 * 16;   // [n/8][k][8] bf16 = 18432
@@ -42,10 +42,11 @@ constexpr float LN_EPS = 1e-5f, ATT_EPS = 1e-6f;
 constexpr int P1_W0B = 0, P1_W2 = 16384, P1_WKV = 32768, P1_WM = 49152, P1_LN = 57344, P1_WBYTES = 57344 + 1024;
 // weights blob of phase 2
 constexpr int P2_WQ = 0, P2_W0 = 8192, P2_W2 = 40960, P2_LN = 57344, P2_WBYTES = 57344 + 1024;
-// per-group shared memory of phase 1: QXa (16K) | HdKV (32K) + ones (4K) | MK1 (18K)
-constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ONES + ONES_BYTES, P1_GBYTES = P1_MK1 + B7_BYTES;
-// per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 (18K)
-constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_GBYTES = P2_B7 + B7_BYTES;
+// per-group shared memory of phase 1: QXa (16K) | HdKV (32K) + ones (4K) | MK1 (18K) | LN exchange (2K)
+constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ONES + ONES_BYTES, P1_XCH = P1_MK1 + B7_BYTES,
+              P1_GBYTES = P1_XCH + 2048;
+// per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 x2 (36K) | exchange
+constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_XCH = P2_B7 + 2 * B7_BYTES, P2_GBYTES = P2_XCH + 2048;
 
 struct P1Args {
   int n_units, NT, role;
@@ -88,12 +89,15 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uin
 #define W_IMG(addr, N) (addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16)
 #define B7_IMG(addr) (addr), 128u, 1024u, 256u
 
+// A group = 8 warps working on one 128-point tile: thread (row, h) owns row `row` of the tile (TMEM lane) and the
+// column half `h` of every accumulator, so the epilogue work of a tile is spread over 256 threads.
 struct Group {
-  int t, warp, gid;          // thread in group, warp in group, group in CTA
+  int t, row, h, gid;        // thread in group, tile row (== TMEM lane), column half, group in CTA
   uint32_t tmem;             // TMEM base of the group (lane 0, first column)
   uint32_t tlane;            // tmem + (lane base of this warp << 16)
   uint64_t* bar;
   uint64_t* bar2;
+  float2* xch;               // [2][128] LayerNorm partial exchange between the two column halves
   uint32_t par, par2;
   __device__ __forceinline__ void sync() { tc::bar_sync(1 + gid, GT); }
   // smem operands written by the group -> visible to the tensor core; returns after the group barrier
@@ -105,168 +109,180 @@ struct Group {
   }
   __device__ __forceinline__ void wait() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); }
   __device__ __forceinline__ void wait2() { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }
+  // LayerNorm statistics over 64 channels from the two 32-channel halves (one-pass: E[x^2] - mean^2, fp32)
+  __device__ __forceinline__ void ln_stats(float s, float ss, float& mean, float& rstd) {
+    xch[h * 128 + row] = make_float2(s, ss);
+    sync();
+    const float2 o = xch[(1 - h) * 128 + row];
+    mean = (s + o.x) * (1.f / 64.f);
+    const float var = fmaxf((ss + o.y) * (1.f / 64.f) - mean * mean, 0.f);
+    rstd = rsqrtf(var + LN_EPS);
+  }
 };
 
-// ---- epilogues (thread == row of the 128-point tile) ---------------------------------------------------------
+// ---- epilogues ------------------------------------------------------------------------------------------------
+// Each starts with its global side loads (if any), THEN waits for the MMA, so the L2 latency hides behind the GEMM.
 
-// attention GEMM (N=144) -> z-normalised, head-merged message -> LayerNorm -> bf16 operand image
-__device__ __forceinline__ void epi_attn_ln(const Group& g, const float* __restrict__ ln, uint8_t* dst) {
-  float m[64];
+// attention GEMM (N=144) -> z-normalised, head-merged message -> LayerNorm -> bf16 operand image (32 channels / thread)
+__device__ __forceinline__ void epi_attn_ln(Group& g, const float* __restrict__ ln, uint8_t* dst) {
+  g.wait();
+  float m[32];
   uint32_t d8[8];
   tc::tmem_ld8(g.tlane + 128, d8);
+  const int cb = 32 * g.h;
+  uint32_t r0[32], r1[32];
+  tc::tmem_ld32(g.tlane + cb, r0);
+  tc::tmem_ld32(g.tlane + 64 + cb, r1);
   tc::tmem_ld_wait();
   const float z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS), z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
+  float s = 0.f, ss = 0.f;
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t r0[16], r1[16];
-    tc::tmem_ld16(g.tlane + c0, r0);
-    tc::tmem_ld16(g.tlane + 64 + c0, r1);
-    tc::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 16; ++j) m[c0 + j] = z0 * __uint_as_float(r0[j]) + z1 * __uint_as_float(r1[j]);
+  for (int j = 0; j < 32; ++j) {
+    m[j] = z0 * __uint_as_float(r0[j]) + z1 * __uint_as_float(r1[j]);
+    s += m[j];
+    ss = fmaf(m[j], m[j], ss);
   }
-  float s = 0.f;
+  float mean, rstd;
+  g.ln_stats(s, ss, mean, rstd);
 #pragma unroll
-  for (int j = 0; j < 64; ++j) s += m[j];
-  const float mean = s * (1.f / 64.f);
-  float v = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { const float d = m[j] - mean; v = fmaf(d, d, v); }
-  const float rstd = rsqrtf(v * (1.f / 64.f) + LN_EPS);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = c * 8 + 2 * j;
-      const float y0 = (m[k] - mean) * rstd * ln[k] + ln[64 + k];
-      const float y1 = (m[k + 1] - mean) * rstd * ln[k + 1] + ln[64 + k + 1];
+      const float y0 = (m[k] - mean) * rstd * ln[cb + k] + ln[64 + cb + k];
+      const float y1 = (m[k + 1] - mean) * rstd * ln[cb + k + 1] + ln[64 + cb + k + 1];
       w[j] = tc::pack_bf16(y0, y1);
     }
-    *reinterpret_cast<uint4*>(dst + c * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (4 * g.h + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
-// acc[ncols] (+ side image from global) -> ReLU -> bf16 operand image with ncols/8 chunks
-template <int NCOLS, bool HAS_SIDE>
-__device__ __forceinline__ void epi_relu(const Group& g, const uint8_t* __restrict__ side, uint8_t* dst) {
+// acc[128] (+ side image from global) -> ReLU -> bf16 operand image (64 channels / thread: chunks 8h .. 8h+7)
+template <bool HAS_SIDE>
+__device__ __forceinline__ void epi_relu128(Group& g, const uint8_t* __restrict__ side, uint8_t* dst) {
+  uint4 sd[8];
+  if (HAS_SIDE) {
 #pragma unroll
-  for (int c0 = 0; c0 < NCOLS; c0 += 16) {
-    uint32_t r[16];
-    tc::tmem_ld16(g.tlane + c0, r);
-    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-    if (HAS_SIDE) {
-      s0 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8) * 2048 + g.t * 16));
-      s1 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8 + 1) * 2048 + g.t * 16));
-    }
+    for (int c = 0; c < 8; ++c) sd[c] = __ldg(reinterpret_cast<const uint4*>(side + (8 * g.h + c) * 2048 + g.row * 16));
+  }
+  g.wait();
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[32];
+    tc::tmem_ld32(g.tlane + 64 * g.h + 32 * half, r);
     tc::tmem_ld_wait();
-    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    uint32_t w[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
-      if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
-      w[j] = tc::pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
+    for (int c = 0; c < 4; ++c) {
+      const uint4 s4 = HAS_SIDE ? sd[4 * half + c] : make_uint4(0, 0, 0, 0);
+      const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
+        if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
+        w[j] = tc::pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
+      }
+      *reinterpret_cast<uint4*>(dst + (8 * g.h + 4 * half + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(dst + (c0 / 8) * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(dst + (c0 / 8 + 1) * 2048 + g.t * 16) = make_uint4(w[4], w[5], w[6], w[7]);
   }
 }
 
-// acc[64] -> LayerNorm -> + residual image (global, bf16) -> out[64] fp32
-__device__ __forceinline__ void epi_ln_res(const Group& g, const float* __restrict__ ln, const uint8_t* __restrict__ res,
-                                           float (&o)[64]) {
+// acc[64] -> LayerNorm -> + residual image (global, bf16) -> o[32] fp32 (channels 32h .. 32h+31)
+__device__ __forceinline__ void epi_ln_res(Group& g, const float* __restrict__ ln, const uint8_t* __restrict__ res, float (&o)[32]) {
+  uint4 rs[4];
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t r[16];
-    tc::tmem_ld16(g.tlane + c0, r);
-    tc::tmem_ld_wait();
+  for (int c = 0; c < 4; ++c) rs[c] = __ldg(reinterpret_cast<const uint4*>(res + (4 * g.h + c) * 2048 + g.row * 16));
+  g.wait();
+  const int cb = 32 * g.h;
+  uint32_t r[32];
+  tc::tmem_ld32(g.tlane + cb, r);
+  tc::tmem_ld_wait();
+  float s = 0.f, ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[c0 + j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 32; ++j) {
+    o[j] = __uint_as_float(r[j]);
+    s += o[j];
+    ss = fmaf(o[j], o[j], ss);
   }
-  float s = 0.f;
+  float mean, rstd;
+  g.ln_stats(s, ss, mean, rstd);
 #pragma unroll
-  for (int j = 0; j < 64; ++j) s += o[j];
-  const float mean = s * (1.f / 64.f);
-  float v = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { const float d = o[j] - mean; v = fmaf(d, d, v); }
-  const float rstd = rsqrtf(v * (1.f / 64.f) + LN_EPS);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 rr = __ldg(reinterpret_cast<const uint4*>(res + c * 2048 + g.t * 16));
-    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t rw[4] = {rs[c].x, rs[c].y, rs[c].z, rs[c].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = c * 8 + 2 * j;
-      o[k] = (o[k] - mean) * rstd * ln[k] + ln[64 + k] + bf_lo(rw[j]);
-      o[k + 1] = (o[k + 1] - mean) * rstd * ln[k + 1] + ln[64 + k + 1] + bf_hi(rw[j]);
+      o[k] = (o[k] - mean) * rstd * ln[cb + k] + ln[64 + cb + k] + bf_lo(rw[j]);
+      o[k + 1] = (o[k + 1] - mean) * rstd * ln[cb + k + 1] + ln[64 + cb + k + 1] + bf_hi(rw[j]);
     }
   }
 }
 
-__device__ __forceinline__ void store_image64(const float (&o)[64], uint8_t* dst, int row) {
+// o[32] (channels 32h ..) -> chunks 4h .. 4h+3 of a 64-channel operand image
+__device__ __forceinline__ void store_image32(const float (&o)[32], uint8_t* dst, int row, int h) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(o[c * 8 + 2 * j], o[c * 8 + 2 * j + 1]);
-    *reinterpret_cast<uint4*>(dst + c * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (4 * h + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
-// acc[cols c_base .. c_base+64) -> elu+1 (or + side image) -> bf16 chunks [chunk0, chunk0+8) of dst
+// 32 accumulator columns starting at col -> (elu+1 | + side) -> 4 chunks starting at chunk0 of dst
 template <bool ELU, bool HAS_SIDE>
-__device__ __forceinline__ void epi_feat64(const Group& g, int c_base, const uint8_t* __restrict__ side, uint8_t* dst, int chunk0) {
+__device__ __forceinline__ void feat32(Group& g, int col, const uint4 (&sd)[4], uint8_t* dst, int chunk0) {
+  uint32_t r[32];
+  tc::tmem_ld32(g.tlane + col, r);
+  tc::tmem_ld_wait();
 #pragma unroll
-  for (int c0 = 0; c0 < 64; c0 += 16) {
-    uint32_t r[16];
-    tc::tmem_ld16(g.tlane + c_base + c0, r);
-    uint4 s0 = make_uint4(0, 0, 0, 0), s1 = s0;
-    if (HAS_SIDE) {
-      s0 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8) * 2048 + g.t * 16));
-      s1 = __ldg(reinterpret_cast<const uint4*>(side + (c0 / 8 + 1) * 2048 + g.t * 16));
-    }
-    tc::tmem_ld_wait();
-    const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    uint32_t w[8];
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t sw[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
+    uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = __uint_as_float(r[2 * j]), b = __uint_as_float(r[2 * j + 1]);
+    for (int j = 0; j < 4; ++j) {
+      float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
       if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
       if (ELU) { a = elu1(a); b = elu1(b); }
       w[j] = tc::pack_bf16(a, b);
     }
-    *reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8) * 2048 + g.t * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(dst + (chunk0 + c0 / 8 + 1) * 2048 + g.t * 16) = make_uint4(w[4], w[5], w[6], w[7]);
+    *reinterpret_cast<uint4*>(dst + (chunk0 + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
-// row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]  (MN-major image [n/8][k=d][8])
-__device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
-  const int h = d >> 5;
+// chunks [c_lo, c_hi) of row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]
+// (MN-major image [n/8][k=d][8]); M32 holds M[d][8*c_lo .. 8*c_hi)
+__device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, float ksum, bool tail, int d, uint8_t* dst) {
+  const int hd = d >> 5;
   const uint4 zero = make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(M[c * 8 + 2 * j], M[c * 8 + 2 * j + 1]);
+    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(M32[c * 8 + 2 * j], M32[c * 8 + 2 * j + 1]);
     const uint4 val = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(dst + c * 1024 + d * 16) = h == 0 ? val : zero;
-    *reinterpret_cast<uint4*>(dst + (8 + c) * 1024 + d * 16) = h == 1 ? val : zero;
+    *reinterpret_cast<uint4*>(dst + (c_lo + c) * 1024 + d * 16) = hd == 0 ? val : zero;
+    *reinterpret_cast<uint4*>(dst + (8 + c_lo + c) * 1024 + d * 16) = hd == 1 ? val : zero;
   }
-  *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) = make_uint4(h == 0 ? tc::pack_bf16(ksum, 0.f) : tc::pack_bf16(0.f, ksum), 0, 0, 0);
-  *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
+  if (tail) {
+    *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) =
+        make_uint4(hd == 0 ? tc::pack_bf16(ksum, 0.f) : tc::pack_bf16(0.f, ksum), 0, 0, 0);
+    *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
+  }
 }
 
-__device__ __forceinline__ void group_setup(Group& g, uint64_t* bars, uint32_t tmem_base) {
+__device__ __forceinline__ void group_setup(Group& g, uint64_t* bars, uint32_t tmem_base, uint8_t* xch) {
   g.gid = threadIdx.x / GT;
   g.t = threadIdx.x % GT;
-  g.warp = g.t >> 5;
+  const int warp = g.t >> 5;
+  g.row = 32 * (warp & 3) + (g.t & 31);
+  g.h = warp >> 2;
   g.tmem = tmem_base + g.gid * 256;
-  g.tlane = g.tmem + ((uint32_t)(g.warp * 32) << 16);
+  g.tlane = g.tmem + ((uint32_t)((warp & 3) * 32) << 16);
   g.bar = bars + 2 * g.gid;
   g.bar2 = bars + 2 * g.gid + 1;
+  g.xch = reinterpret_cast<float2*>(xch);
   g.par = 0;
   g.par2 = 0;
 }
@@ -294,15 +310,15 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
   __syncthreads();
   tc::tc_fence_after();
   Group g;
-  group_setup(g, bars, tmem_base_s);
-  uint8_t* G = smem + P1_WBYTES + g.gid * P1_GBYTES;
+  uint8_t* G = smem + P1_WBYTES + (threadIdx.x / GT) * P1_GBYTES;
+  group_setup(g, bars, tmem_base_s, G + P1_XCH);
   uint8_t* QXa = G + P1_QXA;
   uint8_t* HdKV = G + P1_HDKV;
   uint8_t* MK1 = G + P1_MK1;
-  {   // the two constant chunks appended to V: column 64 of B == 1 for every point
+  if (g.t < 128) {   // the two constant chunks appended to V: column 64 of B == 1 for every point
     uint4* ones = reinterpret_cast<uint4*>(G + P1_ONES);
     ones[g.t] = make_uint4(0x00003f80u, 0, 0, 0);      // bf16 1.0 in element 0 of the chunk
-    ones[GT + g.t] = make_uint4(0, 0, 0, 0);
+    ones[128 + g.t] = make_uint4(0, 0, 0, 0);
   }
   const uint32_t sQXa = tc::smem_u32(QXa), sHd = tc::smem_u32(HdKV), sMK1 = tc::smem_u32(MK1), sW = tc::smem_u32(Wsm);
   const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
@@ -313,39 +329,71 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
   const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
   int cur_templ = -1;
+  // register prefetch of the next tile's query image (16 KB / 256 threads = 4 x 16 B each)
+  uint4 pre[4];
+  if (u0 < u1) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.QF1 + (size_t)a.u_search[u0] * a.NT * IMG);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+  }
   for (int u = u0; u < u1; ++u) {
     const int so = a.u_search[u], te = a.u_templ[u], slot = a.u_slot[u];
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
       if (tile > 0) g.wait2();                                            // previous tile's KV GEMM still reads HdKV
       // ---- stage operands of G1
-      copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GT);
-      if (te != cur_templ) copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GT);
-      cur_templ = te;
-      cp_async_commit();
-      cp_async_wait<0>();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(QXa)[g.t + i * GT] = pre[i];
+      if (te != cur_templ) {
+        copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GT);
+        cp_async_commit();
+        cp_async_wait<0>();
+        cur_templ = te;
+      }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), B7_IMG(sMK1), id144, 4, false); tc::umma_commit(g.bar); }
-      g.wait();
+      {   // prefetch the next (unit, tile) query image while the tensor core works
+        int nu = u, nt = tile + 1;
+        if (nt == a.NT) { nu = u + 1; nt = 0; }
+        if (nu < u1) {
+          const uint4* src = reinterpret_cast<const uint4*>(a.QF1 + ((size_t)a.u_search[nu] * a.NT + nt) * IMG);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+        }
+      }
       epi_attn_ln(g, ln1, QXa);                                           // X
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_W0B, 128), id128, 4, false); tc::umma_commit(g.bar); }
-      g.wait();
-      epi_relu<128, true>(g, a.U + ti * 2 * IMG, HdKV);                   // Hd = relu(X W0b^T + W0a h)
+      epi_relu128<true>(g, a.U + ti * 2 * IMG, HdKV);                     // Hd = relu(X W0b^T + W0a h)
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sHd), W_IMG(sW + P1_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
-      g.wait();
       {
-        float o[64];
+        float o[32];
         epi_ln_res(g, ln2, a.H + ti * IMG, o);                            // a = h + LN2(.)
-        store_image64(o, QXa, g.t);
-        store_image64(o, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, g.t);
+        store_image32(o, QXa, g.row, g.h);
+        store_image32(o, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, g.row, g.h);
       }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WKV, 128), id128, 4, false); tc::umma_commit(g.bar); }
-      g.wait();
-      epi_feat64<true, false>(g, 0, nullptr, HdKV, 0);                    // Kf = elu(k)+1      -> chunks 0..7
-      epi_feat64<false, true>(g, 64, a.PV + ti * IMG, HdKV, 8);           // V = v + Wv pos     -> chunks 8..15
+      {   // column half 0: Kf = elu(k)+1 -> chunks 0..7 ; column half 1: V = v + Wv pos -> chunks 8..15
+        uint4 sd0[4], sd1[4];
+        if (g.h == 1) {
+          const uint8_t* pv = a.PV + ti * IMG;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            sd0[c] = __ldg(reinterpret_cast<const uint4*>(pv + c * 2048 + g.row * 16));
+            sd1[c] = __ldg(reinterpret_cast<const uint4*>(pv + (4 + c) * 2048 + g.row * 16));
+          }
+        }
+        g.wait();
+        if (g.h == 0) {
+          feat32<true, false>(g, 0, sd0, HdKV, 0);
+          feat32<true, false>(g, 32, sd1, HdKV, 4);
+        } else {
+          feat32<false, true>(g, 64, sd0, HdKV, 8);
+          feat32<false, true>(g, 96, sd1, HdKV, 12);
+        }
+      }
       g.publish();
       if (g.t == 0) {   // KV += [Kf|V]^T [V|1]   (M = 128 channels, N = 80, K = 128 points)
         issue_gemm(g.tmem + KV_COL, sHd, 128u, 2048u, 256u, sHd + 8 * 2048, 128u, 2048u, 256u, idkv, 8, tile > 0);
@@ -353,44 +401,35 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
       }
     }
     g.wait2();
-    // ---- B7 = stage-2 attention operand of this (pair, direction) as template
+    // ---- B7 = stage-2 attention operand of this (pair, direction) as template.  Rows d < 64 of the KV accumulator.
     {
-      float kv[64];
+      float kv[32];
       float ksum = 0.f;
-      if (g.t < 64) {
-#pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t r[16];
-          tc::tmem_ld16(g.tlane + KV_COL + c0, r);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) kv[c0 + j] = __uint_as_float(r[j]);
-        }
+      if (g.row < 64) {
+        uint32_t r[32];
+        tc::tmem_ld32(g.tlane + KV_COL + 32 * g.h, r);
         uint32_t r8[8];
         tc::tmem_ld8(g.tlane + KV_COL + 64, r8);
         tc::tmem_ld_wait();
         ksum = __uint_as_float(r8[0]);
-        const int h = g.t >> 5;
+        const bool keep = (g.row >> 5) == g.h;                            // block diagonal: head of row d == head of columns
 #pragma unroll
-        for (int j = 0; j < 64; ++j) if ((j >> 5) != h) kv[j] = 0.f;     // block diagonal: head h keeps its own values
-        store_image64(kv, QXa, g.t);
+        for (int j = 0; j < 32; ++j) kv[j] = keep ? __uint_as_float(r[j]) : 0.f;
+        store_image32(kv, QXa, g.row, g.h);
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(QXa + c * 2048 + g.t * 16) = make_uint4(0, 0, 0, 0);
+        for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(QXa + (4 * g.h + c) * 2048 + g.row * 16) = make_uint4(0, 0, 0, 0);
       }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WM, 64), id64, 4, false); tc::umma_commit(g.bar); }
       g.wait();
-      if (g.t < 64) {
+      if (g.row < 64) {
+        uint32_t r[32];
+        tc::tmem_ld32(g.tlane + 32 * g.h, r);
+        tc::tmem_ld_wait();
 #pragma unroll
-        for (int c0 = 0; c0 < 64; c0 += 16) {
-          uint32_t r[16];
-          tc::tmem_ld16(g.tlane + c0, r);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) kv[c0 + j] = __uint_as_float(r[j]);
-        }
-        write_b7_row(kv, ksum, g.t, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
+        for (int j = 0; j < 32; ++j) kv[j] = __uint_as_float(r[j]);
+        write_b7_part(kv, 4 * g.h, ksum, g.h == 0, g.row, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
       }
       tc::tc_fence_before();
       g.sync();
@@ -408,7 +447,7 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float comb[2][2][128];
+  __shared__ float comb[2][2][4][64];
   uint8_t* Wsm = smem;
   const float* ln1 = reinterpret_cast<const float*>(Wsm + P2_LN);         // cross_stage2.norm1
   const float* ln2 = ln1 + 128;                                           // cross_stage2.norm2
@@ -425,73 +464,112 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
   __syncthreads();
   tc::tc_fence_after();
   Group g;
-  group_setup(g, bars, tmem_base_s);
-  uint8_t* G = smem + P2_WBYTES + g.gid * P2_GBYTES;
+  uint8_t* G = smem + P2_WBYTES + (threadIdx.x / GT) * P2_GBYTES;
+  group_setup(g, bars, tmem_base_s, G + P2_XCH);
   uint8_t* R1 = G + P2_R1;
-  uint8_t* B7 = G + P2_B7;
   float* R1f = reinterpret_cast<float*>(R1);
-  const uint32_t sR1 = tc::smem_u32(R1), sB7 = tc::smem_u32(B7), sW = tc::smem_u32(Wsm);
+  const uint32_t sR1 = tc::smem_u32(R1), sW = tc::smem_u32(Wsm);
   const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
   const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
 
   const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
-  const int pc = g.t & 63, phalf = g.t >> 6;                              // pooling: channel, row half
+  const int pc = g.t & 63, pq = g.t >> 6;                                 // pooling: channel, row quarter
+  // prefetch: the next tile's `a` image travels through registers (16 KB / 256 threads = 4 x 16 B each), the next
+  // unit's attention operand through cp.async into the second B7 buffer, both while the current tile computes
+  auto a_image = [&](int u, int tile) {
+    return a.A_in + (((size_t)a.u_slot[u] * 2 + a.role) * a.NT + tile) * IMG;
+  };
+  uint4 pre[4];
+  if (u0 < u1) {
+    const uint4* src = reinterpret_cast<const uint4*>(a_image(u0, 0));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+    copy_to_smem(G + P2_B7, a.B7_in + ((size_t)a.u_slot[u0] * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GT);
+  }
+  cp_async_commit();
+  int b7buf = 0;
   for (int u = u0; u < u1; ++u) {
     const int slot = a.u_slot[u];
-    copy_to_smem(B7, a.B7_in + ((size_t)slot * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GT);
+    const uint32_t sB7 = tc::smem_u32(G + P2_B7 + b7buf * B7_BYTES);
     float pmax = -INFINITY, psum = 0.f;
     for (int tile = 0; tile < a.NT; ++tile) {
-      const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
-      copy_to_smem(R1, a_img, IMG, g.t, GT);
-      cp_async_commit();
-      cp_async_wait<0>();
+      const uint8_t* a_img = a_image(u, tile);
+      cp_async_wait<0>();                                                 // this thread's share of B7 has landed
+      g.sync();                                                           // previous tile's pooling reads of R1 are done
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(R1)[g.t + i * GT] = pre[i];
       g.publish();
+      {   // prefetch the next tile (and, at the end of the unit, the next unit's attention operand)
+        int nu = u, nt = tile + 1;
+        if (nt == a.NT) { nu = u + 1; nt = 0; }
+        if (nu < u1) {
+          const uint4* src = reinterpret_cast<const uint4*>(a_image(nu, nt));
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+          if (nt == 0)
+            copy_to_smem(G + P2_B7 + (1 - b7buf) * B7_BYTES, a.B7_in + ((size_t)a.u_slot[nu] * 2 + (1 - a.role)) * B7_BYTES,
+                         B7_BYTES, g.t, GT);
+        }
+        cp_async_commit();
+      }
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_WQ, 64), id64, 4, false); tc::umma_commit(g.bar); }
-      g.wait();
-      epi_feat64<true, false>(g, 0, nullptr, R1 + IMG, 0);                // Qf = elu(q)+1
+      {
+        uint4 none[4];
+        g.wait();
+        feat32<true, false>(g, 32 * g.h, none, R1 + IMG, 4 * g.h);        // Qf = elu(q)+1
+      }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1 + IMG), B7_IMG(sB7), id144, 4, false); tc::umma_commit(g.bar); }
-      g.wait();
       epi_attn_ln(g, ln1, R1 + IMG);                                      // X next to a: [a | X] is the K=128 operand
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W0, 128), id128, 8, false); tc::umma_commit(g.bar); }
-      g.wait();
-      epi_relu<128, false>(g, nullptr, R1);                               // Hd over [a | X]
+      epi_relu128<false>(g, nullptr, R1);                                 // Hd over [a | X]
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
-      g.wait();
       {
-        float o[64];
+        float o[32];
         epi_ln_res(g, ln2, a_img, o);                                     // o = a + LN2(.)
         // transpose through shared memory (R1 is free: G9 has completed) with a rotation that keeps both the
         // row-wise writes and the channel-wise reads bank-conflict free
 #pragma unroll
-        for (int c = 0; c < 64; ++c) R1f[c * 128 + ((g.t + c) & 127)] = o[c];
+        for (int c = 0; c < 32; ++c) {
+          const int ch = 32 * g.h + c;
+          R1f[ch * 128 + ((g.row + ch) & 127)] = o[c];
+        }
       }
       g.sync();
 #pragma unroll 8
-      for (int i = 0; i < 64; ++i) {
-        const float v = R1f[pc * 128 + ((phalf * 64 + i + pc) & 127)];
+      for (int i = 0; i < 32; ++i) {
+        const float v = R1f[pc * 128 + ((pq * 32 + i + pc) & 127)];
         pmax = fmaxf(pmax, v);
         psum += v;
       }
-      g.sync();                                                           // R1 is overwritten by the next tile
     }
-    comb[g.gid][0][g.t] = pmax;
-    comb[g.gid][1][g.t] = psum;
+    comb[g.gid][0][pq][pc] = pmax;
+    comb[g.gid][1][pq][pc] = psum;
     g.sync();
     if (g.t < 64) {
       float* out = a.pool_part + ((size_t)slot * 2 + a.role) * 128;
-      out[g.t] = fmaxf(comb[g.gid][0][g.t], comb[g.gid][0][g.t + 64]);
-      out[64 + g.t] = comb[g.gid][1][g.t] + comb[g.gid][1][g.t + 64];
+      out[g.t] = fmaxf(fmaxf(comb[g.gid][0][0][g.t], comb[g.gid][0][1][g.t]), fmaxf(comb[g.gid][0][2][g.t], comb[g.gid][0][3][g.t]));
+      out[64 + g.t] = (comb[g.gid][1][0][g.t] + comb[g.gid][1][1][g.t]) + (comb[g.gid][1][2][g.t] + comb[g.gid][1][3][g.t]);
     }
-    g.sync();
+    b7buf ^= 1;
   }
+  cp_async_wait<0>();
   tc::tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// row d of the stage operand (used by the per-object packer): all 64 columns at once
+__device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
+  float lo[32], hi[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { lo[j] = M[j]; hi[j] = M[32 + j]; }
+  write_b7_part(lo, 0, ksum, true, d, dst);
+  write_b7_part(hi, 4, ksum, false, d, dst);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
