@@ -123,58 +123,81 @@ struct Group {
 // ---- epilogues ------------------------------------------------------------------------------------------------
 // Each starts with its global side loads (if any), THEN waits for the MMA, so the L2 latency hides behind the GEMM.
 
+// LayerNorm affine + bf16 pack of 32 channels (cb .. cb+31) into chunks 4h .. 4h+3 of an operand image.
+// y = x * (rstd * gamma) + (beta - mean * rstd * gamma): two FMAs per element, gamma/beta read as float4 from smem.
+__device__ __forceinline__ void ln_apply_store(const float (&x)[32], float mean, float rstd, const float* __restrict__ ln, int cb,
+                                               uint8_t* dst_row) {
+  const float4* g4 = reinterpret_cast<const float4*>(ln + cb);
+  const float4* b4 = reinterpret_cast<const float4*>(ln + 64 + cb);
+  const float nm = -mean * rstd;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 ga = g4[2 * c], gb = g4[2 * c + 1], ba = b4[2 * c], bb = b4[2 * c + 1];
+    const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float y0 = fmaf(fmaf(x[c * 8 + 2 * j], rstd, nm), gam[2 * j], bet[2 * j]);
+      const float y1 = fmaf(fmaf(x[c * 8 + 2 * j + 1], rstd, nm), gam[2 * j + 1], bet[2 * j + 1]);
+      w[j] = tc::pack_bf16(y0, y1);
+    }
+    *reinterpret_cast<uint4*>(dst_row + c * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 // attention GEMM (N=144) -> z-normalised, head-merged message -> LayerNorm -> bf16 operand image (32 channels / thread)
 __device__ __forceinline__ void epi_attn_ln(Group& g, const float* __restrict__ ln, uint8_t* dst) {
-  g.wait();
   float m[32];
   uint32_t d8[8];
   tc::tmem_ld8(g.tlane + 128, d8);
   const int cb = 32 * g.h;
-  uint32_t r0[32], r1[32];
-  tc::tmem_ld32(g.tlane + cb, r0);
-  tc::tmem_ld32(g.tlane + 64 + cb, r1);
-  tc::tmem_ld_wait();
-  const float z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS), z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
-  float s = 0.f, ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    m[j] = z0 * __uint_as_float(r0[j]) + z1 * __uint_as_float(r1[j]);
-    s += m[j];
-    ss = fmaf(m[j], m[j], ss);
-  }
-  float mean, rstd;
-  g.ln_stats(s, ss, mean, rstd);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int k = c * 8 + 2 * j;
-      const float y0 = (m[k] - mean) * rstd * ln[cb + k] + ln[64 + cb + k];
-      const float y1 = (m[k + 1] - mean) * rstd * ln[cb + k + 1] + ln[64 + cb + k + 1];
-      w[j] = tc::pack_bf16(y0, y1);
-    }
-    *reinterpret_cast<uint4*>(dst + (4 * g.h + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-}
-
-// acc[128] (+ side image from global) -> ReLU -> bf16 operand image (64 channels / thread: chunks 8h .. 8h+7)
-template <bool HAS_SIDE>
-__device__ __forceinline__ void epi_relu128(Group& g, const uint8_t* __restrict__ side, uint8_t* dst) {
-  uint4 sd[8];
-  if (HAS_SIDE) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) sd[c] = __ldg(reinterpret_cast<const uint4*>(side + (8 * g.h + c) * 2048 + g.row * 16));
-  }
-  g.wait();
+  float s = 0.f, ss = 0.f, s2 = 0.f, ss2 = 0.f;
+  float z0 = 0.f, z1 = 0.f;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    uint32_t r[32];
-    tc::tmem_ld32(g.tlane + 64 * g.h + 32 * half, r);
+    uint32_t r0[16], r1[16];
+    tc::tmem_ld16(g.tlane + cb + 16 * half, r0);
+    tc::tmem_ld16(g.tlane + 64 + cb + 16 * half, r1);
+    tc::tmem_ld_wait();
+    if (half == 0) {
+      z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS);
+      z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float a = fmaf(z0, __uint_as_float(r0[j]), z1 * __uint_as_float(r1[j]));
+      const float b = fmaf(z0, __uint_as_float(r0[j + 1]), z1 * __uint_as_float(r1[j + 1]));
+      m[16 * half + j] = a;
+      m[16 * half + j + 1] = b;
+      s += a; ss = fmaf(a, a, ss);
+      s2 += b; ss2 = fmaf(b, b, ss2);
+    }
+  }
+  float mean, rstd;
+  g.ln_stats(s + s2, ss + ss2, mean, rstd);
+  ln_apply_store(m, mean, rstd, ln, cb, dst + (4 * g.h) * 2048 + g.row * 16);
+}
+
+// 8 x 16 B of a side image row (chunks c0 .. c0+7) -> registers (issued early so the L2 latency hides behind a stage)
+template <int NCH>
+__device__ __forceinline__ void load_side(uint4 (&sd)[NCH], const uint8_t* __restrict__ img, int chunk0, int row) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) sd[c] = __ldg(reinterpret_cast<const uint4*>(img + (chunk0 + c) * 2048 + row * 16));
+}
+
+// acc[128] (+ side registers) -> ReLU -> bf16 operand image (64 channels / thread: chunks 8h .. 8h+7)
+template <bool HAS_SIDE>
+__device__ __forceinline__ void epi_relu128(Group& g, const uint4 (&sd)[8], uint8_t* dst) {
+  uint8_t* drow = dst + (8 * g.h) * 2048 + g.row * 16;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + 64 * g.h + 16 * q, r);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const uint4 s4 = HAS_SIDE ? sd[4 * half + c] : make_uint4(0, 0, 0, 0);
+    for (int c = 0; c < 2; ++c) {
+      const uint4 s4 = HAS_SIDE ? sd[2 * q + c] : make_uint4(0, 0, 0, 0);
       const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
       uint32_t w[4];
 #pragma unroll
@@ -183,38 +206,45 @@ __device__ __forceinline__ void epi_relu128(Group& g, const uint8_t* __restrict_
         if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
         w[j] = tc::pack_bf16(fmaxf(a, 0.f), fmaxf(b, 0.f));
       }
-      *reinterpret_cast<uint4*>(dst + (8 * g.h + 4 * half + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(drow + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }
 }
 
-// acc[64] -> LayerNorm -> + residual image (global, bf16) -> o[32] fp32 (channels 32h .. 32h+31)
-__device__ __forceinline__ void epi_ln_res(Group& g, const float* __restrict__ ln, const uint8_t* __restrict__ res, float (&o)[32]) {
-  uint4 rs[4];
-#pragma unroll
-  for (int c = 0; c < 4; ++c) rs[c] = __ldg(reinterpret_cast<const uint4*>(res + (4 * g.h + c) * 2048 + g.row * 16));
-  g.wait();
+// acc[64] -> LayerNorm -> + residual registers (bf16 chunks 4h .. 4h+3 of the row) -> o[32] fp32 (channels 32h .. 32h+31)
+__device__ __forceinline__ void epi_ln_res(Group& g, const float* __restrict__ ln, const uint4 (&rs)[4], float (&o)[32]) {
   const int cb = 32 * g.h;
-  uint32_t r[32];
-  tc::tmem_ld32(g.tlane + cb, r);
-  tc::tmem_ld_wait();
-  float s = 0.f, ss = 0.f;
+  float s = 0.f, ss = 0.f, s2 = 0.f, ss2 = 0.f;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    o[j] = __uint_as_float(r[j]);
-    s += o[j];
-    ss = fmaf(o[j], o[j], ss);
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + cb + 16 * half, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+      const float a = __uint_as_float(r[j]), b = __uint_as_float(r[j + 1]);
+      o[16 * half + j] = a;
+      o[16 * half + j + 1] = b;
+      s += a; ss = fmaf(a, a, ss);
+      s2 += b; ss2 = fmaf(b, b, ss2);
+    }
   }
   float mean, rstd;
-  g.ln_stats(s, ss, mean, rstd);
+  g.ln_stats(s + s2, ss + ss2, mean, rstd);
+  const float4* g4 = reinterpret_cast<const float4*>(ln + cb);
+  const float4* b4 = reinterpret_cast<const float4*>(ln + 64 + cb);
+  const float nm = -mean * rstd;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
+    const float4 ga = g4[2 * c], gb = g4[2 * c + 1], ba = b4[2 * c], bb = b4[2 * c + 1];
+    const float gam[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+    const float bet[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
     const uint32_t rw[4] = {rs[c].x, rs[c].y, rs[c].z, rs[c].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int k = c * 8 + 2 * j;
-      o[k] = (o[k] - mean) * rstd * ln[cb + k] + ln[64 + cb + k] + bf_lo(rw[j]);
-      o[k + 1] = (o[k + 1] - mean) * rstd * ln[cb + k + 1] + ln[64 + cb + k + 1] + bf_hi(rw[j]);
+      o[k] = fmaf(fmaf(o[k], rstd, nm), gam[2 * j], bet[2 * j]) + bf_lo(rw[j]);
+      o[k + 1] = fmaf(fmaf(o[k + 1], rstd, nm), gam[2 * j + 1], bet[2 * j + 1]) + bf_hi(rw[j]);
     }
   }
 }
@@ -232,22 +262,27 @@ __device__ __forceinline__ void store_image32(const float (&o)[32], uint8_t* dst
 
 // 32 accumulator columns starting at col -> (elu+1 | + side) -> 4 chunks starting at chunk0 of dst
 template <bool ELU, bool HAS_SIDE>
-__device__ __forceinline__ void feat32(Group& g, int col, const uint4 (&sd)[4], uint8_t* dst, int chunk0) {
-  uint32_t r[32];
-  tc::tmem_ld32(g.tlane + col, r);
-  tc::tmem_ld_wait();
+__device__ __forceinline__ void feat32(Group& g, int col, const uint4* sd, uint8_t* dst, int chunk0) {
+  uint8_t* drow = dst + chunk0 * 2048 + g.row * 16;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t sw[4] = {sd[c].x, sd[c].y, sd[c].z, sd[c].w};
-    uint32_t w[4];
+  for (int q = 0; q < 2; ++q) {
+    uint32_t r[16];
+    tc::tmem_ld16(g.tlane + col + 16 * q, r);
+    tc::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
-      if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
-      if (ELU) { a = elu1(a); b = elu1(b); }
-      w[j] = tc::pack_bf16(a, b);
+    for (int c = 0; c < 2; ++c) {
+      uint32_t sw[4] = {0, 0, 0, 0};
+      if (HAS_SIDE) { sw[0] = sd[2 * q + c].x; sw[1] = sd[2 * q + c].y; sw[2] = sd[2 * q + c].z; sw[3] = sd[2 * q + c].w; }
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = __uint_as_float(r[c * 8 + 2 * j]), b = __uint_as_float(r[c * 8 + 2 * j + 1]);
+        if (HAS_SIDE) { a += bf_lo(sw[j]); b += bf_hi(sw[j]); }
+        if (ELU) { a = elu1(a); b = elu1(b); }
+        w[j] = tc::pack_bf16(a, b);
+      }
+      *reinterpret_cast<uint4*>(drow + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(dst + (chunk0 + c) * 2048 + g.row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -361,38 +396,34 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
           for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
         }
       }
+      uint4 sdU[8], sdH[4], sdPV[8];
+      g.wait();
+      load_side<8>(sdU, a.U + ti * 2 * IMG, 8 * g.h, g.row);              // consumed one stage later (after G2)
       epi_attn_ln(g, ln1, QXa);                                           // X
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_W0B, 128), id128, 4, false); tc::umma_commit(g.bar); }
-      epi_relu128<true>(g, a.U + ti * 2 * IMG, HdKV);                     // Hd = relu(X W0b^T + W0a h)
+      g.wait();
+      load_side<4>(sdH, a.H + ti * IMG, 4 * g.h, g.row);                  // consumed after G3
+      epi_relu128<true>(g, sdU, HdKV);                                    // Hd = relu(X W0b^T + W0a h)
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sHd), W_IMG(sW + P1_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      g.wait();
+      if (g.h == 1) load_side<8>(sdPV, a.PV + ti * IMG, 0, g.row);        // consumed after G4
       {
         float o[32];
-        epi_ln_res(g, ln2, a.H + ti * IMG, o);                            // a = h + LN2(.)
+        epi_ln_res(g, ln2, sdH, o);                                       // a = h + LN2(.)
         store_image32(o, QXa, g.row, g.h);
         store_image32(o, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, g.row, g.h);
       }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WKV, 128), id128, 4, false); tc::umma_commit(g.bar); }
-      {   // column half 0: Kf = elu(k)+1 -> chunks 0..7 ; column half 1: V = v + Wv pos -> chunks 8..15
-        uint4 sd0[4], sd1[4];
-        if (g.h == 1) {
-          const uint8_t* pv = a.PV + ti * IMG;
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            sd0[c] = __ldg(reinterpret_cast<const uint4*>(pv + c * 2048 + g.row * 16));
-            sd1[c] = __ldg(reinterpret_cast<const uint4*>(pv + (4 + c) * 2048 + g.row * 16));
-          }
-        }
-        g.wait();
-        if (g.h == 0) {
-          feat32<true, false>(g, 0, sd0, HdKV, 0);
-          feat32<true, false>(g, 32, sd1, HdKV, 4);
-        } else {
-          feat32<false, true>(g, 64, sd0, HdKV, 8);
-          feat32<false, true>(g, 96, sd1, HdKV, 12);
-        }
+      g.wait();
+      if (g.h == 0) {   // column half 0: Kf = elu(k)+1 -> chunks 0..7 ; column half 1: V = v + Wv pos -> chunks 8..15
+        feat32<true, false>(g, 0, nullptr, HdKV, 0);
+        feat32<true, false>(g, 32, nullptr, HdKV, 4);
+      } else {
+        feat32<false, true>(g, 64, sdPV, HdKV, 8);
+        feat32<false, true>(g, 96, sdPV + 4, HdKV, 12);
       }
       g.publish();
       if (g.t == 0) {   // KV += [Kf|V]^T [V|1]   (M = 128 channels, N = 80, K = 128 points)
@@ -515,22 +546,27 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
         cp_async_commit();
       }
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_WQ, 64), id64, 4, false); tc::umma_commit(g.bar); }
-      {
-        uint4 none[4];
-        g.wait();
-        feat32<true, false>(g, 32 * g.h, none, R1 + IMG, 4 * g.h);        // Qf = elu(q)+1
-      }
+      uint4 sdA[4];
+      g.wait();
+      feat32<true, false>(g, 32 * g.h, nullptr, R1 + IMG, 4 * g.h);       // Qf = elu(q)+1
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1 + IMG), B7_IMG(sB7), id144, 4, false); tc::umma_commit(g.bar); }
+      g.wait();
       epi_attn_ln(g, ln1, R1 + IMG);                                      // X next to a: [a | X] is the K=128 operand
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W0, 128), id128, 8, false); tc::umma_commit(g.bar); }
-      epi_relu128<false>(g, nullptr, R1);                                 // Hd over [a | X]
+      g.wait();
+      load_side<4>(sdA, a_img, 4 * g.h, g.row);                           // residual a, consumed after G9
+      {
+        uint4 none[8];
+        epi_relu128<false>(g, none, R1);                                  // Hd over [a | X]
+      }
       g.publish();
       if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      g.wait();
       {
         float o[32];
-        epi_ln_res(g, ln2, a_img, o);                                     // o = a + LN2(.)
+        epi_ln_res(g, ln2, sdA, o);                                       // o = a + LN2(.)
         // transpose through shared memory (R1 is free: G9 has completed) with a rotation that keeps both the
         // row-wise writes and the channel-wise reads bank-conflict free
 #pragma unroll
