@@ -136,7 +136,7 @@ def main():
     import helpers
     from oracle import reid_oracle as O            # synthetic input generator + cpu_baseline leg only
     from pcreid_b200 import _lib
-    from pcreid_b200.parallel import match_all_pairs_sharded, shard_range
+    from pcreid_b200.parallel import encode_and_gather, match_all_pairs_sharded, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -152,7 +152,7 @@ def main():
     torch.manual_seed(66)
     from pcreid_b200.models import build_model
     model = build_model(helpers.model_cfg("pt", BLIST)).eval().to(dev)
-    model.match_mode = args.mode
+    model.set_mode(args.mode)
     tracks_h = O.synth_objects(T_loc, NPTS, 1000 + rank).pin_memory()
     dets_h = O.synth_objects(D, NPTS, 1)[d0:d1].contiguous().pin_memory()
     tracks_d, dets_d = tracks_h.to(dev), dets_h.to(dev)
@@ -200,17 +200,15 @@ def main():
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     torch.cuda.synchronize()
     e0.record()
-    xt, ht = model.encode(tracks_d)
-    xd, hd = model.encode(dets_d)
+    xt, ht, xd, hd = encode_and_gather(model, tracks_d, dets_d, det_counts)
     e1.record()
-    if world == 1:
-        model.match_all_pairs(ht, xt, hd, xd)
+    model.match_all_pairs(ht, xt, hd, xd)
     e2.record()
     torch.cuda.synchronize()
     enc_ms, match_ms = e0.elapsed_time(e1), e0.elapsed_time(e2) - e0.elapsed_time(e1)
     # per-launch durations of the fused kernels (CUDA events on the launching stream), one more match pass
     kern = {}
-    if args.mode == "fast" and world == 1 and model._fused is not None:
+    if args.mode == "fast" and model._fused is not None:
         model._fused.timing = []
         model.match_all_pairs(ht, xt, hd, xd)
         torch.cuda.synchronize()
@@ -230,16 +228,19 @@ def main():
         ms_step = total_ms / args.steps
         value = pairs_total / (ms_step * 1e-3)
         n_enc = T_loc + (d1 - d0)
-        match_tflops = FLOP_PER_PAIR * T_loc * D / (match_ms * 1e-3) / 1e12 if world == 1 and match_ms > 0 else None
+        match_tflops = FLOP_PER_PAIR * T_loc * D / (match_ms * 1e-3) / 1e12 if match_ms > 0 else None
         peak_tf = pk["bf16_tflops_sustained"]
         roof_kernel = "match stage (cn_linear_kernel<*> dominates; unfused fp32 parity path)"
-        roof_extra = {}
+        roof_extra, roof_traffic = {}, None
         if kern:
             # dominant kernels: the two fused phases; algorithmic FLOPs of the reference formulation (101.25 MFLOP/pair:
             # stage 1 both ways = 33.9 %, stage 2 + pool + head = 66.1 %) / their summed CUDA-event durations
             tot_ms = sum(k["ms"] for k in kern.values())
             match_tflops = FLOP_PER_PAIR * T_loc * D / (tot_ms * 1e-3) / 1e12
             roof_kernel = "pair_p1_kernel + pair_p2_kernel (fused tcgen05 xcorr_eff)"
+            # DRAM traffic per unit (pair, direction) from the ncu --set full capture in profiles/r01_ncu_pair_kernels.md
+            # (dram__bytes_read.sum + dram__bytes_write.sum per launch / units per launch): p1 59.3 KB, p2 52.1 KB
+            roof_traffic = 2 * T_loc * D * (59.3e3 + 52.1e3)
             roof_extra = {"kernels": {n: {"launches": k["launches"], "avg_ms_per_launch": k["ms"] / k["launches"],
                                           "share_of_match": k["ms"] / match_ms} for n, k in kern.items()}}
         line = {
@@ -248,7 +249,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"configs[1]: Point Transformer encode of {T_loc} tracks/GPU + {D} detections x {NPTS} pts "
                                    f"(backbone_list {list(BLIST)}), {T_loc}x{D} all-pairs xcorr_eff match per GPU",
-                       "mode": ("fast: fused bf16 tcgen05 matcher, fp32 accumulate/norms, |dlogit| <= 3e-2 (measured 4e-3); fp32 encoder"
+                       "mode": ("fast: fused bf16 tcgen05 matcher, fp32 accumulate/norms, tf32 tcgen05 SA shared MLPs, |dlogit| <= 3e-2"
                                 if args.mode == "fast" else "parity: fp32 FFMA kernels, logits within 1e-4 of the reference"),
                        "l2": "no flush needed: each step streams >1 GB of activations (>> 126 MB L2)",
                        "sharding": f"track rows over {world} rank(s), one all-gather of detection embeddings"},
@@ -260,7 +261,8 @@ def main():
             "e2e": {"value": pairs_total / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": (tracks_h.numel() + dets_h.numel()) * 4, "d2h_bytes_per_step": out_h.numel() * 4},
             "roofline": {"bound": "tensor", "achieved": match_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (match_tflops / peak_tf) if match_tflops else None, "traffic": None,
+                         "frac": (match_tflops / peak_tf) if match_tflops else None, "traffic": roof_traffic if kern else None,
+                         "per": "all fused launches of one step (both phases, both directions), rank 0",
                          "kernel": roof_kernel, "peak_source": pk_src + " bf16 sustained (MEASURED_PEAKS.json)", **roof_extra},
         }
         if not args.no_cpu_baseline and world == 1:

@@ -158,6 +158,13 @@ int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void*
 /* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor */
 int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream);
 
+/* tensor-core (tcgen05 kind::tf32, fp32 accumulate) version of pcreid_sa_edge_mlp: same arguments except that the
+ * two weight matrices are fp32 operand images [k/4][n][4] of the (C_out, C_in) BatchNorm-folded weights; C in
+ * {32, 64, 128}.  Fast mode of the encoder (error ~1e-3 relative: tf32 operands). */
+int pcreid_sa_edge_mlp_tc(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
+                          const float* W2img, const float* b2, const float* W3img, const float* b3, float* out,
+                          int n_ctas, void* stream);
+
 /* ------------------------------------------------------------------ C. tcgen05 self-test ------- */
 /* One 128 x n x k GEMM on the 5th-gen tensor cores in each operand configuration the fused kernels use
  * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM);

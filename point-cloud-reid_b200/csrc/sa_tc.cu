@@ -1,0 +1,170 @@
+// Set-abstraction edge MLP on the 5th-gen tensor cores (tcgen05, kind::tf32, fp32 accumulate in TMEM) -- the
+// "fast" mode counterpart of sa_edge_mlp_kernel (rowops.cu).
+//
+//   out[b,c,s] = max_j relu(W3 relu(W2 relu(P1[b,:,idx[b,s,j]] + Cc[b,:,s]) + b2) + b3)[c]
+// (PointNetSetAbstractionEdgeSA.forward, mmdet3d/models/pointnet2_utils.py:333-357, first conv factorised per point /
+// per centre on the host side, eval BatchNorm folded).
+//
+// One persistent CTA per SM (8 warps = 4 TMEM lane quadrants x 2 column halves).  A tile is the 128-row GEMM M
+// dimension = floor(128/k) centres x k neighbours.  Per tile: gather + ReLU straight into the fp32 operand image
+// [c/4][row][4] (no-swizzle K-major), GEMM (K = N = C) -> bias + ReLU epilogue back into the operand image ->
+// second GEMM -> bias + ReLU -> shared-memory transpose -> max over the k rows of each centre.  The grouped
+// (B, C, S, k) tensor of the reference never exists; both weight matrices stay resident in shared memory.
+#include "../../include/pcreid.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+constexpr int NT_ = 256;
+
+template <int C>
+__global__ void __launch_bounds__(NT_, (C == 128 ? 1 : 2)) sa_edge_mlp_tc_kernel(int N, int S, int k, int cpt, int tiles_per_obj, int total_tiles,
+                                                               const float* __restrict__ P1, const float* __restrict__ Cc,
+                                                               const int* __restrict__ idx, const float* __restrict__ W2img,
+                                                               const float* __restrict__ b2, const float* __restrict__ W3img,
+                                                               const float* __restrict__ b3, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[2][C];
+  constexpr int WBYTES = C * C * 4;            // one weight image [C/4][C][4]
+  constexpr int ABYTES = C * 128 * 4;          // activation image [C/4][128][4] == transpose buffer [C][128]
+  constexpr int TCOLS = C < 32 ? 32 : C;
+  uint8_t* W2s = smem;
+  uint8_t* W3s = smem + WBYTES;
+  uint8_t* As = smem + 2 * WBYTES;
+  float* Tf = reinterpret_cast<float*>(As);
+  const int t = threadIdx.x, warp = t >> 5;
+  const int row = 32 * (warp & 3) + (t & 31), h = warp >> 2;
+  if (t == 0) { tc::mbar_init(&bar, 1); tc::fence_mbar_init(); }
+  if (warp == 0) { tc::tmem_alloc(&tmem_base_s, TCOLS); tc::tmem_relinquish(); }
+  for (int i = t * 16; i < WBYTES; i += NT_ * 16) {
+    cp_async16(W2s + i, reinterpret_cast<const uint8_t*>(W2img) + i);
+    cp_async16(W3s + i, reinterpret_cast<const uint8_t*>(W3img) + i);
+  }
+  cp_async_commit();
+  for (int i = t; i < C; i += NT_) { bias_s[0][i] = b2[i]; bias_s[1][i] = b3[i]; }
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t sA = tc::smem_u32(As), sW2 = tc::smem_u32(W2s), sW3 = tc::smem_u32(W3s);
+  const uint32_t idesc = tc::instr_desc(128, C, tc::FMT_TF32, tc::MAJOR_K, tc::MAJOR_K);
+  uint32_t par = 0;
+  constexpr int CH = C / 2;                    // channels (columns) per thread
+
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int b = tile / tiles_per_obj, s0 = (tile % tiles_per_obj) * cpt;
+    const int ncen = min(cpt, S - s0), nedge = ncen * k;
+    const float* Pb = P1 + (size_t)b * C * N;
+    const float* Cb = Cc + (size_t)b * C * S;
+    // ---- gather + relu(P1 + Cc) -> operand image
+    {
+      int src = -1, cen = 0;
+      if (row < nedge) { cen = s0 + row / k; src = __ldg(idx + ((size_t)b * S + cen) * k + (row % k)); }
+#pragma unroll 4
+      for (int c = h * CH; c < (h + 1) * CH; c += 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) {
+          v.x = fmaxf(__ldg(Pb + (size_t)(c + 0) * N + src) + __ldg(Cb + (size_t)(c + 0) * S + cen), 0.f);
+          v.y = fmaxf(__ldg(Pb + (size_t)(c + 1) * N + src) + __ldg(Cb + (size_t)(c + 1) * S + cen), 0.f);
+          v.z = fmaxf(__ldg(Pb + (size_t)(c + 2) * N + src) + __ldg(Cb + (size_t)(c + 2) * S + cen), 0.f);
+          v.w = fmaxf(__ldg(Pb + (size_t)(c + 3) * N + src) + __ldg(Cb + (size_t)(c + 3) * S + cen), 0.f);
+        }
+        *reinterpret_cast<float4*>(As + (c / 4) * 2048 + row * 16) = v;
+      }
+    }
+    for (int layer = 0; layer < 2; ++layer) {
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      tc::tc_fence_after();
+      if (t == 0) {
+        const uint32_t sW = layer == 0 ? sW2 : sW3;
+        for (int ks = 0; ks < C / 8; ++ks) {
+          const uint64_t ad = tc::smem_desc(sA + ks * 4096, 2048, 128, tc::LAYOUT_NONE);
+          const uint64_t bd = tc::smem_desc(sW + ks * 2 * (C * 16), C * 16, 128, tc::LAYOUT_NONE);
+          tc::umma_tf32(tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        tc::umma_commit(&bar);
+      }
+      tc::mbar_wait(&bar, par);
+      par ^= 1u;
+      tc::tc_fence_after();
+      // ---- epilogue: + bias, ReLU; layer 0 -> operand image, layer 1 -> rotated transpose buffer
+#pragma unroll
+      for (int q = 0; q < CH / 16; ++q) {
+        uint32_t r[16];
+        const int c0 = h * CH + 16 * q;
+        tc::tmem_ld16(tlane + c0, r);
+        tc::tmem_ld_wait();
+        if (layer == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 v;
+            v.x = fmaxf(__uint_as_float(r[j + 0]) + bias_s[0][c0 + j + 0], 0.f);
+            v.y = fmaxf(__uint_as_float(r[j + 1]) + bias_s[0][c0 + j + 1], 0.f);
+            v.z = fmaxf(__uint_as_float(r[j + 2]) + bias_s[0][c0 + j + 2], 0.f);
+            v.w = fmaxf(__uint_as_float(r[j + 3]) + bias_s[0][c0 + j + 3], 0.f);
+            *reinterpret_cast<float4*>(As + ((c0 + j) / 4) * 2048 + row * 16) = v;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = c0 + j;
+            Tf[c * 128 + ((row + c) & 127)] = fmaxf(__uint_as_float(r[j]) + bias_s[1][c], 0.f);
+          }
+        }
+      }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    // ---- max over the k edges of each centre
+    for (int i = t; i < C * ncen; i += NT_) {
+      const int c = i / ncen, cl = i % ncen;
+      float mx = 0.f;                                   // values are post-ReLU (>= 0)
+      for (int j = 0; j < k; ++j) mx = fmaxf(mx, Tf[c * 128 + ((cl * k + j + c) & 127)]);
+      out[((size_t)b * C + c) * S + s0 + cl] = mx;
+    }
+    __syncthreads();                                    // the next tile's gather overwrites the buffer
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
+}
+
+template <int C>
+int launch(int B, int N, int S, int k, const float* P1, const float* Cc, const int* idx, const float* W2img, const float* b2,
+           const float* W3img, const float* b3, float* out, int n_ctas, cudaStream_t st) {
+  const int cpt = 128 / k, tiles_per_obj = (S + cpt - 1) / cpt;
+  const long long total = (long long)B * tiles_per_obj;
+  if (total > 0x7fffffffLL) return PCREID_ERR_UNSUPPORTED;
+  const int smem = 2 * C * C * 4 + C * 128 * 4;
+  cudaFuncSetAttribute(sa_edge_mlp_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int ctas_per_sm = C == 128 ? 1 : 2;                      // shared memory (192 / 64 / 24 KB) and registers bound residency
+  int grid = (n_ctas > 0 ? n_ctas : 148) * ctas_per_sm;
+  if (grid > total) grid = (int)total;
+  sa_edge_mlp_tc_kernel<C><<<grid, NT_, smem, st>>>(N, S, k, cpt, tiles_per_obj, (int)total, P1, Cc, idx, W2img, b2, W3img, b3, out);
+  return pcreid_launch_status();
+}
+
+}  // namespace
+
+extern "C" int pcreid_sa_edge_mlp_tc(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
+                                     const float* W2img, const float* b2, const float* W3img, const float* b3, float* out,
+                                     int n_ctas, void* stream) {
+  if (B <= 0 || S <= 0) return PCREID_OK;
+  if (!P1 || !Cc || !idx || !W2img || !b2 || !W3img || !b3 || !out || k <= 0 || N <= 0) return PCREID_ERR_ARG;
+  if (k > 128) return PCREID_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 32: return launch<32>(B, N, S, k, P1, Cc, idx, W2img, b2, W3img, b3, out, n_ctas, st);
+    case 64: return launch<64>(B, N, S, k, P1, Cc, idx, W2img, b2, W3img, b3, out, n_ctas, st);
+    case 128: return launch<128>(B, N, S, k, P1, Cc, idx, W2img, b2, W3img, b3, out, n_ctas, st);
+    default: return PCREID_ERR_UNSUPPORTED;
+  }
+}

@@ -217,6 +217,26 @@ def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
     return out
 
 
+def tf32_image(w):
+    """(C_out, C_in) fp32 weight -> tcgen05 K-major operand image [k/4][n][4] (fp32 bits, read as tf32)."""
+    n, kd = w.shape
+    return w.detach().float().reshape(n, kd // 4, 4).permute(1, 0, 2).contiguous()
+
+
+def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
+    """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image()."""
+    _need_cuda(p1, cc, idx)
+    B, C, N = p1.shape
+    S, k = idx.shape[1], idx.shape[2]
+    if not (p1.is_contiguous() and cc.is_contiguous() and idx.is_contiguous()):
+        raise ValueError("sa_edge_mlp_tc inputs must be contiguous")
+    out = torch.empty((B, C, S), device=p1.device, dtype=torch.float32)
+    n_ctas = torch.cuda.get_device_properties(p1.device).multi_processor_count
+    _lib.check(_lib.lib().pcreid_sa_edge_mlp_tc(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2img), _p(b2), _p(w3img), _p(b3),
+                                                _p(out), n_ctas, _stream()), "pcreid_sa_edge_mlp_tc")
+    return out
+
+
 def edge_gather_max(p, q, idx, act, out=None):
     _need_cuda(p, q, idx)
     B, C, N = p.shape

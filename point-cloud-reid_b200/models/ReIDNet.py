@@ -97,6 +97,16 @@ class ReIDNet(nn.Module):
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
                                       "(shipped point configs use 'xcorr_eff'; the baseline uses 'concat')")
 
+    def set_mode(self, mode):
+        """'parity': fp32 kernels everywhere (1e-4).  'fast': fused bf16 tcgen05 matcher + tf32 tensor-core shared MLPs in
+        the Point Transformer set-abstraction layers (|dlogit| <= 3e-2)."""
+        assert mode in ('parity', 'fast')
+        self.match_mode = mode
+        for m in self.modules():
+            if hasattr(m, 'tc_mode'):
+                m.tc_mode = (mode == 'fast')
+        return self
+
     # ------------------------------------------------------------------ encoders
     def _encode(self, pts):
         """pts (B, N, 3) -> (xyz (B, N, 3), h (B, C, N)); applies the per-point `downsample` for DGCNN / PointNet

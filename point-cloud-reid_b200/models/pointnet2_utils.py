@@ -91,6 +91,7 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
             last_channel = out_channel
         self.group_all = group_all
         self.self_attention = Self_Attention(last_channel, 2, 'linear')
+        self.tc_mode = False      # True: shared MLP on the tensor cores (tcgen05 kind::tf32), "fast" encoder mode
         if group_all or not use_knn or sampling != "RANDOM" or not use_xyz or len(mlp) != 4:
             raise NotImplementedError("only the configuration the reference backbone instantiates is built: "
                                       "sampling='RANDOM', use_knn=True, use_xyz=True, 3-layer MLP (backbone_net.py:49-81)")
@@ -105,6 +106,8 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         w3, b3 = fold_bn(self.mlp_convs[2].weight, self.mlp_convs[2].bias, self.mlp_bns[2])
         pk = dict(D=D, pa=wa.t().contiguous(), ca=(-wa).t().contiguous(), cbias=b1,
                   w2=w2.t().contiguous(), b2=b2, w3=w3.t().contiguous(), b3=b3)
+        if w2.shape[0] in (32, 64, 128):
+            pk["w2img"], pk["w3img"] = K.tf32_image(w2), K.tf32_image(w3)
         if D > 0:
             pk["pc"] = wc.t().contiguous()
             pk["cb"] = (wb - wc).t().contiguous()
@@ -123,7 +126,10 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         else:
             p1 = K.cn_linear(xyz, pk["pa"], x1_pm=True)
             cc = K.cn_linear(xyz, pk["ca"], bias=pk["cbias"], x1_pm=True, rows=S)
-        feat = K.sa_edge_mlp(p1, cc, idx, pk["w2"], pk["b2"], pk["w3"], pk["b3"])
+        if self.tc_mode and "w2img" in pk:
+            feat = K.sa_edge_mlp_tc(p1, cc, idx, pk["w2img"], pk["b2"], pk["w3img"], pk["b3"])
+        else:
+            feat = K.sa_edge_mlp(p1, cc, idx, pk["w2"], pk["b2"], pk["w3"], pk["b3"])
         return new_xyz, self.self_attention(feat, new_xyz)
 
 

@@ -33,16 +33,22 @@ def _all_gather_rows(t, counts, group):
     return torch.cat([out[r * mx:r * mx + c] for r, c in enumerate(counts)], dim=0)
 
 
-def match_all_pairs_sharded(model, tracks_local, dets_local, det_counts, pair_mask_rows=None, group=None,
-                            gather_scores=False, track_counts=None, chunk=8192):
-    """tracks_local (T_r, N, 3), dets_local (D_r, N, 3) on this rank; det_counts = [D_0 .. D_{G-1}].
-    Returns this rank's (T_r, D) score rows, or the full (T, D) matrix on every rank if gather_scores
-    (then track_counts = [T_0 .. T_{G-1}] is required)."""
+def encode_and_gather(model, tracks_local, dets_local, det_counts, group=None):
+    """encode this rank's tracks / detection slice, all-gather the detection embeddings -> (xyz_t, h_t, xyz_d, h_d)."""
     xyz_t, h_t = model.encode(tracks_local)
     xyz_d, h_d = model.encode(dets_local)
     if len(det_counts) > 1:
         h_d = _all_gather_rows(h_d.contiguous(), det_counts, group)
         xyz_d = _all_gather_rows(xyz_d.contiguous(), det_counts, group)
+    return xyz_t, h_t, xyz_d, h_d
+
+
+def match_all_pairs_sharded(model, tracks_local, dets_local, det_counts, pair_mask_rows=None, group=None,
+                            gather_scores=False, track_counts=None, chunk=8192):
+    """tracks_local (T_r, N, 3), dets_local (D_r, N, 3) on this rank; det_counts = [D_0 .. D_{G-1}].
+    Returns this rank's (T_r, D) score rows, or the full (T, D) matrix on every rank if gather_scores
+    (then track_counts = [T_0 .. T_{G-1}] is required)."""
+    xyz_t, h_t, xyz_d, h_d = encode_and_gather(model, tracks_local, dets_local, det_counts, group)
     rows = model.match_all_pairs(h_t, xyz_t, h_d, xyz_d, pair_mask=pair_mask_rows, chunk=chunk)
     if gather_scores and len(det_counts) > 1:
         return _all_gather_rows(rows.contiguous(), track_counts, group)

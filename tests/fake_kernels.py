@@ -120,6 +120,17 @@ def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
     return h.max(-1)[0].contiguous()
 
 
+def tf32_image(w):
+    n, kd = w.shape
+    return w.detach().float().reshape(n, kd // 4, 4).permute(1, 0, 2).contiguous()
+
+
+def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
+    C = p1.shape[1]
+    unimg = lambda im: im.permute(1, 0, 2).reshape(C, C).t().contiguous()      # -> k-major (C_in, C_out)
+    return sa_edge_mlp(p1, cc, idx, unimg(w2img), b2, unimg(w3img), b3)
+
+
 def edge_gather_max(p, q, idx, act, out=None):
     y = _act(_gather_pts(p, idx).max(-1)[0] + q, act)
     if out is not None:
@@ -144,7 +155,7 @@ def install(monkeypatch=None):
     """Replaces pcreid_b200.kernels' entry points by the emulations above (optionally via pytest's monkeypatch)."""
     import pcreid_b200.kernels as K
     names = ["cn_linear", "cn_groupnorm", "linattn_kv", "linattn_scale", "cn_pool", "cn_chanmax", "knn_point",
-             "knn_feature", "sa_edge_mlp", "edge_gather_max", "pair_concat_head"]
+             "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head"]
     for n in names:
         if monkeypatch is not None:
             monkeypatch.setattr(K, n, globals()[n])

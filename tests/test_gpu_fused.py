@@ -51,3 +51,22 @@ def test_fused_symmetry_and_determinism():
     L2 = m.match_all_pairs(ha, xa, ha, xa)
     assert torch.equal(L1, L2)
     assert (L1 - L1.t()).abs().max() < TOL_FAST
+
+
+@pytest.mark.parametrize("N", [256, 128])
+def test_full_fast_mode_end_to_end(N):
+    """set_mode('fast'): tf32 tensor-core SA MLPs in the encoder + fused bf16 matcher, against the oracle end to end."""
+    m, orc = helpers.build_pair("pt", (N, N // 2, N // 4), device=DEV)
+    m.set_mode('fast')
+    t, d = O.synth_objects(6, N, 10), O.synth_objects(5, N, 11)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    assert (ht.cpu() - oht).abs().max() < 2e-2       # tf32 operands in the three SA shared MLPs
+    Lf = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    err = (Lf - Lo).abs().max().item()
+    assert err < TOL_FAST, f"fast-mode logits off by {err}"
+    ok, agree, n = helpers.margin_aware_top1(Lo, Lf, err)
+    assert ok, f"top-1 changed on a decisive row (agreement {agree}, {n} decisive rows)"

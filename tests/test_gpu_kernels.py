@@ -95,6 +95,21 @@ def test_sa_edge_mlp(C, N, S, k):
     close(got, F.sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3))
 
 
+@pytest.mark.parametrize("C,N,S,k", [(32, 256, 256, 32), (64, 256, 128, 48), (128, 128, 64, 48), (64, 160, 80, 48), (32, 40, 37, 20),
+                                     (128, 1024, 512, 48)])
+def test_sa_edge_mlp_tensor_core(C, N, S, k):
+    """tcgen05 kind::tf32 version against the fp32 specification: tf32 operands (10-bit mantissa) -> 5e-3 of the scale."""
+    g = torch.Generator().manual_seed(C + k)
+    B = 3 if N < 1024 else 160        # the large case spans several persistent waves
+    p1, cc = rnd(B, C, N, seed=1), rnd(B, C, S, seed=2)
+    idx = torch.randint(0, N, (B, S, k), generator=g, dtype=torch.int32)
+    w2, w3 = rnd(C, C, seed=3) / C ** 0.5, rnd(C, C, seed=4) / C ** 0.5      # (C_out, C_in)
+    b2, b3 = rnd(C, seed=5) * 0.1, rnd(C, seed=6) * 0.1
+    got = K.sa_edge_mlp_tc(p1.to(DEV), cc.to(DEV), idx.to(DEV), K.tf32_image(w2).to(DEV), b2.to(DEV), K.tf32_image(w3).to(DEV),
+                           b3.to(DEV))
+    close(got, F.sa_edge_mlp(p1, cc, idx, w2.t().contiguous(), b2, w3.t().contiguous(), b3), 5e-3)
+
+
 def test_edge_gather_max_into_strided_output():
     g = torch.Generator().manual_seed(3)
     p, q = rnd(2, 64, 300, seed=1), rnd(2, 64, 300, seed=2)
