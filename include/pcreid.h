@@ -145,6 +145,7 @@ int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const fl
  * Operand "images" are bf16 [k/8][row][8] tiles of 128 points x 64 channels (16 KB); d_model = 64, 2 heads,
  * points per object a multiple of 128.  See point-cloud-reid_b200/models/fused_pairs.py for the host side. */
 int pcreid_pair_tc_smem_bytes(int phase);
+int pcreid_pair_tc_set_trace(void* dev_buffer);   /* debug: int64[2048] cycle trace of one group of pair_p2, NULL = off */
 /* (B, C, N) channel-major fp32 -> [B][N/128][C/8][128][8] bf16 (act: PCREID_ACT_NONE or PCREID_ACT_ELU1) */
 int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, void* dst, void* stream);
 /* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 18432 bytes) */

@@ -61,6 +61,7 @@ _SIGS = {
     "pcreid_sa_edge_mlp": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_edge_gather_max": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_ll, c_int, c_vp],
     "pcreid_pair_tc_smem_bytes": [c_int],
+    "pcreid_pair_tc_set_trace": [c_vp],
     "pcreid_pack_image": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_vp],
     "pcreid_pack_b7": [c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_p1": [c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],

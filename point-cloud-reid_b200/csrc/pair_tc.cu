@@ -48,6 +48,15 @@ constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ON
 // per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 x2 (36K) | exchange
 constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_XCH = P2_B7 + 2 * B7_BYTES, P2_GBYTES = P2_XCH + 2048;
 
+// optional cycle trace (debug): when set, thread 0 of group 0 in CTA 0 records clock64() at stage boundaries
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int& n, int tag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && n < 2040 && g_trace != nullptr) {
+    g_trace[n++] = clock64();
+    g_trace[n++] = tag;
+  }
+}
+
 struct P1Args {
   int n_units, NT, role;
   const int *u_search, *u_templ, *u_slot;
@@ -70,29 +79,49 @@ __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __ex
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
+// 16-byte read-only global load that the compiler may NOT sink to its first use (plain __ldg of data consumed a whole
+// stage later was being moved next to the consumer, which exposed the full L2 latency there)
+__device__ __forceinline__ uint4 ldg_early(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, int bytes, int t, int nthr) {
   for (int i = t * 16; i < bytes; i += nthr * 16) cp_async16(dst + i, src + i);
 }
 
-// one thread: D[tmem_d] (+)= A x B^T over `ksteps` K=16 steps
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kstep,
-                                           uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, uint32_t idesc,
-                                           int ksteps, bool accumulate) {
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint64_t ad = tc::smem_desc(a_addr + ks * a_kstep, a_lbo, a_sbo, tc::LAYOUT_NONE);
-    const uint64_t bd = tc::smem_desc(b_addr + ks * b_kstep, b_lbo, b_sbo, tc::LAYOUT_NONE);
-    tc::umma_f16(tmem_d, ad, bd, idesc, (accumulate || ks > 0) ? 1u : 0u);
-  }
+// Descriptors are built once per operand buffer; stepping along K only adds (bytes >> 4) to the 14-bit start-address
+// field (shared memory is < 256 KB, so the field never carries).  Building them per MMA cost ~130 cycles of dependent
+// 64-bit arithmetic on the single issuing thread (measured with the cycle trace) -- a quarter of the tile time.
+struct Opnd {
+  uint64_t desc;     // descriptor at k = 0
+  uint32_t kstep;    // (bytes per K=16 step) >> 4
+};
+__device__ __forceinline__ Opnd opnd(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes) {
+  Opnd o;
+  o.desc = tc::smem_desc(addr, lbo, sbo, tc::LAYOUT_NONE);
+  o.kstep = kstep_bytes >> 4;
+  return o;
 }
 // operand geometry (bytes): K-major activation image (128 rows), K-major weight image (N rows), MN-major attention operand
-#define A_IMG(addr) (addr), 2048u, 128u, 4096u
-#define W_IMG(addr, N) (addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16)
-#define B7_IMG(addr) (addr), 128u, 1024u, 256u
+#define A_IMG(addr) opnd((addr), 2048u, 128u, 4096u)
+#define W_IMG(addr, N) opnd((addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16))
+#define B7_IMG(addr) opnd((addr), 128u, 1024u, 256u)
+
+// one thread: D[tmem_d] (+)= A x B^T over KSTEPS K=16 steps
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Opnd& A, const Opnd& B, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::umma_f16(tmem_d, A.desc + (uint64_t)(ks * A.kstep), B.desc + (uint64_t)(ks * B.kstep), idesc, (accumulate || ks > 0) ? 1u : 0u);
+}
 
 // A group = 8 warps working on one 128-point tile: thread (row, h) owns row `row` of the tile (TMEM lane) and the
 // column half `h` of every accumulator, so the epilogue work of a tile is spread over 256 threads.
 struct Group {
-  int t, row, h, gid;        // thread in group, tile row (== TMEM lane), column half, group in CTA
+  int t, row, h, gid;        // thread in group, tile row (== TMEM lane), column half, group in CTA (gid is warp-uniform)
+  bool issuer;               // warp 0 of the group (warp-uniform): one elected lane issues the MMAs
   uint32_t tmem;             // TMEM base of the group (lane 0, first column)
   uint32_t tlane;            // tmem + (lane base of this warp << 16)
   uint64_t* bar;
@@ -308,9 +337,12 @@ __device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, 
 }
 
 __device__ __forceinline__ void group_setup(Group& g, uint64_t* bars, uint32_t tmem_base, uint8_t* xch) {
-  g.gid = threadIdx.x / GT;
+  const int warp_u = (int)tc::uniform(threadIdx.x >> 5);      // warp index, known uniform to the compiler
+  g.gid = warp_u / (GT / 32);
   g.t = threadIdx.x % GT;
-  const int warp = g.t >> 5;
+  const int warp = warp_u % (GT / 32);
+  g.issuer = warp == 0;
+  tmem_base = tc::uniform(tmem_base);
   g.row = 32 * (warp & 3) + (g.t & 31);
   g.h = warp >> 2;
   g.tmem = tmem_base + g.gid * 256;
@@ -345,7 +377,7 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
   __syncthreads();
   tc::tc_fence_after();
   Group g;
-  uint8_t* G = smem + P1_WBYTES + (threadIdx.x / GT) * P1_GBYTES;
+  uint8_t* G = smem + P1_WBYTES + tc::uniform(threadIdx.x / GT) * P1_GBYTES;
   group_setup(g, bars, tmem_base_s, G + P1_XCH);
   uint8_t* QXa = G + P1_QXA;
   uint8_t* HdKV = G + P1_HDKV;
@@ -360,6 +392,9 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
   const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t idkv = tc::instr_desc(128, 80, tc::FMT_BF16, tc::MAJOR_MN, tc::MAJOR_MN);
+  const Opnd oQXa = A_IMG(sQXa), oHd = A_IMG(sHd), oMK1 = B7_IMG(sMK1), oW0b = W_IMG(sW + P1_W0B, 128), oW2 = W_IMG(sW + P1_W2, 64),
+             oWkv = W_IMG(sW + P1_WKV, 128), oWm = W_IMG(sW + P1_WM, 64), oKfV = opnd(sHd, 128u, 2048u, 256u),
+             oVones = opnd(sHd + 8 * 2048, 128u, 2048u, 256u);
 
   const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
@@ -371,8 +406,10 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
   }
+  int so_next = u0 < u1 ? a.u_search[u0] : 0, te_next = u0 < u1 ? a.u_templ[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
   for (int u = u0; u < u1; ++u) {
-    const int so = a.u_search[u], te = a.u_templ[u], slot = a.u_slot[u];
+    const int so = so_next, te = te_next, slot = slot_next;
+    if (u + 1 < u1) { so_next = a.u_search[u + 1]; te_next = a.u_templ[u + 1]; slot_next = a.u_slot[u + 1]; }
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
       if (tile > 0) g.wait2();                                            // previous tile's KV GEMM still reads HdKV
@@ -386,12 +423,12 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
         cur_templ = te;
       }
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), B7_IMG(sMK1), id144, 4, false); tc::umma_commit(g.bar); }
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oMK1, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
       {   // prefetch the next (unit, tile) query image while the tensor core works
         int nu = u, nt = tile + 1;
         if (nt == a.NT) { nu = u + 1; nt = 0; }
         if (nu < u1) {
-          const uint4* src = reinterpret_cast<const uint4*>(a.QF1 + ((size_t)a.u_search[nu] * a.NT + nt) * IMG);
+          const uint4* src = reinterpret_cast<const uint4*>(a.QF1 + ((size_t)(nt == 0 ? so_next : so) * a.NT + nt) * IMG);
 #pragma unroll
           for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
         }
@@ -401,12 +438,12 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
       load_side<8>(sdU, a.U + ti * 2 * IMG, 8 * g.h, g.row);              // consumed one stage later (after G2)
       epi_attn_ln(g, ln1, QXa);                                           // X
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_W0B, 128), id128, 4, false); tc::umma_commit(g.bar); }
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oW0b, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       load_side<4>(sdH, a.H + ti * IMG, 4 * g.h, g.row);                  // consumed after G3
       epi_relu128<true>(g, sdU, HdKV);                                    // Hd = relu(X W0b^T + W0a h)
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sHd), W_IMG(sW + P1_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oHd, oW2, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       if (g.h == 1) load_side<8>(sdPV, a.PV + ti * IMG, 0, g.row);        // consumed after G4
       {
@@ -416,7 +453,7 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
         store_image32(o, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, g.row, g.h);
       }
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WKV, 128), id128, 4, false); tc::umma_commit(g.bar); }
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oWkv, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       if (g.h == 0) {   // column half 0: Kf = elu(k)+1 -> chunks 0..7 ; column half 1: V = v + Wv pos -> chunks 8..15
         feat32<true, false>(g, 0, nullptr, HdKV, 0);
@@ -426,9 +463,12 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
         feat32<false, true>(g, 96, sdPV + 4, HdKV, 12);
       }
       g.publish();
-      if (g.t == 0) {   // KV += [Kf|V]^T [V|1]   (M = 128 channels, N = 80, K = 128 points)
-        issue_gemm(g.tmem + KV_COL, sHd, 128u, 2048u, 256u, sHd + 8 * 2048, 128u, 2048u, 256u, idkv, 8, tile > 0);
-        tc::umma_commit(g.bar2);
+      if (g.issuer) {   // KV += [Kf|V]^T [V|1]   (M = 128 channels, N = 80, K = 128 points)
+        if (tc::elect_one()) {
+          issue_gemm<8>(g.tmem + KV_COL, oKfV, oVones, idkv, tile > 0);
+          tc::umma_commit(g.bar2);
+        }
+        __syncwarp();
       }
     }
     g.wait2();
@@ -452,7 +492,7 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p1_kernel(const P1Args a) {
         for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(QXa + (4 * g.h + c) * 2048 + g.row * 16) = make_uint4(0, 0, 0, 0);
       }
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sQXa), W_IMG(sW + P1_WM, 64), id64, 4, false); tc::umma_commit(g.bar); }
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oWm, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       if (g.row < 64) {
         uint32_t r[32];
@@ -495,7 +535,7 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
   __syncthreads();
   tc::tc_fence_after();
   Group g;
-  uint8_t* G = smem + P2_WBYTES + (threadIdx.x / GT) * P2_GBYTES;
+  uint8_t* G = smem + P2_WBYTES + tc::uniform(threadIdx.x / GT) * P2_GBYTES;
   group_setup(g, bars, tmem_base_s, G + P2_XCH);
   uint8_t* R1 = G + P2_R1;
   float* R1f = reinterpret_cast<float*>(R1);
@@ -503,32 +543,38 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
   const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
   const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const Opnd oR1 = A_IMG(sR1), oQf = A_IMG(sR1 + IMG), oWq = W_IMG(sW + P2_WQ, 64), oW0 = W_IMG(sW + P2_W0, 128),
+             oW2 = W_IMG(sW + P2_W2, 64);
+  const Opnd oB7[2] = {B7_IMG(tc::smem_u32(G + P2_B7)), B7_IMG(tc::smem_u32(G + P2_B7 + B7_BYTES))};
 
   const int ngroups = gridDim.x * 2, gg = blockIdx.x * 2 + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
   const int pc = g.t & 63, pq = g.t >> 6;                                 // pooling: channel, row quarter
   // prefetch: the next tile's `a` image travels through registers (16 KB / 256 threads = 4 x 16 B each), the next
   // unit's attention operand through cp.async into the second B7 buffer, both while the current tile computes
-  auto a_image = [&](int u, int tile) {
-    return a.A_in + (((size_t)a.u_slot[u] * 2 + a.role) * a.NT + tile) * IMG;
-  };
+  auto a_image_slot = [&](int slot_, int tile) { return a.A_in + (((size_t)slot_ * 2 + a.role) * a.NT + tile) * IMG; };
+  auto a_image = [&](int u, int tile) { return a_image_slot(a.u_slot[u], tile); };
   uint4 pre[4];
   if (u0 < u1) {
     const uint4* src = reinterpret_cast<const uint4*>(a_image(u0, 0));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+    for (int i = 0; i < 4; ++i) pre[i] = ldg_early(src + g.t + i * GT);
     copy_to_smem(G + P2_B7, a.B7_in + ((size_t)a.u_slot[u0] * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GT);
   }
   cp_async_commit();
   int b7buf = 0;
+  int ntr = 0;
+  int slot_next = u0 < u1 ? a.u_slot[u0] : 0;
   for (int u = u0; u < u1; ++u) {
-    const int slot = a.u_slot[u];
-    const uint32_t sB7 = tc::smem_u32(G + P2_B7 + b7buf * B7_BYTES);
+    const int slot = slot_next;
+    if (u + 1 < u1) slot_next = a.u_slot[u + 1];                          // loaded a whole unit before it is needed
     float pmax = -INFINITY, psum = 0.f;
     for (int tile = 0; tile < a.NT; ++tile) {
-      const uint8_t* a_img = a_image(u, tile);
+      const uint8_t* a_img = a_image_slot(slot, tile);
+      trace_mark(ntr, 100);
       cp_async_wait<0>();                                                 // this thread's share of B7 has landed
       g.sync();                                                           // previous tile's pooling reads of R1 are done
+      trace_mark(ntr, 101);
 #pragma unroll
       for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(R1)[g.t + i * GT] = pre[i];
       g.publish();
@@ -536,34 +582,50 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
         int nu = u, nt = tile + 1;
         if (nt == a.NT) { nu = u + 1; nt = 0; }
         if (nu < u1) {
-          const uint4* src = reinterpret_cast<const uint4*>(a_image(nu, nt));
+          const int nslot = nt == 0 ? slot_next : slot;
+          const uint4* src = reinterpret_cast<const uint4*>(a_image_slot(nslot, nt));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) pre[i] = __ldg(src + g.t + i * GT);
+          for (int i = 0; i < 4; ++i) pre[i] = ldg_early(src + g.t + i * GT);
           if (nt == 0)
-            copy_to_smem(G + P2_B7 + (1 - b7buf) * B7_BYTES, a.B7_in + ((size_t)a.u_slot[nu] * 2 + (1 - a.role)) * B7_BYTES,
+            copy_to_smem(G + P2_B7 + (1 - b7buf) * B7_BYTES, a.B7_in + ((size_t)nslot * 2 + (1 - a.role)) * B7_BYTES,
                          B7_BYTES, g.t, GT);
         }
         cp_async_commit();
       }
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_WQ, 64), id64, 4, false); tc::umma_commit(g.bar); }
+      trace_mark(ntr, 102);
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      trace_mark(ntr, 103);
       uint4 sdA[4];
       g.wait();
+      trace_mark(ntr, 104);
       feat32<true, false>(g, 32 * g.h, nullptr, R1 + IMG, 4 * g.h);       // Qf = elu(q)+1
+      trace_mark(ntr, 105);
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1 + IMG), B7_IMG(sB7), id144, 4, false); tc::umma_commit(g.bar); }
+      trace_mark(ntr, 106);
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7[b7buf], id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      trace_mark(ntr, 107);
       g.wait();
+      trace_mark(ntr, 108);
       epi_attn_ln(g, ln1, R1 + IMG);                                      // X next to a: [a | X] is the K=128 operand
+      trace_mark(ntr, 109);
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W0, 128), id128, 8, false); tc::umma_commit(g.bar); }
+      trace_mark(ntr, 110);
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW0, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      trace_mark(ntr, 111);
       g.wait();
+      trace_mark(ntr, 112);
       load_side<4>(sdA, a_img, 4 * g.h, g.row);                           // residual a, consumed after G9
       {
         uint4 none[8];
         epi_relu128<false>(g, none, R1);                                  // Hd over [a | X]
       }
+      trace_mark(ntr, 113);
       g.publish();
-      if (g.t == 0) { issue_gemm(g.tmem, A_IMG(sR1), W_IMG(sW + P2_W2, 64), id64, 8, false); tc::umma_commit(g.bar); }
+      trace_mark(ntr, 114);
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW2, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      trace_mark(ntr, 115);
       g.wait();
+      trace_mark(ntr, 116);
       {
         float o[32];
         epi_ln_res(g, ln2, sdA, o);                                       // o = a + LN2(.)
@@ -575,7 +637,9 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
           R1f[ch * 128 + ((g.row + ch) & 127)] = o[c];
         }
       }
+      trace_mark(ntr, 117);
       g.sync();
+      trace_mark(ntr, 118);
 #pragma unroll 8
       for (int i = 0; i < 32; ++i) {
         const float v = R1f[pc * 128 + ((pq * 32 + i + pc) & 127)];
@@ -654,6 +718,11 @@ __global__ void __launch_bounds__(256) pool_finish_kernel(int P, int npts, const
 }  // namespace
 
 extern "C" {
+
+int pcreid_pair_tc_set_trace(void* dev_buffer) {   /* debug: device buffer of >= 2048 int64, or NULL to disable */
+  long long* p = (long long*)dev_buffer;
+  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? PCREID_OK : PCREID_ERR_LAUNCH;
+}
 
 int pcreid_pair_tc_smem_bytes(int phase) { return phase == 1 ? P1_WBYTES + 2 * P1_GBYTES : P2_WBYTES + 2 * P2_GBYTES; }
 
