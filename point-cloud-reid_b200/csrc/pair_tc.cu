@@ -663,6 +663,224 @@ __global__ void __launch_bounds__(2 * GT, 1) pair_p2_kernel(const P2Args a) {
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// phase 2, three-tile variant: 3 groups of 4 warps per CTA (one thread per tile row, both column halves), so that
+// three independent tiles are in flight per SM.  Same arithmetic as pair_p2_kernel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int GX = 128, NGX = 3;
+constexpr int P2X_R1 = 0, P2X_B7 = 2 * IMG, P2X_GBYTES = P2X_B7 + B7_BYTES;      // 51200 B per group
+
+struct GroupX {
+  int t, gid;
+  bool issuer;
+  uint32_t tmem, tlane;
+  uint64_t* bar;
+  uint32_t par;
+  __device__ __forceinline__ void sync() { tc::bar_sync(1 + gid, GX); }
+  __device__ __forceinline__ void publish() { tc::fence_async_smem(); tc::tc_fence_before(); sync(); tc::tc_fence_after(); }
+  __device__ __forceinline__ void wait() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); }
+};
+
+// 32 accumulator columns -> fp32 registers, with running sum / sum of squares
+__device__ __forceinline__ void ld32_stats(uint32_t taddr, float (&o)[32], float& s, float& ss) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[16];
+    tc::tmem_ld16(taddr + 16 * half, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = __uint_as_float(r[j]);
+      o[16 * half + j] = v;
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[NGX];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float comb[NGX][2][2][64];
+  uint8_t* Wsm = smem;
+  const float* ln1 = reinterpret_cast<const float*>(Wsm + P2_LN);
+  const float* ln2 = ln1 + 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NGX; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P2_WBYTES, threadIdx.x, NGX * GX);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  GroupX g;
+  {
+    const int warp_u = (int)tc::uniform(threadIdx.x >> 5);
+    g.gid = warp_u / 4;
+    g.t = threadIdx.x % GX;
+    g.issuer = (warp_u % 4) == 0;
+    g.tmem = tc::uniform(tmem_base_s) + g.gid * 160;
+    g.tlane = g.tmem + ((uint32_t)((warp_u % 4) * 32) << 16);
+    g.bar = bars + g.gid;
+    g.par = 0;
+  }
+  uint8_t* G = smem + P2_WBYTES + g.gid * P2X_GBYTES;
+  uint8_t* R1 = G + P2X_R1;
+  uint8_t* B7 = G + P2X_B7;
+  float* R1f = reinterpret_cast<float*>(R1);
+  const uint32_t sR1 = tc::smem_u32(R1), sW = tc::smem_u32(Wsm);
+  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const Opnd oR1 = A_IMG(sR1), oQf = A_IMG(sR1 + IMG), oWq = W_IMG(sW + P2_WQ, 64), oW0 = W_IMG(sW + P2_W0, 128),
+             oW2 = W_IMG(sW + P2_W2, 64), oB7 = B7_IMG(tc::smem_u32(B7));
+  const int row = g.t;
+  uint8_t* arow = R1 + row * 16;            // this thread's row inside the operand images
+
+  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  const int pc = g.t & 63, ph = g.t >> 6;
+  int slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  for (int u = u0; u < u1; ++u) {
+    const int slot = slot_next;
+    if (u + 1 < u1) slot_next = a.u_slot[u + 1];
+    float pmax = -INFINITY, psum = 0.f;
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
+      g.sync();                                                           // previous tile's pooling reads of R1 are done
+      copy_to_smem(R1, a_img, IMG, g.t, GX);
+      if (tile == 0) copy_to_smem(B7, a.B7_in + ((size_t)slot * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
+      cp_async_commit();
+      cp_async_wait<0>();
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      {   // Qf = elu(q)+1 -> second half of R1
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = tc::pack_bf16(elu1(__uint_as_float(r[c * 8 + 2 * j])), elu1(__uint_as_float(r[c * 8 + 2 * j + 1])));
+            *reinterpret_cast<uint4*>(arow + IMG + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      {   // attention epilogue: z-normalise, merge heads, LayerNorm1 -> X (second half of R1)
+        uint32_t d8[8];
+        tc::tmem_ld8(g.tlane + 128, d8);
+        tc::tmem_ld_wait();
+        const float z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS), z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
+        float m0[32], m1[32];
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float (&m)[32] = hh == 0 ? m0 : m1;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r0[16], r1[16];
+            tc::tmem_ld16(g.tlane + 32 * hh + 16 * half, r0);
+            tc::tmem_ld16(g.tlane + 64 + 32 * hh + 16 * half, r1);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = fmaf(z0, __uint_as_float(r0[j]), z1 * __uint_as_float(r1[j]));
+              m[16 * half + j] = v;
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+          }
+        }
+        const float mean = s * (1.f / 64.f);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / 64.f) - mean * mean, 0.f) + LN_EPS);
+        ln_apply_store(m0, mean, rstd, ln1, 0, arow + IMG);
+        ln_apply_store(m1, mean, rstd, ln1, 32, arow + IMG + 4 * 2048);
+      }
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW0, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      uint4 sdA[8];
+      g.wait();
+      load_side<8>(sdA, a_img, 0, row);                                   // residual a, consumed after G9
+      {   // Hd = relu(acc) over [a | X]
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = tc::pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 2 * j]), 0.f), fmaxf(__uint_as_float(r[c * 8 + 2 * j + 1]), 0.f));
+            *reinterpret_cast<uint4*>(arow + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW2, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      {   // o = a + LN2(acc); transposed (rotated) store for the pooling
+        float o0[32], o1[32];
+        float s = 0.f, ss = 0.f;
+        ld32_stats(g.tlane, o0, s, ss);
+        ld32_stats(g.tlane + 32, o1, s, ss);
+        const float mean = s * (1.f / 64.f);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / 64.f) - mean * mean, 0.f) + LN_EPS);
+        const float nm = -mean * rstd;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float (&o)[32] = hh == 0 ? o0 : o1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 rs = sdA[4 * hh + c];
+            const uint32_t rw[4] = {rs.x, rs.y, rs.z, rs.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = c * 8 + 2 * j, ch = 32 * hh + k;
+              const float y0 = fmaf(fmaf(o[k], rstd, nm), ln2[ch], ln2[64 + ch]) + bf_lo(rw[j]);
+              const float y1 = fmaf(fmaf(o[k + 1], rstd, nm), ln2[ch + 1], ln2[64 + ch + 1]) + bf_hi(rw[j]);
+              R1f[ch * 128 + ((row + ch) & 127)] = y0;
+              R1f[(ch + 1) * 128 + ((row + ch + 1) & 127)] = y1;
+            }
+          }
+        }
+      }
+      g.sync();
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const float v = R1f[pc * 128 + ((ph * 64 + i + pc) & 127)];
+        pmax = fmaxf(pmax, v);
+        psum += v;
+      }
+    }
+    comb[g.gid][0][ph][pc] = pmax;
+    comb[g.gid][1][ph][pc] = psum;
+    g.sync();
+    if (g.t < 64) {
+      float* out = a.pool_part + ((size_t)slot * 2 + a.role) * 128;
+      out[g.t] = fmaxf(comb[g.gid][0][0][g.t], comb[g.gid][0][1][g.t]);
+      out[64 + g.t] = comb[g.gid][1][0][g.t] + comb[g.gid][1][1][g.t];
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
 // row d of the stage operand (used by the per-object packer): all 64 columns at once
 __device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
   float lo[32], hi[32];
@@ -768,6 +986,14 @@ int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void*
   if (n_units <= 0) return PCREID_OK;
   if (!u_slot || !A_in || !B7_in || !W || !pool_part || NT <= 0) return PCREID_ERR_ARG;
   P2Args a{n_units, NT, role, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
+  if (n_ctas < 0) {   // three-tile variant (3 groups x 4 warps per CTA)
+    const int smemx = P2_WBYTES + NGX * P2X_GBYTES;
+    cudaFuncSetAttribute(pair_p2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemx);
+    int gridx = -n_ctas;
+    if (gridx * NGX > n_units) gridx = (n_units + NGX - 1) / NGX;
+    pair_p2x_kernel<<<gridx, NGX * GX, smemx, (cudaStream_t)stream>>>(a);
+    return pcreid_launch_status();
+  }
   const int smem = P2_WBYTES + 2 * P2_GBYTES;
   cudaFuncSetAttribute(pair_p2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   int grid = n_ctas > 0 ? n_ctas : 148;

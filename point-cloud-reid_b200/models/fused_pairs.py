@@ -9,6 +9,7 @@ attention operands (36 KB / pair).
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
 """
 import ctypes
+import os
 
 import torch
 
@@ -57,6 +58,7 @@ class FusedXcorr:
         self._w1 = self._w2 = None
         self.n_ctas = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
+        self.p2_three_tiles = os.environ.get("PCREID_P2_VARIANT", "3") == "3"   # 3 groups x 4 warps (default) or 2 x 8
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
@@ -135,7 +137,8 @@ class FusedXcorr:
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         for role in (0, 1):
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part), self.n_ctas, _stream()),
+            _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part),
+                                        -self.n_ctas if self.p2_three_tiles else self.n_ctas, _stream()),
                        "pcreid_pair_p2")
             self._tock("pair_p2_kernel", e0, P)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
