@@ -237,7 +237,7 @@ def main():
             # stage 1 both ways = 33.9 %, stage 2 + pool + head = 66.1 %) / their summed CUDA-event durations
             tot_ms = sum(k["ms"] for k in kern.values())
             match_tflops = FLOP_PER_PAIR * T_loc * D / (tot_ms * 1e-3) / 1e12
-            roof_kernel = "pair_p1_kernel + pair_p2_kernel (fused tcgen05 xcorr_eff)"
+            roof_kernel = " + ".join(sorted(kern)) + " (fused tcgen05 xcorr_eff)"
             # DRAM traffic per unit (pair, direction) from the ncu --set full capture in profiles/r01_ncu_pair_kernels.md
             # (dram__bytes_read.sum + dram__bytes_write.sum per launch / units per launch): p1 59.3 KB, p2 52.1 KB
             roof_traffic = 2 * T_loc * D * (59.3e3 + 52.1e3)

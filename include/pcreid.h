@@ -154,6 +154,11 @@ int pcreid_pack_b7(int B, const float* M, const float* ksum, void* dst, void* st
 int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
                    const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out, void* B7_out,
                    int n_ctas, void* stream);
+/* three-tiles-in-flight split of phase 1: which = 0 (attention + MLP -> stage-1 outputs a; W = [W0b | W2 | LN] blob) or
+ * which = 1 (key/value summaries -> B7; W = [Wkv | Wm] blob; reads A_out of which = 0) */
+int pcreid_pair_p1ab(int which, int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot,
+                     const void* QF1, const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out,
+                     void* B7_out, int n_ctas, void* stream);
 int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
                    float* pool_part, int n_ctas, void* stream);
 /* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor */

@@ -65,6 +65,7 @@ _SIGS = {
     "pcreid_pack_image": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_vp],
     "pcreid_pack_b7": [c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_p1": [c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],
+    "pcreid_pair_p1ab": [c_int, c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],
     "pcreid_pair_p2": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
     "pcreid_pool_finish": [c_int, c_int, c_vp, c_vp, c_vp],
     "pcreid_sa_edge_mlp_tc": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_vp],

@@ -891,6 +891,340 @@ __device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, i
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// phase 1, three-tile variants: the monolithic phase-1 kernel needs 72 KB of shared memory and 224 TMEM columns per
+// group, which caps it at two tiles in flight.  Split in two kernels that each fit three 4-warp groups per SM:
+//   pair_p1a_kernel : G1 (attention, smem operands) -> LN1 -> G2 (+U, ReLU; result written back to TMEM in place as the
+//                     bf16 A operand of G3: tcgen05.st, no shared memory) -> G3 -> LN2 + h -> a (global, bf16 image)
+//   pair_p1b_kernel : a -> G4k -> Kf, G4v -> V (+Wv pos) -> G5 (KV accumulated in TMEM over the tiles) -> G6 -> B7 (global)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int P1A_W0B = 0, P1A_W2 = 16384, P1A_LN = 32768, P1A_WBYTES = 32768 + 1024;
+constexpr int P1A_QXA = 0, P1A_MK1 = IMG, P1A_GBYTES = IMG + B7_BYTES;                       // 34816 B per group
+constexpr int P1B_WKV = 0, P1B_WM = 16384, P1B_WBYTES = 24576;
+constexpr int P1B_AIMG = 0, P1B_KFV = IMG, P1B_GBYTES = IMG + 2 * IMG + ONES_BYTES;          // 53248 B per group
+
+__device__ __forceinline__ void groupx_setup(GroupX& g, uint64_t* bars, uint32_t tmem_base) {
+  const int warp_u = (int)tc::uniform(threadIdx.x >> 5);
+  g.gid = warp_u / 4;
+  g.t = threadIdx.x % GX;
+  g.issuer = (warp_u % 4) == 0;
+  g.tmem = tc::uniform(tmem_base) + g.gid * 160;
+  g.tlane = g.tmem + ((uint32_t)((warp_u % 4) * 32) << 16);
+  g.bar = bars + g.gid;
+  g.par = 0;
+}
+
+__global__ void __launch_bounds__(NGX * GX, 1) pair_p1a_kernel(const P1Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[NGX];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* Wsm = smem;
+  const float* ln1 = reinterpret_cast<const float*>(Wsm + P1A_LN);
+  const float* ln2 = ln1 + 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NGX; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P1A_WBYTES, threadIdx.x, NGX * GX);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  GroupX g;
+  groupx_setup(g, bars, tmem_base_s);
+  uint8_t* G = smem + P1A_WBYTES + g.gid * P1A_GBYTES;
+  uint8_t* QXa = G + P1A_QXA;
+  uint8_t* MK1 = G + P1A_MK1;
+  const uint32_t sQXa = tc::smem_u32(QXa), sW = tc::smem_u32(Wsm);
+  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const Opnd oQXa = A_IMG(sQXa), oMK1 = B7_IMG(tc::smem_u32(MK1)), oW0b = W_IMG(sW + P1A_W0B, 128), oW2 = W_IMG(sW + P1A_W2, 64);
+  const int row = g.t;
+  uint8_t* xrow = QXa + row * 16;
+
+  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  int cur_templ = -1;
+  int so_next = u0 < u1 ? a.u_search[u0] : 0, te_next = u0 < u1 ? a.u_templ[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  for (int u = u0; u < u1; ++u) {
+    const int so = so_next, te = te_next, slot = slot_next;
+    if (u + 1 < u1) { so_next = a.u_search[u + 1]; te_next = a.u_templ[u + 1]; slot_next = a.u_slot[u + 1]; }
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const size_t ti = (size_t)so * a.NT + tile;
+      copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GX);                  // QXa is free: G2 of the previous tile completed
+      if (te != cur_templ) { copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GX); cur_templ = te; }
+      cp_async_commit();
+      cp_async_wait<0>();
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oMK1, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      {   // z-normalise, merge heads, LayerNorm1 -> X (over the query image)
+        uint32_t d8[8];
+        tc::tmem_ld8(g.tlane + 128, d8);
+        tc::tmem_ld_wait();
+        const float z0 = 1.f / (__uint_as_float(d8[0]) + ATT_EPS), z1 = 1.f / (__uint_as_float(d8[1]) + ATT_EPS);
+        float m0[32], m1[32];
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float (&m)[32] = hh == 0 ? m0 : m1;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t r0[16], r1[16];
+            tc::tmem_ld16(g.tlane + 32 * hh + 16 * half, r0);
+            tc::tmem_ld16(g.tlane + 64 + 32 * hh + 16 * half, r1);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float v = fmaf(z0, __uint_as_float(r0[j]), z1 * __uint_as_float(r1[j]));
+              m[16 * half + j] = v;
+              s += v;
+              ss = fmaf(v, v, ss);
+            }
+          }
+        }
+        const float mean = s * (1.f / 64.f);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / 64.f) - mean * mean, 0.f) + LN_EPS);
+        ln_apply_store(m0, mean, rstd, ln1, 0, xrow);
+        ln_apply_store(m1, mean, rstd, ln1, 32, xrow + 4 * 2048);
+      }
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oW0b, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      {   // Hd = relu(acc + U) -> bf16, written back IN PLACE to TMEM columns [0, 64): the A operand of G3.
+          // One thread owns one lane, and the packed write [8q, 8q+8) never passes the unread columns >= 16(q+1).
+        uint4 sdU[16];
+        load_side<16>(sdU, a.U + ti * 2 * IMG, 0, row);
+        g.wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+          uint32_t w[8];
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint4 s4 = sdU[2 * q + c];
+            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float x0 = __uint_as_float(r[c * 8 + 2 * j]) + bf_lo(sw[j]);
+              const float x1 = __uint_as_float(r[c * 8 + 2 * j + 1]) + bf_hi(sw[j]);
+              w[c * 4 + j] = tc::pack_bf16(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+            }
+          }
+          tc::tmem_st8(g.tlane + 8 * q, w);
+        }
+        tc::tmem_st_wait();
+      }
+      tc::tc_fence_before();
+      g.sync();
+      tc::tc_fence_after();
+      if (g.issuer) {
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            tc::umma_f16_ts(g.tmem + 64, g.tmem + 8 * ks, oW2.desc + (uint64_t)(ks * oW2.kstep), id64, ks > 0 ? 1u : 0u);
+          tc::umma_commit(g.bar);
+        }
+        __syncwarp();
+      }
+      {   // a = h + LN2(acc) -> global bf16 image (stage-1 output)
+        uint4 sdH[8];
+        load_side<8>(sdH, a.H + ti * IMG, 0, row);
+        g.wait();
+        float o0[32], o1[32];
+        float s = 0.f, ss = 0.f;
+        ld32_stats(g.tlane + 64, o0, s, ss);
+        ld32_stats(g.tlane + 96, o1, s, ss);
+        const float mean = s * (1.f / 64.f);
+        const float rstd = rsqrtf(fmaxf(ss * (1.f / 64.f) - mean * mean, 0.f) + LN_EPS);
+        const float nm = -mean * rstd;
+        uint8_t* orow = a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG + row * 16;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float (&o)[32] = hh == 0 ? o0 : o1;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 rs = sdH[4 * hh + c];
+            const uint32_t rw[4] = {rs.x, rs.y, rs.z, rs.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = c * 8 + 2 * j, ch = 32 * hh + k;
+              const float y0 = fmaf(fmaf(o[k], rstd, nm), ln2[ch], ln2[64 + ch]) + bf_lo(rw[j]);
+              const float y1 = fmaf(fmaf(o[k + 1], rstd, nm), ln2[ch + 1], ln2[64 + ch + 1]) + bf_hi(rw[j]);
+              w[j] = tc::pack_bf16(y0, y1);
+            }
+            *reinterpret_cast<uint4*>(orow + (4 * hh + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc::tc_fence_before();                                              // TMEM reads done before the next tile's G1 overwrites
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+__global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2 * NGX];
+  __shared__ uint32_t tmem_base_s;
+  uint8_t* Wsm = smem;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * NGX; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P1B_WBYTES, threadIdx.x, NGX * GX);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  GroupX g;
+  groupx_setup(g, bars, tmem_base_s);
+  uint64_t* bar2 = bars + NGX + g.gid;
+  uint32_t par2 = 0;
+  uint8_t* G = smem + P1B_WBYTES + g.gid * P1B_GBYTES;
+  uint8_t* Aimg = G + P1B_AIMG;
+  uint8_t* KfV = G + P1B_KFV;
+  {
+    uint4* ones = reinterpret_cast<uint4*>(KfV + 2 * IMG);
+    ones[g.t] = make_uint4(0x00003f80u, 0, 0, 0);
+    ones[128 + g.t] = make_uint4(0, 0, 0, 0);
+  }
+  const uint32_t sA = tc::smem_u32(Aimg), sKfV = tc::smem_u32(KfV), sW = tc::smem_u32(Wsm);
+  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t idkv = tc::instr_desc(128, 80, tc::FMT_BF16, tc::MAJOR_MN, tc::MAJOR_MN);
+  // Wkv image is [k/8][128 rows: Wk 0..63 | Wv 64..127][8]: an N=64 operand is the same image entered at row 0 / row 64
+  const Opnd oA = A_IMG(sA), oWk = W_IMG(sW + P1B_WKV, 128), oWv = W_IMG(sW + P1B_WKV + 64 * 16, 128), oWm = W_IMG(sW + P1B_WM, 64),
+             oKfV = opnd(sKfV, 128u, 2048u, 256u), oVones = opnd(sKfV + 8 * 2048, 128u, 2048u, 256u);
+  const int row = g.t;
+  const uint32_t KVC = 64;                                                // TMEM columns [64, 144): KV / Ksum accumulator
+
+  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  int so_next = u0 < u1 ? a.u_search[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  for (int u = u0; u < u1; ++u) {
+    const int so = so_next, slot = slot_next;
+    if (u + 1 < u1) { so_next = a.u_search[u + 1]; slot_next = a.u_slot[u + 1]; }
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const size_t ti = (size_t)so * a.NT + tile;
+      copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, g.t, GX);
+      cp_async_commit();
+      cp_async_wait<0>();
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWk, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      if (tile > 0) { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }   // previous KV GEMM still reads KfV
+      {   // Kf = elu(k)+1 -> chunks 0..7
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = tc::pack_bf16(elu1(__uint_as_float(r[c * 8 + 2 * j])), elu1(__uint_as_float(r[c * 8 + 2 * j + 1])));
+            *reinterpret_cast<uint4*>(KfV + (2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      g.sync();                                                           // everybody has read k before v overwrites the columns
+      tc::tc_fence_after();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWv, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      {   // V = v + Wv pos -> chunks 8..15
+        uint4 sdPV[8];
+        load_side<8>(sdPV, a.PV + ti * IMG, 0, row);
+        g.wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint4 s4 = sdPV[2 * q + c];
+            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]) + bf_lo(sw[j]), __uint_as_float(r[c * 8 + 2 * j + 1]) + bf_hi(sw[j]));
+            *reinterpret_cast<uint4*>(KfV + (8 + 2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      g.publish();
+      if (g.issuer) {   // KV += [Kf|V]^T [V|1]
+        if (tc::elect_one()) { issue_gemm<8>(g.tmem + KVC, oKfV, oVones, idkv, tile > 0); tc::umma_commit(bar2); }
+        __syncwarp();
+      }
+    }
+    tc::mbar_wait(bar2, par2);
+    par2 ^= 1u;
+    tc::tc_fence_after();
+    {   // B7 = [head-split blockdiag(KV) Wm^T | Ksum dots] of this (pair, direction) as template
+      float kv[64];
+      float ksum = 0.f;
+      if (row < 64) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + KVC + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]);
+        }
+        uint32_t r8[8];
+        tc::tmem_ld8(g.tlane + KVC + 64, r8);
+        tc::tmem_ld_wait();
+        ksum = __uint_as_float(r8[0]);
+        const int hd = row >> 5;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = ((c >> 2) == hd) ? tc::pack_bf16(kv[c * 8 + 2 * j], kv[c * 8 + 2 * j + 1]) : 0u;
+          *reinterpret_cast<uint4*>(Aimg + c * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(Aimg + c * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+      }
+      g.publish();
+      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWm, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      g.wait();
+      if (row < 64) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]);
+        }
+        write_b7_row(kv, ksum, row, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
+      }
+      tc::tc_fence_before();
+      g.sync();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // packing kernels (fp32 per-object tensors of the parity path -> bf16 operand images)
 // ---------------------------------------------------------------------------------------------------------------
 // src (B, C, N) channel-major fp32 -> dst [B][N/128][C/8][128][8] bf16, optional elu+1
@@ -978,6 +1312,29 @@ int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * 2 > n_units) grid = (n_units + 1) / 2;
   pair_p1_kernel<<<grid, 2 * GT, smem, (cudaStream_t)stream>>>(a);
+  return pcreid_launch_status();
+}
+
+int pcreid_pair_p1ab(int which, int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot,
+                     const void* QF1, const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out,
+                     void* B7_out, int n_ctas, void* stream) {
+  if (n_units <= 0) return PCREID_OK;
+  if (!u_search || !u_templ || !u_slot || !W || !A_out || !B7_out || NT <= 0 || (which != 0 && which != 1)) return PCREID_ERR_ARG;
+  if (which == 0 && (!QF1 || !U || !H || !MK1)) return PCREID_ERR_ARG;
+  if (which == 1 && !PV) return PCREID_ERR_ARG;
+  P1Args a{n_units, NT, role, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+           (const uint8_t*)PV, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
+  if (which == 0) {
+    const int smem = P1A_WBYTES + NGX * P1A_GBYTES;
+    cudaFuncSetAttribute(pair_p1a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pair_p1a_kernel<<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    const int smem = P1B_WBYTES + NGX * P1B_GBYTES;
+    cudaFuncSetAttribute(pair_p1b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pair_p1b_kernel<<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
+  }
   return pcreid_launch_status();
 }
 

@@ -59,6 +59,7 @@ class FusedXcorr:
         self.n_ctas = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
         self.p2_three_tiles = os.environ.get("PCREID_P2_VARIANT", "3") == "3"   # 3 groups x 4 warps (default) or 2 x 8
+        self.p1_split = os.environ.get("PCREID_P1_VARIANT", "split") == "split"   # p1a + p1b (3 tiles in flight) or monolithic
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
@@ -73,7 +74,13 @@ class FusedXcorr:
                 self._w2 = torch.cat([
                     _w_image(X2.q_proj.weight), _w_image(X2.mlp[0].weight), _w_image(X2.mlp[2].weight),
                     _f32_bytes(X2.norm1.weight, X2.norm1.bias, X2.norm2.weight, X2.norm2.bias)]).contiguous()
+                self._w1a = torch.cat([
+                    _w_image(X1.mlp[0].weight[:, d:]), _w_image(X1.mlp[2].weight),
+                    _f32_bytes(X1.norm1.weight, X1.norm1.bias, X1.norm2.weight, X1.norm2.bias)]).contiguous()
+                self._w1b = torch.cat([
+                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)), _w_image(X2.merge.weight)]).contiguous()
                 assert self._w1.numel() == 58368 and self._w2.numel() == 58368
+                assert self._w1a.numel() == 33792 and self._w1b.numel() == 24576
             self._key = key
         return self._w1, self._w2
 
@@ -130,6 +137,14 @@ class FusedXcorr:
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             order = torch.argsort(tmpl, stable=True)                        # runs of units share the template operand
             us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+            if self.p1_split:
+                for which, blob, name in ((0, self._w1a, "pair_p1a_kernel"), (1, self._w1b, "pair_p1b_kernel")):
+                    e0 = self._tick()
+                    _lib.check(L.pcreid_pair_p1ab(which, P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H),
+                                                  _p(ps.PV), _p(pm.MK1), _p(blob), _p(A), _p(B7), self.n_ctas, _stream()),
+                               "pcreid_pair_p1ab")
+                    self._tock(name, e0, P)
+                continue
             e0 = self._tick()
             _lib.check(L.pcreid_pair_p1(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(ps.PV),
                                         _p(pm.MK1), _p(w1), _p(A), _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1")
