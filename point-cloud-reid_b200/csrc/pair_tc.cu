@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              w[j] = tc::pack_bf16(elu1(__uint_as_float(r[c * 8 + 2 * j])), elu1(__uint_as_float(r[c * 8 + 2 * j + 1])));
+              w[j] = tc::bf2_elu1(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])));
             *reinterpret_cast<uint4*>(arow + IMG + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              w[j] = tc::pack_bf16(fmaxf(__uint_as_float(r[c * 8 + 2 * j]), 0.f), fmaxf(__uint_as_float(r[c * 8 + 2 * j + 1]), 0.f));
+              w[j] = tc::bf2_max(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])), 0u);
             *reinterpret_cast<uint4*>(arow + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -1009,11 +1009,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a_kernel(const P1Args a) {
             const uint4 s4 = sdU[2 * q + c];
             const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float x0 = __uint_as_float(r[c * 8 + 2 * j]) + bf_lo(sw[j]);
-              const float x1 = __uint_as_float(r[c * 8 + 2 * j + 1]) + bf_hi(sw[j]);
-              w[c * 4 + j] = tc::pack_bf16(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
-            }
+            for (int j = 0; j < 4; ++j)
+              w[c * 4 + j] = tc::bf2_max(tc::bf2_add(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])), sw[j]), 0u);
           }
           tc::tmem_st8(g.tlane + 8 * q, w);
         }
@@ -1134,7 +1131,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              w[j] = tc::pack_bf16(elu1(__uint_as_float(r[c * 8 + 2 * j])), elu1(__uint_as_float(r[c * 8 + 2 * j + 1])));
+              w[j] = tc::bf2_elu1(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])));
             *reinterpret_cast<uint4*>(KfV + (2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -1159,7 +1156,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              w[j] = tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]) + bf_lo(sw[j]), __uint_as_float(r[c * 8 + 2 * j + 1]) + bf_hi(sw[j]));
+              w[j] = tc::bf2_add(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])), sw[j]);
             *reinterpret_cast<uint4*>(KfV + (8 + 2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }

@@ -135,6 +135,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// ---- packed bf16x2 arithmetic for epilogues whose result is rounded to bf16 anyway (2 elements per instruction) ----
+__device__ __forceinline__ uint32_t bf2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t bf2_max(uint32_t a, uint32_t b) { uint32_t r; asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t bf2_min(uint32_t a, uint32_t b) { uint32_t r; asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t bf2_ex2(uint32_t a) { uint32_t r; asm("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(r) : "r"(a)); return r; }
+// elu(x)+1 = max(x,0) + exp(min(x,0)) on a packed pair (one MUFU for two elements)
+__device__ __forceinline__ uint32_t bf2_elu1(uint32_t x) {
+  const uint32_t LOG2E = 0x3fb93fb9u;   // bf16(1.4427) in both halves
+  return bf2_add(bf2_max(x, 0u), bf2_ex2(bf2_mul(bf2_min(x, 0u), LOG2E)));
+}
+
 // warp-uniform helpers: values produced through these are known to be warp-uniform by the compiler, so descriptor
 // arithmetic and tcgen05.mma operands stay on the uniform datapath (no per-MMA R2UR moves)
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
