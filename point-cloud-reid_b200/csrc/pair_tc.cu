@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float comb[NGX][2][2][64];
+  __shared__ float comb[NGX][2][4][64];
   uint8_t* Wsm = smem;
   const float* ln1 = reinterpret_cast<const float*>(Wsm + P2_LN);
   const float* ln2 = ln1 + 128;
@@ -744,19 +744,21 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
 
   const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
-  const int pc = g.t & 63, ph = g.t >> 6;
+  const int pc = g.t & 31, pq = g.t >> 5;                                 // pooling: channel within a 32-channel pass, row quarter
+  float* Tb = reinterpret_cast<float*>(R1 + IMG);                         // 16 KB transpose buffer: [32 ch][128 rows] fp32, rotated
   int slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  if (u0 < u1) {   // first tile of this group: nothing to hide the loads behind
+    copy_to_smem(R1, a.A_in + ((size_t)slot_next * 2 + a.role) * a.NT * IMG, IMG, g.t, GX);
+    copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
+  }
+  cp_async_commit();
   for (int u = u0; u < u1; ++u) {
     const int slot = slot_next;
     if (u + 1 < u1) slot_next = a.u_slot[u + 1];
-    float pmax = -INFINITY, psum = 0.f;
+    float pmax0 = -INFINITY, psum0 = 0.f, pmax1 = -INFINITY, psum1 = 0.f;  // channels pc and 32 + pc
     for (int tile = 0; tile < a.NT; ++tile) {
       const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
-      g.sync();                                                           // previous tile's pooling reads of R1 are done
-      copy_to_smem(R1, a_img, IMG, g.t, GX);
-      if (tile == 0) copy_to_smem(B7, a.B7_in + ((size_t)slot * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
-      cp_async_commit();
-      cp_async_wait<0>();
+      cp_async_wait<0>();                                                 // `a` image (and B7 at a unit start) prefetched earlier
       g.publish();
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
@@ -779,6 +781,10 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
       g.publish();
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
+      if (tile + 1 == a.NT && u + 1 < u1) {   // last attention GEMM of the unit is done: next unit's B7 streams in
+        copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
+        cp_async_commit();
+      }
       {   // attention epilogue: z-normalise, merge heads, LayerNorm1 -> X (second half of R1)
         uint32_t d8[8];
         tc::tmem_ld8(g.tlane + 128, d8);
@@ -813,37 +819,53 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW0, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
       uint4 sdA[8];
       g.wait();
-      load_side<8>(sdA, a_img, 0, row);                                   // residual a, consumed after G9
-      {   // Hd = relu(acc) over [a | X]
+      load_side<8>(sdA, a_img, 0, row);                                   // residual a (this tile), consumed after G9
+      {   // G8 has consumed [a | X]: the next tile's `a` image streams into R1 behind the rest of this tile
+        int nu = u, nt = tile + 1;
+        if (nt == a.NT) { nu = u + 1; nt = 0; }
+        if (nu < u1) {
+          copy_to_smem(R1, a.A_in + (((size_t)(nt == 0 ? slot_next : slot) * 2 + a.role) * a.NT + nt) * IMG, IMG, g.t, GX);
+          cp_async_commit();
+        }
+      }
+      {   // Hd = relu(acc) -> bf16, written back in place to TMEM columns [0, 64): the A operand of G9 (no shared memory)
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint32_t r[16];
           tc::tmem_ld16(g.tlane + 16 * q, r);
           tc::tmem_ld_wait();
+          uint32_t w[8];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              w[j] = tc::bf2_max(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])), 0u);
-            *reinterpret_cast<uint4*>(arow + (2 * q + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
+          for (int j = 0; j < 8; ++j) w[j] = tc::bf2_max(tc::pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1])), 0u);
+          tc::tmem_st8(g.tlane + 8 * q, w);
         }
+        tc::tmem_st_wait();
       }
-      g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<8>(g.tmem, oR1, oW2, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      tc::tc_fence_before();
+      g.sync();
+      tc::tc_fence_after();
+      if (g.issuer) {
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            tc::umma_f16_ts(g.tmem + 64, g.tmem + 8 * ks, oW2.desc + (uint64_t)(ks * oW2.kstep), id64, ks > 0 ? 1u : 0u);
+          tc::umma_commit(g.bar);
+        }
+        __syncwarp();
+      }
       g.wait();
-      {   // o = a + LN2(acc); transposed (rotated) store for the pooling
+      {   // o = a + LN2(acc); pooled over the points through a 16 KB rotated transpose buffer, 32 channels per pass
         float o0[32], o1[32];
         float s = 0.f, ss = 0.f;
-        ld32_stats(g.tlane, o0, s, ss);
-        ld32_stats(g.tlane + 32, o1, s, ss);
+        ld32_stats(g.tlane + 64, o0, s, ss);
+        ld32_stats(g.tlane + 96, o1, s, ss);
         const float mean = s * (1.f / 64.f);
         const float rstd = rsqrtf(fmaxf(ss * (1.f / 64.f) - mean * mean, 0.f) + LN_EPS);
         const float nm = -mean * rstd;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           float (&o)[32] = hh == 0 ? o0 : o1;
+          if (hh == 1) g.sync();                                          // pass-0 reads are done before pass 1 overwrites
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 rs = sdA[4 * hh + c];
@@ -853,29 +875,36 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2x_kernel(const P2Args a) {
               const int k = c * 8 + 2 * j, ch = 32 * hh + k;
               const float y0 = fmaf(fmaf(o[k], rstd, nm), ln2[ch], ln2[64 + ch]) + bf_lo(rw[j]);
               const float y1 = fmaf(fmaf(o[k + 1], rstd, nm), ln2[ch + 1], ln2[64 + ch + 1]) + bf_hi(rw[j]);
-              R1f[ch * 128 + ((row + ch) & 127)] = y0;
-              R1f[(ch + 1) * 128 + ((row + ch + 1) & 127)] = y1;
+              Tb[k * 128 + ((row + k) & 127)] = y0;
+              Tb[(k + 1) * 128 + ((row + k + 1) & 127)] = y1;
             }
           }
+          g.sync();
+          float mx = -INFINITY, sm = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; ++i) {
+            const float v = Tb[pc * 128 + ((pq * 32 + i + pc) & 127)];
+            mx = fmaxf(mx, v);
+            sm += v;
+          }
+          if (hh == 0) { pmax0 = fmaxf(pmax0, mx); psum0 += sm; } else { pmax1 = fmaxf(pmax1, mx); psum1 += sm; }
         }
       }
-      g.sync();
-#pragma unroll 8
-      for (int i = 0; i < 64; ++i) {
-        const float v = R1f[pc * 128 + ((ph * 64 + i + pc) & 127)];
-        pmax = fmaxf(pmax, v);
-        psum += v;
-      }
+      tc::tc_fence_before();
+      g.sync();                                                           // transpose buffer (= Qf region) is rewritten by the next tile
     }
-    comb[g.gid][0][ph][pc] = pmax;
-    comb[g.gid][1][ph][pc] = psum;
+    comb[g.gid][0][pq][pc] = pmax0;
+    comb[g.gid][0][pq][32 + pc] = pmax1;
+    comb[g.gid][1][pq][pc] = psum0;
+    comb[g.gid][1][pq][32 + pc] = psum1;
     g.sync();
     if (g.t < 64) {
       float* out = a.pool_part + ((size_t)slot * 2 + a.role) * 128;
-      out[g.t] = fmaxf(comb[g.gid][0][0][g.t], comb[g.gid][0][1][g.t]);
-      out[64 + g.t] = comb[g.gid][1][0][g.t] + comb[g.gid][1][1][g.t];
+      out[g.t] = fmaxf(fmaxf(comb[g.gid][0][0][g.t], comb[g.gid][0][1][g.t]), fmaxf(comb[g.gid][0][2][g.t], comb[g.gid][0][3][g.t]));
+      out[64 + g.t] = (comb[g.gid][1][0][g.t] + comb[g.gid][1][1][g.t]) + (comb[g.gid][1][2][g.t] + comb[g.gid][1][3][g.t]);
     }
   }
+  cp_async_wait<0>();
   tc::tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
@@ -948,13 +977,15 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a_kernel(const P1Args a) {
   const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
   int cur_templ = -1;
+  bool prefetched = false;
   int so_next = u0 < u1 ? a.u_search[u0] : 0, te_next = u0 < u1 ? a.u_templ[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
   for (int u = u0; u < u1; ++u) {
     const int so = so_next, te = te_next, slot = slot_next;
     if (u + 1 < u1) { so_next = a.u_search[u + 1]; te_next = a.u_templ[u + 1]; slot_next = a.u_slot[u + 1]; }
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
-      copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GX);                  // QXa is free: G2 of the previous tile completed
+      if (!prefetched) copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GX);  // first tile of this group only
+      prefetched = false;
       if (te != cur_templ) { copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GX); cur_templ = te; }
       cp_async_commit();
       cp_async_wait<0>();
@@ -998,6 +1029,15 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a_kernel(const P1Args a) {
         uint4 sdU[16];
         load_side<16>(sdU, a.U + ti * 2 * IMG, 0, row);
         g.wait();
+        {   // G2 has consumed X: the query image of the next (unit, tile) streams into QXa behind the rest of this tile
+          int nu = u, nt = tile + 1;
+          if (nt == a.NT) { nu = u + 1; nt = 0; }
+          if (nu < u1) {
+            copy_to_smem(QXa, a.QF1 + ((size_t)(nt == 0 ? so_next : so) * a.NT + nt) * IMG, IMG, g.t, GX);
+            cp_async_commit();
+            prefetched = true;
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           uint32_t r[16];
@@ -1108,12 +1148,14 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
   const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
   int so_next = u0 < u1 ? a.u_search[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  bool prefetched = false;
   for (int u = u0; u < u1; ++u) {
     const int so = so_next, slot = slot_next;
     if (u + 1 < u1) { so_next = a.u_search[u + 1]; slot_next = a.u_slot[u + 1]; }
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
-      copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, g.t, GX);
+      if (!prefetched) copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, g.t, GX);
+      prefetched = false;
       cp_async_commit();
       cp_async_wait<0>();
       g.publish();
@@ -1144,6 +1186,11 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
         uint4 sdPV[8];
         load_side<8>(sdPV, a.PV + ti * IMG, 0, row);
         g.wait();
+        if (tile + 1 < a.NT) {   // both projections have consumed `a`: stream the unit's next tile in behind the V epilogue + KV GEMM
+          copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile + 1) * IMG, IMG, g.t, GX);
+          cp_async_commit();
+          prefetched = true;
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t r[16];
@@ -1201,6 +1248,11 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
       g.publish();
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWm, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
+      if (u + 1 < u1) {   // G6 has consumed the operand buffer: the next unit's first tile streams in behind the B7 write-out
+        copy_to_smem(Aimg, a.A_out + ((size_t)slot_next * 2 + a.role) * a.NT * IMG, IMG, g.t, GX);
+        cp_async_commit();
+        prefetched = true;
+      }
       if (row < 64) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
