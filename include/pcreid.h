@@ -85,6 +85,10 @@ typedef struct pcreid_linear_args {
   float* Y; long long y_bs; int ldy; int y_pm;   /* y_pm=1: Y written point-major (rows, CO), ldy = row stride */
 } pcreid_linear_args;
 int pcreid_cn_linear(const pcreid_linear_args* args, void* stream);
+/* same contract on the tensor cores (tcgen05 kind::tf32, fp32 accumulate): fast mode.  Returns PCREID_ERR_UNSUPPORTED
+ * for shapes it was not built for (object maps, point-major inputs, K < 8);
+ * callers then use pcreid_cn_linear. */
+int pcreid_cn_linear_tc(const pcreid_linear_args* args, void* stream);
 
 /* GroupNorm over channel groups per (object, point) -- LayerNorm is G=1 (eps 1e-5, torch default):
  * Y = act( GN(X)*gamma + beta (+R) ).  Used for nn.LayerNorm (pointnet2_utils.py:87-88, attention.py:187-188)

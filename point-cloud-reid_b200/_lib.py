@@ -53,6 +53,7 @@ _SIGS = {
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_cn_linear": [ctypes.POINTER(LinearArgs), c_vp],
+    "pcreid_cn_linear_tc": [ctypes.POINTER(LinearArgs), c_vp],
     "pcreid_cn_groupnorm": [ctypes.POINTER(NormArgs), c_vp],
     "pcreid_linattn_kv": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_linattn_scale": [c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp],

@@ -5,6 +5,7 @@
 //   mode 1: bf16, A and B MN-major in shared memory  (same physical image, roles of row / k swapped)
 //   mode 2: tf32, A and B K-major in shared memory   ([k/4][row][4] fp32)
 //   mode 3: bf16, A from tensor memory (tcgen05.st by the row-owning threads), B K-major in shared memory
+//   mode 4: tf32, A and B MN-major in shared memory  ([mn/4][k][4] fp32; global holds A^T (K x 128), B^T (K x N))
 // D (128 x N, fp32, row-major) = A (128 x K) * B (N x K)^T.
 #include "../../include/pcreid.h"
 #include "common.cuh"
@@ -18,7 +19,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int esz = mode == 2 ? 4 : 2;            // bytes per element
+  const int esz = (mode == 2 || mode == 4) ? 4 : 2;   // bytes per element
   const int cpe = 16 / esz;                     // elements per 16-byte chunk
   uint8_t* As = smem;
   uint8_t* Bs = smem + (size_t)128 * K * esz;
@@ -46,6 +47,18 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
       size_t off = (size_t)(k / cpe) * ((size_t)N * 16) + (size_t)r * 16 + (size_t)(k % cpe) * esz;
       if (esz == 2) *reinterpret_cast<uint16_t*>(Bs + off) = reinterpret_cast<const uint16_t*>(Bg)[i];
       else *reinterpret_cast<uint32_t*>(Bs + off) = reinterpret_cast<const uint32_t*>(Bg)[i];
+    }
+  } else if (mode == 4) {
+    // tf32 MN-major: element (mn, k) at (mn/4)*(K*16) + k*16 + (mn%4)*4
+    for (int i = tid; i < 128 * K; i += 128) {
+      int k = i / 128, m = i % 128;
+      *reinterpret_cast<uint32_t*>(As + (size_t)(m / 4) * ((size_t)K * 16) + (size_t)k * 16 + (size_t)(m % 4) * 4) =
+          reinterpret_cast<const uint32_t*>(Ag)[i];
+    }
+    for (int i = tid; i < N * K; i += 128) {
+      int k = i / N, n = i % N;
+      *reinterpret_cast<uint32_t*>(Bs + (size_t)(n / 4) * ((size_t)K * 16) + (size_t)k * 16 + (size_t)(n % 4) * 4) =
+          reinterpret_cast<const uint32_t*>(Bg)[i];
     }
   } else {
     // MN-major: global holds A^T (K x 128) and B^T (K x N); element (mn, k) at (mn/8)*(K*16) + k*16 + (mn%8)*2
@@ -101,6 +114,13 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
         uint64_t bd = tc::smem_desc(b0 + ks * 2 * 128, 128, K * 16, tc::LAYOUT_NONE);
         tc::umma_f16(tmem_acc, ad, bd, idesc, ks > 0);
       }
+    } else if (mode == 4) {
+      const uint32_t idesc = tc::instr_desc(128, N, tc::FMT_TF32, tc::MAJOR_MN, tc::MAJOR_MN);
+      for (int ks = 0; ks < K / 8; ++ks) {   // K step of 8 = one k-group of 8 x 16 B
+        uint64_t ad = tc::smem_desc(a0 + ks * 128, 128, K * 16, tc::LAYOUT_NONE);
+        uint64_t bd = tc::smem_desc(b0 + ks * 128, 128, K * 16, tc::LAYOUT_NONE);
+        tc::umma_tf32(tmem_acc, ad, bd, idesc, ks > 0);
+      }
     } else {
       const uint32_t idesc = tc::instr_desc(128, N, tc::FMT_TF32, tc::MAJOR_K, tc::MAJOR_K);
       for (int ks = 0; ks < K / 8; ++ks) {
@@ -128,9 +148,9 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
 }  // namespace
 
 extern "C" int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream) {
-  if (!a || !b || !d || mode < 0 || mode > 3) return PCREID_ERR_ARG;
+  if (!a || !b || !d || mode < 0 || mode > 4) return PCREID_ERR_ARG;
   if (n < 16 || n > 256 || n % 16 || k < 16 || k > 256 || k % 16) return PCREID_ERR_UNSUPPORTED;
-  const int esz = mode == 2 ? 4 : 2;
+  const int esz = (mode == 2 || mode == 4) ? 4 : 2;
   size_t smem = (size_t)(128 + n) * k * esz;
   if (smem > 200 * 1024) return PCREID_ERR_UNSUPPORTED;
   cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -12,6 +12,23 @@ from . import _lib
 
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_ELU1 = 0, 1, 2, 3
 
+# fast mode switch for cn_linear: tcgen05 kind::tf32 GEMM where the shape allows it (set by ReIDNet.set_mode / tensor_core_linear)
+_TC_LINEAR = {"on": False}
+
+
+class tensor_core_linear:
+    """context manager: `with tensor_core_linear(True): ...` routes cn_linear through pcreid_cn_linear_tc."""
+
+    def __init__(self, on):
+        self.on, self.prev = bool(on), None
+
+    def __enter__(self):
+        self.prev = _TC_LINEAR["on"]
+        _TC_LINEAR["on"] = self.on
+
+    def __exit__(self, *exc):
+        _TC_LINEAR["on"] = self.prev
+
 
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -102,6 +119,14 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
             out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
         a.y_bs, a.ldy = _cn(out, "out")
     a.Y = _p(out)
+    # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernel wins from K >= 256 (2.2x at 512x1024);
+    # below that the FFMA kernel (up to 48 TFLOP/s) is faster
+    if (_TC_LINEAR["on"] and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None
+            and r_map is None and not x1_pm and not x2_pm):
+        rc = _lib.lib().pcreid_cn_linear_tc(ctypes.byref(a), _stream())
+        if rc != 3:                      # 3 == PCREID_ERR_UNSUPPORTED: shape stays on the FFMA kernel
+            _lib.check(rc, "pcreid_cn_linear_tc")
+            return out
     _lib.check(_lib.lib().pcreid_cn_linear(ctypes.byref(a), _stream()), "pcreid_cn_linear")
     return out
 

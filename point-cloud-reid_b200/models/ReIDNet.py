@@ -92,6 +92,7 @@ class ReIDNet(nn.Module):
         # 'parity': fp32 kernels (logits within 1e-4 of the reference); 'fast': fused bf16 tcgen05 matcher where the
         # configuration allows it (d_model 64, 2 heads, point-cat + both pooling, points a multiple of 128)
         self.match_mode = 'parity'
+        self.tc_encoder = True      # in 'fast' mode the encoder's 1x1 convs / Linears run as tf32 tcgen05 GEMMs
         self._fused = None
         if self.match_type not in ('xcorr_eff', 'concat'):
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
@@ -127,7 +128,7 @@ class ReIDNet(nn.Module):
 
     def encode(self, pts):
         """public inference entry: pts (B, N, 3) -> (xyz (B, N, 3), per-point embedding (B, C, N))."""
-        with torch.no_grad():
+        with torch.no_grad(), K.tensor_core_linear(self.match_mode == 'fast' and self.tc_encoder):
             return self._encode(pts)
 
     def forward_inference(self, pts_batched):

@@ -54,6 +54,42 @@ def test_cn_linear_two_inputs_residual_maps_strides():
     assert float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
 
 
+@pytest.mark.parametrize("B,K1,CO,N", [(3, 64, 64, 256), (2, 128, 192, 132), (2, 1024, 512, 256), (5, 72, 12, 36), (1, 512, 1024, 100)])
+@pytest.mark.parametrize("act", [0, 2])
+def test_cn_linear_tensor_core(B, K1, CO, N, act):
+    """tcgen05 kind::tf32 GEMM against the fp32 specification (tf32 operands: 10-bit mantissa)."""
+    x, w, b = rnd(B, K1, N, seed=1), rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
+    K._TC_LINEAR["min_k"] = 8            # force the tensor-core kernel for every shape under test
+    try:
+        with K.tensor_core_linear(True):
+            got = K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act)
+    finally:
+        K._TC_LINEAR.pop("min_k")
+    close(got, F.cn_linear(x, w, bias=b, act=act), 3e-3)
+
+
+def test_cn_linear_tensor_core_options():
+    N = 200
+    x1, x2, res = rnd(4, 64, N, seed=1), rnd(4, 32, N, seed=2), rnd(4, 128, N, seed=5)
+    w1, w2 = rnd(64, 128, seed=3) / 8, rnd(32, 128, seed=4) / 6
+    wk = rnd(4, 64, 64, seed=7) / 8                          # per-object weights
+    qkv = rnd(3, 192, N, seed=6)
+    K._TC_LINEAR["min_k"] = 8
+    with K.tensor_core_linear(True):
+        for after in (False, True):
+            got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), act=1, res=res.to(DEV), res_after_act=after)
+            close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, act=1, res=res, res_after_act=after), 3e-3)
+        close(K.cn_linear(x1.to(DEV), wk.to(DEV)), F.cn_linear(x1, wk), 3e-3)
+        qd = qkv.to(DEV)
+        close(K.cn_linear(qd[:, 64:128], wk[0].contiguous().to(DEV), rows=96), F.cn_linear(qkv[:, 64:128], wk[0], rows=96), 3e-3)
+        close(K.cn_linear(qd[:, 128:], wk[1].contiguous().to(DEV), y_pm=True), F.cn_linear(qkv[:, 128:], wk[1], y_pm=True), 3e-3)
+        # shapes outside the tensor-core kernel silently use the FFMA kernel (exact to 2e-5)
+        xyz = rnd(2, N, 3, seed=9)
+        w3 = rnd(3, 32, seed=10)
+        close(K.cn_linear(xyz.to(DEV), w3.to(DEV), x1_pm=True), F.cn_linear(xyz, w3, x1_pm=True))
+    K._TC_LINEAR.pop("min_k")
+
+
 @pytest.mark.parametrize("C,G,N", [(64, 1, 256), (128, 8, 100), (512, 64, 33), (32, 1, 7)])
 def test_cn_groupnorm(C, G, N):
     x, g, b, r = rnd(3, C, N, seed=1) * 3 + 1, rnd(C, seed=2), rnd(C, seed=3), rnd(2, C, N, seed=4)
