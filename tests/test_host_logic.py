@@ -78,3 +78,32 @@ def test_kernels_refuse_cpu_tensors():
     from pcreid_b200.ops import knn
     with pytest.raises(RuntimeError):
         knn(3, torch.zeros(1, 8, 3))
+
+
+def test_feature_bank_and_reidentifier_match_the_tracker_semantics(fake):
+    """PointFeatureSet.store_new / replace_old (tracking_feature_set.py:36-63) and the class-gated all-pairs scoring
+    (tracking_point_reid.py:15-33, 95-116) against the oracle's pair-list formulation."""
+    from pcreid_b200.models.tracking import PointFeatureSet, PointReidentifier, class_gate
+    m, orc = helpers.build_pair("pt")
+    bank = PointFeatureSet(replace_all=False)
+    t0 = O.synth_objects(4, 128, 0)
+    xyz, h = m.encode(t0)
+    bank.store_new(xyz, h, torch.tensor([50, 10, 3, 1]))
+    assert len(bank) == 4
+    # a denser observation replaces track 1, a sparser one does not replace track 0
+    t1 = O.synth_objects(2, 128, 5)
+    x1, h1 = m.encode(t1)
+    old0 = bank.pts_feats[0].clone()
+    bank.replace_old(torch.tensor([0, 1]), x1, h1, torch.tensor([20, 30]))
+    assert torch.equal(bank.pts_feats[0], old0) and torch.equal(bank.pts_feats[1], h1[1]) and bank.lengths.tolist() == [50, 30, 3, 1]
+    dets = O.synth_objects(3, 128, 7)
+    det_labels, det_len = torch.tensor([1, 2, 1]), torch.tensor([9, 9, 1])
+    track_labels = torch.tensor([1, 1, 2, 1])
+    reid = PointReidentifier(m, bank)
+    cost, xd, hd = reid(dets, det_labels, det_len, torch.arange(4), track_labels)
+    mask = class_gate(det_labels, track_labels, det_len, bank.lengths)
+    assert mask.tolist() == O.class_gated_pairs(track_labels, bank.lengths, det_labels, det_len).tolist()
+    assert mask.tolist() == [[True, False, False], [True, False, False], [False, True, False], [False, False, False]]
+    xt, ht = bank.get_features(torch.arange(4))
+    ref = orc.match_all_pairs(ht, xt, hd, xd, pair_mask=mask)
+    assert (cost - ref).abs().max() < 2e-5 and (cost[~mask] == 0).all()
