@@ -169,8 +169,8 @@ int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void*
 int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream);
 
 /* tensor-core (tcgen05 kind::tf32, fp32 accumulate) version of pcreid_sa_edge_mlp: same arguments except that the
- * two weight matrices are fp32 operand images [k/4][n][4] of the (C_out, C_in) BatchNorm-folded weights; C in
- * {32, 64, 128}.  Fast mode of the encoder (error ~1e-3 relative: tf32 operands). */
+ * two weight matrices are fp32 operand images [k/4][n][4] of the (C_out, C_in) BatchNorm-folded weights and that P1 / Cc
+ * are POINT-major ((b,n,C) / (b,S,C): a gathered neighbour is one contiguous vector); C in {32, 64, 128}.  Fast mode of the encoder (error ~1e-3 relative: tf32 operands). */
 int pcreid_sa_edge_mlp_tc(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
                           const float* W2img, const float* b2, const float* W3img, const float* b3, float* out,
                           int n_ctas, void* stream);

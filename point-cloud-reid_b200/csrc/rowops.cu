@@ -165,6 +165,29 @@ __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_arg
   const float* R = nullptr;
   if (a.R) R = a.R + (size_t)(a.r_map ? a.r_map[b] : b) * a.r_bs;
   const bool vy = !a.y_pm && (a.ldy % 4 == 0) && (a.rows % 4 == 0) && aligned16(Y) && (!R || ((a.ldr % 4 == 0) && aligned16(R)));
+  if (a.y_pm && !R && (a.ldy % 4 == 0) && (a.CO % 4 == 0) && aligned16(Y)) {
+    // point-major output without residual: each thread writes its 4 (or 2 x 4) consecutive channels of a row as 128-bit stores
+#pragma unroll
+    for (int jb = 0; jb < TN; jb += 4) {
+      const int co = co0 + col_of<TN>(ty, jb);
+      if (co >= a.CO) continue;
+      float bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = a.bias ? __ldg(a.bias + co + j) : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int n = n0 + (i >= 4 ? 64 : 0) + tx * 4 + (i & 3);
+        if (n >= a.rows) continue;
+        float4 v;
+        v.x = apply_act(acc[i][jb + 0] + bv[0], a.act);
+        v.y = apply_act(acc[i][jb + 1] + bv[1], a.act);
+        v.z = apply_act(acc[i][jb + 2] + bv[2], a.act);
+        v.w = apply_act(acc[i][jb + 3] + bv[3], a.act);
+        *reinterpret_cast<float4*>(Y + (size_t)n * a.ldy + co) = v;
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int j = 0; j < TN; ++j) {
     const int co = co0 + col_of<TN>(ty, j);

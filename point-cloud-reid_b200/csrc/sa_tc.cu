@@ -1,7 +1,7 @@
 // Set-abstraction edge MLP on the 5th-gen tensor cores (tcgen05, kind::tf32, fp32 accumulate in TMEM) -- the
 // "fast" mode counterpart of sa_edge_mlp_kernel (rowops.cu).
 //
-//   out[b,c,s] = max_j relu(W3 relu(W2 relu(P1[b,:,idx[b,s,j]] + Cc[b,:,s]) + b2) + b3)[c]
+//   out[b,c,s] = max_j relu(W3 relu(W2 relu(P1[b,idx[b,s,j],:] + Cc[b,s,:]) + b2) + b3)[c]      (P1, Cc point-major)
 // (PointNetSetAbstractionEdgeSA.forward, mmdet3d/models/pointnet2_utils.py:333-357, first conv factorised per point /
 // per centre on the host side, eval BatchNorm folded).
 //
@@ -60,22 +60,23 @@ __global__ void __launch_bounds__(NT_, (C == 128 ? 1 : 2)) sa_edge_mlp_tc_kernel
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_obj, s0 = (tile % tiles_per_obj) * cpt;
     const int ncen = min(cpt, S - s0), nedge = ncen * k;
-    const float* Pb = P1 + (size_t)b * C * N;
-    const float* Cb = Cc + (size_t)b * C * S;
-    // ---- gather + relu(P1 + Cc) -> operand image
+    // P1 / Cc are point-major here ((B, N, C) / (B, S, C)): a gathered neighbour is one contiguous C-vector
+    const float* Pb = P1 + (size_t)b * N * C;
+    const float* Cb = Cc + (size_t)b * S * C;
+    // ---- gather + relu(P1 + Cc) -> operand image (128-bit loads; chunk of 4 channels == one 16-byte image chunk)
     {
       int src = -1, cen = 0;
       if (row < nedge) { cen = s0 + row / k; src = __ldg(idx + ((size_t)b * S + cen) * k + (row % k)); }
-#pragma unroll 4
-      for (int c = h * CH; c < (h + 1) * CH; c += 4) {
+      const float4* prow = reinterpret_cast<const float4*>(Pb + (size_t)max(src, 0) * C) + h * (CH / 4);
+      const float4* crow = reinterpret_cast<const float4*>(Cb + (size_t)cen * C) + h * (CH / 4);
+#pragma unroll
+      for (int c4 = 0; c4 < CH / 4; ++c4) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (src >= 0) {
-          v.x = fmaxf(__ldg(Pb + (size_t)(c + 0) * N + src) + __ldg(Cb + (size_t)(c + 0) * S + cen), 0.f);
-          v.y = fmaxf(__ldg(Pb + (size_t)(c + 1) * N + src) + __ldg(Cb + (size_t)(c + 1) * S + cen), 0.f);
-          v.z = fmaxf(__ldg(Pb + (size_t)(c + 2) * N + src) + __ldg(Cb + (size_t)(c + 2) * S + cen), 0.f);
-          v.w = fmaxf(__ldg(Pb + (size_t)(c + 3) * N + src) + __ldg(Cb + (size_t)(c + 3) * S + cen), 0.f);
+          const float4 p = __ldg(prow + c4), q = __ldg(crow + c4);
+          v = make_float4(fmaxf(p.x + q.x, 0.f), fmaxf(p.y + q.y, 0.f), fmaxf(p.z + q.z, 0.f), fmaxf(p.w + q.w, 0.f));
         }
-        *reinterpret_cast<float4*>(As + (c / 4) * 2048 + row * 16) = v;
+        *reinterpret_cast<float4*>(As + (h * (CH / 4) + c4) * 2048 + row * 16) = v;
       }
     }
     for (int layer = 0; layer < 2; ++layer) {

@@ -249,9 +249,9 @@ def tf32_image(w):
 
 
 def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
-    """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image()."""
+    """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image(); p1 (B, N, C) and cc (B, S, C) point-major."""
     _need_cuda(p1, cc, idx)
-    B, C, N = p1.shape
+    B, N, C = p1.shape
     S, k = idx.shape[1], idx.shape[2]
     if not (p1.is_contiguous() and cc.is_contiguous() and idx.is_contiguous()):
         raise ValueError("sa_edge_mlp_tc inputs must be contiguous")

@@ -120,13 +120,14 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         S = int(numpoints)
         new_xyz = xyz[:, :S, :].contiguous()              # sampling == "RANDOM": the first S points
         idx = K.knn_point(self.nsample, xyz, new_xyz)     # (B, S, k) int32
+        tc = self.tc_mode and "w2img" in pk          # tensor-core kernel gathers point-major rows
         if pk["D"] > 0:
-            p1 = K.cn_linear(xyz, pk["pa"], x2=points, w2=pk["pc"], x1_pm=True)
-            cc = K.cn_linear(xyz, pk["ca"], x2=points, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S)
+            p1 = K.cn_linear(xyz, pk["pa"], x2=points, w2=pk["pc"], x1_pm=True, y_pm=tc)
+            cc = K.cn_linear(xyz, pk["ca"], x2=points, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
         else:
-            p1 = K.cn_linear(xyz, pk["pa"], x1_pm=True)
-            cc = K.cn_linear(xyz, pk["ca"], bias=pk["cbias"], x1_pm=True, rows=S)
-        if self.tc_mode and "w2img" in pk:
+            p1 = K.cn_linear(xyz, pk["pa"], x1_pm=True, y_pm=tc)
+            cc = K.cn_linear(xyz, pk["ca"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
+        if tc:
             feat = K.sa_edge_mlp_tc(p1, cc, idx, pk["w2img"], pk["b2"], pk["w3img"], pk["b3"])
         else:
             feat = K.sa_edge_mlp(p1, cc, idx, pk["w2"], pk["b2"], pk["w3"], pk["b3"])

@@ -126,9 +126,9 @@ def tf32_image(w):
 
 
 def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
-    C = p1.shape[1]
+    C = p1.shape[2]                                                            # p1 (B, N, C), cc (B, S, C) point-major
     unimg = lambda im: im.permute(1, 0, 2).reshape(C, C).t().contiguous()      # -> k-major (C_in, C_out)
-    return sa_edge_mlp(p1, cc, idx, unimg(w2img), b2, unimg(w3img), b3)
+    return sa_edge_mlp(p1.transpose(1, 2).contiguous(), cc.transpose(1, 2).contiguous(), idx, unimg(w2img), b2, unimg(w3img), b3)
 
 
 def edge_gather_max(p, q, idx, act, out=None):

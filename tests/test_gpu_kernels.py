@@ -141,8 +141,8 @@ def test_sa_edge_mlp_tensor_core(C, N, S, k):
     idx = torch.randint(0, N, (B, S, k), generator=g, dtype=torch.int32)
     w2, w3 = rnd(C, C, seed=3) / C ** 0.5, rnd(C, C, seed=4) / C ** 0.5      # (C_out, C_in)
     b2, b3 = rnd(C, seed=5) * 0.1, rnd(C, seed=6) * 0.1
-    got = K.sa_edge_mlp_tc(p1.to(DEV), cc.to(DEV), idx.to(DEV), K.tf32_image(w2).to(DEV), b2.to(DEV), K.tf32_image(w3).to(DEV),
-                           b3.to(DEV))
+    got = K.sa_edge_mlp_tc(p1.transpose(1, 2).contiguous().to(DEV), cc.transpose(1, 2).contiguous().to(DEV), idx.to(DEV),
+                           K.tf32_image(w2).to(DEV), b2.to(DEV), K.tf32_image(w3).to(DEV), b3.to(DEV))
     close(got, F.sa_edge_mlp(p1, cc, idx, w2.t().contiguous(), b2, w3.t().contiguous(), b3), 5e-3)
 
 
