@@ -168,6 +168,19 @@ int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void*
 /* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor */
 int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream);
 
+/* Second generation of the phase-1a / phase-2 kernels (csrc/pair_tc2.cu): same operand images and GEMM chain, epilogues
+ * with less than half the instructions.  The host folds LayerNorm1's affine into the following Linear, centres the
+ * merge / mlp[2] weights over their output channels (LayerNorm inputs become zero-mean), pre-scales q_proj by
+ * 1/bf16(ln 2), adds LayerNorm2's beta to the residual image (stage 1: pcreid_pack_image_bias) or after the pooling
+ * (stage 2: pcreid_pool_finish2).  Weight blob layouts: see pair_tc2.cu (Q1A_*, Q2_*) and models/fused_pairs.py. */
+int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst,
+                           void* stream);
+int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /* (64) or NULL */, float* out, void* stream);
+int pcreid_pair_p1a2(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
+                     const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream);
+int pcreid_pair_p2y(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
+                    float* pool_part, int n_ctas, void* stream);
+
 /* tensor-core (tcgen05 kind::tf32, fp32 accumulate) version of pcreid_sa_edge_mlp: same arguments except that the
  * two weight matrices are fp32 operand images [k/4][n][4] of the (C_out, C_in) BatchNorm-folded weights and that P1 / Cc
  * are POINT-major ((b,n,C) / (b,S,C): a gathered neighbour is one contiguous vector); C in {32, 64, 128}.  Fast mode of the encoder (error ~1e-3 relative: tf32 operands). */

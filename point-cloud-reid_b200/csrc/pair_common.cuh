@@ -1,0 +1,176 @@
+// Shared pieces of the fused tensor-core matcher kernels (pair_tc.cu, pair_tc2.cu): operand-image geometry, kernel
+// argument blocks, descriptor helpers, the 4-warp group abstraction.  Everything lives in an anonymous namespace: each
+// translation unit gets its own copy.
+#pragma once
+#include "../../include/pcreid.h"
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace {
+
+
+constexpr int GT = 256;                 // threads per group: 8 warps = 4 TMEM lane quadrants x 2 column halves
+constexpr int IMG = 16384;              // bytes of a 128 x 64 bf16 operand image  [k/8][row][8]
+constexpr int NB7 = 144;                // columns of the attention operand: 64 (head 0) | 64 (head 1) | 16 (2 dots + pad)
+constexpr int B7_BYTES = (NB7 / 8) * 64 * 16;   // [n/8][k][8] bf16 = 18432
+constexpr int ONES_BYTES = 2 * 2048;    // two extra 8-column chunks appended to V: column 64 == 1 (Ksum), rest 0
+constexpr int KV_COL = 144;             // TMEM columns [144, 224) of a group: KV / Ksum accumulator
+constexpr float LN_EPS = 1e-5f, ATT_EPS = 1e-6f;
+
+// weights blob of phase 1 (bytes)
+constexpr int P1_W0B = 0, P1_W2 = 16384, P1_WKV = 32768, P1_WM = 49152, P1_LN = 57344, P1_WBYTES = 57344 + 1024;
+// weights blob of phase 2
+constexpr int P2_WQ = 0, P2_W0 = 8192, P2_W2 = 40960, P2_LN = 57344, P2_WBYTES = 57344 + 1024;
+// per-group shared memory of phase 1: QXa (16K) | HdKV (32K) + ones (4K) | MK1 (18K) | LN exchange (2K)
+constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ONES + ONES_BYTES, P1_XCH = P1_MK1 + B7_BYTES,
+              P1_GBYTES = P1_XCH + 2048;
+// per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 x2 (36K) | exchange
+constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_XCH = P2_B7 + 2 * B7_BYTES, P2_GBYTES = P2_XCH + 2048;
+
+// optional cycle trace (debug): when set, thread 0 of group 0 in CTA 0 records clock64() at stage boundaries
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace_mark(int& n, int tag) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && n < 2040 && g_trace != nullptr) {
+    g_trace[n++] = clock64();
+    g_trace[n++] = tag;
+  }
+}
+
+struct P1Args {
+  int n_units, NT, role;
+  const int *u_search, *u_templ, *u_slot;
+  const uint8_t *QF1, *U, *H, *PV;      // search-side per-object images: [obj][NT][IMG] (U: [obj][NT][2*IMG])
+  const uint8_t* MK1;                    // template-side per-object stage-1 attention operand [obj][B7_BYTES]
+  const uint8_t* W;                      // P1 weights blob
+  uint8_t* A_out;                        // [slot][2][NT][IMG]   stage-1 outputs (bf16 operand images)
+  uint8_t* B7_out;                       // [slot][2][B7_BYTES]  stage-2 attention operands
+};
+struct P2Args {
+  int n_units, NT, role;
+  const int* u_slot;
+  const uint8_t* A_in;                   // == A_out of phase 1
+  const uint8_t* B7_in;                  // == B7_out of phase 1
+  const uint8_t* W;                      // P2 weights blob
+  float* pool_part;                      // [slot][2][128]: max (64) | sum (64) over the search object's points
+};
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// 16-byte read-only global load that the compiler may NOT sink to its first use (plain __ldg of data consumed a whole
+// stage later was being moved next to the consumer, which exposed the full L2 latency there)
+__device__ __forceinline__ uint4 ldg_early(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, int bytes, int t, int nthr) {
+  for (int i = t * 16; i < bytes; i += nthr * 16) cp_async16(dst + i, src + i);
+}
+
+// Descriptors are built once per operand buffer; stepping along K only adds (bytes >> 4) to the 14-bit start-address
+// field (shared memory is < 256 KB, so the field never carries).  Building them per MMA cost ~130 cycles of dependent
+// 64-bit arithmetic on the single issuing thread (measured with the cycle trace) -- a quarter of the tile time.
+struct Opnd {
+  uint64_t desc;     // descriptor at k = 0
+  uint32_t kstep;    // (bytes per K=16 step) >> 4
+};
+__device__ __forceinline__ Opnd opnd(uint32_t addr, uint32_t lbo, uint32_t sbo, uint32_t kstep_bytes) {
+  Opnd o;
+  o.desc = tc::smem_desc(addr, lbo, sbo, tc::LAYOUT_NONE);
+  o.kstep = kstep_bytes >> 4;
+  return o;
+}
+// operand geometry (bytes): K-major activation image (128 rows), K-major weight image (N rows), MN-major attention operand
+#define A_IMG(addr) opnd((addr), 2048u, 128u, 4096u)
+#define W_IMG(addr, N) opnd((addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16))
+#define B7_IMG(addr) opnd((addr), 128u, 1024u, 256u)
+
+// one thread: D[tmem_d] (+)= A x B^T over KSTEPS K=16 steps
+template <int KSTEPS>
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const Opnd& A, const Opnd& B, uint32_t idesc, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < KSTEPS; ++ks)
+    tc::umma_f16(tmem_d, A.desc + (uint64_t)(ks * A.kstep), B.desc + (uint64_t)(ks * B.kstep), idesc, (accumulate || ks > 0) ? 1u : 0u);
+}
+
+// 8 x 16 B of a side image row (chunks c0 .. c0+7) -> registers (issued early so the L2 latency hides behind a stage)
+template <int NCH>
+__device__ __forceinline__ void load_side(uint4 (&sd)[NCH], const uint8_t* __restrict__ img, int chunk0, int row) {
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) sd[c] = __ldg(reinterpret_cast<const uint4*>(img + (chunk0 + c) * 2048 + row * 16));
+}
+
+// chunks [c_lo, c_hi) of row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]
+// (MN-major image [n/8][k=d][8]); M32 holds M[d][8*c_lo .. 8*c_hi)
+__device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, float ksum, bool tail, int d, uint8_t* dst) {
+  const int hd = d >> 5;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(M32[c * 8 + 2 * j], M32[c * 8 + 2 * j + 1]);
+    const uint4 val = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(dst + (c_lo + c) * 1024 + d * 16) = hd == 0 ? val : zero;
+    *reinterpret_cast<uint4*>(dst + (8 + c_lo + c) * 1024 + d * 16) = hd == 1 ? val : zero;
+  }
+  if (tail) {
+    *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) =
+        make_uint4(hd == 0 ? tc::pack_bf16(ksum, 0.f) : tc::pack_bf16(0.f, ksum), 0, 0, 0);
+    *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
+  }
+}
+
+constexpr int GX = 128, NGX = 3;     // three-tile variants: 3 groups of 4 warps per CTA, one thread per tile row
+struct GroupX {
+  int t, gid;
+  bool issuer;
+  uint32_t tmem, tlane;
+  uint64_t* bar;
+  uint32_t par;
+  __device__ __forceinline__ void sync() { tc::bar_sync(1 + gid, GX); }
+  __device__ __forceinline__ void publish() { tc::fence_async_smem(); tc::tc_fence_before(); sync(); tc::tc_fence_after(); }
+  __device__ __forceinline__ void wait() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); }
+};
+
+// 32 accumulator columns -> fp32 registers, with running sum / sum of squares
+__device__ __forceinline__ void ld32_stats(uint32_t taddr, float (&o)[32], float& s, float& ss) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    uint32_t r[16];
+    tc::tmem_ld16(taddr + 16 * half, r);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float v = __uint_as_float(r[j]);
+      o[16 * half + j] = v;
+      s += v;
+      ss = fmaf(v, v, ss);
+    }
+  }
+}
+
+// row d of the stage operand (used by the per-object packer): all 64 columns at once
+__device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
+  float lo[32], hi[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { lo[j] = M[j]; hi[j] = M[32 + j]; }
+  write_b7_part(lo, 0, ksum, true, d, dst);
+  write_b7_part(hi, 4, ksum, false, d, dst);
+}
+
+__device__ __forceinline__ void groupx_setup(GroupX& g, uint64_t* bars, uint32_t tmem_base) {
+  const int warp_u = (int)tc::uniform(threadIdx.x >> 5);
+  g.gid = warp_u / 4;
+  g.t = threadIdx.x % GX;
+  g.issuer = (warp_u % 4) == 0;
+  g.tmem = tc::uniform(tmem_base) + g.gid * 160;
+  g.tlane = g.tmem + ((uint32_t)((warp_u % 4) * 32) << 16);
+  g.bar = bars + g.gid;
+  g.par = 0;
+}
+
+}  // namespace

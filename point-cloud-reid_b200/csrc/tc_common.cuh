@@ -128,6 +128,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
@@ -145,6 +155,17 @@ __device__ __forceinline__ uint32_t bf2_ex2(uint32_t a) { uint32_t r; asm("ex2.a
 __device__ __forceinline__ uint32_t bf2_elu1(uint32_t x) {
   const uint32_t LOG2E = 0x3fb93fb9u;   // bf16(1.4427) in both halves
   return bf2_add(bf2_max(x, 0u), bf2_ex2(bf2_mul(bf2_min(x, 0u), LOG2E)));
+}
+
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t bf2_fma_relu(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.relu.bf16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+// fp32 pair -> relu -> packed bf16x2 in ONE instruction (F2FP.RELU)
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) { uint32_t r; asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r; }
+// elu(x)+1 on a packed pair whose producer weights were pre-scaled by 1/bf16(ln 2): x' = x / LN2B, so
+//   max(x',0) * LN2B + 2^min(x',0) = max(x,0) + exp(min(x,0) * ln2/LN2B)       (4 instructions, one MUFU, per two elements)
+__device__ __forceinline__ uint32_t bf2_elu1s(uint32_t x) {
+  const uint32_t LN2B = 0x3f313f31u;    // bf16(0.69140625) in both halves
+  return bf2_fma(bf2_max(x, 0u), LN2B, bf2_ex2(bf2_min(x, 0u)));
 }
 
 // warp-uniform helpers: values produced through these are known to be warp-uniform by the compiler, so descriptor

@@ -15,9 +15,18 @@ import torch
 
 from .. import _lib
 from .. import kernels as K
+from ._packing import kmajor
 
 IMG = 16384
 B7_BYTES = 18432
+LN2B = 0.69140625          # bf16(ln 2): the packed elu epilogue of pair_tc2.cu multiplies by this constant
+
+
+def _center_out(w):
+    """(out, in) weight minus its mean over the output axis: the Linear's output has zero mean over channels, so the
+    LayerNorm that follows needs no mean (LayerNorm is invariant to a per-row shift of its input)."""
+    w = w.detach().float()
+    return w - w.mean(0, keepdim=True)
 
 
 def _p(t):
@@ -60,6 +69,7 @@ class FusedXcorr:
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
         self.p2_three_tiles = os.environ.get("PCREID_P2_VARIANT", "3") == "3"   # 3 groups x 4 warps (default) or 2 x 8
         self.p1_split = os.environ.get("PCREID_P1_VARIANT", "split") == "split"   # p1a + p1b (3 tiles in flight) or monolithic
+        self.gen2 = os.environ.get("PCREID_PAIR_GEN", "2") == "2"       # pair_tc2.cu kernels (default) or the first generation
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
@@ -81,6 +91,27 @@ class FusedXcorr:
                     _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)), _w_image(X2.merge.weight)]).contiguous()
                 assert self._w1.numel() == 58368 and self._w2.numel() == 58368
                 assert self._w1a.numel() == 33792 and self._w1b.numel() == 24576
+                # ---- second generation (pair_tc2.cu): LN1 affine folded forward, centred merge / mlp[2], scaled q_proj
+                f = lambda t: t.detach().float()
+                W0_1, W0_2 = f(X1.mlp[0].weight), f(X2.mlp[0].weight)
+                self._w1a2 = torch.cat([
+                    _w_image(W0_1[:, d:] * f(X1.norm1.weight)[None, :]), _w_image(_center_out(X1.mlp[2].weight)),
+                    _f32_bytes(X1.norm2.weight)]).contiguous()
+                self._c1 = (W0_1[:, d:] @ f(X1.norm1.bias)).contiguous()           # W0b.beta1 -> bias of the per-object term U
+                self._b2_1 = f(X1.norm2.bias).contiguous()                         # added to the residual image H
+                self._merge1c = kmajor(_center_out(X1.merge.weight))
+                self._w1b2 = torch.cat([
+                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)),
+                    _w_image(_center_out(X2.merge.weight))]).contiguous()
+                W0ext = torch.zeros((2 * d, 2 * d + 16), device=W0_2.device)
+                W0ext[:, :d] = W0_2[:, :d]
+                W0ext[:, d:2 * d] = W0_2[:, d:] * f(X2.norm1.weight)[None, :]
+                W0ext[:, 2 * d] = W0_2[:, d:] @ f(X2.norm1.bias)
+                self._w2y = torch.cat([
+                    _w_image(f(X2.q_proj.weight) / LN2B), _w_image(W0ext), _w_image(_center_out(X2.mlp[2].weight)),
+                    _f32_bytes(X2.norm2.weight)]).contiguous()
+                self._b2_2 = f(X2.norm2.bias).contiguous()                         # added after the pooling
+                assert self._w1a2.numel() == 33024 and self._w2y.numel() == 61696 and self._w1b2.numel() == 24576
             self._key = key
         return self._w1, self._w2
 
@@ -109,15 +140,22 @@ class FusedXcorr:
         """h (B, 64, N) fp32 channel-major, xyz (B, N, 3) -> ObjectPack."""
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
         pk1, pk2 = X1.packed(), X2.packed()
+        self._weights()
         B, C, N = h.shape
         o = ObjectPack()
         o.n, o.npts = B, N
         o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
-        o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"]))
-        o.H = self._pack_image(h)
+        if self.gen2:
+            o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
+            o.H = torch.empty((B, N // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
+            _lib.check(_lib.lib().pcreid_pack_image_bias(B, C, N, _p(h), h.stride(0), h.stride(1), _p(self._b2_1), _p(o.H),
+                                                         _stream()), "pcreid_pack_image_bias")   # h + beta2
+        else:
+            o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"]))
+            o.H = self._pack_image(h)
         o.PV = self._pack_image(K.cn_linear(X2.position_code(xyz), pk2["v"]))
         wkv, ksum = X1.template_summary(h, X1.position_code(xyz))          # (B, 64, 64) [d][v] block diagonal, (B, 64)
-        M = K.cn_linear(wkv, pk1["merge"], x1_pm=True, y_pm=True)           # (B, d, out) = blockdiag(KV) Wm^T
+        M = K.cn_linear(wkv, self._merge1c if self.gen2 else pk1["merge"], x1_pm=True, y_pm=True)   # (B, d, out) = blockdiag(KV) Wm^T
         M.mul_(float(N))                                                    # undo the reference's values / S (attention.py:47)
         o.MK1 = torch.empty((B, B7_BYTES), device=h.device, dtype=torch.uint8)
         _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), _p(o.MK1), _stream()), "pcreid_pack_b7")
@@ -137,6 +175,17 @@ class FusedXcorr:
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             order = torch.argsort(tmpl, stable=True)                        # runs of units share the template operand
             us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+            if self.gen2:
+                e0 = self._tick()
+                _lib.check(L.pcreid_pair_p1a2(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(pm.MK1),
+                                              _p(self._w1a2), _p(A), self.n_ctas, _stream()), "pcreid_pair_p1a2")
+                self._tock("pair_p1a2_kernel", e0, P)
+                e0 = self._tick()
+                _lib.check(L.pcreid_pair_p1ab(1, P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H),
+                                              _p(ps.PV), _p(pm.MK1), _p(self._w1b2), _p(A), _p(B7), self.n_ctas, _stream()),
+                           "pcreid_pair_p1ab")
+                self._tock("pair_p1b_kernel", e0, P)
+                continue
             if self.p1_split:
                 for which, blob, name in ((0, self._w1a, "pair_p1a_kernel"), (1, self._w1b, "pair_p1b_kernel")):
                     e0 = self._tick()
@@ -150,13 +199,23 @@ class FusedXcorr:
                                         _p(pm.MK1), _p(w1), _p(A), _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1")
             self._tock("pair_p1_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
+        pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
+        if self.gen2:
+            for role in (0, 1):
+                e0 = self._tick()
+                _lib.check(L.pcreid_pair_p2y(P, NT, role, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part), self.n_ctas,
+                                             _stream()), "pcreid_pair_p2y")
+                self._tock("pair_p2y_kernel", e0, P)
+            _lib.check(L.pcreid_pool_finish2(P, N, _p(part), _p(self._b2_2), _p(pooled), _stream()), "pcreid_pool_finish2")
+            if debug is not None:
+                debug.update(A=A, B7=B7, part=part, pooled=pooled)
+            return self.model._head_cn(pooled)
         for role in (0, 1):
             e0 = self._tick()
             _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part),
                                         -self.n_ctas if self.p2_three_tiles else self.n_ctas, _stream()),
                        "pcreid_pair_p2")
             self._tock("pair_p2_kernel", e0, P)
-        pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
         _lib.check(L.pcreid_pool_finish(P, N, _p(part), _p(pooled), _stream()), "pcreid_pool_finish")
         if debug is not None:
             debug.update(A=A, B7=B7, part=part, pooled=pooled)

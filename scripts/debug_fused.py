@@ -36,7 +36,7 @@ pt, pd = f.prepare(ht, xt), f.prepare(hd, xd)
 pk1 = X1.packed()
 q1 = K.cn_linear(ht, pk1["q"])
 rep("pack QF1", FP.decode_image(pt.QF1).permute(0, 2, 1, 3).reshape(T, 64, N), torch.nn.functional.elu(q1) + 1)
-rep("pack H", FP.decode_image(pt.H).permute(0, 2, 1, 3).reshape(T, 64, N), ht)
+rep("pack H (+beta2 in gen2)", FP.decode_image(pt.H).permute(0, 2, 1, 3).reshape(T, 64, N), ht + (f._b2_1[None, :, None] if f.gen2 else 0))
 dbg = {}
 logits = f.match(pt, pd, ti, dj, debug=dbg)
 torch.cuda.synchronize()
@@ -57,6 +57,8 @@ wkv_a, ks_a = X2.template_summary(a, pos2_t, pos_map=ti32)
 pk2 = X2.packed()
 for role, (wkv, ks) in enumerate(((wkv_a, ks_a), (wkv_b, ks_b))):
     M = K.cn_linear(wkv, pk2["merge"], x1_pm=True, y_pm=True) * N       # (P, d, out)
+    if f.gen2:
+        M = M - M.mean(2, keepdim=True)                                  # centred merge weight
     B7 = FP.decode_b7(dbg["B7"][:, role])                               # (P, 64, 144)
     exp = torch.zeros_like(B7)
     exp[:, :32, :64] = M[:, :32]
@@ -67,10 +69,11 @@ for role, (wkv, ks) in enumerate(((wkv_a, ks_a), (wkv_b, ks_b))):
 o1 = X2.attend(a, X2.search_query(a), wkv_b, ks_b, N)
 o2 = X2.attend(b, X2.search_query(b), wkv_a, ks_a, N)
 part = dbg["part"]
-rep("pool max role0", part[:, 0, :64], o1.max(2)[0])
-rep("pool sum role0", part[:, 0, 64:], o1.sum(2))
-rep("pool max role1", part[:, 1, :64], o2.max(2)[0])
-rep("pool sum role1", part[:, 1, 64:], o2.sum(2))
+bb = f._b2_2[None, :] if f.gen2 else 0          # gen2 adds LayerNorm2's beta after the pooling
+rep("pool max role0", part[:, 0, :64] + bb, o1.max(2)[0])
+rep("pool sum role0", part[:, 0, 64:] + N * bb, o1.sum(2))
+rep("pool max role1", part[:, 1, :64] + bb, o2.max(2)[0])
+rep("pool sum role1", part[:, 1, 64:] + N * bb, o2.sum(2))
 pooled_ref = K.cn_pool(o1, o2, mode=0, transposed=True)
 rep("pooled", dbg["pooled"], pooled_ref)
 ref_logits = m._head_cn(pooled_ref)

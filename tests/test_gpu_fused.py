@@ -72,17 +72,19 @@ def test_full_fast_mode_end_to_end(N):
     assert ok, f"top-1 changed on a decisive row (agreement {agree}, {n} decisive rows)"
 
 
-@pytest.mark.parametrize("p1_split,p2_three", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("p1_split,p2_three", [(False, False), (True, False), (False, True), (True, True)])
 def test_kernel_variants_agree(p1_split, p2_three):
-    """the monolithic / split phase-1 kernels and the 2x8-warp / 3x4-warp phase-2 kernels compute the same logits."""
+    """the first-generation kernels (monolithic / split phase 1, 2x8-warp / 3x4-warp phase 2) and the default
+    second-generation kernels (pair_tc2.cu) compute the same logits."""
     from pcreid_b200.models import fused_pairs
     m, orc = helpers.build_pair("pt", (256, 128, 64), device=DEV)
     t, d = O.synth_objects(7, 256, 20), O.synth_objects(9, 256, 21)
     xt, ht = m.encode(t.to(DEV))
     xd, hd = m.encode(d.to(DEV))
     m.match_mode = 'fast'
-    Lref = m.match_all_pairs(ht, xt, hd, xd).cpu()                 # default variants (split phase 1, 3-tile phase 2)
-    m._fused.p1_split, m._fused.p2_three_tiles = p1_split, p2_three
+    Lref = m.match_all_pairs(ht, xt, hd, xd).cpu()                 # default: second-generation kernels
+    assert m._fused.gen2
+    m._fused.gen2, m._fused.p1_split, m._fused.p2_three_tiles = False, p1_split, p2_three
     Lv = m.match_all_pairs(ht, xt, hd, xd).cpu()
     Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu())
     assert (Lv - Lo).abs().max() < TOL_FAST
