@@ -173,6 +173,7 @@ int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* str
  * merge / mlp[2] weights over their output channels (LayerNorm inputs become zero-mean), pre-scales q_proj by
  * 1/bf16(ln 2), adds LayerNorm2's beta to the residual image (stage 1: pcreid_pack_image_bias) or after the pooling
  * (stage 2: pcreid_pool_finish2).  Weight blob layouts: see pair_tc2.cu (Q1A_*, Q2_*) and models/fused_pairs.py. */
+int pcreid_pair_tc2_set_trace(void* dev_buffer);   /* debug: int64[2048] cycle trace of one group of pair_p2y, NULL = off */
 int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst,
                            void* stream);
 int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /* (64) or NULL */, float* out, void* stream);

@@ -227,7 +227,10 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
 // ---------------------------------------------------------------------------------------------------------------
 // phase 2: q projection -> attention against B7 -> LN1 -> [a | X' | 1] W0'^T, ReLU (TMEM-resident) -> W2 -> LN2 + a -> pooling
 // ---------------------------------------------------------------------------------------------------------------
+#define TR(tag) do { if constexpr (TRACE) trace_mark(ntr, tag); } while (0)
+template <bool TRACE>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
+  int ntr = 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
   __shared__ uint32_t tmem_base_s;
@@ -281,10 +284,13 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
     psm[0] = psm[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = 0; tile < a.NT; ++tile) {
       const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
+      TR(0);
       cp_async_wait<0>();                                                 // `a` image (and B7 at a unit start) prefetched earlier
       g.publish();
+      TR(1);
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
+      TR(2);
       {   // Qf = elu(q)+1 -> second half of R1
         uint32_t r0[32], r1[32];
         tc::tmem_ld32(g.tlane, r0);
@@ -302,15 +308,20 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
           *reinterpret_cast<uint4*>(arow + IMG + (4 + c) * 2048) = make_uint4(v[0], v[1], v[2], v[3]);
         }
       }
+      TR(3);
       g.publish();
+      TR(4);
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
+      TR(5);
       if (tile + 1 == a.NT && u + 1 < u1) {   // last attention GEMM of the unit is done: next unit's B7 streams in
         copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
         cp_async_commit();
       }
       epi_attn_norm(g.tlane, arow + IMG);                                 // X' next to a: [a | X' | 1] is the K = 144 operand
+      TR(6);
       g.publish();
+      TR(7);
       if (g.issuer) {
         if (tc::elect_one()) {
           issue_gemm<8>(g.tmem, oR1, oW0, id128, false);
@@ -322,6 +333,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
       uint4 sdA[8];
       load_side<8>(sdA, a_img, 0, row);                                   // residual a (this tile), consumed after G9
       g.wait();
+      TR(8);
       {   // G8 has consumed [a | X']: the next tile's `a` image streams into R1 behind the rest of this tile
         int nu = u, nt = tile + 1;
         if (nt == a.NT) { nu = u + 1; nt = 0; }
@@ -344,9 +356,11 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         tc::tmem_st32(g.tlane + 32 * b, w);
       }
       tc::tmem_st_wait();
+      TR(9);
       tc::tc_fence_before();
       g.sync();
       tc::tc_fence_after();
+      TR(10);
       if (g.issuer) {
         if (tc::elect_one()) {
 #pragma unroll
@@ -357,13 +371,15 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         __syncwarp();
       }
       g.wait();
+      TR(11);
       {   // o - beta2 = a + gamma2 * acc * rstd ; pooled over the points, 32 channels per pass
         uint32_t x0[32], x1[32];
         const float rstd = rsqrtf(ld64_sumsq(g.tlane + 64, x0, x1) * (1.f / 64.f) + LN_EPS);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t (&x)[32] = hh == 0 ? x0 : x1;
-          if (hh == 1) g.sync();                                          // pass-0 reads are done before pass 1 overwrites
+          if (hh == 1) __syncwarp();                                      // pass-0 reads are done before pass 1 overwrites (a warp only
+                                                                          // ever touches the 32 transpose-buffer rows it owns)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             const uint4 rs = sdA[4 * hh + c];
@@ -380,7 +396,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
             Tb[row * 8 + ((2 * c) ^ (row & 7))] = oa;
             Tb[row * 8 + ((2 * c + 1) ^ (row & 7))] = ob;
           }
-          g.sync();
+          __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v = Tb[(rsub * 8 + i) * 8 + (jg ^ i)];
@@ -390,6 +406,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
           }
         }
       }
+      TR(12);
       tc::tc_fence_before();      // the next tile's publish() orders these TMEM / transpose-buffer reads before its writes
     }
     // unit done: combine the row blocks (lanes with equal jg inside a warp, then the 4 warps through shared memory)
@@ -424,6 +441,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
+#undef TR
+
 // pool_part (P, 2, 128) [max | sum of (o - beta2)] -> pooled^T (128, P): max over both directions | mean over the 2*npts points
 __global__ void __launch_bounds__(256) pool_finish2_kernel(int P, int npts, const float* __restrict__ part, const float* __restrict__ bias,
                                                            float* __restrict__ out) {
@@ -455,7 +474,15 @@ __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int 
 
 }  // namespace
 
+static bool g_trace_host = false;
+
 extern "C" {
+
+int pcreid_pair_tc2_set_trace(void* dev_buffer) {   /* debug: int64[2048] cycle trace of group 0 / CTA 0 of pair_p2y, NULL = off */
+  long long* p = (long long*)dev_buffer;
+  g_trace_host = p != nullptr;
+  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? PCREID_OK : PCREID_ERR_LAUNCH;
+}
 
 int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst, void* stream) {
   if (B <= 0) return PCREID_OK;
@@ -494,8 +521,13 @@ int pcreid_pair_p2y(int n_units, int NT, int role, const int* u_slot, const void
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
   const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;
-  cudaFuncSetAttribute(pair_p2y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p2y_kernel<<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
+  if (g_trace_host) {
+    cudaFuncSetAttribute(pair_p2y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pair_p2y_kernel<true><<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
+    return pcreid_launch_status();
+  }
+  cudaFuncSetAttribute(pair_p2y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p2y_kernel<false><<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
   return pcreid_launch_status();
 }
 
