@@ -239,8 +239,8 @@ def main():
             match_tflops = FLOP_PER_PAIR * T_loc * D / (tot_ms * 1e-3) / 1e12
             roof_kernel = " + ".join(sorted(kern)) + " (fused tcgen05 xcorr_eff)"
             # DRAM traffic per unit (pair, direction) from the ncu --set full capture in profiles/r01_ncu_pair_kernels.md
-            # (dram__bytes_read.sum + dram__bytes_write.sum per launch / units per launch): p1 59.3 KB, p2 52.1 KB
-            roof_traffic = 2 * T_loc * D * (59.3e3 + 52.1e3)
+            # (dram__bytes_read.sum + dram__bytes_write.sum per launch / units per launch): p1a2 31.4 KB, p1b 49.8 KB, p2y 52.0 KB
+            roof_traffic = 2 * T_loc * D * (31.4e3 + 49.8e3 + 52.0e3)
             roof_extra = {"kernels": {n: {"launches": k["launches"], "avg_ms_per_launch": k["ms"] / k["launches"],
                                           "share_of_match": k["ms"] / match_ms} for n, k in kern.items()}}
         line = {
@@ -249,7 +249,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": f"configs[1]: Point Transformer encode of {T_loc} tracks/GPU + {D} detections x {NPTS} pts "
                                    f"(backbone_list {list(BLIST)}), {T_loc}x{D} all-pairs xcorr_eff match per GPU",
-                       "mode": ("fast: fused bf16 tcgen05 matcher, fp32 accumulate/norms, tf32 tcgen05 SA shared MLPs, |dlogit| <= 3e-2"
+                       "mode": ("fast: fused bf16 tcgen05 matcher (pair_tc2.cu), fp32 accumulate/norms, tf32 tcgen05 SA shared MLPs, |dlogit| <= 3e-2"
                                 if args.mode == "fast" else "parity: fp32 FFMA kernels, logits within 1e-4 of the reference"),
                        "l2": "no flush needed: each step streams >1 GB of activations (>> 126 MB L2)",
                        "sharding": f"track rows over {world} rank(s), one all-gather of detection embeddings"},
@@ -262,7 +262,7 @@ def main():
                     "h2d_bytes_per_step": (tracks_h.numel() + dets_h.numel()) * 4, "d2h_bytes_per_step": out_h.numel() * 4},
             "roofline": {"bound": "tensor", "achieved": match_tflops, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": (match_tflops / peak_tf) if match_tflops else None, "traffic": roof_traffic if kern else None,
-                         "per": "all fused launches of one step (both phases, both directions), rank 0",
+                         "per": "all fused launches of one step (three kernels x both directions x pair chunks), rank 0",
                          "kernel": roof_kernel, "peak_source": pk_src + " bf16 sustained (MEASURED_PEAKS.json)", **roof_extra},
         }
         if not args.no_cpu_baseline and world == 1:
