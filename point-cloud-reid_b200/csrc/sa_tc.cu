@@ -19,7 +19,7 @@ namespace {
 constexpr int NT_ = 256;
 
 template <int C>
-__global__ void __launch_bounds__(NT_, (C == 128 ? 1 : 2)) sa_edge_mlp_tc_kernel(int N, int S, int k, int cpt, int tiles_per_obj, int total_tiles,
+__global__ void __launch_bounds__(NT_, (C == 128 ? 1 : (C == 64 ? 3 : 4))) sa_edge_mlp_tc_kernel(int N, int S, int k, int cpt, int tiles_per_obj, int total_tiles,
                                                                const float* __restrict__ P1, const float* __restrict__ Cc,
                                                                const int* __restrict__ idx, const float* __restrict__ W2img,
                                                                const float* __restrict__ b2, const float* __restrict__ W3img,
@@ -57,16 +57,26 @@ __global__ void __launch_bounds__(NT_, (C == 128 ? 1 : 2)) sa_edge_mlp_tc_kernel
   uint32_t par = 0;
   constexpr int CH = C / 2;                    // channels (columns) per thread
 
+  // neighbour index of this thread's row, fetched one tile ahead so that the dependent row gather of the next tile does
+  // not start with an exposed L2 round trip
+  auto fetch_idx = [&](int tile_) {
+    const int b_ = tile_ / tiles_per_obj, s0_ = (tile_ % tiles_per_obj) * cpt;
+    const int nedge_ = min(cpt, S - s0_) * k;
+    return row < nedge_ ? __ldg(idx + ((size_t)b_ * S + s0_ + row / k) * k + (row % k)) : -1;
+  };
+  int src_next = blockIdx.x < total_tiles ? fetch_idx(blockIdx.x) : -1;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int b = tile / tiles_per_obj, s0 = (tile % tiles_per_obj) * cpt;
     const int ncen = min(cpt, S - s0), nedge = ncen * k;
+    const int src_cur = src_next;
+    if (tile + (int)gridDim.x < total_tiles) src_next = fetch_idx(tile + gridDim.x);
     // P1 / Cc are point-major here ((B, N, C) / (B, S, C)): a gathered neighbour is one contiguous C-vector
     const float* Pb = P1 + (size_t)b * N * C;
     const float* Cb = Cc + (size_t)b * S * C;
     // ---- gather + relu(P1 + Cc) -> operand image (128-bit loads; chunk of 4 channels == one 16-byte image chunk)
     {
       int src = -1, cen = 0;
-      if (row < nedge) { cen = s0 + row / k; src = __ldg(idx + ((size_t)b * S + cen) * k + (row % k)); }
+      if (row < nedge) { cen = s0 + row / k; src = src_cur; }
       const float4* prow = reinterpret_cast<const float4*>(Pb + (size_t)max(src, 0) * C) + h * (CH / 4);
       const float4* crow = reinterpret_cast<const float4*>(Cb + (size_t)cen * C) + h * (CH / 4);
 #pragma unroll
@@ -146,7 +156,7 @@ int launch(int B, int N, int S, int k, const float* P1, const float* Cc, const i
   if (total > 0x7fffffffLL) return PCREID_ERR_UNSUPPORTED;
   const int smem = 2 * C * C * 4 + C * 128 * 4;
   cudaFuncSetAttribute(sa_edge_mlp_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  int ctas_per_sm = C == 128 ? 1 : 2;                      // shared memory (192 / 64 / 24 KB) and registers bound residency
+  int ctas_per_sm = C == 128 ? 1 : (C == 64 ? 3 : 4);      // shared memory (192 / 64 / 24 KB) and registers bound residency
   int grid = (n_ctas > 0 ? n_ctas : 148) * ctas_per_sm;
   if (grid > total) grid = (int)total;
   sa_edge_mlp_tc_kernel<C><<<grid, NT_, smem, st>>>(N, S, k, cpt, tiles_per_obj, (int)total, P1, Cc, idx, W2img, b2, W3img, b3, out);
