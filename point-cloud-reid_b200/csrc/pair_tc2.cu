@@ -132,18 +132,23 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   int cur_templ = -1;
   bool prefetched = false;
   int so_next = u0 < u1 ? a.u_search[u0] : 0, te_next = u0 < u1 ? a.u_templ[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  // attention GEMM of a tile (query image ti against the template operand te).  Called for tile n+1 as soon as tile n's
+  // last accumulator has been read into registers, so that it runs behind tile n's LayerNorm2 epilogue.
+  auto start_tile = [&](size_t ti_, int te_) {
+    if (!prefetched) copy_to_smem(QXa, a.QF1 + ti_ * IMG, IMG, g.t, GX);   // first tile of this group only
+    prefetched = false;
+    if (te_ != cur_templ) { copy_to_smem(MK1, a.MK1 + (size_t)te_ * B7_BYTES, B7_BYTES, g.t, GX); cur_templ = te_; }
+    cp_async_commit();
+    cp_async_wait<0>();
+    g.publish();
+    if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oMK1, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+  };
   for (int u = u0; u < u1; ++u) {
     const int so = so_next, te = te_next, slot = slot_next;
     if (u + 1 < u1) { so_next = a.u_search[u + 1]; te_next = a.u_templ[u + 1]; slot_next = a.u_slot[u + 1]; }
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
-      if (!prefetched) copy_to_smem(QXa, a.QF1 + ti * IMG, IMG, g.t, GX);  // first tile of this group only
-      prefetched = false;
-      if (te != cur_templ) { copy_to_smem(MK1, a.MK1 + (size_t)te * B7_BYTES, B7_BYTES, g.t, GX); cur_templ = te; }
-      cp_async_commit();
-      cp_async_wait<0>();
-      g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oMK1, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      if (u == u0 && tile == 0) start_tile(ti, te);                       // every later tile was started by its predecessor
       g.wait();
       epi_attn_norm(g.tlane, xrow);                                       // X' over the query image
       g.publish();
@@ -199,6 +204,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
         g.wait();
         uint32_t x0[32], x1[32];
         const float rstd = rsqrtf(ld64_sumsq(g.tlane + 64, x0, x1) * (1.f / 64.f) + LN_EPS);
+        if (tile + 1 < a.NT) start_tile(ti + 1, te);                      // the accumulator now lives in registers:
+        else if (u + 1 < u1) start_tile((size_t)so_next * a.NT, te_next);  // the next G1 may overwrite the columns
         uint8_t* orow = a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG + row * 16;
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -276,6 +283,14 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
     copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
   }
   cp_async_commit();
+  // q projection of a tile: its `a` image (and, at a unit start, B7) was prefetched by cp.async.  Called for tile n+1
+  // right after tile n's last GEMM has completed, so that the projection runs behind tile n's LayerNorm2 + pooling
+  // epilogue instead of in front of an idle group (it writes TMEM columns [0, 64): the dead hidden layer of tile n).
+  auto start_tile = [&]() {
+    cp_async_wait<0>();
+    g.publish();
+    if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+  };
   for (int u = u0; u < u1; ++u) {
     const int slot = slot_next;
     if (u + 1 < u1) slot_next = a.u_slot[u + 1];
@@ -285,10 +300,9 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
     for (int tile = 0; tile < a.NT; ++tile) {
       const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
       TR(0);
-      cp_async_wait<0>();                                                 // `a` image (and B7 at a unit start) prefetched earlier
-      g.publish();
+      if (u == u0 && tile == 0) start_tile();                             // every later tile was started by its predecessor
+      else g.sync();              // the Qf image below overwrites the transpose buffer: every warp has finished its pooling reads
       TR(1);
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oR1, oWq, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       TR(2);
       {   // Qf = elu(q)+1 -> second half of R1
@@ -375,6 +389,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
       {   // o - beta2 = a + gamma2 * acc * rstd ; pooled over the points, 32 channels per pass
         uint32_t x0[32], x1[32];
         const float rstd = rsqrtf(ld64_sumsq(g.tlane + 64, x0, x1) * (1.f / 64.f) + LN_EPS);
+        if (tile + 1 < a.NT || u + 1 < u1) start_tile();                  // the accumulator now lives in registers
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t (&x)[32] = hh == 0 ? x0 : x1;
