@@ -66,6 +66,12 @@ __device__ __forceinline__ uint4 ldg_early(const void* p) {
   return v;
 }
 
+// one 128-byte line per thread pulled into L2 (no registers, no shared memory): used a whole tile ahead of the cp.async
+// that needs the data, so that the later copy pays an L2 hit instead of a DRAM round trip
+__device__ __forceinline__ void prefetch_l2_16k(const uint8_t* img, int t) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(img + (size_t)t * 128));
+}
+
 __device__ __forceinline__ void copy_to_smem(uint8_t* dst, const uint8_t* __restrict__ src, int bytes, int t, int nthr) {
   for (int i = t * 16; i < bytes; i += nthr * 16) cp_async16(dst + i, src + i);
 }

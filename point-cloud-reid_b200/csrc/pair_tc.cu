@@ -991,6 +991,11 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
       if (!prefetched) copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, g.t, GX);
       prefetched = false;
       cp_async_commit();
+      {   // L2 prefetch of the image after this one (the shared-memory copy can only start once both projections have read Aimg)
+        int ns = slot, nt = tile + 1;
+        if (nt == a.NT) { ns = slot_next; nt = 0; }
+        if (nt != 0 || u + 1 < u1) prefetch_l2_16k(a.A_out + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG, g.t);
+      }
       cp_async_wait<0>();
       g.publish();
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWk, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }

@@ -303,6 +303,12 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
       if (u == u0 && tile == 0) start_tile();                             // every later tile was started by its predecessor
       else g.sync();              // the Qf image below overwrites the transpose buffer: every warp has finished its pooling reads
       TR(1);
+      {   // L2 prefetch of the next tile's `a` image (its shared-memory copy is issued after this tile's G8)
+        int ns = slot, nt = tile + 1;
+        if (nt == a.NT) { ns = slot_next; nt = 0; }
+        if (nt != 0 || u + 1 < u1) prefetch_l2_16k(a.A_in + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG, g.t);
+        if (tile == 0 && u + 1 < u1) prefetch_l2_16k(a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, g.t);
+      }
       g.wait();
       TR(2);
       {   // Qf = elu(q)+1 -> second half of R1
