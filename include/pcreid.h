@@ -129,6 +129,13 @@ int pcreid_cn_chanmax(int B, int C, int rows, const float* X, long long x_bs, in
 int pcreid_sa_edge_mlp(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
                        const float* W2, const float* b2, const float* W3, const float* b3, float* out, void* stream);
 
+/* Unfused SA edge path for channel counts above the fused kernel's tile (C > 128: the mul=2 / mul=4 variants,
+ * configs_reid/_base_/reidentifiers/reid_pts_point-transformer-{1.5M,7M}_point-cat.py):
+ *   edge_build: H1[b,c,s*k+j] = relu(P1[b,c,idx[b,s,j]] + Cc[b,c,s])  (P1 (B,C,N), Cc (B,C,S), idx int32 (B,S,k), H1 (B,C,S*k));
+ *   seg_max:    out[i] = max_j x[i*k + j]  (rows = B*C*S).  pointnet2_utils.py:353-357. */
+int pcreid_edge_build(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx, float* out, void* stream);
+int pcreid_seg_max(long long rows, int k, const float* x, float* out, void* stream);
+
 /* EdgeConv gather-max (dgcnn_orig.py:31-54,129-147 with the bias-free conv factorised):
  *   out[b,c,i] = act( max_j P[b,c,idx[b,i,j]] + Q[b,c,i] ),  element (b,c,i) at out + b*o_bs + c*ldo + i */
 int pcreid_edge_gather_max(int B, int C, int N, int k, const float* P, const float* Q, const int* idx, int act,

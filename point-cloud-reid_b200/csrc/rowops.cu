@@ -259,13 +259,16 @@ __global__ void __launch_bounds__(128) cn_groupnorm_kernel(const pcreid_norm_arg
 // ------------------------------------------------------------------------------------------------
 // linear attention reductions
 // ------------------------------------------------------------------------------------------------
-constexpr int KV_SC = 128;   // points per staged chunk
+constexpr int KV_SC_DEFAULT = 128;   // points per staged chunk (head dim <= 64)
 // grid (H, B); Wkv[b][(h*D+i)*d + h*D+j] = sum_s elu1(k[h*D+i][s]) * (v[h*D+j][s] / S); D <= 64
+// head dims above 64 (the mul=2 / mul=4 model variants: D up to 256) split the D x D outputs of a head over blockIdx.z in
+// blocks of 4096 and stage shorter point chunks (KV_SC_ template parameter) so that the tiles still fit shared memory
+template <int KV_SC>
 __global__ void __launch_bounds__(256) linattn_kv_kernel(int S, int d, int H, const float* __restrict__ K, long long k_bs,
                                                          int ldk, const float* __restrict__ V, long long v_bs, int ldv,
                                                          float* __restrict__ Wkv, float* __restrict__ ksum) {
   extern __shared__ float sm[];
-  const int D = d / H, h = blockIdx.x, b = blockIdx.y;
+  const int D = d / H, h = blockIdx.x, b = blockIdx.y, e0 = blockIdx.z * 4096;
   float* Ks = sm;                        // [D][KV_SC+1]
   float* Vs = sm + D * (KV_SC + 1);      // [D][KV_SC+1]
   const float* Kb = K + (size_t)b * k_bs + (size_t)h * D * ldk;
@@ -291,7 +294,7 @@ __global__ void __launch_bounds__(256) linattn_kv_kernel(int S, int d, int H, co
     __syncthreads();
 #pragma unroll
     for (int o = 0; o < 16; ++o) {
-      int e = threadIdx.x + o * 256;
+      int e = e0 + threadIdx.x + o * 256;
       if (e < nout) {
         const float* kr = Ks + (e / D) * (KV_SC + 1);
         const float* vr = Vs + (e % D) * (KV_SC + 1);
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(256) linattn_kv_kernel(int S, int d, int H, co
         acc[o] = s;
       }
     }
-    if (threadIdx.x < D) {
+    if (blockIdx.z == 0 && threadIdx.x < D) {
       const float* kr = Ks + threadIdx.x * (KV_SC + 1);
       for (int t = 0; t < sc; ++t) ks += kr[t];
     }
@@ -309,10 +312,10 @@ __global__ void __launch_bounds__(256) linattn_kv_kernel(int S, int d, int H, co
   float* Wb = Wkv + (size_t)b * d * d;
 #pragma unroll
   for (int o = 0; o < 16; ++o) {
-    int e = threadIdx.x + o * 256;
+    int e = e0 + threadIdx.x + o * 256;
     if (e < nout) Wb[(size_t)(h * D + e / D) * d + h * D + (e % D)] = acc[o];
   }
-  if (threadIdx.x < D) ksum[(size_t)b * d + h * D + threadIdx.x] = ks;
+  if (blockIdx.z == 0 && threadIdx.x < D) ksum[(size_t)b * d + h * D + threadIdx.x] = ks;
 }
 
 __global__ void __launch_bounds__(128) linattn_scale_kernel(int rows, int d, int H, int S, const float* __restrict__ Q,
@@ -331,6 +334,33 @@ __global__ void __launch_bounds__(128) linattn_scale_kernel(int rows, int d, int
     const float z = (1.f / (dot + 1e-6f)) * (float)S;
     for (int c = h * D; c < (h + 1) * D; ++c) o[(size_t)c * ldqs] = apply_act(q[(size_t)c * ldq], ACT_ELU1) * z;
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unfused SA edge path for channel counts above the fused kernel's tile (C > 128: the mul=2 / mul=4 model variants):
+//   edge_build : H1[b,c,s*k+j] = relu(P1[b,c,idx[b,s,j]] + Cc[b,c,s])       (then two cn_linear calls)
+//   seg_max    : out[b,c,s]    = max_j X[b,c,s*k+j]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) edge_build_kernel(int C, int N, int S, int k, const float* __restrict__ P1,
+                                                         const float* __restrict__ Cc, const int* __restrict__ idx,
+                                                         float* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.z;
+  const int E = S * k;
+  if (e >= E) return;
+  const int s = e / k, src = idx[(size_t)b * E + e];
+  const int c0 = blockIdx.y * 16;
+#pragma unroll 4
+  for (int c = c0; c < min(c0 + 16, C); ++c)
+    out[((size_t)b * C + c) * E + e] = fmaxf(__ldg(P1 + ((size_t)b * C + c) * N + src) + __ldg(Cc + ((size_t)b * C + c) * S + s), 0.f);
+}
+
+__global__ void __launch_bounds__(256) seg_max_kernel(long long rows, int k, const float* __restrict__ x, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* r = x + i * k;
+  float mx = r[0];
+  for (int j = 1; j < k; ++j) mx = fmaxf(mx, r[j]);
+  out[i] = mx;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -629,15 +659,23 @@ int pcreid_linattn_kv(int B, int S, int d, int H, const float* K, long long k_bs
   if (B <= 0) return PCREID_OK;
   if (!K || !V || !Wkv || !ksum || S <= 0 || H <= 0 || d % H) return PCREID_ERR_ARG;
   const int D = d / H;
-  if (D > 64) return PCREID_ERR_UNSUPPORTED;
+  if (D > 256) return PCREID_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemsetAsync(Wkv, 0, (size_t)B * d * d * sizeof(float), st);
-  size_t smem = (size_t)2 * D * (KV_SC + 1) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(linattn_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int nz = ceil_div(D * D, 4096);
   for (int b0 = 0; b0 < B; b0 += 65535) {
     int nb = B - b0 < 65535 ? B - b0 : 65535;
-    linattn_kv_kernel<<<dim3(H, nb), 256, smem, st>>>(S, d, H, K + (size_t)b0 * k_bs, k_bs, ldk, V + (size_t)b0 * v_bs, v_bs,
-                                                      ldv, Wkv + (size_t)b0 * d * d, ksum + (size_t)b0 * d);
+    if (D <= 64) {
+      size_t smem = (size_t)2 * D * (KV_SC_DEFAULT + 1) * sizeof(float);
+      if (smem > 48 * 1024) cudaFuncSetAttribute(linattn_kv_kernel<KV_SC_DEFAULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      linattn_kv_kernel<KV_SC_DEFAULT><<<dim3(H, nb, nz), 256, smem, st>>>(S, d, H, K + (size_t)b0 * k_bs, k_bs, ldk, V + (size_t)b0 * v_bs,
+                                                                       v_bs, ldv, Wkv + (size_t)b0 * d * d, ksum + (size_t)b0 * d);
+    } else {
+      size_t smem = (size_t)2 * D * (32 + 1) * sizeof(float);
+      if (smem > 48 * 1024) cudaFuncSetAttribute(linattn_kv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      linattn_kv_kernel<32><<<dim3(H, nb, nz), 256, smem, st>>>(S, d, H, K + (size_t)b0 * k_bs, k_bs, ldk, V + (size_t)b0 * v_bs, v_bs, ldv,
+                                                                Wkv + (size_t)b0 * d * d, ksum + (size_t)b0 * d);
+    }
   }
   return pcreid_launch_status();
 }
@@ -697,6 +735,21 @@ int pcreid_sa_edge_mlp(int B, int C, int N, int S, int k, const float* P1, const
     cudaFuncSetAttribute(sa_edge_mlp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     sa_edge_mlp_kernel<4><<<grid, NTHR, smem, st>>>(C, N, S, k, cpt, P1, Cc, idx, W2, b2, W3, b3, out);
   }
+  return pcreid_launch_status();
+}
+
+int pcreid_edge_build(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx, float* out, void* stream) {
+  if (B <= 0 || S <= 0) return PCREID_OK;
+  if (!P1 || !Cc || !idx || !out || C <= 0 || k <= 0 || N <= 0) return PCREID_ERR_ARG;
+  if (B > 65535 || ceil_div(C, 16) > 65535) return PCREID_ERR_UNSUPPORTED;
+  edge_build_kernel<<<dim3(ceil_div(S * k, 256), ceil_div(C, 16), B), 256, 0, (cudaStream_t)stream>>>(C, N, S, k, P1, Cc, idx, out);
+  return pcreid_launch_status();
+}
+
+int pcreid_seg_max(long long rows, int k, const float* x, float* out, void* stream) {
+  if (rows <= 0) return PCREID_OK;
+  if (!x || !out || k <= 0) return PCREID_ERR_ARG;
+  seg_max_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, k, x, out);
   return pcreid_launch_status();
 }
 

@@ -237,6 +237,19 @@ def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
     if not (p1.is_contiguous() and cc.is_contiguous() and idx.is_contiguous()):
         raise ValueError("sa_edge_mlp inputs must be contiguous")
     out = torch.empty((B, C, S), device=p1.device, dtype=torch.float32)
+    if C > 128 or C % 16 or k > 128:
+        # wider than the fused kernel's tile (mul=2 / mul=4 variants): edge tensor materialised per object chunk
+        L = _lib.lib()
+        step = max(1, (256 << 20) // (C * S * k * 4))
+        for b0 in range(0, B, step):
+            b1 = min(B, b0 + step)
+            nb = b1 - b0
+            h1 = torch.empty((nb, C, S * k), device=p1.device, dtype=torch.float32)
+            _lib.check(L.pcreid_edge_build(nb, C, N, S, k, _p(p1[b0:b1]), _p(cc[b0:b1]), _p(idx[b0:b1]), _p(h1), _stream()),
+                       "pcreid_edge_build")
+            h3 = cn_linear(cn_linear(h1, w2, bias=b2, act=ACT_RELU), w3, bias=b3, act=ACT_RELU)
+            _lib.check(L.pcreid_seg_max(nb * C * S, k, _p(h3), _p(out[b0:b1]), _stream()), "pcreid_seg_max")
+        return out
     _lib.check(_lib.lib().pcreid_sa_edge_mlp(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2), _p(b2), _p(w3), _p(b3), _p(out),
                                              _stream()), "pcreid_sa_edge_mlp")
     return out

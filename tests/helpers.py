@@ -27,6 +27,15 @@ def model_cfg(kind="pt", backbone_list=(128, 64, 32)):
         c.update(match_type='concat', combine='cat', pool_type='max', cross_stage1=None, cross_stage2=None, local_stage1=None,
                  local_stage2=None, match_head=[dict(type='LinearRes', n_in=256, n_out=256, norm='GN', ng=32),
                                                 dict(type='Linear', in_features=256, out_features=1)])
+    elif kind in ("pt15m", "pt7m"):
+        # reid_pts_point-transformer-1.5M_point-cat.py (mul=2, width 64) / -7M_point-cat.py (mul=4, width 128)
+        mul, w, ng = (2, 64, 8) if kind == "pt15m" else (4, 128, 16)
+        c.update(hidden_size=2 * w, output_sequence_size=w,
+                 backbone=dict(type='Pointnet_Backbone', input_channels=0, use_xyz=True, conv_out=w, mul=mul),
+                 match_head=[dict(type='LinearRes', n_in=2 * w, n_out=2 * w, norm='GN', ng=ng),
+                             dict(type='Linear', in_features=2 * w, out_features=1)],
+                 cross_stage1=dict(type='corss_attention', d_model=w, nhead=2, attention='linear'),
+                 cross_stage2=dict(type='corss_attention', d_model=w, nhead=2, attention='linear'))
     elif kind == "dgcnn":
         c.update(use_dgcnn=True, backbone=dict(type='dgcnn', dropout=0.5, emb_dims=1024, k=20, output_channels=40), downsample=_DS,
                  match_head=[dict(type='LinearRes', n_in=128, n_out=128, norm='GN', ng=16), dict(type='Linear', in_features=128, out_features=1)])
@@ -40,6 +49,8 @@ ORACLE_KW = {
     "concat": dict(backbone='Pointnet_Backbone', match_type='concat', pool_type='max', combine='cat', head_ng=32),
     "dgcnn": dict(backbone='dgcnn', head_ng=16),
     "pointnet": dict(backbone='PointNet', head_ng=8),
+    "pt15m": dict(backbone='Pointnet_Backbone', head_ng=8),
+    "pt7m": dict(backbone='Pointnet_Backbone', head_ng=16),
 }
 
 

@@ -34,7 +34,8 @@ def test_golden_vectors(name, kind):
 
 @pytest.mark.parametrize("kind,N,blist", [("pt", 128, (128, 64, 32)), ("pt", 256, (256, 128, 64)), ("pt", 160, (160, 80, 40)),
                                           ("concat", 128, (128, 64, 32)), ("dgcnn", 256, (128, 64, 32)),
-                                          ("pointnet", 128, (128, 64, 32))])
+                                          ("pointnet", 128, (128, 64, 32)),
+                                          ("pt15m", 128, (128, 64, 32)), ("pt7m", 128, (128, 64, 32))])
 @pytest.mark.parametrize("dup", [False, True])
 def test_model_vs_oracle(kind, N, blist, dup):
     m, orc = helpers.build_pair(kind, blist, device=DEV)

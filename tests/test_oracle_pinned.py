@@ -30,6 +30,22 @@ def test_pt_backbone_bit_exact_vs_reference(canonical):
 
 
 @needs_ref
+@pytest.mark.parametrize("mul,conv_out", [(2, 64), (4, 128)])
+def test_pt_backbone_size_variants_bit_exact_vs_reference(mul, conv_out):
+    """the 1.5M / 7M configs (reid_pts_point-transformer-{1.5M,7M}_point-cat.py: mul=2 / mul=4)"""
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    bb = R.Pointnet_Backbone(input_channels=0, use_xyz=True, conv_out=conv_out, mul=mul).eval()
+    sd = O.perturb_norm_state({"backbone." + k: v for k, v in bb.state_dict().items()})
+    _load_ref_sd(bb, "backbone.", sd)
+    x = O.synth_objects(2, 128, 0)
+    with torch.no_grad():
+        _, h_r = bb(x, [128, 64, 32])
+        _, h_o = O.pt_backbone(sd, "backbone", x, [128, 64, 32])
+    assert torch.equal(h_r, h_o)
+
+
+@needs_ref
 def test_dgcnn_pointnet_heads_bit_exact_vs_reference():
     R = ref_loader.load()
     x = O.synth_objects(2, 128, 1).permute(0, 2, 1).contiguous()
