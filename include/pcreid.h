@@ -184,9 +184,12 @@ int pcreid_pair_tc2_set_trace(void* dev_buffer);   /* debug: int64[2048] cycle t
 int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst,
                            void* stream);
 int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /* (64) or NULL */, float* out, void* stream);
-int pcreid_pair_p1a2(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
+/* npts = points per object (any value >= 1; objects are zero-padded to a multiple of 128 rows inside the operand images) */
+int pcreid_pair_p1a2(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
                      const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream);
-int pcreid_pair_p2y(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
+int pcreid_pair_p1b_n(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* PV,
+                      const void* W, void* A_out, void* B7_out, int n_ctas, void* stream);
+int pcreid_pair_p2y(int n_units, int npts, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
                     float* pool_part, int n_ctas, void* stream);
 
 /* tensor-core (tcgen05 kind::tf32, fp32 accumulate) version of pcreid_sa_edge_mlp: same arguments except that the

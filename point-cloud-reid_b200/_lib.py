@@ -75,6 +75,7 @@ _SIGS = {
     "pcreid_pool_finish2": [c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_tc2_set_trace": [c_vp],
     "pcreid_pair_p1a2": [c_int, c_int, c_int] + [c_vp] * 9 + [c_int, c_vp],
+    "pcreid_pair_p1b_n": [c_int, c_int, c_int] + [c_vp] * 7 + [c_int, c_vp],
     "pcreid_pair_p2y": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
     "pcreid_sa_edge_mlp_tc": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_vp],
     "pcreid_tc_probe": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],

@@ -38,6 +38,7 @@ __device__ __forceinline__ void trace_mark(int& n, int tag) {
 
 struct P1Args {
   int n_units, NT, role;
+  int npts;                              // true points per object (<= 128 NT; rows beyond it are zero padding)
   const int *u_search, *u_templ, *u_slot;
   const uint8_t *QF1, *U, *H, *PV;      // search-side per-object images: [obj][NT][IMG] (U: [obj][NT][2*IMG])
   const uint8_t* MK1;                    // template-side per-object stage-1 attention operand [obj][B7_BYTES]
@@ -47,6 +48,7 @@ struct P1Args {
 };
 struct P2Args {
   int n_units, NT, role;
+  int npts;
   const int* u_slot;
   const uint8_t* A_in;                   // == A_out of phase 1
   const uint8_t* B7_in;                  // == B7_out of phase 1

@@ -1001,7 +1001,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWk, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       if (tile > 0) { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }   // previous KV GEMM still reads KfV
-      {   // Kf = elu(k)+1 -> chunks 0..7
+      {   // Kf = elu(k)+1 -> chunks 0..7 ; zero for padding rows (point index >= npts): they must not enter KV / Ksum
+        const bool keep = tile * 128 + row < a.npts;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t r[16];
@@ -1012,7 +1013,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              w[j] = tc::bf2_elu1(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])));
+              w[j] = keep ? tc::bf2_elu1(tc::pack_bf16(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]))) : 0u;
             *reinterpret_cast<uint4*>(KfV + (2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -1118,7 +1119,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
 // src (B, C, N) channel-major fp32 -> dst [B][N/128][C/8][128][8] bf16, optional elu+1
 __global__ void __launch_bounds__(256) pack_image_kernel(int B, int C, int N, const float* __restrict__ src, long long s_bs,
                                                          int lds, int act, uint8_t* __restrict__ dst) {
-  const int nt = N / 128, nch = C / 8;
+  const int nt = (N + 127) / 128, nch = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(idx % 128);
   const int chunk = (int)((idx / 128) % nch);
@@ -1126,12 +1127,14 @@ __global__ void __launch_bounds__(256) pack_image_kernel(int B, int C, int N, co
   const long long b = idx / (128LL * nch * nt);
   if (b >= B) return;
   const float* s = src + b * s_bs + (size_t)(chunk * 8) * lds + tile * 128 + row;
-  uint32_t w[4];
+  uint32_t w[4] = {0u, 0u, 0u, 0u};                   // rows beyond N (last tile of a ragged object) are zero padding
+  if (tile * 128 + row < N) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float x0 = s[(size_t)(2 * j) * lds], x1 = s[(size_t)(2 * j + 1) * lds];
-    if (act == ACT_ELU1) { x0 = x0 > 0.f ? x0 + 1.f : expf(x0); x1 = x1 > 0.f ? x1 + 1.f : expf(x1); }
-    w[j] = tc::pack_bf16(x0, x1);
+    for (int j = 0; j < 4; ++j) {
+      float x0 = s[(size_t)(2 * j) * lds], x1 = s[(size_t)(2 * j + 1) * lds];
+      if (act == ACT_ELU1) { x0 = x0 > 0.f ? x0 + 1.f : expf(x0); x1 = x1 > 0.f ? x1 + 1.f : expf(x1); }
+      w[j] = tc::pack_bf16(x0, x1);
+    }
   }
   *reinterpret_cast<uint4*>(dst + (((size_t)b * nt + tile) * nch + chunk) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -1168,8 +1171,8 @@ int pcreid_pair_tc_smem_bytes(int phase) { return phase == 1 ? P1_WBYTES + 2 * P
 
 int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, void* dst, void* stream) {
   if (B <= 0) return PCREID_OK;
-  if (!src || !dst || C % 8 || N % 128) return PCREID_ERR_ARG;
-  const long long per = 128LL * (C / 8) * (N / 128);
+  if (!src || !dst || C % 8 || N <= 0) return PCREID_ERR_ARG;
+  const long long per = 128LL * (C / 8) * ((N + 127) / 128);
   pack_image_kernel<<<(unsigned)((per * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, act, (uint8_t*)dst);
   return pcreid_launch_status();
 }
@@ -1193,7 +1196,7 @@ int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int
                    int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
   if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !PV || !MK1 || !W || !A_out || !B7_out || NT <= 0) return PCREID_ERR_ARG;
-  P1Args a{n_units, NT, role, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+  P1Args a{n_units, NT, role, 128 * NT, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
            (const uint8_t*)PV, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
   const int smem = P1_WBYTES + 2 * P1_GBYTES;
   cudaFuncSetAttribute(pair_p1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1210,7 +1213,7 @@ int pcreid_pair_p1ab(int which, int n_units, int NT, int role, const int* u_sear
   if (!u_search || !u_templ || !u_slot || !W || !A_out || !B7_out || NT <= 0 || (which != 0 && which != 1)) return PCREID_ERR_ARG;
   if (which == 0 && (!QF1 || !U || !H || !MK1)) return PCREID_ERR_ARG;
   if (which == 1 && !PV) return PCREID_ERR_ARG;
-  P1Args a{n_units, NT, role, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+  P1Args a{n_units, NT, role, 128 * NT, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
            (const uint8_t*)PV, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
@@ -1226,11 +1229,26 @@ int pcreid_pair_p1ab(int which, int n_units, int NT, int role, const int* u_sear
   return pcreid_launch_status();
 }
 
+int pcreid_pair_p1b_n(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* PV,
+                      const void* W, void* A_out, void* B7_out, int n_ctas, void* stream) {
+  if (n_units <= 0) return PCREID_OK;
+  if (!u_search || !u_templ || !u_slot || !PV || !W || !A_out || !B7_out || npts <= 0) return PCREID_ERR_ARG;
+  const int NT = (npts + 127) / 128;
+  P1Args a{n_units, NT, role, npts, u_search, u_templ, u_slot, nullptr, nullptr, nullptr, (const uint8_t*)PV, nullptr,
+           (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
+  int grid = n_ctas > 0 ? n_ctas : 148;
+  if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
+  const int smem = P1B_WBYTES + NGX * P1B_GBYTES;
+  cudaFuncSetAttribute(pair_p1b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p1b_kernel<<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
+  return pcreid_launch_status();
+}
+
 int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
                    float* pool_part, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
   if (!u_slot || !A_in || !B7_in || !W || !pool_part || NT <= 0) return PCREID_ERR_ARG;
-  P2Args a{n_units, NT, role, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
+  P2Args a{n_units, NT, role, 128 * NT, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
   if (n_ctas < 0) {   // three-tile variant (3 groups x 4 warps per CTA)
     const int smemx = P2_WBYTES + NGX * P2X_GBYTES;
     cudaFuncSetAttribute(pair_p2x_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemx);

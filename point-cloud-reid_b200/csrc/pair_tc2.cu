@@ -418,12 +418,24 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
             Tb[row * 8 + ((2 * c + 1) ^ (row & 7))] = ob;
           }
           __syncwarp();
+          if ((tile + 1) * 128 <= a.npts) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v = Tb[(rsub * 8 + i) * 8 + (jg ^ i)];
-            pmx[hh].x = fmaxf(pmx[hh].x, v.x); pmx[hh].y = fmaxf(pmx[hh].y, v.y);
-            pmx[hh].z = fmaxf(pmx[hh].z, v.z); pmx[hh].w = fmaxf(pmx[hh].w, v.w);
-            psm[hh].x += v.x; psm[hh].y += v.y; psm[hh].z += v.z; psm[hh].w += v.w;
+            for (int i = 0; i < 8; ++i) {
+              const float4 v = Tb[(rsub * 8 + i) * 8 + (jg ^ i)];
+              pmx[hh].x = fmaxf(pmx[hh].x, v.x); pmx[hh].y = fmaxf(pmx[hh].y, v.y);
+              pmx[hh].z = fmaxf(pmx[hh].z, v.z); pmx[hh].w = fmaxf(pmx[hh].w, v.w);
+              psm[hh].x += v.x; psm[hh].y += v.y; psm[hh].z += v.z; psm[hh].w += v.w;
+            }
+          } else {   // ragged last tile: rows beyond the object's point count are padding and stay out of the pooling
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (tile * 128 + rsub * 8 + i < a.npts) {
+                const float4 v = Tb[(rsub * 8 + i) * 8 + (jg ^ i)];
+                pmx[hh].x = fmaxf(pmx[hh].x, v.x); pmx[hh].y = fmaxf(pmx[hh].y, v.y);
+                pmx[hh].z = fmaxf(pmx[hh].z, v.z); pmx[hh].w = fmaxf(pmx[hh].w, v.w);
+                psm[hh].x += v.x; psm[hh].y += v.y; psm[hh].z += v.z; psm[hh].w += v.w;
+              }
+            }
           }
         }
       }
@@ -478,7 +490,7 @@ __global__ void __launch_bounds__(256) pool_finish2_kernel(int P, int npts, cons
 // src (B, C, N) channel-major fp32 + per-channel bias -> dst [B][N/128][C/8][128][8] bf16
 __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int N, const float* __restrict__ src, long long s_bs,
                                                               int lds, const float* __restrict__ bias, uint8_t* __restrict__ dst) {
-  const int nt = N / 128, nch = C / 8;
+  const int nt = (N + 127) / 128, nch = C / 8;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int row = (int)(idx % 128);
   const int chunk = (int)((idx / 128) % nch);
@@ -486,10 +498,12 @@ __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int 
   const long long b = idx / (128LL * nch * nt);
   if (b >= B) return;
   const float* s = src + b * s_bs + (size_t)(chunk * 8) * lds + tile * 128 + row;
-  uint32_t w[4];
+  uint32_t w[4] = {0u, 0u, 0u, 0u};                   // zero padding beyond N
+  if (tile * 128 + row < N) {
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    w[j] = tc::pack_bf16(s[(size_t)(2 * j) * lds] + bias[chunk * 8 + 2 * j], s[(size_t)(2 * j + 1) * lds] + bias[chunk * 8 + 2 * j + 1]);
+    for (int j = 0; j < 4; ++j)
+      w[j] = tc::pack_bf16(s[(size_t)(2 * j) * lds] + bias[chunk * 8 + 2 * j], s[(size_t)(2 * j + 1) * lds] + bias[chunk * 8 + 2 * j + 1]);
+  }
   *reinterpret_cast<uint4*>(dst + (((size_t)b * nt + tile) * nch + chunk) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
@@ -507,8 +521,8 @@ int pcreid_pair_tc2_set_trace(void* dev_buffer) {   /* debug: int64[2048] cycle 
 
 int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst, void* stream) {
   if (B <= 0) return PCREID_OK;
-  if (!src || !dst || !bias || C % 8 || N % 128) return PCREID_ERR_ARG;
-  const long long per = 128LL * (C / 8) * (N / 128);
+  if (!src || !dst || !bias || C % 8 || N <= 0) return PCREID_ERR_ARG;
+  const long long per = 128LL * (C / 8) * ((N + 127) / 128);
   pack_image_bias_kernel<<<(unsigned)((per * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, bias, (uint8_t*)dst);
   return pcreid_launch_status();
 }
@@ -520,11 +534,12 @@ int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias, f
   return pcreid_launch_status();
 }
 
-int pcreid_pair_p1a2(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
+int pcreid_pair_p1a2(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
                      const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
-  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !MK1 || !W || !A_out || NT <= 0) return PCREID_ERR_ARG;
-  P1Args a{n_units, NT, role, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !MK1 || !W || !A_out || npts <= 0) return PCREID_ERR_ARG;
+  const int NT = (npts + 127) / 128;
+  P1Args a{n_units, NT, role, npts, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
            nullptr, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, nullptr};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
@@ -534,11 +549,12 @@ int pcreid_pair_p1a2(int n_units, int NT, int role, const int* u_search, const i
   return pcreid_launch_status();
 }
 
-int pcreid_pair_p2y(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
+int pcreid_pair_p2y(int n_units, int npts, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
                     float* pool_part, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
-  if (!u_slot || !A_in || !B7_in || !W || !pool_part || NT <= 0) return PCREID_ERR_ARG;
-  P2Args a{n_units, NT, role, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
+  if (!u_slot || !A_in || !B7_in || !W || !pool_part || npts <= 0) return PCREID_ERR_ARG;
+  const int NT = (npts + 127) / 128;
+  P2Args a{n_units, NT, role, npts, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
   const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;

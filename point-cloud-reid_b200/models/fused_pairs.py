@@ -51,7 +51,11 @@ def supported(model, n_points):
     X1, X2 = model.cross_stage1, model.cross_stage2
     ok = (model.match_type == 'xcorr_eff' and model.combine == 'point-cat' and model.pool_type == 'both'
           and X1 is not None and X2 is not None and X1.q_proj.weight.shape == (64, 64) and X1.nhead == 2
-          and X2.q_proj.weight.shape == (64, 64) and X2.nhead == 2 and n_points % 128 == 0)
+          and X2.q_proj.weight.shape == (64, 64) and X2.nhead == 2 and n_points >= 1)
+    if ok and n_points % 128:
+        # ragged point counts (160 / 192 / 224 in the reference's ablation configs) are zero-padded to 128-row tiles by
+        # the second-generation kernels only
+        ok = os.environ.get("PCREID_PAIR_GEN", "2") == "2"
     return ok
 
 
@@ -131,7 +135,7 @@ class FusedXcorr:
     @staticmethod
     def _pack_image(x, act=K.ACT_NONE):
         B, C, N = x.shape
-        out = torch.empty((B, N // 128, C // 8, 128, 16), device=x.device, dtype=torch.uint8)
+        out = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=x.device, dtype=torch.uint8)
         _lib.check(_lib.lib().pcreid_pack_image(B, C, N, _p(x), x.stride(0), x.stride(1), act, _p(out), _stream()),
                    "pcreid_pack_image")
         return out
@@ -147,7 +151,7 @@ class FusedXcorr:
         o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
         if self.gen2:
             o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
-            o.H = torch.empty((B, N // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
+            o.H = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
             _lib.check(_lib.lib().pcreid_pack_image_bias(B, C, N, _p(h), h.stride(0), h.stride(1), _p(self._b2_1), _p(o.H),
                                                          _stream()), "pcreid_pack_image_bias")   # h + beta2
         else:
@@ -166,7 +170,8 @@ class FusedXcorr:
         assert pt.npts == pd.npts, "fused matcher expects equal point counts on both sides"
         w1, w2 = self._weights()
         dev = pt.H.device
-        P, NT, N = ti.numel(), pt.npts // 128, pt.npts
+        P, NT, N = ti.numel(), (pt.npts + 127) // 128, pt.npts
+        assert N % 128 == 0 or self.gen2, "ragged point counts need the second-generation kernels"
         ti, dj = ti.long(), dj.long()
         A = torch.empty((P, 2, NT, IMG), device=dev, dtype=torch.uint8)
         B7 = torch.empty((P, 2, B7_BYTES), device=dev, dtype=torch.uint8)
@@ -177,13 +182,12 @@ class FusedXcorr:
             us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
             if self.gen2:
                 e0 = self._tick()
-                _lib.check(L.pcreid_pair_p1a2(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(pm.MK1),
+                _lib.check(L.pcreid_pair_p1a2(P, N, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(pm.MK1),
                                               _p(self._w1a2), _p(A), self.n_ctas, _stream()), "pcreid_pair_p1a2")
                 self._tock("pair_p1a2_kernel", e0, P)
                 e0 = self._tick()
-                _lib.check(L.pcreid_pair_p1ab(1, P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H),
-                                              _p(ps.PV), _p(pm.MK1), _p(self._w1b2), _p(A), _p(B7), self.n_ctas, _stream()),
-                           "pcreid_pair_p1ab")
+                _lib.check(L.pcreid_pair_p1b_n(P, N, role, _p(us), _p(ut), _p(sl), _p(ps.PV), _p(self._w1b2), _p(A), _p(B7),
+                                               self.n_ctas, _stream()), "pcreid_pair_p1b_n")
                 self._tock("pair_p1b_kernel", e0, P)
                 continue
             if self.p1_split:
@@ -203,7 +207,7 @@ class FusedXcorr:
         if self.gen2:
             for role in (0, 1):
                 e0 = self._tick()
-                _lib.check(L.pcreid_pair_p2y(P, NT, role, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part), self.n_ctas,
+                _lib.check(L.pcreid_pair_p2y(P, N, role, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part), self.n_ctas,
                                              _stream()), "pcreid_pair_p2y")
                 self._tock("pair_p2y_kernel", e0, P)
             _lib.check(L.pcreid_pool_finish2(P, N, _p(part), _p(self._b2_2), _p(pooled), _stream()), "pcreid_pool_finish2")

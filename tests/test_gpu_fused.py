@@ -12,14 +12,17 @@ DEV = "cuda"
 TOL_FAST = 3e-2
 
 
-@pytest.mark.parametrize("N,T,D", [(256, 5, 7), (128, 6, 4), (512, 2, 3)])
+@pytest.mark.parametrize("N,T,D", [(256, 5, 7), (128, 6, 4), (512, 2, 3), (160, 5, 4), (192, 3, 5), (224, 4, 4)])
 def test_fused_matches_parity_and_oracle(N, T, D):
+    """point counts of the reference's ablation configs, including the ragged ones (160 / 192 / 224: zero-padded tiles)"""
+    from pcreid_b200.models import fused_pairs
     m, orc = helpers.build_pair("pt", (N, N // 2, N // 4), device=DEV)
     t, d = O.synth_objects(T, N, 0), O.synth_objects(D, N, 1)
     xt, ht = m.encode(t.to(DEV))
     xd, hd = m.encode(d.to(DEV))
     Lp = m.match_all_pairs(ht, xt, hd, xd).cpu()
     m.match_mode = 'fast'
+    assert fused_pairs.supported(m, N)
     Lf = m.match_all_pairs(ht, xt, hd, xd).cpu()
     Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu())
     err = (Lf - Lo).abs().max().item()
