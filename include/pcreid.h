@@ -55,6 +55,14 @@ int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const flo
 /* replaces gather_points_kernel_launcher(b,c,n,npoints,points,idx,out,stream)
  * (ops/gather_points/src/gather_points_cuda.cu:28-49): out[b,c,m] = points[b,c,idx[b,m]]. */
 int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream);
+/* replaces three_nn_kernel_launcher(b,n,m,unknown,known,dist2,idx,stream) (ops/interpolate/src/three_nn_cuda.cu:68-90):
+ * the three nearest known (B,M,3) points of every unknown (B,N,3) point, ascending (d2, index); dist2 (B,N,3) SQUARED
+ * distances (the Python wrapper takes the root, three_nn.py:37), idx int32 (B,N,3); unfilled slots (M < 3) = (0, +inf). */
+int pcreid_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, void* stream);
+/* replaces three_interpolate_kernel_launcher(b,c,m,n,points,idx,weight,out,stream)
+ * (ops/interpolate/src/three_interpolate_cuda.cu:40-62): out[b,c,n] = sum_j weight[b,n,j] * points[b,c,idx[b,n,j]]. */
+int pcreid_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight, float* out,
+                             void* stream);
 
 /* ------------------------------------------------------------------ B. encoder / match path ---- */
 /* All feature tensors are channel-major per object, exactly the reference's (B, C, N) layout:

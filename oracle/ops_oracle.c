@@ -173,6 +173,43 @@ void oracle_gather_points(int b, int c, int n, int m, const float *points, const
         out[((size_t)bi * c + ci) * m + s] = points[((size_t)bi * c + ci) * n + idx[(size_t)bi * m + s]];
 }
 
+/* three_nn (mmdet3d/ops/interpolate/src/three_nn_cuda.cu:11-66): sequential scan, running best three in DOUBLES initialised
+ * to 1e40, strict `<`; dist2 written back as float (an empty slot becomes +inf), same contracted distance as kNN. */
+void oracle_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int p = 0; p < n; ++p) {
+      const float *u = unknown + ((size_t)bi * n + p) * 3;
+      double best1 = 1e40, best2 = 1e40, best3 = 1e40;
+      int besti1 = 0, besti2 = 0, besti3 = 0;
+      for (int k = 0; k < m; ++k) {
+        const float *q = known + ((size_t)bi * m + k) * 3;
+        float d = sqdist(u[0], u[1], u[2], q[0], q[1], q[2]);
+        if (d < best1) { best3 = best2; besti3 = besti2; best2 = best1; besti2 = besti1; best1 = d; besti1 = k; }
+        else if (d < best2) { best3 = best2; besti3 = besti2; best2 = d; besti2 = k; }
+        else if (d < best3) { best3 = d; besti3 = k; }
+      }
+      float *od = dist2 + ((size_t)bi * n + p) * 3;
+      int *oi = idx + ((size_t)bi * n + p) * 3;
+      od[0] = (float)best1; od[1] = (float)best2; od[2] = (float)best3;
+      oi[0] = besti1; oi[1] = besti2; oi[2] = besti3;
+    }
+}
+
+/* three_interpolate (three_interpolate_cuda.cu:11-38): w0*p0 + w1*p1 + w2*p2, contracted by nvcc to
+ * fma(w2,p2, fma(w0,p0, fl(w1*p1))) (SASS of the reference file built for sm_100a with nvcc 12.9). */
+void oracle_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int ci = 0; ci < c; ++ci)
+      for (int p = 0; p < n; ++p) {
+        const int *ip = idx + ((size_t)bi * n + p) * 3;
+        const float *w = weight + ((size_t)bi * n + p) * 3;
+        const float *pr = points + ((size_t)bi * c + ci) * m;
+        float t = w[1] * pr[ip[1]];
+        t = fmaf(w[0], pr[ip[0]], t);
+        out[((size_t)bi * c + ci) * n + p] = fmaf(w[2], pr[ip[2]], t);
+      }
+}
+
 /* ---- canonical arithmetic of the torch-path distances (what the CUDA kNN kernels reproduce) ----
  * square_distance (models/pointnet2_utils.py:169-188) as torch/MKL evaluates it on the CPU oracle:
  *   m = fma chain over (x,y,z); |v|^2 = (x*x + y*y) + z*z; d = (-2*m + |q|^2) + |p|^2             */

@@ -124,6 +124,32 @@ def gather_points(features, indices):
     return torch.from_numpy(out)
 
 
+def three_nn_dist2(target, source):
+    """-> (dist2 (B,N,3) squared distances, idx int32 (B,N,3)): what the reference kernel writes."""
+    t, s = _c(target, np.float32), _c(source, np.float32)
+    B, N, _ = t.shape
+    M = s.shape[1]
+    d2 = np.zeros((B, N, 3), np.float32)
+    idx = np.zeros((B, N, 3), np.int32)
+    _cpu().oracle_three_nn(B, N, M, _fp(t), _fp(s), _fp(d2), _fp(idx))
+    return torch.from_numpy(d2), torch.from_numpy(idx)
+
+
+def three_nn(target, source):
+    """-> (dist (B,N,3) = sqrt(dist2), idx int32 (B,N,3)) as mmdet3d/ops/interpolate/three_nn.py:9-46."""
+    d2, idx = three_nn_dist2(target, source)
+    return torch.sqrt(d2), idx
+
+
+def three_interpolate(features, indices, weight):
+    f, i, w = _c(features, np.float32), _c(indices, np.int32), _c(weight, np.float32)
+    B, C, M = f.shape
+    N = i.shape[1]
+    out = np.zeros((B, C, N), np.float32)
+    _cpu().oracle_three_interpolate(B, C, M, N, _fp(f), _fp(i), _fp(w), _fp(out))
+    return torch.from_numpy(out)
+
+
 # ---------------------------------------------------------------- reference .cu on the GPU (oracle/_ref)
 def _p(t):
     return ctypes.c_void_p(t.data_ptr())
@@ -184,6 +210,23 @@ def ref_gather_points(features, indices):
     M = indices.shape[1]
     out = torch.zeros(B, C, M, device=features.device)
     _ref().ref_gather_points(B, C, N, M, _p(features), _p(indices), _p(out), _s())
+    return out
+
+
+def ref_three_nn(target, source):
+    B, N, _ = target.shape
+    M = source.shape[1]
+    d2 = torch.zeros(B, N, 3, device=target.device)
+    idx = torch.zeros(B, N, 3, dtype=torch.int32, device=target.device)
+    _ref().ref_three_nn(B, N, M, _p(target), _p(source), _p(d2), _p(idx), _s())
+    return torch.sqrt(d2), idx
+
+
+def ref_three_interpolate(features, indices, weight):
+    B, C, M = features.shape
+    N = indices.shape[1]
+    out = torch.zeros(B, C, N, device=features.device)
+    _ref().ref_three_interpolate(B, C, M, N, _p(features), _p(indices), _p(weight), _p(out), _s())
     return out
 
 

@@ -13,7 +13,16 @@ void ball_query_kernel_launcher(int b, int n, int m, float min_radius, float max
 void group_points_kernel_launcher(int b, int c, int n, int npoints, int nsample, const float *points, const int *idx, float *out, cudaStream_t stream);
 void gather_points_kernel_launcher(int b, int c, int n, int npoints, const float *points, const int *idx, float *out, cudaStream_t stream);
 
+void three_nn_kernel_launcher(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, cudaStream_t stream);
+void three_interpolate_kernel_launcher(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out, cudaStream_t stream);
+
 extern "C" {
+void ref_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2, int *idx, void *stream) {
+  three_nn_kernel_launcher(b, n, m, unknown, known, dist2, idx, (cudaStream_t)stream);
+}
+void ref_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx, const float *weight, float *out, void *stream) {
+  three_interpolate_kernel_launcher(b, c, m, n, points, idx, weight, out, (cudaStream_t)stream);
+}
 void ref_fps(int b, int n, int m, const float *xyz, float *temp, int *idx, void *stream) {
   furthest_point_sampling_kernel_launcher(b, n, m, xyz, temp, idx, (cudaStream_t)stream);
 }

@@ -52,6 +52,8 @@ _SIGS = {
     "pcreid_ball_query": [c_int, c_int, c_int, c_float, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_three_nn": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_three_interpolate": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_cn_linear": [ctypes.POINTER(LinearArgs), c_vp],
     "pcreid_cn_linear_tc": [ctypes.POINTER(LinearArgs), c_vp],
     "pcreid_cn_groupnorm": [ctypes.POINTER(NormArgs), c_vp],

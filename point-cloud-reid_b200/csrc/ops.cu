@@ -474,6 +474,75 @@ static int group_launch(int b, int c, int n, int p, const float* points, const i
 // ------------------------------------------------------------------------------------------------
 // C ABI (declared in include/pcreid.h)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// three_nn / three_interpolate (mmdet3d/ops/interpolate/src/three_nn_cuda.cu:11-66, three_interpolate_cuda.cu:11-38)
+//   three_nn: the three nearest `known` points of every `unknown` point, ascending (d2, index) -- the reference's
+//   sequential scan with strict `<` inserts ties after the earlier index.  d2 = fma(dz,dz, fma(dx,dx, dy*dy)) (the
+//   contraction nvcc applies to the reference expression, SASS-verified); slots that no point fills keep
+//   (index 0, d2 = float(1e40) = +inf).  The known points stream through shared memory in tiles that all 256 queries
+//   of the CTA scan with broadcast reads, instead of every thread walking global memory on its own.
+//   three_interpolate: out[b,c,n] = fma(w2,p2, fma(w0,p0, w1*p1)) (same contraction); index / weight triples are read
+//   once per point and reused over a block of channels, not once per (channel, point).
+// ------------------------------------------------------------------------------------------------
+constexpr int TNN_TILE = 1024;
+__global__ void __launch_bounds__(256) three_nn_kernel(int n, int m, const float* __restrict__ unknown, const float* __restrict__ known,
+                                                       float* __restrict__ dist2, int* __restrict__ idx) {
+  __shared__ float ks[TNN_TILE * 3];
+  const int b = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = q < n;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (live) {
+    const float* u = unknown + ((size_t)b * n + q) * 3;
+    ux = u[0]; uy = u[1]; uz = u[2];
+  }
+  // the reference keeps its running best in doubles initialised to 1e40 and inserts on strict `<`: every finite float
+  // beats an empty slot, +inf and NaN never enter, an empty slot is written back as float(1e40) = +inf
+  const float INF = __int_as_float(0x7f800000);
+  float b1 = INF, b2 = INF, b3 = INF;
+  int i1 = 0, i2 = 0, i3 = 0;
+  for (int k0 = 0; k0 < m; k0 += TNN_TILE) {
+    const int kt = min(TNN_TILE, m - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kt * 3; i += blockDim.x) ks[i] = known[((size_t)b * m + k0) * 3 + i];
+    __syncthreads();
+    if (!live) continue;
+    for (int k = 0; k < kt; ++k) {
+      const float d = dist_direct(ux, uy, uz, ks[3 * k], ks[3 * k + 1], ks[3 * k + 2]);
+      if (d < b1) {
+        b3 = b2; i3 = i2; b2 = b1; i2 = i1; b1 = d; i1 = k0 + k;
+      } else if (d < b2) {
+        b3 = b2; i3 = i2; b2 = d; i2 = k0 + k;
+      } else if (d < b3) {
+        b3 = d; i3 = k0 + k;
+      }
+    }
+  }
+  if (live) {
+    float* od = dist2 + ((size_t)b * n + q) * 3;
+    int* oi = idx + ((size_t)b * n + q) * 3;
+    od[0] = b1; od[1] = b2; od[2] = b3;
+    oi[0] = i1; oi[1] = i2; oi[2] = i3;
+  }
+}
+
+__global__ void __launch_bounds__(256) three_interpolate_kernel(int c, int m, int n, const float* __restrict__ points,
+                                                                const int* __restrict__ idx, const float* __restrict__ weight,
+                                                                float* __restrict__ out) {
+  const int b = blockIdx.z, p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int* ip = idx + ((size_t)b * n + p) * 3;
+  const float* wp = weight + ((size_t)b * n + p) * 3;
+  const int i0 = ip[0], i1 = ip[1], i2 = ip[2];
+  const float w0 = wp[0], w1 = wp[1], w2 = wp[2];
+  const int c0 = blockIdx.y * 16;
+#pragma unroll 4
+  for (int ch = c0; ch < min(c0 + 16, c); ++ch) {
+    const float* pr = points + ((size_t)b * c + ch) * m;
+    const float t = __fmul_rn(w1, __ldg(pr + i1));
+    out[((size_t)b * c + ch) * n + p] = __fmaf_rn(w2, __ldg(pr + i2), __fmaf_rn(w0, __ldg(pr + i0), t));
+  }
+}
+
 extern "C" {
 
 int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, void* stream) {
@@ -537,6 +606,23 @@ int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const flo
 }
 int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream) {
   return group_launch(b, c, n, npoints, points, idx, out, (cudaStream_t)stream);
+}
+
+int pcreid_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, void* stream) {
+  if (b <= 0 || n <= 0) return PCREID_OK;
+  if (!unknown || !dist2 || !idx || m < 0 || (m > 0 && !known)) return PCREID_ERR_ARG;
+  if (b > 65535) return PCREID_ERR_UNSUPPORTED;
+  three_nn_kernel<<<dim3(ceil_div(n, 256), b), 256, 0, (cudaStream_t)stream>>>(n, m, unknown, known, dist2, idx);
+  return pcreid_launch_status();
+}
+
+int pcreid_three_interpolate(int b, int c, int m, int n, const float* points, const int* idx, const float* weight, float* out,
+                             void* stream) {
+  if (b <= 0 || c <= 0 || n <= 0) return PCREID_OK;
+  if (!points || !idx || !weight || !out || m <= 0) return PCREID_ERR_ARG;
+  if (b > 65535 || ceil_div(c, 16) > 65535) return PCREID_ERR_UNSUPPORTED;
+  three_interpolate_kernel<<<dim3(ceil_div(n, 256), ceil_div(c, 16), b), 256, 0, (cudaStream_t)stream>>>(c, m, n, points, idx, weight, out);
+  return pcreid_launch_status();
 }
 
 }  // extern "C"

@@ -5,8 +5,10 @@ from .furthest_point_sample import (FurthestPointSampling, FurthestPointSampling
                                     furthest_point_sample, furthest_point_sample_with_dist)
 from .gather_points import GatherPoints, gather_points
 from .group_points import GroupAll, GroupingOperation, QueryAndGroup, grouping_operation
+from .interpolate import ThreeInterpolate, ThreeNN, three_interpolate, three_nn
 from .knn import KNN, knn
 
 __all__ = ["ball_query", "BallQuery", "furthest_point_sample", "furthest_point_sample_with_dist", "Points_Sampler",
            "FurthestPointSampling", "FurthestPointSamplingWithDist", "gather_points", "GatherPoints", "GroupAll",
-           "QueryAndGroup", "group_points", "grouping_operation", "GroupingOperation", "knn", "KNN"]
+           "QueryAndGroup", "group_points", "grouping_operation", "GroupingOperation", "knn", "KNN",
+           "three_nn", "three_interpolate", "ThreeNN", "ThreeInterpolate"]

@@ -13,7 +13,8 @@ import torch
 from oracle import ops_oracle as P
 from oracle import reid_oracle as O
 import pcreid_b200.kernels as K
-from pcreid_b200.ops import ball_query, furthest_point_sample, gather_points, grouping_operation, knn
+from pcreid_b200.ops import (ball_query, furthest_point_sample, gather_points, grouping_operation, knn, three_interpolate,
+                             three_nn)
 
 dev = "cuda"
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -80,6 +81,17 @@ i2 = torch.randint(0, 256, (B, 128), device=dev, dtype=torch.int32)
 ms = timeit(lambda: gather_points(f, i2))
 ref = timeit(lambda: P.ref_gather_points(f, i2)) if have_ref else None
 add("gather_points", ms, B * (4 * 128 + 4 * 64 * 256 + 4 * 64 * 128), None, ref, f"B={B} C=64 N=256 M=128")
+# feature propagation ops: 256 fine points interpolate from 64 coarse points, 128 channels
+tgt, srcp = O.synth_objects(B, 256, 3).to(dev), O.synth_objects(B, 64, 4).to(dev)
+ms = timeit(lambda: three_nn(tgt, srcp))
+ref = timeit(lambda: P.ref_three_nn(tgt, srcp)) if have_ref else None
+add("three_nn", ms, B * (12 * (256 + 64) + 24 * 256), B * 256 * 64, ref, f"B={B} N=256 M=64")
+fz = torch.randn(B, 128, 64, device=dev)
+dz, iz = three_nn(tgt, srcp)
+wz = torch.softmax(-dz, 2).contiguous()
+ms = timeit(lambda: three_interpolate(fz, iz, wz))
+ref = timeit(lambda: P.ref_three_interpolate(fz, iz, wz)) if have_ref else None
+add("three_interpolate", ms, B * (24 * 256 + 4 * 128 * 64 + 4 * 128 * 256), None, ref, f"B={B} C=128 M=64 N=256")
 xf = torch.randn(B, 64, 256, device=dev)
 ms = timeit(lambda: K.knn_feature(xf, 20))
 add("knn_feature (DGCNN)", ms, B * (4 * 64 * 256 + 4 * 256 * 20), B * 256 * 256, None, f"B={B} C=64 N=256 k=20")

@@ -182,3 +182,33 @@ def test_large_scene_scale_sortedness_property():
     assert (d2[:, 1:, :] >= d2[:, :-1, :]).all()
     assert (idx[:, 0, :] == torch.arange(1024, device=DEV, dtype=torch.int32)).all()
     assert int(idx.min()) >= 0 and int(idx.max()) < 4096
+
+
+@pytest.mark.parametrize("kind", KINDS)
+@pytest.mark.parametrize("N,M", [(256, 64), (1000, 37), (64, 2500), (5, 2), (33, 1)])
+def test_three_nn_bit_exact(kind, N, M):
+    """three_nn: indices and squared distances bit-identical to the C restatement of the reference
+    kernel and to the reference .cu itself, including exact ties and fewer than three sources."""
+    from pcreid_b200.ops import three_nn
+    t, s = clouds(2, N, 3, kind), clouds(2, M, 4 if kind != "same" else 3, kind)
+    d, idx = three_nn(t.to(DEV), s.to(DEV))
+    d2o, io = P.three_nn_dist2(t, s)
+    assert idx.dtype == torch.int32 and torch.equal(idx.cpu(), io)
+    assert torch.equal(d, torch.sqrt(d2o.to(DEV)))            # same device for the root: torch's CPU / CUDA sqrt differ in the last bit
+    if P.ref_available():
+        dr, ir = P.ref_three_nn(t.to(DEV), s.to(DEV))
+        assert torch.equal(idx, ir) and torch.equal(d, dr)
+
+
+@pytest.mark.parametrize("C,M,N", [(64, 128, 256), (3, 7, 1000), (130, 64, 33)])
+def test_three_interpolate_bit_exact(C, M, N):
+    from pcreid_b200.ops import three_interpolate, three_nn
+    f = torch.randn(2, C, M, generator=torch.Generator().manual_seed(0))
+    t, s = O.synth_objects(2, N, 5), O.synth_objects(2, M, 6)
+    d, idx = three_nn(t.to(DEV), s.to(DEV))
+    w = 1.0 / (d + 1e-8)
+    w = (w / w.sum(2, keepdim=True)).contiguous()             # PointFPModule.forward weights (point_fp_module.py:60-64)
+    out = three_interpolate(f.to(DEV), idx, w)
+    assert torch.equal(out.cpu(), P.three_interpolate(f, idx.cpu(), w.cpu()))
+    if P.ref_available():
+        assert torch.equal(out, P.ref_three_interpolate(f.to(DEV), idx, w))

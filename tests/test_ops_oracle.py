@@ -95,3 +95,28 @@ def test_group_gather():
     assert torch.equal(g, torch.gather(f.unsqueeze(2).expand(2, 5, 4, 9), 3, idx.long().unsqueeze(1).expand(2, 5, 4, 3)))
     i2 = torch.randint(0, 9, (2, 6), dtype=torch.int32)
     assert torch.equal(P.gather_points(f, i2), torch.gather(f, 2, i2.long().unsqueeze(1).expand(2, 5, 6)))
+
+
+def test_three_nn_oracle_semantics():
+    """three_nn_cuda.cu:11-66: ascending (d2, index) on ties, sentinel (0, +inf) when fewer than 3 sources exist."""
+    t, s = O.synth_objects(2, 50, 0), O.synth_objects(2, 40, 1)
+    d, idx = P.three_nn(t, s)
+    d2 = ((t[:, :, None, :] - s[:, None, :, :]) ** 2).sum(-1)
+    ref = torch.sort(d2, dim=2, stable=True)[1][:, :, :3]
+    assert torch.equal(idx.long(), ref)                       # tie-free input: plain 3 nearest
+    assert torch.allclose(d, torch.gather(d2, 2, ref).sqrt(), atol=1e-6)
+    dup = O.synth_objects(1, 30, 2, dup=True)                 # duplicate points: lower index first
+    _, idup = P.three_nn(dup, dup)
+    d2d = ((dup[:, :, None, :] - dup[:, None, :, :]) ** 2).sum(-1)
+    assert torch.equal(idup.long(), torch.sort(d2d, dim=2, stable=True)[1][:, :, :3])
+    d1, i1 = P.three_nn(t, s[:, :2].contiguous())             # M = 2 < 3
+    assert (i1[:, :, 2] == 0).all() and torch.isinf(d1[:, :, 2]).all()
+
+
+def test_three_interpolate_oracle():
+    f = torch.randn(2, 5, 20, generator=torch.Generator().manual_seed(0))
+    idx = torch.randint(0, 20, (2, 9, 3), generator=torch.Generator().manual_seed(1)).int()
+    w = torch.rand(2, 9, 3, generator=torch.Generator().manual_seed(2))
+    out = P.three_interpolate(f, idx, w)
+    ref = (torch.gather(f[:, :, None, :].expand(2, 5, 9, 20), 3, idx.long()[:, None].expand(2, 5, 9, 3)) * w[:, None]).sum(-1)
+    assert torch.allclose(out, ref, atol=1e-6)
