@@ -55,6 +55,19 @@ int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const flo
 /* replaces gather_points_kernel_launcher(b,c,n,npoints,points,idx,out,stream)
  * (ops/gather_points/src/gather_points_cuda.cu:28-49): out[b,c,m] = points[b,c,idx[b,m]]. */
 int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream);
+/* Crop -> centre -> resample front-end (csrc/frontend.cu; reference: models/trackers/deprecated/pc_utils.py:31-96 +
+ * DepthInstance3DBoxes.points_in_boxes, core/bbox/structures/depth_box3d.py:256-282 +
+ * ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:24-105).  pts (P, >=3) with row stride pts_stride floats, boxes (B, 7)
+ * = (x, y, z centre, dx, dy, dz, yaw) in the depth frame.
+ *   pcreid_crop_mask:   mask (B, ntiles, 32) uint32, bit i of word w <-> point tile*1024 + 32 w + i lies in box b;
+ *                       counts (B, ntiles) int32; ntiles = pcreid_crop_tiles(P).
+ *   pcreid_crop_gather: prefix (B, ntiles+1) = exclusive scan of counts; rank (B, N) int64 in [0, length_b): out (B, N, 3)
+ *                       = box-frame coordinates of the rank-th in-box point (point order), zeros where length_b == 0. */
+int pcreid_crop_tiles(int P);
+int pcreid_crop_mask(int P, int B, const float* pts, int pts_stride, const float* boxes, void* mask, int* counts, void* stream);
+int pcreid_crop_gather(int P, int B, int N, const float* pts, int pts_stride, const float* boxes, const void* mask,
+                       const int* prefix, const long long* rank, float* out, void* stream);
+
 /* replaces three_nn_kernel_launcher(b,n,m,unknown,known,dist2,idx,stream) (ops/interpolate/src/three_nn_cuda.cu:68-90):
  * the three nearest known (B,M,3) points of every unknown (B,N,3) point, ascending (d2, index); dist2 (B,N,3) SQUARED
  * distances (the Python wrapper takes the root, three_nn.py:37), idx int32 (B,N,3); unfilled slots (M < 3) = (0, +inf). */

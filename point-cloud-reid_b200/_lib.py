@@ -52,6 +52,9 @@ _SIGS = {
     "pcreid_ball_query": [c_int, c_int, c_int, c_float, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_crop_tiles": [c_int],
+    "pcreid_crop_mask": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_crop_gather": [c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_three_nn": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_three_interpolate": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_cn_linear": [ctypes.POINTER(LinearArgs), c_vp],

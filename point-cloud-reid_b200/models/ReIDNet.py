@@ -248,6 +248,12 @@ class ReIDNet(nn.Module):
                 pairs = pair_mask.nonzero()
                 total = pairs.shape[0]
             flat = out.view(-1)
+            if pairs is None and fused is not None and D > 0:
+                rows_per_chunk = max(1, chunk // D)                          # dense all-pairs: whole rows per chunk
+                for r0 in range(0, T, rows_per_chunk):
+                    nrows = min(rows_per_chunk, T - r0)
+                    flat[r0 * D:(r0 + nrows) * D] = fused.match(pk_t, pk_d, None, None, dense=(r0, nrows, D))
+                return out
             for s in range(0, total, chunk):
                 e = min(total, s + chunk)
                 if pairs is None:

@@ -165,21 +165,36 @@ class FusedXcorr:
         _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), _p(o.MK1), _stream()), "pcreid_pack_b7")
         return o
 
-    def match(self, pt, pd, ti, dj, debug=None):
-        """logits (P,) for the pairs (ti[p], dj[p]); ti / dj int64 or int32 index tensors on the device."""
+    def match(self, pt, pd, ti, dj, debug=None, dense=None):
+        """logits (P,) for the pairs (ti[p], dj[p]); ti / dj int64 or int32 index tensors on the device.
+        dense=(r0, nrows, D): the pairs are the full row block [r0, r0+nrows) x [0, D) in row-major order (ti, dj may be
+        None) -- the unit lists are then generated arithmetically instead of by a stable argsort over the templates."""
         assert pt.npts == pd.npts, "fused matcher expects equal point counts on both sides"
         w1, w2 = self._weights()
         dev = pt.H.device
-        P, NT, N = ti.numel(), (pt.npts + 127) // 128, pt.npts
+        if dense is not None:
+            r0, nrows, Dn = dense
+            P = nrows * Dn
+            u = torch.arange(P, device=dev, dtype=torch.int32)
+            t_of, d_of = r0 + u % nrows, u // nrows                          # role 0: runs of equal detection (template)
+            unit_lists = ((t_of, d_of, (t_of - r0) * Dn + d_of),             # (search, template, slot)
+                          (u % Dn, r0 + u // Dn, u))                          # role 1: row-major order is already sorted by track
+        else:
+            P = ti.numel()
+            ti, dj = ti.long(), dj.long()
+            unit_lists = None
+        NT, N = (pt.npts + 127) // 128, pt.npts
         assert N % 128 == 0 or self.gen2, "ragged point counts need the second-generation kernels"
-        ti, dj = ti.long(), dj.long()
         A = torch.empty((P, 2, NT, IMG), device=dev, dtype=torch.uint8)
         B7 = torch.empty((P, 2, B7_BYTES), device=dev, dtype=torch.uint8)
         part = torch.empty((P, 2, 128), device=dev, dtype=torch.float32)
         L = _lib.lib()
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
-            order = torch.argsort(tmpl, stable=True)                        # runs of units share the template operand
-            us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+            if unit_lists is not None:
+                us, ut, sl = (x.contiguous() for x in unit_lists[role])
+            else:
+                order = torch.argsort(tmpl, stable=True)                    # runs of units share the template operand
+                us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
             if self.gen2:
                 e0 = self._tick()
                 _lib.check(L.pcreid_pair_p1a2(P, N, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(pm.MK1),
