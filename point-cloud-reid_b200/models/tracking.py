@@ -6,9 +6,12 @@
   mask instead of a concatenated cartesian-product index list.
 * ``PointReidentifier`` -- the scoring part of ``PointReidentifier.__call__`` (L88-116): encode the detections, gate,
   score every admissible track x detection pair, return the dense (T, D) cost matrix (zeros where not compared).
-  Cropping / pose normalisation / resampling of the sweep (pc_utils.py:31-96) stay upstream of this class.
+  ``from_sweep`` runs the whole of ``__call__`` (L74-116): crop / centre / resample the sweep with the fused front-end
+  (models/frontend.py replaces pc_utils.py:31-96), then encode, gate and score.
 """
 import torch
+
+from .frontend import crop_center_resample
 
 
 class PointFeatureSet:
@@ -63,10 +66,25 @@ def class_gate(det_labels, track_labels, det_lengths=None, track_lengths=None, u
 class PointReidentifier:
     """cost = reid(model, bank)(det_points, det_labels, det_lengths, track_index, track_labels)"""
 
-    def __init__(self, model, feature_set=None, use_lengths=True):
+    def __init__(self, model, feature_set=None, use_lengths=True, subsample_number=128):
         self.model = model
         self.feature_set = feature_set if feature_set is not None else PointFeatureSet(replace_all=False)
         self.use_lengths = use_lengths
+        self.subsample_number = subsample_number
+
+    @torch.no_grad()
+    def from_sweep(self, sweep, bboxes, det_labels, track_index, track_labels, sample_rank=None):
+        """sweep (P, >=3) LiDAR points, bboxes (D, 7) depth-frame boxes of the detections -> (cost (T, D) or None when
+        there are no active tracks, xyz_det, feat_det, lengths_det): PointReidentifier.__call__
+        (tracking_point_reid.py:74-116) from the raw sweep."""
+        batch, lengths = crop_center_resample(bboxes[:, :7].float().contiguous(), sweep.float(), self.subsample_number,
+                                              sample_rank=sample_rank)
+        det_points, det_lengths = batch[0], lengths[0]
+        if track_index is None or len(track_index) == 0:
+            xyz_d, h_d = self.encode(det_points)
+            return None, xyz_d, h_d, det_lengths
+        cost, xyz_d, h_d = self(det_points, det_labels, det_lengths, track_index, track_labels)
+        return cost, xyz_d, h_d, det_lengths
 
     @torch.no_grad()
     def encode(self, det_points):

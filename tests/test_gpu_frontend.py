@@ -73,3 +73,33 @@ def test_device_side_ranks_and_scale_properties():
     assert (ln[0].cpu() - torch.from_numpy(inside.sum(1))).abs().max() <= 2
     # feeds the encoder unchanged: (B, N, 3) float32 contiguous
     assert o.dtype == torch.float32 and o.is_contiguous()
+
+
+def test_reidentifier_from_sweep_equals_manual_pipeline():
+    """sweep -> crop / centre / resample -> encode -> class gate -> cost matrix in one call == the same steps by hand"""
+    import helpers
+    from oracle import reid_oracle as O
+    from pcreid_b200.models.frontend import crop_center_resample
+    from pcreid_b200.models.tracking import PointFeatureSet, PointReidentifier
+    m, orc = helpers.build_pair("pt", (128, 64, 32), device=DEV)
+    pts, boxes = scene(60000, 9, 8)
+    bt, pt = torch.from_numpy(boxes).to(DEV), torch.from_numpy(pts).to(DEV)
+    rank = torch.randint(0, 1 << 30, (9, 128), generator=torch.Generator().manual_seed(1))
+    bank = PointFeatureSet()
+    tr = O.synth_objects(5, 128, 9).to(DEV)
+    xt, ht = m.encode(tr)
+    bank.store_new(xt, ht, torch.full((5,), 128, device=DEV))
+    reid = PointReidentifier(m, bank, subsample_number=128)
+    dl = torch.tensor([0, 1, 2, 0, 1, 2, 0, 1, 9], device=DEV)
+    tl = torch.tensor([0, 1, 2, 0, 7], device=DEV)
+    ti = torch.arange(5, device=DEV)
+    cost, xyz_d, h_d, len_d = reid.from_sweep(pt, bt, dl, ti, tl, sample_rank=rank)
+    batch, lengths = crop_center_resample(bt, pt, 128, sample_rank=rank)
+    cost2, _, _ = reid(batch[0], dl, lengths[0], ti, tl)
+    assert torch.equal(cost, cost2) and torch.equal(len_d, lengths[0]) and cost.shape == (5, 9)
+    # against the oracle on the same crops
+    oxd, ohd = orc.encode(batch[0].cpu())
+    mask = O.class_gated_pairs(tl.cpu(), torch.full((5,), 128), dl.cpu(), lengths[0].cpu())
+    Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), ohd, oxd, pair_mask=mask)
+    assert (cost.cpu() - Lo).abs().max() < 1e-4
+    assert (cost[:, 8] == 0).all()                                           # class 9 is never compared
