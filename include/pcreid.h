@@ -168,6 +168,11 @@ int pcreid_edge_gather_max(int B, int C, int N, int k, const float* P, const flo
  * A (T,Hd) = W1[:, :E] e_t, Bv (D,Hd) = W1[:, E:] e_d (row-major, from cn_linear), E_t (T,E), E_d (D,E),
  * Hd = 2E <= 256, G groups.  mask (T,D) u8 optional: 0 -> logit 0 (class gating,
  * tracking_point_reid.py:15-33).  out (T,D) f32 row-major. */
+/* tensor-core ("fast") version for the shipped head LinearRes(256, 256, GN 32 groups) + Linear(256, 1), E = 128:
+ * W2img = bf16 K-major operand image [k/8][256 n][8] of linear2.weight (csrc/concat_tc.cu); other arguments as below. */
+int pcreid_pair_concat_head_tc(int T, int D, int E, int G, const float* A, const float* Bv, const float* Et, const float* Ed,
+                               const void* W2img, const float* g1, const float* be1, const float* g2, const float* be2,
+                               const float* w, float b0, const unsigned char* mask, float* out, int n_ctas, void* stream);
 int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const float* Bv, const float* Et, const float* Ed,
                             const float* W2, const float* g1, const float* be1, const float* g2, const float* be2,
                             const float* w, float b0, const unsigned char* mask, float* out, void* stream);

@@ -297,3 +297,21 @@ def pair_concat_head(a, bv, et, ed, w2, g1, be1, g2, be2, w, b0, groups, mask=No
                                                   _p(g2), _p(be2), _p(w), float(b0), _p(mask), _p(out), _stream()),
                "pcreid_pair_concat_head")
     return out
+
+
+def bf16_kmajor_image(w):
+    """torch weight (N, K) -> bf16 K-major tcgen05 operand image [K/8][N][8] (uint8 view)."""
+    n, kd = w.shape
+    return w.detach().to(torch.bfloat16).view(n, kd // 8, 8).permute(1, 0, 2).contiguous().view(torch.uint8).flatten()
+
+
+def pair_concat_head_tc(a, bv, et, ed, w2img, g1, be1, g2, be2, w, b0, groups, mask=None):
+    """tensor-core version of pair_concat_head (bf16 operands for the 256 x 256 Linear, fp32 GroupNorms / accumulation)."""
+    _need_cuda(a, bv, et, ed, w2img)
+    T, D, E = a.shape[0], bv.shape[0], et.shape[1]
+    out = torch.empty((T, D), device=a.device, dtype=torch.float32)
+    n_ctas = torch.cuda.get_device_properties(a.device).multi_processor_count
+    _lib.check(_lib.lib().pcreid_pair_concat_head_tc(T, D, E, groups, _p(a), _p(bv), _p(et), _p(ed), _p(w2img), _p(g1), _p(be1),
+                                                     _p(g2), _p(be2), _p(w), float(b0), _p(mask), _p(out), n_ctas, _stream()),
+               "pcreid_pair_concat_head_tc")
+    return out

@@ -280,6 +280,13 @@ class ReIDNet(nn.Module):
         A = K.cn_linear(e_t.unsqueeze(0), w1a, x1_pm=True, y_pm=True)[0]     # (T, 2E)
         Bv = K.cn_linear(e_d.unsqueeze(0), w1b, x1_pm=True, y_pm=True)[0]    # (D, 2E)
         mask = None if pair_mask is None else pair_mask.to(torch.uint8).contiguous()
+        if self.match_mode == 'fast' and E == 128 and lr.groups * 8 == 2 * E:
+            # tensor-core head (csrc/concat_tc.cu): bf16 operands for the 256 x 256 Linear, everything else fp32
+            if "w2img" not in pk:
+                pk["w2img"] = K.bf16_kmajor_image(lr.linear2.weight)
+            return K.pair_concat_head_tc(A, Bv, e_t, e_d, pk["w2img"], pk["g1"], pk["b1"], pk["g2"], pk["b2"],
+                                         fin.weight.detach().float().reshape(-1).contiguous(), float(fin.bias.detach()[0]),
+                                         lr.groups, mask)
         return K.pair_concat_head(A, Bv, e_t, e_d, pk["w2"], pk["g1"], pk["b1"], pk["g2"], pk["b2"],
                                   fin.weight.detach().float().reshape(-1).contiguous(), float(fin.bias.detach()[0]),
                                   lr.groups, mask)

@@ -1,0 +1,68 @@
+"""North-star target shape (BASELINE.json): Point Transformer encode + 4096 x 4096 all-pairs match, rows sharded over the GPUs of
+one box, with the 'concat' head (the only head for which the 10 ms target is reachable; its config pools with
+MaxPool1d(64) over channels, which fixes 128 points per object).  One process per GPU:
+  python -m torch.distributed.run --nproc-per-node G --master-addr 127.0.0.1 scripts/bench_target.py [--T 4096 --D 4096 --steps 20]
+Prints one JSON line (rank 0): ms per step = max over ranks of (encode own shard + all-gather + score own row block)."""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, torch.distributed as dist
+import helpers
+from oracle import reid_oracle as O
+from pcreid_b200.models import build_model
+from pcreid_b200.parallel import encode_and_gather, shard_range
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--T", type=int, default=4096); ap.add_argument("--D", type=int, default=4096)
+ap.add_argument("--steps", type=int, default=20); ap.add_argument("--warmup", type=int, default=5)
+ap.add_argument("--mode", default="fast")
+args = ap.parse_args()
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+torch.manual_seed(66)
+m = build_model(helpers.model_cfg("concat", (128, 64, 32))).eval().to(dev)
+m.set_mode(args.mode)
+t0, t1 = shard_range(args.T, rank, world)
+d0, d1 = shard_range(args.D, rank, world)
+counts = [shard_range(args.D, r, world)[1] - shard_range(args.D, r, world)[0] for r in range(world)]
+tracks = O.synth_objects(args.T, 128, 0)[t0:t1].contiguous().to(dev)
+dets = O.synth_objects(args.D, 128, 1)[d0:d1].contiguous().to(dev)
+
+
+def step():
+    xt, ht, xd, hd = encode_and_gather(m, tracks, dets, counts)
+    return m.match_all_pairs(ht, xt, hd, xd)
+
+
+def barrier():
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+for _ in range(args.warmup):
+    step()
+ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+barrier(); ev[0].record()
+for _ in range(args.steps):
+    step()
+ev[1].record(); barrier()
+ms = ev[0].elapsed_time(ev[1]) / args.steps
+e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+torch.cuda.synchronize(); e[0].record()
+xt, ht, xd, hd = encode_and_gather(m, tracks, dets, counts); e[1].record()
+m.match_all_pairs(ht, xt, hd, xd); e[2].record(); torch.cuda.synchronize()
+t = torch.tensor([ms, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], device=dev)
+if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+if rank == 0:
+    print(json.dumps({"workload": f"PT encode ({args.T}+{args.D} objects x 128 pts) + {args.T}x{args.D} all-pairs 'concat' match, row-sharded",
+                      "n_gpus": world, "mode": args.mode, "ms_per_step_max_over_ranks": float(t[0]),
+                      "encode_plus_allgather_ms": float(t[1]), "match_ms": float(t[2]),
+                      "pairs_per_s": args.T * args.D / (float(t[0]) * 1e-3), "objects_per_s": (args.T + args.D) / (float(t[1]) * 1e-3),
+                      "target_ms": 10.0}))
+if world > 1:
+    dist.destroy_process_group()

@@ -1,3 +1,4 @@
+"""Per-kernel CUDA time of one encoder pass (torch profiler): python scripts/profile_encode.py [mode] [objects] [points]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -5,9 +6,12 @@ import torch, helpers
 from torch.profiler import profile, ProfilerActivity
 from oracle import reid_oracle as O
 dev = "cuda"
-m, _ = helpers.build_pair("pt", (256, 128, 64), device=dev, perturb=False)
-m.set_mode(sys.argv[1] if len(sys.argv) > 1 else 'fast')
-x = O.synth_objects(2048, 256, 0).to(dev)
+mode = sys.argv[1] if len(sys.argv) > 1 else 'fast'
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 2048
+N = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+m, _ = helpers.build_pair("pt", (N, N // 2, N // 4), device=dev, perturb=False)
+m.set_mode(mode)
+x = O.synth_objects(B, N, 0).to(dev)
 for _ in range(3): m.encode(x)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA]) as prof:

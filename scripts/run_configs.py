@@ -46,6 +46,8 @@ jobs = [
     ("c5", lambda: run("C5 sweep PT 4096x4096 @256", "pt", 256, (256, 128, 64), 4096, 4096, "fast", reps=1)),
     # the 'concat' baseline config pools with MaxPool1d(64) over the channel axis -> width N per object: only consistent at N=128
     ("concat", lambda: run("C5 concat head PT 4096x4096 @128", "concat", 128, (128, 64, 32), 4096, 4096, "parity")),
+    ("concat", lambda: run("C5 concat head PT 4096x4096 @128 (tensor-core head)", "concat", 128, (128, 64, 32), 4096, 4096, "fast")),
+    ("concat", lambda: run("target shape: concat head PT 16384x16384 @128 (tensor-core head)", "concat", 128, (128, 64, 32), 16384, 16384, "fast", reps=1)),
     ("concat", lambda: run("target shape: concat head PT 4096x4096 @128, 16384x16384", "concat", 128, (128, 64, 32), 16384, 16384, "parity", reps=1)),
 ]
 for tag, job in jobs:

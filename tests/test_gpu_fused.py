@@ -92,3 +92,27 @@ def test_kernel_variants_agree(p1_split, p2_three):
     Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu())
     assert (Lv - Lo).abs().max() < TOL_FAST
     assert (Lv - Lref).abs().max() < 1.5e-2                        # variants differ only in bf16 rounding points
+
+
+@pytest.mark.parametrize("T,D,masked", [(37, 70, False), (5, 3, True), (130, 257, True)])
+def test_concat_head_tensor_core_matches_parity_and_oracle(T, D, masked):
+    """'concat' baseline head (reid_pts_point-transformer_baseline.py) on the tensor cores (csrc/concat_tc.cu): ragged T / D,
+    class-gate mask, against the fp32 kernel and the oracle."""
+    m, orc = helpers.build_pair("concat", (128, 64, 32), device=DEV)
+    t, d = O.synth_objects(T, 128, 30), O.synth_objects(D, 128, 31)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    mask = (torch.rand(T, D, generator=torch.Generator().manual_seed(2)) > 0.4) if masked else None
+    mk = None if mask is None else mask.to(DEV)
+    Lp = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mk).cpu()
+    m.match_mode = 'fast'
+    Lf = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mk).cpu()
+    Lo = orc.match_all_pairs(ht.cpu(), xt.cpu(), hd.cpu(), xd.cpu(), pair_mask=mask)
+    assert (Lp - Lo).abs().max() < 1e-4
+    err = (Lf - Lo).abs().max().item()
+    assert err < TOL_FAST, f"tensor-core concat head off by {err}"
+    if masked:
+        assert (Lf[~mask] == 0).all()
+    if T > 8:
+        ok, agree, n = helpers.margin_aware_top1(Lo, Lf, err)
+        assert ok, f"top-1 changed on a decisive row (agreement {agree}, {n} decisive rows)"
