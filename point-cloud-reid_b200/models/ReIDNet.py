@@ -268,10 +268,18 @@ class ReIDNet(nn.Module):
                     flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
             return out
 
+    def pooled_embedding(self, h):
+        """'concat' match type: the per-object vector the head consumes (max over the channel axis, ReIDNet.py:455-458);
+        128 floats per object -- what the row-sharded driver all-gathers instead of the per-point maps."""
+        return K.cn_chanmax(_cn(h))
+
     def _concat_all_pairs(self, h_t, h_d, pair_mask):
-        """'concat' head over all pairs, first Linear hoisted per object (W1 [e_t; e_d] = W1a e_t + W1b e_d)."""
+        return self.concat_all_pairs_pooled(K.cn_chanmax(h_t), K.cn_chanmax(h_d), pair_mask)
+
+    def concat_all_pairs_pooled(self, e_t, e_d, pair_mask=None):
+        """'concat' head over all pairs of pooled embeddings e_t (T, E), e_d (D, E); first Linear hoisted per object
+        (W1 [e_t; e_d] = W1a e_t + W1b e_d)."""
         lr, fin = self.match_head[0], self.match_head[1]
-        e_t, e_d = K.cn_chanmax(h_t), K.cn_chanmax(h_d)                      # (T, E), (D, E)
         E = e_t.shape[1]
         pk = lr.packed()
         if lr.transform is not None or pk["w1"].shape[0] != 2 * E:

@@ -48,8 +48,18 @@ def match_all_pairs_sharded(model, tracks_local, dets_local, det_counts, pair_ma
     """tracks_local (T_r, N, 3), dets_local (D_r, N, 3) on this rank; det_counts = [D_0 .. D_{G-1}].
     Returns this rank's (T_r, D) score rows, or the full (T, D) matrix on every rank if gather_scores
     (then track_counts = [T_0 .. T_{G-1}] is required)."""
-    xyz_t, h_t, xyz_d, h_d = encode_and_gather(model, tracks_local, dets_local, det_counts, group)
-    rows = model.match_all_pairs(h_t, xyz_t, h_d, xyz_d, pair_mask=pair_mask_rows, chunk=chunk)
+    if getattr(model, "match_type", None) == 'concat':
+        # the head only needs the pooled vectors: pool locally, all-gather 128 floats per detection instead of the maps
+        with torch.no_grad():
+            _, h_t = model.encode(tracks_local)
+            _, h_d = model.encode(dets_local)
+            e_t, e_d = model.pooled_embedding(h_t), model.pooled_embedding(h_d)
+            if len(det_counts) > 1:
+                e_d = _all_gather_rows(e_d.contiguous(), det_counts, group)
+            rows = model.concat_all_pairs_pooled(e_t, e_d, pair_mask_rows)
+    else:
+        xyz_t, h_t, xyz_d, h_d = encode_and_gather(model, tracks_local, dets_local, det_counts, group)
+        rows = model.match_all_pairs(h_t, xyz_t, h_d, xyz_d, pair_mask=pair_mask_rows, chunk=chunk)
     if gather_scores and len(det_counts) > 1:
         return _all_gather_rows(rows.contiguous(), track_counts, group)
     return rows

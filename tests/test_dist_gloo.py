@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, T, D, ret):
+def _worker(rank, world, port, T, D, kind, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -23,7 +23,7 @@ def _worker(rank, world, port, T, D, ret):
     from pcreid_b200.parallel import match_all_pairs_sharded, shard_range
     fake_kernels.install()
     torch.set_num_threads(2)
-    m, orc = helpers.build_pair("pt")
+    m, orc = helpers.build_pair(kind)
     tracks, dets = O.synth_objects(T, 128, 0), O.synth_objects(D, 128, 1)
     t0, t1 = shard_range(T, rank, world)
     d0, d1 = shard_range(D, rank, world)
@@ -54,11 +54,12 @@ def test_shard_range_covers_and_balances():
 
 
 @pytest.mark.timeout(300)
-def test_row_sharded_matcher_world2_gloo():
+@pytest.mark.parametrize("kind", ["pt", "concat"])     # 'concat' all-gathers the pooled vectors only
+def test_row_sharded_matcher_world2_gloo(kind):
     T, D = 5, 3      # uneven shards on purpose: tracks 3+2, detections 2+1
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(2, port, T, D, ret), nprocs=2, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if kind == "concat" else 0)
+    mp.spawn(_worker, args=(2, port, T, D, kind, ret), nprocs=2, join=True)
     assert ret["shape"] == (T, D)
     assert ret["rows_err"] < 2e-5 and ret["full_err"] < 2e-5
