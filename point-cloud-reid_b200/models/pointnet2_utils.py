@@ -19,10 +19,11 @@ class LinearAttention(nn.Module):
 
 
 def attention_message(q, wkv, ksum, nhead, s_len, pk, q_map=None, t_map=None, B=None):
-    """scale -> (Q.KV) -> merge -> LayerNorm1."""
+    """scale -> (Q.KV) -> merge -> LayerNorm1.  The per-object KV summary and the merge projection are multiplied once per
+    template object (d x d x d), so each point sees ONE d x d GEMM instead of two."""
     qs = K.linattn_scale(q, ksum, nhead, s_len, q_map=q_map, ksum_map=t_map, B=B)
-    msg = K.cn_linear(qs, wkv, w1_map=t_map)
-    msg = K.cn_linear(msg, pk["merge"])
+    m = K.cn_linear(wkv, pk["merge"], x1_pm=True, y_pm=True)        # (B_t, d, d) = blockdiag(KV) Wm^T, k-major per object
+    msg = K.cn_linear(qs, m, w1_map=t_map)
     return K.cn_groupnorm(msg, pk["n1w"], pk["n1b"], 1)
 
 

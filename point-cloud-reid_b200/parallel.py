@@ -33,10 +33,21 @@ def _all_gather_rows(t, counts, group):
     return torch.cat([out[r * mx:r * mx + c] for r, c in enumerate(counts)], dim=0)
 
 
-def encode_and_gather(model, tracks_local, dets_local, det_counts, group=None):
-    """encode this rank's tracks / detection slice, all-gather the detection embeddings -> (xyz_t, h_t, xyz_d, h_d)."""
+def _encode_both(model, tracks_local, dets_local):
+    """tracks and detections of equal point count go through the encoder as ONE batch (objects are independent; larger
+    launches), exactly like ReIDNet.siamese_forward concatenates the two sides (ReIDNet.py:311-332)."""
+    if tracks_local.shape[1:] == dets_local.shape[1:] and tracks_local.shape[0] > 0 and dets_local.shape[0] > 0:
+        nt = tracks_local.shape[0]
+        xyz, h = model.encode(torch.cat([tracks_local, dets_local], dim=0))
+        return xyz[:nt], h[:nt], xyz[nt:], h[nt:]
     xyz_t, h_t = model.encode(tracks_local)
     xyz_d, h_d = model.encode(dets_local)
+    return xyz_t, h_t, xyz_d, h_d
+
+
+def encode_and_gather(model, tracks_local, dets_local, det_counts, group=None):
+    """encode this rank's tracks / detection slice, all-gather the detection embeddings -> (xyz_t, h_t, xyz_d, h_d)."""
+    xyz_t, h_t, xyz_d, h_d = _encode_both(model, tracks_local, dets_local)
     if len(det_counts) > 1:
         h_d = _all_gather_rows(h_d.contiguous(), det_counts, group)
         xyz_d = _all_gather_rows(xyz_d.contiguous(), det_counts, group)
@@ -51,8 +62,7 @@ def match_all_pairs_sharded(model, tracks_local, dets_local, det_counts, pair_ma
     if getattr(model, "match_type", None) == 'concat':
         # the head only needs the pooled vectors: pool locally, all-gather 128 floats per detection instead of the maps
         with torch.no_grad():
-            _, h_t = model.encode(tracks_local)
-            _, h_d = model.encode(dets_local)
+            _, h_t, _, h_d = _encode_both(model, tracks_local, dets_local)
             e_t, e_d = model.pooled_embedding(h_t), model.pooled_embedding(h_d)
             if len(det_counts) > 1:
                 e_d = _all_gather_rows(e_d.contiguous(), det_counts, group)

@@ -15,7 +15,7 @@ from pcreid_b200.parallel import match_all_pairs_sharded, shard_range
 ap = argparse.ArgumentParser()
 ap.add_argument("--T", type=int, default=4096); ap.add_argument("--D", type=int, default=4096)
 ap.add_argument("--steps", type=int, default=20); ap.add_argument("--warmup", type=int, default=5)
-ap.add_argument("--mode", default="fast")
+ap.add_argument("--mode", default="fast"); ap.add_argument("--graphs", type=int, default=1)
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -25,6 +25,7 @@ if world > 1:
 torch.manual_seed(66)
 m = build_model(helpers.model_cfg("concat", (128, 64, 32))).eval().to(dev)
 m.set_mode(args.mode)
+m.enable_cuda_graphs(bool(args.graphs))
 t0, t1 = shard_range(args.T, rank, world)
 d0, d1 = shard_range(args.D, rank, world)
 counts = [shard_range(args.D, r, world)[1] - shard_range(args.D, r, world)[0] for r in range(world)]
@@ -58,7 +59,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"workload": f"PT encode ({args.T}+{args.D} objects x 128 pts) + {args.T}x{args.D} all-pairs 'concat' match, row-sharded",
-                      "n_gpus": world, "mode": args.mode, "ms_per_step_max_over_ranks": float(t[0]),
+                      "n_gpus": world, "mode": args.mode, "cuda_graphs": bool(args.graphs), "ms_per_step_max_over_ranks": float(t[0]),
                       "encode_only_ms": float(t[1]),
                       "pairs_per_s": args.T * args.D / (float(t[0]) * 1e-3), "objects_per_s": (args.T + args.D) / (float(t[1]) * 1e-3),
                       "target_ms": 10.0}))

@@ -106,3 +106,23 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(bld, "build_library", lambda *a, **k: None)
     with pytest.raises((RuntimeError, OSError)):
         _lib.lib()
+
+
+def test_cuda_graph_encode_is_identical_and_survives_weight_updates():
+    """encode() through a captured CUDA graph: bit-identical to the eager launches, results stay valid across calls, the
+    graph is rebuilt when a parameter changes"""
+    m, orc = helpers.build_pair("pt", (128, 64, 32), device=DEV)
+    m.set_mode('fast')
+    a, b = O.synth_objects(9, 128, 40).to(DEV), O.synth_objects(9, 128, 41).to(DEV)
+    xa, ha = m.encode(a)
+    xb, hb = m.encode(b)
+    m.enable_cuda_graphs(True)
+    xa2, ha2 = m.encode(a)
+    xb2, hb2 = m.encode(b)                      # same shape: replays the same graph, must not clobber (xa2, ha2)
+    assert torch.equal(ha, ha2) and torch.equal(hb, hb2) and torch.equal(xa, xa2)
+    with torch.no_grad():
+        m.backbone.cov_final.bias.add_(0.5)
+    _, ha3 = m.encode(a)
+    assert (ha3 - (ha + 0.5)).abs().max() < 1e-5
+    m.enable_cuda_graphs(False)
+    assert torch.equal(m.encode(a)[1], ha3)
