@@ -103,18 +103,87 @@ __device__ __forceinline__ void load_x_chunk(float* __restrict__ Xs, const float
   }
 }
 
+// packed variant: the 128-row tile holds TR / rows whole objects (rows < TR, TR % rows == 0, rows % 4 == 0): tile row r is
+// point r % rows of object b0 + r / rows.  Channel-major, 16-byte aligned sources only.
+__device__ __forceinline__ void load_x_chunk_packed(float* __restrict__ Xs, const float* __restrict__ X, long long bs, int K, int ld,
+                                                    int rows, int k0, int b0, int B) {
+  for (int i = threadIdx.x; i < KC * TR / 4; i += NTHR) {
+    int kk = i / (TR / 4), r4 = (i % (TR / 4)) * 4;
+    float* dst = Xs + kk * TR + r4;
+    int k = k0 + kk, ob = b0 + r4 / rows, n = r4 % rows;
+    if (k < K && ob < B) cp_async16(dst, X + (size_t)ob * bs + (size_t)k * ld + n);
+    else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // ------------------------------------------------------------------------------------------------
 // cn_linear
 // ------------------------------------------------------------------------------------------------
-template <int TN>
+// PACK: objects with fewer than 128 rows share a tile (shared weights, channel-major, no gather maps): the deep levels of the
+// encoders (64 / 32 points per object) otherwise run the 128-row tile 50 % / 75 % empty
+template <int TN, bool PACK = false>
 __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_args a) {
   constexpr int TC = TileCols<TN>::value;
   __shared__ __align__(16) float Xs[2][KC * TR];
   __shared__ __align__(16) float Ws[2][KC * TC];
-  const int b = blockIdx.z, n0 = blockIdx.x * TR, co0 = blockIdx.y * TC;
+  const int b = PACK ? blockIdx.z * (TR / a.rows) : blockIdx.z, n0 = blockIdx.x * TR, co0 = blockIdx.y * TC;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  if (PACK) {
+    const float* W1 = a.W1;
+    const float* W2 = a.K2 > 0 ? a.W2 : nullptr;
+    const int nch1 = ceil_div(a.K1, KC), nch2 = a.K2 > 0 ? ceil_div(a.K2, KC) : 0, nch = nch1 + nch2;
+    auto load = [&](int stage, int ch) {
+      if (ch < nch1) {
+        load_x_chunk_packed(Xs[stage], a.X1, a.x1_bs, a.K1, a.ldx1, a.rows, ch * KC, b, a.B);
+        load_w_chunk<TN>(Ws[stage], W1, a.K1, a.CO, ch * KC, co0, true);
+      } else {
+        load_x_chunk_packed(Xs[stage], a.X2, a.x2_bs, a.K2, a.ldx2, a.rows, (ch - nch1) * KC, b, a.B);
+        load_w_chunk<TN>(Ws[stage], W2, a.K2, a.CO, (ch - nch1) * KC, co0, true);
+      }
+    };
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    load(0, 0);
+    cp_async_commit();
+    for (int ch = 0; ch < nch; ++ch) {
+      if (ch + 1 < nch) load((ch + 1) & 1, ch + 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncthreads();
+      fma_chunk<TN>(Xs[ch & 1], Ws[ch & 1], tx, ty, acc);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int co = co0 + col_of<TN>(ty, j);
+      if (co >= a.CO) continue;
+      const float bv = a.bias ? __ldg(a.bias + co) : 0.f;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = h * 64 + tx * 4, ob = b + r / a.rows, n = r % a.rows;
+        if (ob >= a.B) continue;
+        float4 rr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.R) rr = *reinterpret_cast<const float4*>(a.R + (size_t)ob * a.r_bs + (size_t)co * a.ldr + n);
+        const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float x = acc[h * 4 + i][j] + bv;
+          if (a.R && !a.res_after_act) x += rv[i];
+          x = apply_act(x, a.act);
+          if (a.R && a.res_after_act) x += rv[i];
+          v[i] = x;
+        }
+        *reinterpret_cast<float4*>(a.Y + (size_t)ob * a.y_bs + (size_t)co * a.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+      }
+    }
+    return;
+  }
 
   const int xb1 = a.x1_map ? a.x1_map[b] : b;
   const float* X1 = a.X1 + (size_t)xb1 * a.x1_bs;
@@ -232,8 +301,10 @@ __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_arg
 // cn_groupnorm: one thread per (object, point); channels strided by ld (coalesced across points)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) cn_groupnorm_kernel(const pcreid_norm_args a) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
-  if (n >= a.rows) return;
+  // one thread per (object, point), flattened so that objects with few points still fill the CTAs
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)a.B * a.rows) return;
+  const int b = (int)(idx / a.rows), n = (int)(idx % a.rows);
   const float* X = a.X + (size_t)b * a.x_bs + n;
   const float* R = a.R ? a.R + (size_t)(a.r_map ? a.r_map[b] : b) * a.r_bs + n : nullptr;
   float* Y = a.Y + (size_t)b * a.y_bs + n;
@@ -624,7 +695,17 @@ int pcreid_cn_linear(const pcreid_linear_args* p, void* stream) {
       if (s.R) { if (s.r_map) s.r_map += b0; else s.R += (size_t)b0 * s.r_bs; }
       s.Y += (size_t)b0 * s.y_bs;
     }
-    if (a.CO > 64) {
+    auto a16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool pack = s.rows < TR && TR % s.rows == 0 && s.rows % 4 == 0 && s.B > 1 && !s.x1_map && !s.x2_map && !s.w1_map && !s.r_map &&
+                      !s.x1_pm && !s.x2_pm && !s.y_pm && s.w1_bs == 0 && (s.K2 == 0 || s.w2_bs == 0) && s.CO % 4 == 0 &&
+                      a16(s.X1) && s.ldx1 % 4 == 0 && s.x1_bs % 4 == 0 && a16(s.W1) && a16(s.Y) && s.ldy % 4 == 0 && s.y_bs % 4 == 0 &&
+                      (s.K2 == 0 || (a16(s.X2) && s.ldx2 % 4 == 0 && s.x2_bs % 4 == 0 && a16(s.W2))) &&
+                      (!s.R || (a16(s.R) && s.ldr % 4 == 0 && s.r_bs % 4 == 0));
+    if (pack) {
+      const int nz = ceil_div(s.B, TR / s.rows);
+      if (a.CO > 64) cn_linear_kernel<8, true><<<dim3(1, ceil_div(a.CO, 128), nz), NTHR, 0, st>>>(s);
+      else cn_linear_kernel<4, true><<<dim3(1, 1, nz), NTHR, 0, st>>>(s);
+    } else if (a.CO > 64) {
       dim3 grid(ceil_div(a.rows, TR), ceil_div(a.CO, 128), s.B);
       cn_linear_kernel<8><<<grid, NTHR, 0, st>>>(s);
     } else {
@@ -648,8 +729,7 @@ int pcreid_cn_groupnorm(const pcreid_norm_args* p, void* stream) {
     s.X += (size_t)b0 * s.x_bs;
     s.Y += (size_t)b0 * s.y_bs;
     if (s.R) { if (s.r_map) s.r_map += b0; else s.R += (size_t)b0 * s.r_bs; }
-    dim3 grid(ceil_div(a.rows, 128), s.B);
-    cn_groupnorm_kernel<<<grid, 128, 0, st>>>(s);
+    cn_groupnorm_kernel<<<(unsigned)(((long long)s.B * a.rows + 127) / 128), 128, 0, st>>>(s);
   }
   return pcreid_launch_status();
 }
