@@ -60,6 +60,12 @@ _SIGS = {
     "pcreid_cn_linear": [ctypes.POINTER(LinearArgs), c_vp],
     "pcreid_cn_linear_tc": [ctypes.POINTER(LinearArgs), c_vp],
     "pcreid_cn_groupnorm": [ctypes.POINTER(NormArgs), c_vp],
+    "pcreid_attn_front_blob_bytes": [c_int, c_int, c_int, c_int],
+    "pcreid_attn_front": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int,
+                          c_vp],
+    "pcreid_kv_merge": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_attn_back_blob_bytes": [c_int, c_int, c_int, c_int],
+    "pcreid_attn_back": [c_int] * 9 + [c_vp, c_ll, c_int, c_vp, c_ll, c_int] + [c_vp] * 7 + [c_vp, c_ll, c_int, c_vp],
     "pcreid_linattn_kv": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_linattn_scale": [c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp],
     "pcreid_cn_pool": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_ll, c_vp],

@@ -261,6 +261,70 @@ def tf32_image(w):
     return w.detach().float().reshape(n, kd // 4, 4).permute(1, 0, 2).contiguous()
 
 
+def tf32_image_padded(w, k_pad):
+    """tf32_image of a (C_out, C_in) weight whose input channels are zero-padded to k_pad."""
+    w = w.detach().float()
+    if w.shape[1] < k_pad:
+        w = torch.cat([w, w.new_zeros(w.shape[0], k_pad - w.shape[1])], 1)
+    return tf32_image(w)
+
+
+def weight_blob(*images):
+    """concatenation of operand images in the order a fused kernel consumes them (attn_tc.cu)."""
+    return torch.cat([i.reshape(-1) for i in images]).contiguous()
+
+
+def attn_front(xyz, feat, wp0, bp0, bp2, blob, DP, NFP, NF):
+    """key-side half of a linear-attention block on the tensor cores: pos MLP, feat + pos, projections.
+    -> (B, NFP + NF, S): the first NFP channels are projections of feat + pos, the rest of feat."""
+    _need_cuda(xyz, feat, blob)
+    B, C2, S = feat.shape
+    f_bs, ldf = _cn(feat, "feat")
+    if not xyz.is_contiguous():
+        raise ValueError("xyz must be contiguous")
+    L = _lib.lib()
+    if blob.numel() * 4 != L.pcreid_attn_front_blob_bytes(C2, DP, NFP, NF):
+        raise ValueError("attn_front: weight blob does not match the shapes")
+    out = torch.empty((B, NFP + NF, S), device=feat.device, dtype=torch.float32)
+    _lib.check(L.pcreid_attn_front(B, S, C2, DP, NFP, NF, _p(xyz), _p(feat), f_bs, ldf, _p(wp0), _p(bp0), _p(bp2), _p(blob),
+                                   _p(out), out.stride(0), out.stride(1), _stream()), "pcreid_attn_front")
+    return out
+
+
+def kv_merge(wkv, merge_kmajor, nhead):
+    """(B, d, d) block-diagonal KV summaries x merge projection -> per-object tcgen05 operand images (B, d*d)."""
+    _need_cuda(wkv, merge_kmajor)
+    B, d, _ = wkv.shape
+    mimg = torch.empty((B, d * d), device=wkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_kv_merge(B, d, nhead, _p(wkv), _p(merge_kmajor), _p(mimg), _stream()), "pcreid_kv_merge")
+    return mimg
+
+
+def attn_back(feat1, q, ksum, mimg, g1, b1, g2, b2, blob, nhead, CO, s_len, residual, feat1_pm=False):
+    """query-side half of a linear-attention block: (q | Wq feat1) -> scaling -> . M -> LN1 -> mlp -> LN2 (+ feat1)."""
+    _need_cuda(feat1, q, ksum, mimg, blob)
+    D = ksum.shape[1]
+    if feat1_pm:
+        if not feat1.is_contiguous():
+            raise ValueError("point-major feat1 must be contiguous (B, rows, C1)")
+        B, rows, C1 = feat1.shape
+        f1_bs, ldf1 = rows * C1, C1
+    else:
+        B, C1, rows = feat1.shape
+        f1_bs, ldf1 = _cn(feat1, "feat1")
+    q_bs = ldq = 0
+    if q is not None:
+        q_bs, ldq = _cn(q, "q")
+    L = _lib.lib()
+    if blob.numel() * 4 != L.pcreid_attn_back_blob_bytes(D, (C1 + 7) // 8 * 8, CO, int(q is not None)):
+        raise ValueError("attn_back: weight blob does not match the shapes")
+    out = torch.empty((B, CO, rows), device=feat1.device, dtype=torch.float32)
+    _lib.check(L.pcreid_attn_back(B, rows, D, nhead, C1, CO, s_len, int(residual), int(feat1_pm), _p(feat1), f1_bs, ldf1, _p(q), q_bs,
+                                  ldq, _p(ksum), _p(mimg), _p(g1), _p(b1), _p(g2), _p(b2), _p(blob), _p(out), out.stride(0),
+                                  out.stride(1), _stream()), "pcreid_attn_back")
+    return out
+
+
 def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
     """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image(); p1 (B, N, C) and cc (B, S, C) point-major."""
     _need_cuda(p1, cc, idx)

@@ -18,6 +18,12 @@ class LinearAttention(nn.Module):
         self.eps = eps
 
 
+def fused_attention_supported(d, nhead, f1, f2, out):
+    """shapes csrc/attn_tc.cu is built for (the mul=1 configurations); wider models stay on the unfused kernels."""
+    return (d % 16 == 0 and d <= 128 and nhead <= 4 and d % nhead == 0 and (d // nhead) % 16 == 0 and f2 % 16 == 0 and f2 <= 128
+            and (f1 + 7) // 8 * 8 <= 128 and out % 16 == 0 and out <= 2 * d)
+
+
 def attention_message(q, wkv, ksum, nhead, s_len, pk, q_map=None, t_map=None, B=None):
     """scale -> (Q.KV) -> merge -> LayerNorm1.  The per-object KV summary and the merge projection are multiplied once per
     template object (d x d x d), so each point sees ONE d x d GEMM instead of two."""
@@ -50,23 +56,35 @@ class Self_Attention(PackedModule):
                                  nn.Linear(d_model * 2, d_model, bias=False))
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
+        self.tc_mode = False      # True: the block runs as attn_front / kv_merge / attn_back on the tensor cores (fast mode)
 
     def _pack(self):
         d = self.q_proj.weight.shape[0]
         m0 = self.mlp[0].weight.detach()
-        return dict(
+        pk = dict(
             pos0=kmajor(self.pos_mlp[0].weight), pos0b=self.pos_mlp[0].bias.detach().float().contiguous(),
             pos2=kmajor(self.pos_mlp[2].weight), pos2b=self.pos_mlp[2].bias.detach().float().contiguous(),
             qkv=kmajor(torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0)),
             merge=kmajor(self.merge.weight), mlp0a=kmajor(m0[:, :d]), mlp0b=kmajor(m0[:, d:]), mlp2=kmajor(self.mlp[2].weight),
             n1w=self.norm1.weight.detach().float().contiguous(), n1b=self.norm1.bias.detach().float().contiguous(),
             n2w=self.norm2.weight.detach().float().contiguous(), n2b=self.norm2.bias.detach().float().contiguous())
+        if fused_attention_supported(d, self.nhead, d, d, d):
+            pk["front_blob"] = K.weight_blob(K.tf32_image(self.pos_mlp[2].weight),
+                                             K.tf32_image(torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0)))
+            pk["back_blob"] = K.weight_blob(K.tf32_image(m0[:, :d]), K.tf32_image(m0[:, d:]), K.tf32_image(self.mlp[2].weight))
+        return pk
 
     def forward(self, feat, xyz, mask=None):
         """feat (B, C, N), xyz (B, N, 3) -> (B, C, N)."""
         assert mask is None, "masks are never used on the ReID path"
         pk = self.packed()
         C, S = feat.shape[1], feat.shape[2]
+        if self.tc_mode and "front_blob" in pk:
+            qkv = K.attn_front(xyz, feat, pk["pos0"], pk["pos0b"], pk["pos2b"], pk["front_blob"], C, 3 * C, 0)
+            wkv, ksum = K.linattn_kv(qkv[:, C:2 * C], qkv[:, 2 * C:], self.nhead)
+            mimg = K.kv_merge(wkv, pk["merge"], self.nhead)
+            return K.attn_back(feat, qkv[:, :C], ksum, mimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
+                               self.nhead, C, S, residual=True)
         hid = K.cn_linear(xyz, pk["pos0"], bias=pk["pos0b"], act=K.ACT_RELU, x1_pm=True)
         feat_pos = K.cn_linear(hid, pk["pos2"], bias=pk["pos2b"], res=feat)
         qkv = K.cn_linear(feat_pos, pk["qkv"])
@@ -150,22 +168,38 @@ class FP_SA(PackedModule):
                                  nn.Linear(d_model * 2, out_dim, bias=False))
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(out_dim)
+        self.tc_mode = False      # True: the block runs as attn_front / kv_merge / attn_back on the tensor cores (fast mode)
 
     def _pack(self):
         f1 = self.q_proj.weight.shape[1]
         m0 = self.mlp[0].weight.detach()
-        return dict(
+        pk = dict(
             pos0=kmajor(self.pos_mlp2[0].weight), pos0b=self.pos_mlp2[0].bias.detach().float().contiguous(),
             pos2=kmajor(self.pos_mlp2[2].weight), pos2b=self.pos_mlp2[2].bias.detach().float().contiguous(),
             q=kmajor(self.q_proj.weight), k=kmajor(self.k_proj.weight), v=kmajor(self.v_proj.weight),
             merge=kmajor(self.merge.weight), mlp0a=kmajor(m0[:, :f1]), mlp0b=kmajor(m0[:, f1:]), mlp2=kmajor(self.mlp[2].weight),
             n1w=self.norm1.weight.detach().float().contiguous(), n1b=self.norm1.bias.detach().float().contiguous(),
             n2w=self.norm2.weight.detach().float().contiguous(), n2b=self.norm2.bias.detach().float().contiguous())
+        d, f2, out = self.q_proj.weight.shape[0], self.k_proj.weight.shape[1], self.mlp[2].weight.shape[0]
+        if fused_attention_supported(d, self.nhead, f1, f2, out):
+            f1p = (f1 + 7) // 8 * 8
+            pk["front_blob"] = K.weight_blob(K.tf32_image(self.pos_mlp2[2].weight), K.tf32_image(self.v_proj.weight),
+                                             K.tf32_image(self.k_proj.weight))
+            pk["back_blob"] = K.weight_blob(K.tf32_image_padded(self.q_proj.weight, f1p), K.tf32_image_padded(m0[:, :f1], f1p),
+                                            K.tf32_image(m0[:, f1:]), K.tf32_image(self.mlp[2].weight))
+        return pk
 
     def forward(self, feat1, xyz1, feat2, xyz2, mask=None, feat1_point_major=False):
         """feat1 (B, C1, N) queries [or point-major (B, N, C1)], feat2 (B, C2, S) keys/values -> (B, out, N)."""
         pk = self.packed()
         S = feat2.shape[2]
+        if self.tc_mode and "front_blob" in pk:
+            d, out = self.q_proj.weight.shape[0], self.mlp[2].weight.shape[0]
+            vk = K.attn_front(xyz2, feat2, pk["pos0"], pk["pos0b"], pk["pos2b"], pk["front_blob"], d, d, d)
+            wkv, ksum = K.linattn_kv(vk[:, d:], vk[:, :d], self.nhead)
+            mimg = K.kv_merge(wkv, pk["merge"], self.nhead)
+            return K.attn_back(feat1, None, ksum, mimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
+                               self.nhead, out, S, residual=False, feat1_pm=feat1_point_major)
         hid = K.cn_linear(xyz2, pk["pos0"], bias=pk["pos0b"], act=K.ACT_RELU, x1_pm=True)
         feat2_pos = K.cn_linear(hid, pk["pos2"], bias=pk["pos2b"], res=feat2)
         q = K.cn_linear(feat1, pk["q"], x1_pm=feat1_point_major)
