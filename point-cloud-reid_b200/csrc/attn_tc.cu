@@ -563,11 +563,13 @@ struct TabBuilder {
   ChunkTab t;
   uint32_t blob_off = 0;
   bool ok = true;
-  TabBuilder() { t.n = 0; t.slot_bytes = 0; }
+  int cap;
+  // slots of 32 KB when the operand images leave room for one CTA per SM anyway, 8 KB otherwise (2 ... 5 CTAs per SM)
+  explicit TabBuilder(int img_bytes) : cap(img_bytes > 96 * 1024 ? MAX_SLOT : 8192) { t.n = 0; t.slot_bytes = 0; }
   // one GEMM operand W (K x N image); per_obj parts restart at offset 0 of the object's image
   void part(int K, int N, bool per_obj) {
     int kc = K < 32 ? K : 32;
-    while (kc > 8 && kc * N * 4 > MAX_SLOT) kc >>= 1;
+    while (kc > 8 && kc * N * 4 > cap) kc >>= 1;
     if (kc * N * 4 > MAX_SLOT || (K % 8) || (N % 16)) { ok = false; return; }
     uint32_t off = per_obj ? 0u : blob_off;
     for (int kk = 0; kk < K; kk += kc) {
@@ -603,7 +605,7 @@ int pcreid_attn_front(int B, int S, int C2, int DP, int NFP, int NF, const float
   a.B = B; a.S = S; a.C2 = C2; a.DP = DP; a.NFP = NFP; a.NF = NF;
   a.xyz = xyz; a.feat = feat; a.f_bs = f_bs; a.ldf = ldf; a.wp0 = wp0; a.bp0 = bp0; a.bp2 = bp2;
   a.blob = static_cast<const uint8_t*>(blob); a.out = out; a.o_bs = o_bs; a.ldo = ldo;
-  TabBuilder tb;
+  TabBuilder tb((C2 + (DP > C2 ? DP : C2)) * 512);
   tb.part(DP, C2, false);
   tb.part(C2, NFP, false);
   if (NF > 0) tb.part(C2, NF, false);
@@ -649,7 +651,7 @@ int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int s_len, i
   a.feat1 = feat1; a.f1_bs = f1_bs; a.ldf1 = ldf1; a.q = q; a.q_bs = q_bs; a.ldq = ldq; a.ksum = ksum;
   a.mimg = reinterpret_cast<const uint8_t*>(mimg); a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
   a.blob = static_cast<const uint8_t*>(blob); a.out = out; a.o_bs = o_bs; a.ldo = ldo;
-  TabBuilder tb;
+  TabBuilder tb(((C1P + D) > 2 * D ? (C1P + D) : 2 * D) * 512);
   if (!q) tb.part(C1P, D, false);
   tb.part(D, D, true);
   tb.part(C1P, 2 * D, false);
