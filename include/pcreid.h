@@ -85,6 +85,11 @@ int pcreid_three_interpolate(int b, int c, int m, int n, const float* points, co
 /* torch-path kNN of the ReID backbones (models/pointnet2_utils.py:169-216 square_distance + argsort):
  * expansion-form distance, canonical ascending (d, idx) order.  idx (b,m,k) i32. */
 int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream);
+/* The same neighbours as pcreid_knn_point as an UNORDERED set (the order inside idx[b, q, :] is unspecified): the k
+ * nearest points with the ordered kernel's tie rule at the k-th boundary (equal distances: lower index first).  For
+ * consumers that max-pool over the neighbours (PointNetSetAbstractionEdgeSA, pointnet2_utils.py:333-357).
+ * k <= n <= 1024, else PCREID_ERR_UNSUPPORTED. */
+int pcreid_knn_point_set(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream);
 /* DGCNN kNN (models/dgcnn_orig.py:22-28): x (b,c,n) channel-major with object stride x_bs, k largest of
  * pd = -|xi|^2 + 2 xi.xj - |xj|^2, lower index first on ties.  idx (b,n,k) i32. */
 int pcreid_knn_feature(int b, int c, int n, int k, const float* x, long long x_bs, int* idx, void* stream);

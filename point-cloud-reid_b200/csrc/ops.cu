@@ -175,6 +175,92 @@ static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// kNN as an unordered SET (fast-mode encoder): the set-abstraction layers max-pool over the k neighbours, so only
+// the membership of the k nearest points matters, with the ordered kernel's tie rule at the k-th boundary (equal
+// distances: lower index first).  One warp per query, candidates (coordinates, squared norms) in registers and
+// reused for QPW consecutive queries; distances become order-preserving 32-bit keys; the k-th smallest key is found
+// by a most-significant-bit-first radix search over the bits in which the keys of this query differ (one REDUX.ADD
+// per bit instead of k rounds of two REDUX.MIN + rescan), then the members are emitted by ballot / prefix popcount.
+// Same distance arithmetic as knn_kernel<1> (torch path, pointnet2_utils.py:169-216).
+// ------------------------------------------------------------------------------------------------
+template <int KPL>
+__global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int qpw, const float* __restrict__ xyz,
+                                                      const float* __restrict__ qxyz, int* __restrict__ idx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int q0 = (blockIdx.x * 8 + warp) * qpw;
+  if (q0 >= M) return;
+  const float* P = xyz + (size_t)b * N * 3;
+  float px[KPL], py[KPL], pz[KPL], pn[KPL];
+#pragma unroll
+  for (int j = 0; j < KPL; ++j) {
+    const int i = lane + 32 * j;
+    px[j] = py[j] = pz[j] = pn[j] = 0.f;
+    if (i < N) {
+      px[j] = __ldg(P + i * 3); py[j] = __ldg(P + i * 3 + 1); pz[j] = __ldg(P + i * 3 + 2);
+      pn[j] = sqnorm3(px[j], py[j], pz[j]);
+    }
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int qend = min(q0 + qpw, M);
+  for (int q = q0; q < qend; ++q) {
+    const float* Q = qxyz + ((size_t)b * M + q) * 3;
+    const float qx = __ldg(Q), qy = __ldg(Q + 1), qz = __ldg(Q + 2);
+    const float qn = sqnorm3(qx, qy, qz);
+    uint32_t key[KPL];
+    uint32_t lmin = 0xffffffffu, lmax = 0u;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      key[j] = 0xffffffffu;
+      if (lane + 32 * j < N) {
+        key[j] = f32_to_ordered(dist_expand(qx, qy, qz, qn, px[j], py[j], pz[j]));
+        lmin = min(lmin, key[j]);
+        lmax = max(lmax, key[j]);
+      }
+    }
+    const uint32_t kmin = __reduce_min_sync(FULL_MASK, lmin), kmax = __reduce_max_sync(FULL_MASK, lmax);
+    // T = k-th smallest key: largest T with count(key < T) < k; bits above the highest differing bit are common
+    uint32_t T = kmin;
+    if (kmin != kmax) {
+      const int top = 31 - __clz(kmin ^ kmax);
+      T = top == 31 ? 0u : (kmin & ~((2u << top) - 1u));
+      for (int bit = top; bit >= 0; --bit) {
+        const uint32_t t = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) c += key[j] < t ? 1 : 0;
+        c = __reduce_add_sync(FULL_MASK, c);
+        if (c < k) T = t;
+      }
+    }
+    int* oi = idx + ((size_t)b * M + q) * k;
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const bool in = key[j] < T;
+      const uint32_t bal = __ballot_sync(FULL_MASK, in);
+      if (in) oi[base + __popc(bal & lt_mask)] = lane + 32 * j;
+      base += __popc(bal);
+    }
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const bool eq = key[j] == T && lane + 32 * j < N;
+      const uint32_t bal = __ballot_sync(FULL_MASK, eq);
+      const int pos = base + __popc(bal & lt_mask);
+      if (eq && pos < k) oi[pos] = lane + 32 * j;
+      base += __popc(bal);
+    }
+  }
+}
+
+template <int KPL>
+static int knn_set_launch(int b, int n, int m, int k, const float* xyz, const float* q, int* idx, cudaStream_t st) {
+  const int qpw = m >= 64 ? 8 : (m >= 16 ? 2 : 1);
+  knn_set_kernel<KPL><<<dim3(ceil_div(m, 8 * qpw), b), 256, 0, st>>>(n, m, k, qpw, xyz, q, idx);
+  return pcreid_launch_status();
+}
+
+// ------------------------------------------------------------------------------------------------
 // DGCNN kNN in feature space (models/dgcnn_orig.py:22-28)
 //   m_ij  = sequential fma chain over channels (what torch.matmul does on the CPU oracle)
 //   xx_i  = sum_c x_ci^2, ATen cascade: sequential inside blocks of 16 channels, block sums added in order
@@ -565,6 +651,17 @@ int pcreid_knn_t(int b, int n, int m, int k, const float* xyz, const float* new_
 // (d, idx) order, idx [b, m, k] int32.
 int pcreid_knn_point(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream) {
   return knn_launch(1, b, n, m, k, xyz, new_xyz, idx, nullptr, k, 1, 0, (cudaStream_t)stream);
+}
+
+int pcreid_knn_point_set(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, void* stream) {
+  if (b <= 0 || m <= 0 || k <= 0) return PCREID_OK;
+  if (!xyz || !new_xyz || !idx || n <= 0) return PCREID_ERR_ARG;
+  if (k > n || n > 1024 || b > 65535) return PCREID_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n <= 128) return knn_set_launch<4>(b, n, m, k, xyz, new_xyz, idx, st);
+  if (n <= 256) return knn_set_launch<8>(b, n, m, k, xyz, new_xyz, idx, st);
+  if (n <= 512) return knn_set_launch<16>(b, n, m, k, xyz, new_xyz, idx, st);
+  return knn_set_launch<32>(b, n, m, k, xyz, new_xyz, idx, st);
 }
 
 int pcreid_knn_feature(int b, int c, int n, int k, const float* x, long long x_bs, int* idx, void* stream) {

@@ -218,6 +218,20 @@ def knn_point(k, xyz, new_xyz):
     return idx
 
 
+def knn_point_set(k, xyz, new_xyz):
+    """knn_point as an unordered set (same members, unspecified order) for consumers that max-pool over the neighbours."""
+    _need_cuda(xyz, new_xyz)
+    if not (xyz.is_contiguous() and new_xyz.is_contiguous()):
+        raise ValueError("xyz / new_xyz must be contiguous")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    if k > N or N > 512 or B > 65535:       # measured: above 512 candidates the ordered kernel is as fast (register pressure)
+        return knn_point(k, xyz, new_xyz)
+    idx = torch.empty((B, S, k), device=xyz.device, dtype=torch.int32)
+    _lib.check(_lib.lib().pcreid_knn_point_set(B, N, S, k, _p(xyz), _p(new_xyz), _p(idx), _stream()), "pcreid_knn_point_set")
+    return idx
+
+
 def knn_feature(x, k):
     """DGCNN kNN in feature space: x (B, C, N) contiguous -> int32 (B, N, k)."""
     _need_cuda(x)

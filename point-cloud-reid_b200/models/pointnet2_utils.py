@@ -138,8 +138,9 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         pk = self.packed()
         S = int(numpoints)
         new_xyz = xyz[:, :S, :].contiguous()              # sampling == "RANDOM": the first S points
-        idx = K.knn_point(self.nsample, xyz, new_xyz)     # (B, S, k) int32
         tc = self.tc_mode and "w2img" in pk          # tensor-core kernel gathers point-major rows
+        # (B, S, k) int32; the max over the k edges does not depend on their order: fast mode asks for the set only
+        idx = K.knn_point_set(self.nsample, xyz, new_xyz) if tc else K.knn_point(self.nsample, xyz, new_xyz)
         if pk["D"] > 0:
             p1 = K.cn_linear(xyz, pk["pa"], x2=points, w2=pk["pc"], x1_pm=True, y_pm=tc)
             cc = K.cn_linear(xyz, pk["ca"], x2=points, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
