@@ -230,6 +230,15 @@ int pcreid_sa_edge_mlp_tc(int B, int C, int N, int S, int k, const float* P1, co
                           const float* W2img, const float* b2, const float* W3img, const float* b3, float* out,
                           int n_ctas, void* stream);
 
+/* Second generation of pcreid_sa_edge_mlp_tc (csrc/sa_tc2.cu): same arithmetic and arguments; producer warps gather
+ * relu(P1 + Cc) straight into tensor memory (A operand of GEMM 1), the first accumulator becomes the A operand of GEMM 2
+ * in place, max over the k edges by warp redux, P1 of the current object resident in shared memory when it fits.
+ * out element (b, c, s) at b*C*S + c*S + s, or with out_pm != 0 point-major at b*S*C + s*C + c.
+ * 16 <= k <= 128, C in {32, 64, 128}; else PCREID_ERR_UNSUPPORTED (use pcreid_sa_edge_mlp_tc). */
+int pcreid_sa_edge_mlp_tc2(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx,
+                           const float* W2img, const float* b2, const float* W3img, const float* b3, float* out,
+                           int out_pm, int n_sms, void* stream);
+
 /* Fused linear-attention blocks of the Point Transformer encoder on the tensor cores (tcgen05 kind::tf32; fast mode;
  * csrc/attn_tc.cu).  Replace the cn_linear / linattn_scale / cn_groupnorm chains of Self_Attention and FP_SA
  * (mmdet3d/models/pointnet2_utils.py:55-114, 362-437).  All weights are fp32 operand images [k/4][n][4] of the
@@ -255,7 +264,7 @@ int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int s_len, i
 
 /* ------------------------------------------------------------------ C. tcgen05 self-test ------- */
 /* One 128 x n x k GEMM on the 5th-gen tensor cores in each operand configuration the fused kernels use
- * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM);
+ * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM, 5: tf32 A operand from TMEM);
  * d (128, n) f32 = a (128, k) * b (n, k)^T.  Modes 0/2/3 take row-major a, b; mode 1 takes a^T (k,128), b^T (k,n). */
 int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream);
 

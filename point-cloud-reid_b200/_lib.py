@@ -90,6 +90,7 @@ _SIGS = {
     "pcreid_pair_p1b_n": [c_int, c_int, c_int] + [c_vp] * 7 + [c_int, c_vp],
     "pcreid_pair_p2y": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
     "pcreid_sa_edge_mlp_tc": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_vp],
+    "pcreid_sa_edge_mlp_tc2": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_int, c_vp],
     "pcreid_tc_probe": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_concat_head_tc": [c_int, c_int, c_int, c_int] + [c_vp] * 10 + [c_float, c_vp, c_vp, c_int, c_vp],
     "pcreid_pair_concat_head": [c_int, c_int, c_int, c_int] + [c_vp] * 10 + [c_float, c_vp, c_vp, c_vp],

@@ -6,6 +6,7 @@
 //   mode 2: tf32, A and B K-major in shared memory   ([k/4][row][4] fp32)
 //   mode 3: bf16, A from tensor memory (tcgen05.st by the row-owning threads), B K-major in shared memory
 //   mode 4: tf32, A and B MN-major in shared memory  ([mn/4][k][4] fp32; global holds A^T (K x 128), B^T (K x N))
+//   mode 5: tf32, A from tensor memory (one fp32 element per 32-bit column), B K-major in shared memory
 // D (128 x N, fp32, row-major) = A (128 x K) * B (N x K)^T.
 #include "../../include/pcreid.h"
 #include "common.cuh"
@@ -19,7 +20,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int esz = (mode == 2 || mode == 4) ? 4 : 2;   // bytes per element
+  const int esz = (mode == 2 || mode == 4 || mode == 5) ? 4 : 2;   // bytes per element
   const int cpe = 16 / esz;                     // elements per 16-byte chunk
   uint8_t* As = smem;
   uint8_t* Bs = smem + (size_t)128 * K * esz;
@@ -33,9 +34,9 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
     tc::tmem_relinquish();
   }
   // ---- stage operands in the canonical no-swizzle layouts
-  if (mode == 0 || mode == 2 || mode == 3) {
+  if (mode == 0 || mode == 2 || mode == 3 || mode == 5) {
     // K-major: element (r, k) at (k/cpe)*(R*16) + r*16 + (k%cpe)*esz     (LBO = R*16, SBO = 128)
-    if (mode != 3)
+    if (mode != 3 && mode != 5)
       for (int i = tid; i < 128 * K; i += 128) {
         int r = i / K, k = i % K;
         size_t off = (size_t)(k / cpe) * (128 * 16) + (size_t)r * 16 + (size_t)(k % cpe) * esz;
@@ -94,6 +95,20 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
     __syncthreads();
     tc::tc_fence_after();
   }
+  if (mode == 5) {
+    // thread = row: its K fp32 values, one per column
+    const uint32_t* arow = reinterpret_cast<const uint32_t*>(Ag) + (size_t)tid * K;
+    for (int c0 = 0; c0 < K; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = arow[c0 + j];
+      tc::tmem_st8(tmem_a + ((uint32_t)(warp * 32) << 16) + c0, v);
+    }
+    tc::tmem_st_wait();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+  }
   if (tid == 0) {
     const uint32_t a0 = tc::smem_u32(As), b0 = tc::smem_u32(Bs);
     if (mode == 0 || mode == 3) {
@@ -126,7 +141,8 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
       for (int ks = 0; ks < K / 8; ++ks) {
         uint64_t ad = tc::smem_desc(a0 + ks * 2 * (128 * 16), 128 * 16, 128, tc::LAYOUT_NONE);
         uint64_t bd = tc::smem_desc(b0 + ks * 2 * (N * 16), N * 16, 128, tc::LAYOUT_NONE);
-        tc::umma_tf32(tmem_acc, ad, bd, idesc, ks > 0);
+        if (mode == 5) tc::umma_tf32_ts(tmem_acc, tmem_a + ks * 8, bd, idesc, ks > 0);
+        else tc::umma_tf32(tmem_acc, ad, bd, idesc, ks > 0);
       }
     }
     tc::umma_commit(&bar);
@@ -148,9 +164,9 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
 }  // namespace
 
 extern "C" int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream) {
-  if (!a || !b || !d || mode < 0 || mode > 4) return PCREID_ERR_ARG;
+  if (!a || !b || !d || mode < 0 || mode > 5) return PCREID_ERR_ARG;
   if (n < 16 || n > 256 || n % 16 || k < 16 || k > 256 || k % 16) return PCREID_ERR_UNSUPPORTED;
-  const int esz = (mode == 2 || mode == 4) ? 4 : 2;
+  const int esz = (mode == 2 || mode == 4 || mode == 5) ? 4 : 2;
   size_t smem = (size_t)(128 + n) * k * esz;
   if (smem > 200 * 1024) return PCREID_ERR_UNSUPPORTED;
   cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

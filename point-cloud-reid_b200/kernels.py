@@ -339,17 +339,25 @@ def attn_back(feat1, q, ksum, mimg, g1, b1, g2, b2, blob, nhead, CO, s_len, resi
     return out
 
 
-def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3):
-    """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image(); p1 (B, N, C) and cc (B, S, C) point-major."""
+def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3, gen=2):
+    """tensor-core (tf32) version of sa_edge_mlp; w*img from tf32_image(); p1 (B, N, C) and cc (B, S, C) point-major.
+    gen=2: warp-specialised kernel with both A operands in tensor memory (sa_tc2.cu); shapes it does not cover (k < 16)
+    and gen=1 run the first-generation kernel (sa_tc.cu)."""
     _need_cuda(p1, cc, idx)
     B, N, C = p1.shape
     S, k = idx.shape[1], idx.shape[2]
     if not (p1.is_contiguous() and cc.is_contiguous() and idx.is_contiguous()):
         raise ValueError("sa_edge_mlp_tc inputs must be contiguous")
     out = torch.empty((B, C, S), device=p1.device, dtype=torch.float32)
-    n_ctas = torch.cuda.get_device_properties(p1.device).multi_processor_count
+    n_sms = torch.cuda.get_device_properties(p1.device).multi_processor_count
+    if gen == 2:
+        rc = _lib.lib().pcreid_sa_edge_mlp_tc2(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2img), _p(b2), _p(w3img), _p(b3),
+                                               _p(out), 0, n_sms, _stream())
+        if rc != 3:
+            _lib.check(rc, "pcreid_sa_edge_mlp_tc2")
+            return out
     _lib.check(_lib.lib().pcreid_sa_edge_mlp_tc(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2img), _p(b2), _p(w3img), _p(b3),
-                                                _p(out), n_ctas, _stream()), "pcreid_sa_edge_mlp_tc")
+                                                _p(out), n_sms, _stream()), "pcreid_sa_edge_mlp_tc")
     return out
 
 

@@ -131,9 +131,10 @@ def test_sa_edge_mlp(C, N, S, k):
     close(got, F.sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3))
 
 
+@pytest.mark.parametrize("gen", [1, 2])
 @pytest.mark.parametrize("C,N,S,k", [(32, 256, 256, 32), (64, 256, 128, 48), (128, 128, 64, 48), (64, 160, 80, 48), (32, 40, 37, 20),
-                                     (128, 1024, 512, 48)])
-def test_sa_edge_mlp_tensor_core(C, N, S, k):
+                                     (128, 1024, 512, 48), (64, 64, 33, 16), (32, 128, 50, 63), (128, 256, 7, 40)])
+def test_sa_edge_mlp_tensor_core(C, N, S, k, gen):
     """tcgen05 kind::tf32 version against the fp32 specification: tf32 operands (10-bit mantissa) -> 5e-3 of the scale."""
     g = torch.Generator().manual_seed(C + k)
     B = 3 if N < 1024 else 160        # the large case spans several persistent waves
@@ -142,7 +143,7 @@ def test_sa_edge_mlp_tensor_core(C, N, S, k):
     w2, w3 = rnd(C, C, seed=3) / C ** 0.5, rnd(C, C, seed=4) / C ** 0.5      # (C_out, C_in)
     b2, b3 = rnd(C, seed=5) * 0.1, rnd(C, seed=6) * 0.1
     got = K.sa_edge_mlp_tc(p1.transpose(1, 2).contiguous().to(DEV), cc.transpose(1, 2).contiguous().to(DEV), idx.to(DEV),
-                           K.tf32_image(w2).to(DEV), b2.to(DEV), K.tf32_image(w3).to(DEV), b3.to(DEV))
+                           K.tf32_image(w2).to(DEV), b2.to(DEV), K.tf32_image(w3).to(DEV), b3.to(DEV), gen=gen)
     close(got, F.sa_edge_mlp(p1, cc, idx, w2.t().contiguous(), b2, w3.t().contiguous(), b3), 5e-3)
 
 

@@ -13,8 +13,8 @@ def _probe(mode, N, K, seed=0):
     g = torch.Generator().manual_seed(seed)
     a = torch.randn(128, K, generator=g)
     b = torch.randn(N, K, generator=g)
-    if mode in (2, 4):
-        ad, bd = (a.to(DEV), b.to(DEV)) if mode == 2 else (a.t().contiguous().to(DEV), b.t().contiguous().to(DEV))
+    if mode in (2, 4, 5):
+        ad, bd = (a.to(DEV), b.to(DEV)) if mode != 4 else (a.t().contiguous().to(DEV), b.t().contiguous().to(DEV))
         # tf32 keeps 10 mantissa bits: compare against operands truncated the same way with a loose bound
         ref = a @ b.t()
         tol = 8e-3 * K ** 0.5
@@ -39,7 +39,7 @@ def _probe(mode, N, K, seed=0):
 
 # mode 4 (tf32 with MN-major no-swizzle operands) is kept in the probe for reference: it does NOT produce a GEMM on sm_100a,
 # which is why cn_linear_tc stages its operands K-major (mode 2)
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("N,K", [(64, 64), (128, 128), (192, 64), (64, 128), (16, 16), (256, 256), (80, 32)])
 def test_tc_probe(mode, N, K):
     err, tol = _probe(mode, N, K)
