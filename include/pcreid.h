@@ -244,21 +244,25 @@ int pcreid_sa_edge_mlp_tc2(int B, int C, int N, int S, int k, const float* P1, c
  * (mmdet3d/models/pointnet2_utils.py:55-114, 362-437).  All weights are fp32 operand images [k/4][n][4] of the
  * (C_out, C_in) torch weights, concatenated into one blob in the order given below; channel counts are multiples of 16
  * (inputs: of 8, zero padded) and at most 128 model channels, else PCREID_ERR_UNSUPPORTED.
- * front: key-side rows of object b:  pos = Wp2 relu(Wp0 xyz + bp0) + bp2;  out[:, 0:NFP] = Wfp (feat + pos);
+ * front: key-side rows:  pos = Wp2 relu(Wp0 xyz + bp0) + bp2;  out[:, 0:NFP] = Wfp (feat + pos);
  *        out[:, NFP:NFP+NF] = Wf feat.   wp0 (3, DP) k-major; blob = [Wp2 (DP->C2)][Wfp (C2->NFP)][Wf (C2->NF)].
- * kv_merge: mimg[b] = operand image of blockdiag(Wkv[b]) . WmT  (Wkv, ksum from pcreid_linattn_kv; WmT (d, d) k-major).
- * back:  query-side rows: q (B, D, rows) given, or q = Wq feat1 when q == NULL;  Qs = (elu(q)+1) * s_len / ((elu(q_h)+1).ksum_h + 1e-6);
- *        msg = LayerNorm1(Qs . M_b);  out = LayerNorm2(W2 relu(W0 [feat1 ; msg])) (+ feat1 when res);
- *        blob = [Wq (C1P->D) unless q given][W0a (C1P->2D)][W0b (D->2D)][W2 (2D->CO)], C1P = C1 rounded up to 8;
+ * kv_img: per object and head h the operand image of KV_h = sum_s (elu(k_s)+1) (x) v_s (dh x dh: kvimg is (B', H, dh*dh)
+ *        floats, B' = B rounded up to pcreid_attn_back_objects_per_tile) and ksum (B, d) = sum_s (elu(k_s)+1); k, v
+ *        channel-major (B, d, S) views (pre-activation).  The reference's v / S and x S cancel and are not applied.
+ * back:  query-side rows: q (B, D, rows) given, or q = Wq feat1 when q == NULL;  att_h = (elu(q_h)+1) KV_h / ((elu(q_h)+1).ksum_h + 1e-6);
+ *        msg = LayerNorm1(Wm att);  out = LayerNorm2(W2 relu(W0 [feat1 ; msg])) (+ feat1 when res);
+ *        blob = [Wq (C1P->D) unless q given][Wm (D->D)][W0a (C1P->2D)][W0b (D->2D)][W2 (2D->CO)], C1P = C1 rounded up to 8;
  *        feat1 channel-major (B, C1, rows) or, with f1_pm, point-major (B, rows, C1). */
 int pcreid_attn_front_blob_bytes(int C2, int DP, int NFP, int NF);
 int pcreid_attn_front(int B, int S, int C2, int DP, int NFP, int NF, const float* xyz, const float* feat, long long f_bs, int ldf,
                       const float* wp0, const float* bp0, const float* bp2, const void* blob, float* out, long long o_bs, int ldo,
                       void* stream);
-int pcreid_kv_merge(int B, int d, int H, const float* wkv, const float* wmT, float* mimg, void* stream);
+int pcreid_linattn_kv_img(int B, int S, int d, int H, const float* K, long long k_bs, int ldk, const float* V, long long v_bs, int ldv,
+                          float* kvimg, float* ksum, void* stream);
+int pcreid_attn_back_objects_per_tile(int rows, int D);
 int pcreid_attn_back_blob_bytes(int D, int C1P, int CO, int qpre);
-int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int s_len, int res, int f1_pm, const float* feat1, long long f1_bs,
-                     int ldf1, const float* q, long long q_bs, int ldq, const float* ksum, const float* mimg, const float* g1,
+int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int res, int f1_pm, const float* feat1, long long f1_bs,
+                     int ldf1, const float* q, long long q_bs, int ldq, const float* ksum, const float* kvimg, const float* g1,
                      const float* b1, const float* g2, const float* b2, const void* blob, float* out, long long o_bs, int ldo,
                      void* stream);
 

@@ -64,9 +64,10 @@ _SIGS = {
     "pcreid_attn_front_blob_bytes": [c_int, c_int, c_int, c_int],
     "pcreid_attn_front": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int,
                           c_vp],
-    "pcreid_kv_merge": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_linattn_kv_img": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
+    "pcreid_attn_back_objects_per_tile": [c_int, c_int],
     "pcreid_attn_back_blob_bytes": [c_int, c_int, c_int, c_int],
-    "pcreid_attn_back": [c_int] * 9 + [c_vp, c_ll, c_int, c_vp, c_ll, c_int] + [c_vp] * 7 + [c_vp, c_ll, c_int, c_vp],
+    "pcreid_attn_back": [c_int] * 8 + [c_vp, c_ll, c_int, c_vp, c_ll, c_int] + [c_vp] * 7 + [c_vp, c_ll, c_int, c_vp],
     "pcreid_linattn_kv": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_linattn_scale": [c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp],
     "pcreid_cn_pool": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_ll, c_vp],

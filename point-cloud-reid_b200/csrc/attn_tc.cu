@@ -2,15 +2,19 @@
 // accumulation in TMEM) -- the "fast" mode counterpart of the cn_linear / cn_groupnorm / linattn_scale chains that
 // models/pointnet2_utils.py issues for Self_Attention and FP_SA (mmdet3d/models/pointnet2_utils.py:55-114, 362-437).
 //
-// One block = three launches around the per-object key/value reduction (pcreid_linattn_kv, unchanged):
+// One block = three launches:
 //
 //   attn_front : key-side rows.  pos = Wp2 relu(Wp0 xyz + bp0) + bp2 ;  fp = feat + pos ;
 //                out[:, 0:NFP] = Wfp fp ; out[:, NFP:NFP+NF] = Wf feat            (q|k|v of Self_Attention, v|k of FP_SA)
-//   kv_merge   : per object  M = blockdiag(KV) Wm^T, written as a ready-to-use tcgen05 operand image
-//   attn_back  : query-side rows.  q (given, or Wq feat1) -> (elu+1) / (Q.Ksum) scaling -> . M -> LayerNorm1 ->
-//                relu(W0 [feat1 ; msg]) -> W2 -> LayerNorm2 (+ feat1) -> out
+//                Rows are independent, so a tile is 128 consecutive rows of the flattened (object, point) axis.
+//   kv_img     : per object and head  KV_h = sum_s (elu(k_s)+1) (x) v_s  written as a ready-to-use tcgen05 operand
+//                image, Ksum = sum_s (elu(k_s)+1)   (register-tiled FFMA reduction over the points)
+//   attn_back  : query-side rows.  q (given, or Wq feat1) -> (elu+1) -> . KV_h per head -> x 1/(Q.Ksum) -> merge ->
+//                LayerNorm1 -> relu(W0 [feat1 ; msg]) -> W2 -> LayerNorm2 (+ feat1) -> out
+//                (the reference's v / S and x S cancel and are not applied)
 //
-// A CTA owns up to 128 rows of ONE object (thread == row == TMEM lane).  Activations live in shared memory as fp32
+// An attn_back CTA owns 128 rows (thread == row == TMEM lane): up to 128 rows of one object, or 2 / 4 whole objects
+// of 64 / 32 rows (the per-object KV operands then go to separate TMEM column blocks and a row reads its own block).  Activations live in shared memory as fp32
 // K-major operand images [k/4][128][4] (the no-swizzle canonical layout, read by the tensor core as tf32) and never
 // travel to HBM between the stages of a block.  Weights are prepared once on the host as operand images
 // [k/4][n][4], concatenated in the order the kernel consumes them, and streamed global -> shared memory through a
@@ -26,8 +30,8 @@ namespace {
 
 constexpr int NTH = 128;
 constexpr int RING = 3;
-constexpr int MAXCH = 40;
-constexpr int MAX_SLOT = 32768;
+constexpr int MAXCH = 56;
+constexpr int MAX_SLOT = 16384;
 
 struct ChunkTab {
   int n;
@@ -102,22 +106,22 @@ __device__ __forceinline__ void stage_sync() {
 
 __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v + 1.f : __expf(v); }
 
-// channel-major (C, rows) tile -> operand image, zero outside (c < C, valid).  32 channels are fetched per batch so that
-// the loads of a batch are all in flight before the first shared-memory store needs its data.
-__device__ __forceinline__ void load_image_cm(uint8_t* img, const float* __restrict__ X, int ld, int C, int CP, int row, bool valid, int tid) {
+// channel-major source -> operand image, zero outside (c < C, valid); Xr points at (channel 0, this thread's row), ld is the
+// channel stride.  32 channels are fetched per batch so that the loads of a batch are all in flight before the first
+// shared-memory store needs its data.
+__device__ __forceinline__ void load_image_cm(uint8_t* img, const float* __restrict__ Xr, int ld, int C, int CP, bool valid, int tid) {
   for (int c0 = 0; c0 < CP; c0 += 32) {
     float v[32];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (valid && c0 + i < C) ? __ldg(X + (size_t)(c0 + i) * ld + row) : 0.f;
+    for (int i = 0; i < 32; ++i) v[i] = (valid && c0 + i < C) ? __ldg(Xr + (size_t)(c0 + i) * ld) : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (c0 + 4 * j < CP)
         *reinterpret_cast<float4*>(img + ((c0 >> 2) + j) * 2048 + tid * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 }
-// point-major (rows, C) tile -> operand image
-__device__ __forceinline__ void load_image_pm(uint8_t* img, const float* __restrict__ X, int C, int CP, int row, bool valid, int tid) {
-  const float* x = X + (size_t)row * C;
+// point-major source (x = this thread's row of C floats) -> operand image
+__device__ __forceinline__ void load_image_pm(uint8_t* img, const float* __restrict__ x, int C, int CP, bool valid, int tid) {
   for (int c0 = 0; c0 < CP; c0 += 32) {
     float v[32];
 #pragma unroll
@@ -180,9 +184,9 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
   __shared__ uint64_t full[RING], empty[RING], stagebar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tpo = (a.S + 127) / 128;
-  const int b = blockIdx.x / tpo, row = (blockIdx.x % tpo) * 128 + tid;
-  const bool valid = row < a.S;
+  const long long flat = (long long)blockIdx.x * 128 + tid;          // row of the flattened (object, point) axis
+  const bool valid = flat < (long long)a.B * a.S;
+  const int b = valid ? (int)(flat / a.S) : 0, row = valid ? (int)(flat % a.S) : 0;
   const int CA = a.DP > a.C2 ? a.DP : a.C2;
   uint8_t* imgF = smem;                        // feat                     [C2/4][128][4]
   uint8_t* imgA = imgF + a.C2 * 512;           // pos hidden, then feat+pos [CA/4][128][4]
@@ -213,7 +217,7 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
   const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t par = 0;
   // ---- operand images: feat, relu(Wp0 xyz + bp0)
-  load_image_cm(imgF, a.feat + (size_t)b * a.f_bs, a.ldf, a.C2, a.C2, row, valid, tid);
+  load_image_cm(imgF, a.feat + (size_t)b * a.f_bs + row, a.ldf, a.C2, a.C2, valid, tid);
   {
     float x = 0.f, y = 0.f, z = 0.f;
     if (valid) {
@@ -284,40 +288,117 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// M image per object: Mimg[b][k/4][n][k%4] = sum_{j in head(k)} Wkv[b][k][j] * WmT[j][n]
-// (Wkv block-diagonal over the heads as written by linattn_kv; WmT = merge.weight^T, k-major)
-__global__ void __launch_bounds__(256) kv_merge_kernel(int d, int H, const float* __restrict__ Wkv, const float* __restrict__ WmT,
-                                                       float* __restrict__ Mimg) {
-  extern __shared__ float kv_s[];            // [d][dh] : the diagonal blocks only
-  const int b = blockIdx.x, dh = d / H;
-  const float* W = Wkv + (size_t)b * d * d;
-  for (int i = threadIdx.x; i < d * dh; i += blockDim.x) {
-    const int k = i / dh, j = i % dh;
-    kv_s[i] = W[(size_t)k * d + (k / dh) * dh + j];
-  }
-  __syncthreads();
-  float* M = Mimg + (size_t)b * d * d;
-  // one thread per (group of 4 k, n): 4 accumulators, coalesced WmT reads across n, float4 image store
-  for (int e = threadIdx.x; e < (d / 4) * d; e += blockDim.x) {
-    const int k4 = e / d, n = e % d;
-    const int h = (4 * k4) / dh;
-    const float* wm = WmT + (size_t)(h * dh) * d + n;
-    const float* k0 = kv_s + (4 * k4) * dh;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int j = 0; j < dh; ++j) {
-      const float w = __ldg(wm + (size_t)j * d);
-      a0 = fmaf(k0[j], w, a0);
-      a1 = fmaf(k0[dh + j], w, a1);
-      a2 = fmaf(k0[2 * dh + j], w, a2);
-      a3 = fmaf(k0[3 * dh + j], w, a3);
+// KV summaries of linear attention as tcgen05 operand images (one CTA per object):
+//   kvimg[b][h][(i/4)*dh + j][i%4] = sum_s (elu(k[h*dh+i][s]) + 1) * v[h*dh+j][s]          (B operand: N = j, K = i)
+//   ksum[b][c]                     = sum_s (elu(k[c][s]) + 1)
+// Points stream through shared memory in chunks of 64; a thread owns a 4 x 4 block of one head's dh x dh outputs and
+// reads 4 + 4 128-bit rows per 4 points (64 FMA per 8 LDS.128); when there are fewer blocks than threads the points of
+// a chunk are split over thread groups and the partial sums meet in shared memory.
+constexpr int KV_SC = 64, KV_SCP = KV_SC + 4;
+template <int TPT>
+__global__ void __launch_bounds__(256, 3) linattn_kv_img_kernel(int S, int d, int H, const float* __restrict__ K, long long k_bs, int ldk,
+                                                             const float* __restrict__ V, long long v_bs, int ldv,
+                                                             float* __restrict__ kvimg, float* __restrict__ ksum) {
+  extern __shared__ __align__(16) float kvs[];
+  float* Ks = kvs;                        // [d][KV_SCP]  elu(k)+1
+  float* Vs = kvs + d * KV_SCP;           // [d][KV_SCP]
+  const int b = blockIdx.x, tid = threadIdx.x, dh = d / H, nb = dh / 4;
+  const int ntiles = H * nb * nb;         // 4 x 4 output blocks: 512 (d = 128), 128 (64), 32 (32)
+  const int G = ntiles >= 256 ? 1 : 256 / ntiles;      // point groups
+  const float* Kb = K + (size_t)b * k_bs;
+  const float* Vb = V + (size_t)b * v_bs;
+  float acc[TPT][4][4];                                // TPT = 4 x 4 blocks per thread
+#pragma unroll
+  for (int u = 0; u < TPT; ++u)
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[u][i][j] = 0.f;
+  float ks = 0.f;
+  const int g = G > 1 ? tid / ntiles : 0;
+  for (int s0 = 0; s0 < S; s0 += KV_SC) {
+    for (int i0 = tid; i0 < d * KV_SC; i0 += 256 * 8) {      // 16 loads in flight per thread before the first store
+      float kq[8], vq[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e * 256, c = i / KV_SC, s = i % KV_SC;
+        const bool in = i < d * KV_SC && s0 + s < S;
+        kq[e] = in ? __ldg(Kb + (size_t)c * ldk + s0 + s) : 0.f;
+        vq[e] = in ? __ldg(Vb + (size_t)c * ldv + s0 + s) : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e * 256, c = i / KV_SC, s = i % KV_SC;
+        if (i < d * KV_SC) {
+          Ks[c * KV_SCP + s] = s0 + s < S ? elu1(kq[e]) : 0.f;
+          Vs[c * KV_SCP + s] = vq[e];
+        }
+      }
     }
-    *reinterpret_cast<float4*>(M + ((size_t)k4 * d + n) * 4) = make_float4(a0, a1, a2, a3);
+    __syncthreads();
+    if (tid < d) {
+      const float4* kr = reinterpret_cast<const float4*>(Ks + tid * KV_SCP);
+#pragma unroll 4
+      for (int s = 0; s < KV_SC / 4; ++s) { const float4 x = kr[s]; ks += (x.x + x.y) + (x.z + x.w); }
+    }
+#pragma unroll
+    for (int u = 0; u < TPT; ++u) {
+      const int tile = (G > 1 ? tid % ntiles : tid) + u * 256;
+      if (tile < ntiles) {
+        const int h = tile / (nb * nb), ti = (tile % (nb * nb)) / nb, tj = tile % nb;
+        const float* kr = Ks + (h * dh + 4 * ti) * KV_SCP;
+        const float* vr = Vs + (h * dh + 4 * tj) * KV_SCP;
+        for (int s = 4 * g; s < KV_SC; s += 4 * G) {
+          float4 kq[4], vq[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) kq[i] = *reinterpret_cast<const float4*>(kr + i * KV_SCP + s);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) vq[j] = *reinterpret_cast<const float4*>(vr + j * KV_SCP + s);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[u][i][j] = fmaf(kq[i].x, vq[j].x, fmaf(kq[i].y, vq[j].y, fmaf(kq[i].z, vq[j].z, fmaf(kq[i].w, vq[j].w, acc[u][i][j]))));
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < d) ksum[(size_t)b * d + tid] = ks;
+  if (G > 1) {
+    // partial sums of the point groups meet in shared memory: red[g][tile][16]
+    float* red = kvs;
+    const int tile = tid % ntiles;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(red + ((size_t)(g * ntiles + tile) * 16) + 4 * i) = make_float4(acc[0][i][0], acc[0][i][1], acc[0][i][2], acc[0][i][3]);
+    __syncthreads();
+    if (g == 0) {
+      for (int gg = 1; gg < G; ++gg)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 x = *reinterpret_cast<const float4*>(red + ((size_t)(gg * ntiles + tile) * 16) + 4 * i);
+          acc[0][i][0] += x.x; acc[0][i][1] += x.y; acc[0][i][2] += x.z; acc[0][i][3] += x.w;
+        }
+    }
+  }
+  float* img = kvimg + (size_t)b * d * dh;
+#pragma unroll
+  for (int u = 0; u < TPT; ++u) {
+    const int tile = (G > 1 ? tid % ntiles : tid) + u * 256;
+    if (tile < ntiles && g == 0) {
+      const int h = tile / (nb * nb), ti = (tile % (nb * nb)) / nb, tj = tile % nb;
+      float* ih = img + (size_t)h * dh * dh;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<float4*>(ih + ((size_t)ti * dh + 4 * tj + j) * 4) = make_float4(acc[u][0][j], acc[u][1][j], acc[u][2][j], acc[u][3][j]);
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 struct BackArgs {
-  int B, rows, D, H, C1, C1P, CO, s_len;
+  int B, rows, D, H, C1, C1P, CO, opt;       // opt objects of `rows` rows per tile (opt * rows == 128) or opt == 1
   int qpre, res, f1_pm;
   const float* feat1;
   long long f1_bs;
@@ -326,7 +407,7 @@ struct BackArgs {
   long long q_bs;
   int ldq;
   const float* ksum;
-  const uint8_t* mimg;
+  const uint8_t* kvimg;
   const float *g1, *b1, *g2, *b2;
   const uint8_t* blob;
   float* out;
@@ -340,32 +421,37 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
   __shared__ uint64_t full[RING], empty[RING], stagebar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int tpo = (a.rows + 127) / 128;
-  const int b = blockIdx.x / tpo, row = (blockIdx.x % tpo) * 128 + tid;
-  const bool valid = row < a.rows;
   const int D = a.D, D2 = 2 * a.D, dh = a.D / a.H;
+  int b0, ob, row;
+  bool valid;
+  if (a.opt > 1) {
+    b0 = blockIdx.x * a.opt; ob = tid / a.rows; row = tid % a.rows;
+    valid = b0 + ob < a.B;
+  } else {
+    const int tpo = (a.rows + 127) / 128;
+    b0 = blockIdx.x / tpo; ob = 0; row = (blockIdx.x % tpo) * 128 + tid;
+    valid = row < a.rows;
+  }
+  const int b = valid ? b0 + ob : b0;
   const int img_ch = (a.C1P + D) > D2 ? (a.C1P + D) : D2;
   uint8_t* imgF = smem;                       // feat1              [C1P/4][128][4]
-  uint8_t* imgQ = imgF + a.C1P * 512;         // scaled q, then msg [D/4][128][4]
+  uint8_t* imgQ = imgF + a.C1P * 512;         // elu(q)+1, then the attention output, then msg [D/4][128][4]
   uint8_t* imgH = smem;                       // mlp hidden         [2D/4][128][4]  (overlays imgF | imgQ once both are consumed)
   uint8_t* ring = smem + img_ch * 512;
-  float* ksum_s = reinterpret_cast<float*>(ring + RING * a.tab.slot_bytes);    // [D]
-  float* g1_s = ksum_s + D;
+  float* ksum_s = reinterpret_cast<float*>(ring + RING * a.tab.slot_bytes);    // [opt][D]
+  float* g1_s = ksum_s + a.opt * D;
   float* b1_s = g1_s + D;
   float* g2_s = b1_s + D;          // [CO]
   float* b2_s = g2_s + a.CO;
-  const int tcols = tmem_cols(max(D2, a.CO));
+  const int tcols = tmem_cols(max(max(D2, a.CO), a.opt * D));
   if (tid == 0) {
     for (int i = 0; i < RING; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
     tc::mbar_init(&stagebar, 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) { tc::tmem_alloc(&tmem_base_s, (uint32_t)tcols); tc::tmem_relinquish(); }
-  for (int i = tid; i < D; i += NTH) {
-    ksum_s[i] = a.ksum[(size_t)b * D + i];
-    g1_s[i] = a.g1[i];
-    b1_s[i] = a.b1[i];
-  }
+  for (int i = tid; i < a.opt * D; i += NTH) ksum_s[i] = (b0 + i / D < a.B) ? a.ksum[(size_t)(b0 + i / D) * D + i % D] : 0.f;
+  for (int i = tid; i < D; i += NTH) { g1_s[i] = a.g1[i]; b1_s[i] = a.b1[i]; }
   for (int i = tid; i < a.CO; i += NTH) { g2_s[i] = a.g2[i]; b2_s[i] = a.b2[i]; }
   tc::tc_fence_before();
   __syncthreads();
@@ -373,7 +459,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
   Pipe p;
   if (tid == 0) {
     p.full = full; p.empty = empty; p.ring_s = tc::smem_u32(ring); p.blob = a.blob;
-    p.obj = a.mimg + (size_t)b * D * D * 4; p.tab = &a.tab;
+    p.obj = a.kvimg + (size_t)b0 * D * dh * 4; p.tab = &a.tab;
     p.loaded = 0; p.used = 0;
     pipe_prefetch(p);
   }
@@ -381,24 +467,25 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
   const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t par = 0;
   const float* F1 = a.feat1 + (size_t)b * a.f1_bs;
-  if (a.f1_pm) load_image_pm(imgF, F1, a.C1, a.C1P, row, valid, tid);
-  else load_image_cm(imgF, F1, a.ldf1, a.C1, a.C1P, row, valid, tid);
+  if (a.f1_pm) load_image_pm(imgF, F1 + (size_t)row * a.C1, a.C1, a.C1P, valid, tid);
+  else load_image_cm(imgF, F1 + row, a.ldf1, a.C1, a.C1P, valid, tid);
+  const float* ksr = ksum_s + ob * D;
 
-  float z[4] = {0.f, 0.f, 0.f, 0.f};        // per-head 1/(Q.Ksum + eps) * S   (H <= 4)
+  float z[4] = {0.f, 0.f, 0.f, 0.f};        // per-head 1 / (Q.Ksum + eps)   (H <= 4)
   if (a.qpre) {
-    // ---- q from HBM: (elu+1), per-head dot with Ksum, scaled image
-    const float* Q = a.q + (size_t)b * a.q_bs;
+    // ---- q from HBM: elu+1 -> operand image, per-head dot with Ksum
+    const float* Q = a.q + (size_t)b * a.q_bs + row;
     float dot[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c0 = 0; c0 < D; c0 += 16) {              // 16 channels per batch (one head: dh is a multiple of 16)
       float v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(Q + (size_t)(c0 + i) * a.ldq + row) : 0.f;
+      for (int i = 0; i < 16; ++i) v[i] = valid ? __ldg(Q + (size_t)(c0 + i) * a.ldq) : 0.f;
       const int h = c0 / dh;
       float dd = 0.f;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         v[i] = elu1(v[i]);
-        dd = fmaf(v[i], ksum_s[c0 + i], dd);
+        dd = fmaf(v[i], ksr[c0 + i], dd);
       }
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) dot[hh] += (hh == h) ? dd : 0.f;
@@ -407,20 +494,10 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
         *reinterpret_cast<float4*>(imgQ + ((c0 >> 2) + j) * 2048 + tid * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     }
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) z[hh] = (1.f / (dot[hh] + 1e-6f)) * (float)a.s_len;
-    for (int c4 = 0; c4 < D / 4; ++c4) {
-      const int h = (4 * c4) / dh;
-      float zz = z[0];
-#pragma unroll
-      for (int hh = 1; hh < 4; ++hh) zz = (hh == h) ? z[hh] : zz;
-      float4* pq = reinterpret_cast<float4*>(imgQ + c4 * 2048 + tid * 16);
-      float4 v = *pq;
-      v.x *= zz; v.y *= zz; v.z *= zz; v.w *= zz;
-      *pq = v;
-    }
+    for (int hh = 0; hh < 4; ++hh) z[hh] = 1.f / (dot[hh] + 1e-6f);
     stage_sync();
   } else {
-    // ---- GEMM 0: q = feat1 . Wq^T, then the same scaling out of TMEM
+    // ---- GEMM 0: q = feat1 . Wq^T, then the same out of TMEM
     stage_sync();
     if (tid == 0) {
       pipe_gemm(p, tmem, tc::smem_u32(imgF), a.C1P, D, false);
@@ -437,35 +514,50 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
       tc::tmem_ld16(tl + 16 * q, r);
       tc::tmem_ld_wait();
       const int h = (16 * q) / dh;
+      float v[16];
       float dd = 0.f;
 #pragma unroll
-      for (int j = 0; j < 16; ++j) dd = fmaf(elu1(__uint_as_float(r[j])), ksum_s[16 * q + j], dd);
+      for (int j = 0; j < 16; ++j) {
+        v[j] = elu1(__uint_as_float(r[j]));
+        dd = fmaf(v[j], ksr[16 * q + j], dd);
+      }
 #pragma unroll
       for (int hh = 0; hh < 4; ++hh) dot[hh] += (hh == h) ? dd : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
     }
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) z[hh] = (1.f / (dot[hh] + 1e-6f)) * (float)a.s_len;
-    for (int q = 0; q < D / 16; ++q) {
-      uint32_t r[16];
-      tc::tmem_ld16(tl + 16 * q, r);
-      tc::tmem_ld_wait();
-      const int h = (16 * q) / dh;
-      float zz = z[0];
-#pragma unroll
-      for (int hh = 1; hh < 4; ++hh) zz = (hh == h) ? z[hh] : zz;
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        float4 v;
-        v.x = elu1(__uint_as_float(r[j + 0])) * zz;
-        v.y = elu1(__uint_as_float(r[j + 1])) * zz;
-        v.z = elu1(__uint_as_float(r[j + 2])) * zz;
-        v.w = elu1(__uint_as_float(r[j + 3])) * zz;
-        *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) = v;
-      }
-    }
+    for (int hh = 0; hh < 4; ++hh) z[hh] = 1.f / (dot[hh] + 1e-6f);
     stage_sync();
   }
-  // ---- GEMM 1: msg = Qs . M   (per-object operand), LayerNorm1
+  // ---- GEMM 1a: (elu(q)+1)_h . KV_h for every object of the tile and every head (K = N = dh), column block o*D + h*dh
+  if (tid == 0) {
+    for (int o = 0; o < a.opt; ++o)
+      for (int h = 0; h < a.H; ++h)
+        pipe_gemm(p, tmem + (uint32_t)(o * D + h * dh), tc::smem_u32(imgQ) + (uint32_t)((h * dh / 8) * 4096), dh, dh, false);
+    tc::umma_commit(&stagebar);
+    pipe_prefetch(p);
+  }
+  __syncwarp();
+  tc::mbar_wait(&stagebar, par);
+  par ^= 1u;
+  tc::tc_fence_after();
+  for (int q = 0; q < D / 16; ++q) {           // this row's object block, scaled by 1 / (Q.Ksum) of its head
+    uint32_t r[16];
+    tc::tmem_ld16(tl + (uint32_t)(ob * D + 16 * q), r);
+    tc::tmem_ld_wait();
+    const int h = (16 * q) / dh;
+    float zz = z[0];
+#pragma unroll
+    for (int hh = 1; hh < 4; ++hh) zz = (hh == h) ? z[hh] : zz;
+#pragma unroll
+    for (int j = 0; j < 16; j += 4)
+      *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) =
+          make_float4(__uint_as_float(r[j]) * zz, __uint_as_float(r[j + 1]) * zz, __uint_as_float(r[j + 2]) * zz, __uint_as_float(r[j + 3]) * zz);
+  }
+  stage_sync();
+  // ---- GEMM 1b: merge projection, LayerNorm1
   if (tid == 0) {
     pipe_gemm(p, tmem, tc::smem_u32(imgQ), D, D, false);
     tc::umma_commit(&stagebar);
@@ -564,14 +656,14 @@ struct TabBuilder {
   uint32_t blob_off = 0;
   bool ok = true;
   int cap;
-  // slots of 32 KB when the operand images leave room for one CTA per SM anyway, 8 KB otherwise (2 ... 5 CTAs per SM)
+  // slots of 16 KB when the operand images leave room for one CTA per SM anyway, 8 KB otherwise (2 ... 5 CTAs per SM)
   explicit TabBuilder(int img_bytes) : cap(img_bytes > 96 * 1024 ? MAX_SLOT : 8192) { t.n = 0; t.slot_bytes = 0; }
-  // one GEMM operand W (K x N image); per_obj parts restart at offset 0 of the object's image
-  void part(int K, int N, bool per_obj) {
+  // one GEMM operand W (K x N image); per_obj parts live at obj_off in the tile's per-object operand array
+  void part(int K, int N, bool per_obj, uint32_t obj_off = 0) {
     int kc = K < 32 ? K : 32;
     while (kc > 8 && kc * N * 4 > cap) kc >>= 1;
     if (kc * N * 4 > MAX_SLOT || (K % 8) || (N % 16)) { ok = false; return; }
-    uint32_t off = per_obj ? 0u : blob_off;
+    uint32_t off = per_obj ? obj_off : blob_off;
     for (int kk = 0; kk < K; kk += kc) {
       const int k = (K - kk) < kc ? (K - kk) : kc;
       if (t.n >= MAXCH) { ok = false; return; }
@@ -599,7 +691,7 @@ int pcreid_attn_front(int B, int S, int C2, int DP, int NFP, int NF, const float
                       void* stream) {
   if (B <= 0 || S <= 0) return PCREID_OK;
   if (!xyz || !feat || !wp0 || !bp0 || !bp2 || !blob || !out) return PCREID_ERR_ARG;
-  if (C2 % 16 || DP % 16 || NFP % 16 || NF % 16 || NFP <= 0 || C2 > 128 || DP > 128 || NFP + NF > 512 || (long long)B * ((S + 127) / 128) > 0x7fffffffLL)
+  if (C2 % 16 || DP % 16 || NFP % 16 || NF % 16 || NFP <= 0 || C2 > 128 || DP > 128 || NFP + NF > 512 || ((long long)B * S + 127) / 128 > 0x7fffffffLL)
     return PCREID_ERR_UNSUPPORTED;
   FrontArgs a;
   a.B = B; a.S = S; a.C2 = C2; a.DP = DP; a.NFP = NFP; a.NF = NF;
@@ -616,44 +708,66 @@ int pcreid_attn_front(int B, int S, int C2, int DP, int NFP, int NF, const float
   const int smem = (C2 + CA) * 512 + RING * a.tab.slot_bytes + (4 * DP + C2) * 4;
   if (smem > 227 * 1024) return PCREID_ERR_UNSUPPORTED;
   cudaFuncSetAttribute(attn_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  attn_front_kernel<<<(unsigned)(((S + 127) / 128) * (long long)B), NTH, smem, (cudaStream_t)stream>>>(a);
+  attn_front_kernel<<<(unsigned)(((long long)B * S + 127) / 128), NTH, smem, (cudaStream_t)stream>>>(a);
   return pcreid_launch_status();
 }
 
-int pcreid_kv_merge(int B, int d, int H, const float* wkv, const float* wmT, float* mimg, void* stream) {
+int pcreid_linattn_kv_img(int B, int S, int d, int H, const float* K, long long k_bs, int ldk, const float* V, long long v_bs, int ldv,
+                          float* kvimg, float* ksum, void* stream) {
   if (B <= 0) return PCREID_OK;
-  if (!wkv || !wmT || !mimg || H <= 0) return PCREID_ERR_ARG;
-  if (d % 4 || d % H || (d / H) % 4 || d > 256) return PCREID_ERR_UNSUPPORTED;
-  const int smem = d * (d / H) * 4;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kv_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  kv_merge_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(d, H, wkv, wmT, mimg);
+  if (!K || !V || !kvimg || !ksum || H <= 0 || S <= 0) return PCREID_ERR_ARG;
+  if (d % H || (d / H) % 4 || d > 128 || d < 16) return PCREID_ERR_UNSUPPORTED;
+  const int ntiles = H * (d / H / 4) * (d / H / 4);
+  if (ntiles > 512 || (ntiles < 256 && 256 % ntiles)) return PCREID_ERR_UNSUPPORTED;
+  const int G = ntiles >= 256 ? 1 : 256 / ntiles;
+  int smem = 2 * d * KV_SCP * 4;
+  if (G > 1 && G * ntiles * 16 * 4 > smem) smem = G * ntiles * 16 * 4;
+  if (ntiles > 256) {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(linattn_kv_img_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    linattn_kv_img_kernel<2><<<B, 256, smem, (cudaStream_t)stream>>>(S, d, H, K, k_bs, ldk, V, v_bs, ldv, kvimg, ksum);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(linattn_kv_img_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    linattn_kv_img_kernel<1><<<B, 256, smem, (cudaStream_t)stream>>>(S, d, H, K, k_bs, ldk, V, v_bs, ldv, kvimg, ksum);
+  }
   return pcreid_launch_status();
 }
 
-// blob: [Wq (C1P -> D) unless q is given][W0a (C1P -> 2D)][W0b (D -> 2D)][W2 (2D -> CO)]
-int pcreid_attn_back_blob_bytes(int D, int C1P, int CO, int qpre) {
-  return 4 * ((qpre ? 0 : C1P * D) + C1P * 2 * D + D * 2 * D + 2 * D * CO);
+// objects per attn_back tile for `rows` query rows per object
+int pcreid_attn_back_objects_per_tile(int rows, int D) {
+  if (rows >= 128 || rows <= 0 || 128 % rows) return 1;
+  const int opt = 128 / rows;
+  return (opt <= 4 && opt * D <= 512) ? opt : 1;
 }
 
-int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int s_len, int res, int f1_pm, const float* feat1, long long f1_bs,
-                     int ldf1, const float* q, long long q_bs, int ldq, const float* ksum, const float* mimg, const float* g1,
+// blob: [Wq (C1P -> D) unless q is given][Wm (D -> D)][W0a (C1P -> 2D)][W0b (D -> 2D)][W2 (2D -> CO)]
+int pcreid_attn_back_blob_bytes(int D, int C1P, int CO, int qpre) {
+  return 4 * ((qpre ? 0 : C1P * D) + D * D + C1P * 2 * D + D * 2 * D + 2 * D * CO);
+}
+
+int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int res, int f1_pm, const float* feat1, long long f1_bs,
+                     int ldf1, const float* q, long long q_bs, int ldq, const float* ksum, const float* kvimg, const float* g1,
                      const float* b1, const float* g2, const float* b2, const void* blob, float* out, long long o_bs, int ldo,
                      void* stream) {
   if (B <= 0 || rows <= 0) return PCREID_OK;
-  if (!feat1 || !ksum || !mimg || !g1 || !b1 || !g2 || !b2 || !blob || !out || H <= 0) return PCREID_ERR_ARG;
+  if (!feat1 || !ksum || !kvimg || !g1 || !b1 || !g2 || !b2 || !blob || !out || H <= 0) return PCREID_ERR_ARG;
   const int C1P = (C1 + 7) & ~7;
-  if (D % 16 || D > 128 || H > 4 || D % H || (D / H) % 16 || CO % 16 || CO > 2 * D || C1 <= 0 || C1P > 128 || (long long)B * ((rows + 127) / 128) > 0x7fffffffLL)
-    return PCREID_ERR_UNSUPPORTED;
+  if (D % 16 || D > 128 || H > 4 || D % H || (D / H) % 16 || CO % 16 || CO > 2 * D || C1 <= 0 || C1P > 128) return PCREID_ERR_UNSUPPORTED;
   if (res && C1 != CO) return PCREID_ERR_ARG;
+  const int dh = D / H;
   BackArgs a;
-  a.B = B; a.rows = rows; a.D = D; a.H = H; a.C1 = C1; a.C1P = C1P; a.CO = CO; a.s_len = s_len;
+  a.B = B; a.rows = rows; a.D = D; a.H = H; a.C1 = C1; a.C1P = C1P; a.CO = CO;
+  a.opt = pcreid_attn_back_objects_per_tile(rows, D);
   a.qpre = q ? 1 : 0; a.res = res; a.f1_pm = f1_pm;
   a.feat1 = feat1; a.f1_bs = f1_bs; a.ldf1 = ldf1; a.q = q; a.q_bs = q_bs; a.ldq = ldq; a.ksum = ksum;
-  a.mimg = reinterpret_cast<const uint8_t*>(mimg); a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
+  a.kvimg = reinterpret_cast<const uint8_t*>(kvimg); a.g1 = g1; a.b1 = b1; a.g2 = g2; a.b2 = b2;
   a.blob = static_cast<const uint8_t*>(blob); a.out = out; a.o_bs = o_bs; a.ldo = ldo;
+  const long long tiles = a.opt > 1 ? ((long long)B + a.opt - 1) / a.opt : (long long)B * ((rows + 127) / 128);
+  if (tiles > 0x7fffffffLL) return PCREID_ERR_UNSUPPORTED;
   TabBuilder tb(((C1P + D) > 2 * D ? (C1P + D) : 2 * D) * 512);
   if (!q) tb.part(C1P, D, false);
-  tb.part(D, D, true);
+  for (int o = 0; o < a.opt; ++o)
+    for (int h = 0; h < H; ++h) tb.part(dh, dh, true, (uint32_t)((o * H + h) * dh * dh * 4));
+  tb.part(D, D, false);
   tb.part(C1P, 2 * D, false);
   tb.part(D, 2 * D, false);
   tb.part(2 * D, CO, false);
@@ -661,10 +775,10 @@ int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int s_len, i
   if (!tb.ok) return PCREID_ERR_UNSUPPORTED;
   a.tab = tb.t;
   const int img_ch = (C1P + D) > 2 * D ? (C1P + D) : 2 * D;
-  const int smem = img_ch * 512 + RING * a.tab.slot_bytes + (3 * D + 2 * CO) * 4;
-  if (smem > 227 * 1024) return PCREID_ERR_UNSUPPORTED;
+  const int smem = img_ch * 512 + RING * a.tab.slot_bytes + ((a.opt + 2) * D + 2 * CO) * 4;
+  if (smem > 227 * 1024 - 256) return PCREID_ERR_UNSUPPORTED;
   cudaFuncSetAttribute(attn_back_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  attn_back_kernel<<<(unsigned)(((rows + 127) / 128) * (long long)B), NTH, smem, (cudaStream_t)stream>>>(a);
+  attn_back_kernel<<<(unsigned)tiles, NTH, smem, (cudaStream_t)stream>>>(a);
   return pcreid_launch_status();
 }
 

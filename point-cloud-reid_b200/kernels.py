@@ -305,18 +305,27 @@ def attn_front(xyz, feat, wp0, bp0, bp2, blob, DP, NFP, NF):
     return out
 
 
-def kv_merge(wkv, merge_kmajor, nhead):
-    """(B, d, d) block-diagonal KV summaries x merge projection -> per-object tcgen05 operand images (B, d*d)."""
-    _need_cuda(wkv, merge_kmajor)
-    B, d, _ = wkv.shape
-    mimg = torch.empty((B, d * d), device=wkv.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_kv_merge(B, d, nhead, _p(wkv), _p(merge_kmajor), _p(mimg), _stream()), "pcreid_kv_merge")
-    return mimg
+def linattn_kv_img(k, v, nhead, rows_q):
+    """KV summaries of linear attention as per-object, per-head tcgen05 operand images + Ksum, from pre-activation keys /
+    values (B, d, S) channel-major views.  rows_q = query rows per object of the attn_back call that will consume them
+    (objects of a packed tile must be contiguous, so the allocation is rounded up to the tile's object count)."""
+    _need_cuda(k, v)
+    B, d, S = k.shape
+    k_bs, ldk = _cn(k, "k")
+    v_bs, ldv = _cn(v, "v")
+    L = _lib.lib()
+    opt = L.pcreid_attn_back_objects_per_tile(rows_q, d)
+    kvimg = torch.empty(((B + opt - 1) // opt * opt, d * (d // nhead)), device=k.device, dtype=torch.float32)
+    ksum = torch.empty((B, d), device=k.device, dtype=torch.float32)
+    _lib.check(L.pcreid_linattn_kv_img(B, S, d, nhead, _p(k), k_bs, ldk, _p(v), v_bs, ldv, _p(kvimg), _p(ksum), _stream()),
+               "pcreid_linattn_kv_img")
+    return kvimg, ksum
 
 
-def attn_back(feat1, q, ksum, mimg, g1, b1, g2, b2, blob, nhead, CO, s_len, residual, feat1_pm=False):
-    """query-side half of a linear-attention block: (q | Wq feat1) -> scaling -> . M -> LN1 -> mlp -> LN2 (+ feat1)."""
-    _need_cuda(feat1, q, ksum, mimg, blob)
+def attn_back(feat1, q, ksum, kvimg, g1, b1, g2, b2, blob, nhead, CO, residual, feat1_pm=False):
+    """query-side half of a linear-attention block: (q | Wq feat1) -> elu+1 -> . KV per head -> / (Q.Ksum) -> merge -> LN1
+    -> mlp -> LN2 (+ feat1)."""
+    _need_cuda(feat1, q, ksum, kvimg, blob)
     D = ksum.shape[1]
     if feat1_pm:
         if not feat1.is_contiguous():
@@ -332,9 +341,12 @@ def attn_back(feat1, q, ksum, mimg, g1, b1, g2, b2, blob, nhead, CO, s_len, resi
     L = _lib.lib()
     if blob.numel() * 4 != L.pcreid_attn_back_blob_bytes(D, (C1 + 7) // 8 * 8, CO, int(q is not None)):
         raise ValueError("attn_back: weight blob does not match the shapes")
+    opt = L.pcreid_attn_back_objects_per_tile(rows, D)
+    if kvimg.shape[0] < (B + opt - 1) // opt * opt:
+        raise ValueError("attn_back: kvimg must hold the objects of the last tile (use linattn_kv_img(..., rows_q=rows))")
     out = torch.empty((B, CO, rows), device=feat1.device, dtype=torch.float32)
-    _lib.check(L.pcreid_attn_back(B, rows, D, nhead, C1, CO, s_len, int(residual), int(feat1_pm), _p(feat1), f1_bs, ldf1, _p(q), q_bs,
-                                  ldq, _p(ksum), _p(mimg), _p(g1), _p(b1), _p(g2), _p(b2), _p(blob), _p(out), out.stride(0),
+    _lib.check(L.pcreid_attn_back(B, rows, D, nhead, C1, CO, int(residual), int(feat1_pm), _p(feat1), f1_bs, ldf1, _p(q), q_bs,
+                                  ldq, _p(ksum), _p(kvimg), _p(g1), _p(b1), _p(g2), _p(b2), _p(blob), _p(out), out.stride(0),
                                   out.stride(1), _stream()), "pcreid_attn_back")
     return out
 

@@ -56,7 +56,7 @@ class Self_Attention(PackedModule):
                                  nn.Linear(d_model * 2, d_model, bias=False))
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(d_model)
-        self.tc_mode = False      # True: the block runs as attn_front / kv_merge / attn_back on the tensor cores (fast mode)
+        self.tc_mode = False      # True: the block runs as attn_front / linattn_kv_img / attn_back on the tensor cores (fast mode)
 
     def _pack(self):
         d = self.q_proj.weight.shape[0]
@@ -71,7 +71,8 @@ class Self_Attention(PackedModule):
         if fused_attention_supported(d, self.nhead, d, d, d):
             pk["front_blob"] = K.weight_blob(K.tf32_image(self.pos_mlp[2].weight),
                                              K.tf32_image(torch.cat([self.q_proj.weight, self.k_proj.weight, self.v_proj.weight], 0)))
-            pk["back_blob"] = K.weight_blob(K.tf32_image(m0[:, :d]), K.tf32_image(m0[:, d:]), K.tf32_image(self.mlp[2].weight))
+            pk["back_blob"] = K.weight_blob(K.tf32_image(self.merge.weight), K.tf32_image(m0[:, :d]), K.tf32_image(m0[:, d:]),
+                                            K.tf32_image(self.mlp[2].weight))
         return pk
 
     def forward(self, feat, xyz, mask=None):
@@ -81,10 +82,9 @@ class Self_Attention(PackedModule):
         C, S = feat.shape[1], feat.shape[2]
         if self.tc_mode and "front_blob" in pk:
             qkv = K.attn_front(xyz, feat, pk["pos0"], pk["pos0b"], pk["pos2b"], pk["front_blob"], C, 3 * C, 0)
-            wkv, ksum = K.linattn_kv(qkv[:, C:2 * C], qkv[:, 2 * C:], self.nhead)
-            mimg = K.kv_merge(wkv, pk["merge"], self.nhead)
-            return K.attn_back(feat, qkv[:, :C], ksum, mimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
-                               self.nhead, C, S, residual=True)
+            kvimg, ksum = K.linattn_kv_img(qkv[:, C:2 * C], qkv[:, 2 * C:], self.nhead, S)
+            return K.attn_back(feat, qkv[:, :C], ksum, kvimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
+                               self.nhead, C, residual=True)
         hid = K.cn_linear(xyz, pk["pos0"], bias=pk["pos0b"], act=K.ACT_RELU, x1_pm=True)
         feat_pos = K.cn_linear(hid, pk["pos2"], bias=pk["pos2b"], res=feat)
         qkv = K.cn_linear(feat_pos, pk["qkv"])
@@ -169,7 +169,7 @@ class FP_SA(PackedModule):
                                  nn.Linear(d_model * 2, out_dim, bias=False))
         self.norm1 = nn.LayerNorm(d_model)
         self.norm2 = nn.LayerNorm(out_dim)
-        self.tc_mode = False      # True: the block runs as attn_front / kv_merge / attn_back on the tensor cores (fast mode)
+        self.tc_mode = False      # True: the block runs as attn_front / linattn_kv_img / attn_back on the tensor cores (fast mode)
 
     def _pack(self):
         f1 = self.q_proj.weight.shape[1]
@@ -186,8 +186,9 @@ class FP_SA(PackedModule):
             f1p = (f1 + 7) // 8 * 8
             pk["front_blob"] = K.weight_blob(K.tf32_image(self.pos_mlp2[2].weight), K.tf32_image(self.v_proj.weight),
                                              K.tf32_image(self.k_proj.weight))
-            pk["back_blob"] = K.weight_blob(K.tf32_image_padded(self.q_proj.weight, f1p), K.tf32_image_padded(m0[:, :f1], f1p),
-                                            K.tf32_image(m0[:, f1:]), K.tf32_image(self.mlp[2].weight))
+            pk["back_blob"] = K.weight_blob(K.tf32_image_padded(self.q_proj.weight, f1p), K.tf32_image(self.merge.weight),
+                                            K.tf32_image_padded(m0[:, :f1], f1p), K.tf32_image(m0[:, f1:]),
+                                            K.tf32_image(self.mlp[2].weight))
         return pk
 
     def forward(self, feat1, xyz1, feat2, xyz2, mask=None, feat1_point_major=False):
@@ -197,10 +198,10 @@ class FP_SA(PackedModule):
         if self.tc_mode and "front_blob" in pk:
             d, out = self.q_proj.weight.shape[0], self.mlp[2].weight.shape[0]
             vk = K.attn_front(xyz2, feat2, pk["pos0"], pk["pos0b"], pk["pos2b"], pk["front_blob"], d, d, d)
-            wkv, ksum = K.linattn_kv(vk[:, d:], vk[:, :d], self.nhead)
-            mimg = K.kv_merge(wkv, pk["merge"], self.nhead)
-            return K.attn_back(feat1, None, ksum, mimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
-                               self.nhead, out, S, residual=False, feat1_pm=feat1_point_major)
+            rows_q = feat1.shape[1] if feat1_point_major else feat1.shape[2]
+            kvimg, ksum = K.linattn_kv_img(vk[:, d:], vk[:, :d], self.nhead, rows_q)
+            return K.attn_back(feat1, None, ksum, kvimg, pk["n1w"], pk["n1b"], pk["n2w"], pk["n2b"], pk["back_blob"],
+                               self.nhead, out, residual=False, feat1_pm=feat1_point_major)
         hid = K.cn_linear(xyz2, pk["pos0"], bias=pk["pos0b"], act=K.ACT_RELU, x1_pm=True)
         feat2_pos = K.cn_linear(hid, pk["pos2"], bias=pk["pos2b"], res=feat2)
         q = K.cn_linear(feat1, pk["q"], x1_pm=feat1_point_major)
