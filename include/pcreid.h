@@ -138,6 +138,12 @@ int pcreid_linattn_kv(int B, int S, int d, int H, const float* K, long long k_bs
 int pcreid_linattn_scale(int B, int rows, int d, int H, int S, const float* Q, long long q_bs, int ldq, const int* q_map,
                          const float* ksum, const int* ksum_map, float* Qs, long long qs_bs, int ldqs, void* stream);
 
+/* local_self_attention core (attention.py:221-296, the 'xcorr' match type): every point attends its knum feature-space
+ * neighbours (idx from pcreid_knn_feature) with one query: out[b,n,h,:] = sum_j w_j v_j / (sum_j w_j + 1e-6),
+ * w_j = (elu(q_h)+1).(elu(k_jh)+1).  qkv point-major (B, N, 3C) rows [q | k | v] pre-activation, out point-major (B, N, C).
+ * C a multiple of 32 up to 128, H in {1, 2, 4}. */
+int pcreid_local_linattn(int B, int N, int C, int H, int knum, const float* qkv, const int* idx, float* out, void* stream);
+
 /* pooling over points (ReIDNet.get_pooled_feats, ReIDNet.py:526-534; PointNet max-pool pointnet.py:31,70).
  * mode 0: out[b, c] = max_n, out[b, C + c] = mean_n over the rows of X1 (and X2 if given: 'point-cat');
  * mode 1: max only.  Output element (b, c) at out + b*ob + c*oc. */

@@ -30,8 +30,9 @@ def checksum(sd):
     return float(sum(v.double().abs().sum() for k, v in sorted(sd.items()) if v.dtype.is_floating_point))
 
 
-def build_reference(R, kind):
-    """Reference modules in ReIDNet.__init__ construction order (backbone, match_head, downsample, cross_stage1/2)."""
+def build_reference(R, kind, local=False):
+    """Reference modules in ReIDNet.__init__ construction order (backbone, match_head, downsample, cross_stage1,
+    local_stage1, cross_stage2, local_stage2; ReIDNet.py:125-136)."""
     torch.manual_seed(66)
     mods = {}
     if kind == "pt":
@@ -48,7 +49,11 @@ def build_reference(R, kind):
         mods["downsample"] = torch.nn.Sequential(R.LinearRes(1024, 512, norm='GN', ng=64), R.LinearRes(512, 128, norm='GN', ng=16),
                                                  torch.nn.Linear(128, 64))
     mods["cross_stage1"] = R.corss_attention(d_model=64, nhead=2, attention='linear')
+    if local:   # reid_pts_point-transformer_baseline_orig.py
+        mods["local_stage1"] = R.local_self_attention(d_model=64, nhead=2, attention='linear', knum=48, pos_size=64)
     mods["cross_stage2"] = R.corss_attention(d_model=64, nhead=2, attention='linear')
+    if local:
+        mods["local_stage2"] = R.local_self_attention(d_model=64, nhead=2, attention='linear', knum=48, pos_size=64)
     net = torch.nn.ModuleDict(mods).eval()
     sd = O.perturb_norm_state(net.state_dict())
     net.load_state_dict(sd)
@@ -76,9 +81,40 @@ def ref_match(net, h1, h2, xyz1, xyz2):
     return net["match_head"](pooled).squeeze(1)
 
 
+@torch.no_grad()
+def ref_match_search(net, h1, h2, xyz1, xyz2, local):
+    """ReIDNet.xcorr / xcorr_baseline + get_pooled_feats('both') + match_head (ReIDNet.py:250-264, 444-448)."""
+    a = net["cross_stage1"](h1, xyz1, h2, xyz2)
+    if local:
+        a = net["local_stage1"](a, xyz1)
+    a = net["cross_stage2"](a, xyz1, h2, xyz2)
+    if local:
+        a = net["local_stage2"](a, xyz1)
+    pooled = torch.cat((F.adaptive_max_pool1d(a, 1).view(a.size(0), -1), F.adaptive_avg_pool1d(a, 1).view(a.size(0), -1)), 1)
+    return net["match_head"](pooled).squeeze(1)
+
+
+def main_xcorr(R):
+    """'xcorr' (local_self_attention stages) and 'xcorr-baseline' match types of the shipped PT configs."""
+    for kind, local in (("xcorr", True), ("xcorr-baseline", False)):
+        net, sd = build_reference(R, "pt", local=local)
+        T, D, N, blist = 3, 4, 128, [128, 64, 32]
+        t, d = O.synth_objects(T, N, 0), O.synth_objects(D, N, 1)
+        xt, ht = ref_encode(net, "pt", t, blist)
+        xd, hd = ref_encode(net, "pt", d, blist)
+        pairs = torch.cartesian_prod(torch.arange(T), torch.arange(D))
+        logits = ref_match_search(net, ht[pairs[:, 0]], hd[pairs[:, 1]], xt[pairs[:, 0]], xd[pairs[:, 1]], local).reshape(T, D)
+        np.savez_compressed(os.path.join(OUT, f"reid_{kind}.npz"), tracks=t.numpy(), dets=d.numpy(), h_t=ht.numpy(),
+                            h_d=hd.numpy(), logits=logits.numpy(), weight_checksum=np.float64(checksum(sd)),
+                            backbone_list=np.array(blist))
+        print(kind, "logits std", float(logits.std()), "checksum", checksum(sd))
+
+
 def main():
     R = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
+    if "--xcorr-only" in sys.argv:
+        return main_xcorr(R)
     for kind, N, blist, T, D in (("pt", 128, [128, 64, 32], 4, 5), ("pt256", 256, [256, 128, 64], 2, 3),
                                  ("dgcnn", 128, [128, 64, 32], 3, 4), ("pointnet", 128, [128, 64, 32], 4, 4)):
         base = "pt" if kind.startswith("pt") else kind
@@ -102,6 +138,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "knn_torch_path.npz"), xyz=x.numpy(), idx=idx.numpy().astype(np.int32),
                         feat=xf.numpy(), idx_feat=idx_f.numpy().astype(np.int32))
     print("knn golden written")
+    main_xcorr(R)
 
 
 if __name__ == "__main__":

@@ -70,6 +70,7 @@ _SIGS = {
     "pcreid_attn_back": [c_int] * 8 + [c_vp, c_ll, c_int, c_vp, c_ll, c_int] + [c_vp] * 7 + [c_vp, c_ll, c_int, c_vp],
     "pcreid_linattn_kv": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_linattn_scale": [c_int, c_int, c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_ll, c_int, c_vp],
+    "pcreid_local_linattn": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_cn_pool": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_ll, c_vp],
     "pcreid_cn_chanmax": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_ll, c_vp],
     "pcreid_sa_edge_mlp": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],

@@ -408,6 +408,45 @@ __global__ void __launch_bounds__(128) linattn_scale_kernel(int rows, int d, int
 }
 
 // ------------------------------------------------------------------------------------------------
+// local_self_attention (mmdet3d/models/attention.py:221-296): every point attends its knum nearest neighbours in
+// feature space with the linear-attention kernel, one query per point:
+//   w_jh = (elu(q_h)+1) . (elu(k_jh)+1),   out_h = sum_j w_jh v_jh / (sum_j w_jh + 1e-6)
+// (LinearAttention with L = 1, S = knum: the reference's v / S and x S cancel).  One warp per point; lanes own C/32
+// contiguous channels, so a head is a contiguous lane range and its dot products reduce with xor shuffles.
+// qkv point-major (B, N, 3C) rows [q | k | v] (pre-activation), idx (B, N, knum), out point-major (B, N, C).
+// ------------------------------------------------------------------------------------------------
+template <int CPL>
+__global__ void __launch_bounds__(256) local_linattn_kernel(long long rows, int N, int C, int H, int knum, const float* __restrict__ qkv,
+                                                            const int* __restrict__ idx, float* __restrict__ out) {
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const long long b = r / N;
+  const float* base = qkv + (size_t)b * N * 3 * C;
+  const float* qrow = qkv + (size_t)r * 3 * C + lane * CPL;
+  const int lph = 32 / H;                                    // lanes per head
+  float qf[CPL], acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) { qf[i] = apply_act(qrow[i], ACT_ELU1); acc[i] = 0.f; }
+  float wsum = 0.f;
+  const int* ir = idx + (size_t)r * knum;
+  for (int j = 0; j < knum; ++j) {
+    const float* nrow = base + (size_t)__ldg(ir + j) * 3 * C + lane * CPL;
+    float w = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) w = fmaf(qf[i], apply_act(__ldg(nrow + C + i), ACT_ELU1), w);
+    for (int o = lph >> 1; o > 0; o >>= 1) w += __shfl_xor_sync(FULL_MASK, w, o);
+    wsum += w;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) acc[i] = fmaf(w, __ldg(nrow + 2 * C + i), acc[i]);
+  }
+  const float z = 1.f / (wsum + 1e-6f);
+  float* o = out + (size_t)r * C + lane * CPL;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) o[i] = acc[i] * z;
+}
+
+// ------------------------------------------------------------------------------------------------
 // unfused SA edge path for channel counts above the fused kernel's tile (C > 128: the mul=2 / mul=4 model variants):
 //   edge_build : H1[b,c,s*k+j] = relu(P1[b,c,idx[b,s,j]] + Cc[b,c,s])       (then two cn_linear calls)
 //   seg_max    : out[b,c,s]    = max_j X[b,c,s*k+j]
@@ -770,6 +809,22 @@ int pcreid_linattn_scale(int B, int rows, int d, int H, int S, const float* Q, l
     linattn_scale_kernel<<<dim3(ceil_div(rows, 128), nb), 128, 0, st>>>(
         rows, d, H, S, q_map ? Q : Q + (size_t)b0 * q_bs, q_bs, ldq, q_map ? q_map + b0 : nullptr,
         ksum_map ? ksum : ksum + (size_t)b0 * d, ksum_map ? ksum_map + b0 : nullptr, Qs + (size_t)b0 * qs_bs, qs_bs, ldqs);
+  }
+  return pcreid_launch_status();
+}
+
+int pcreid_local_linattn(int B, int N, int C, int H, int knum, const float* qkv, const int* idx, float* out, void* stream) {
+  if (B <= 0 || N <= 0) return PCREID_OK;
+  if (!qkv || !idx || !out || knum <= 0 || H <= 0) return PCREID_ERR_ARG;
+  if (C % 32 || C > 128 || (H != 1 && H != 2 && H != 4) || C % H) return PCREID_ERR_UNSUPPORTED;
+  const long long rows = (long long)B * N;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C / 32) {
+    case 1: local_linattn_kernel<1><<<grid, 256, 0, st>>>(rows, N, C, H, knum, qkv, idx, out); break;
+    case 2: local_linattn_kernel<2><<<grid, 256, 0, st>>>(rows, N, C, H, knum, qkv, idx, out); break;
+    case 3: local_linattn_kernel<3><<<grid, 256, 0, st>>>(rows, N, C, H, knum, qkv, idx, out); break;
+    default: local_linattn_kernel<4><<<grid, 256, 0, st>>>(rows, N, C, H, knum, qkv, idx, out); break;
   }
   return pcreid_launch_status();
 }

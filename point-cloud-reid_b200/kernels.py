@@ -176,6 +176,20 @@ def linattn_scale(q, ksum, nhead, s_len, q_map=None, ksum_map=None, B=None):
     return out
 
 
+def local_linattn(qkv_pm, idx, nhead):
+    """per-point linear attention over gathered neighbours: qkv_pm (B, N, 3C) point-major [q | k | v], idx (B, N, k) int32
+    -> (B, N, C) point-major."""
+    _need_cuda(qkv_pm, idx)
+    if not (qkv_pm.is_contiguous() and idx.is_contiguous()) or idx.dtype != torch.int32:
+        raise ValueError("local_linattn inputs must be contiguous (idx int32)")
+    B, N, C3 = qkv_pm.shape
+    C = C3 // 3
+    out = torch.empty((B, N, C), device=qkv_pm.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_local_linattn(B, N, C, nhead, idx.shape[2], _p(qkv_pm), _p(idx), _p(out), _stream()),
+               "pcreid_local_linattn")
+    return out
+
+
 def cn_pool(x1, x2=None, mode=0, out=None, transposed=False):
     """mode 0: cat(max, mean) over points of x1 (and x2); mode 1: max.  -> (B, C') or, transposed, (1, C', B)."""
     _need_cuda(x1, x2)

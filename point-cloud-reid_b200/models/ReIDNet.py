@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from .. import kernels as K
-from .attention import corss_attention
+from .attention import corss_attention, local_self_attention
 from .backbone_net import Pointnet_Backbone
 from .builder import FUSIONMODELS
 from .dgcnn_orig import DGCNN
@@ -24,9 +24,9 @@ module_obj = {
     'Linear': nn.Linear, 'ReLU': nn.ReLU, 'LSTM': nn.LSTM, 'GroupNorm': nn.GroupNorm, 'Embedding': nn.Embedding,
     'LayerNorm': nn.LayerNorm, 'LinearRes': LinearRes, 'Pointnet_Backbone': Pointnet_Backbone,
     'corss_attention': corss_attention, 'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d, 'BatchNorm1d': nn.BatchNorm1d,
-    'Sigmoid': nn.Sigmoid, 'dgcnn': DGCNN, 'PointNet': PointNet,
+    'Sigmoid': nn.Sigmoid, 'dgcnn': DGCNN, 'PointNet': PointNet, 'local_self_attention': local_self_attention,
 }
-_OUT_OF_SCOPE = ('PostRes', 'local_self_attention', 'cross_lin_attn')   # image / 'xcorr' matchers
+_OUT_OF_SCOPE = ('PostRes', 'cross_lin_attn')   # image-token matcher
 
 
 def build_module(cfg):
@@ -98,7 +98,7 @@ class ReIDNet(nn.Module):
         # are issued by the GPU front-end instead of by ~90 Python -> ctypes -> cudaLaunchKernel round trips
         self.cuda_graphs = False
         self._graphs = {}
-        if self.match_type not in ('xcorr_eff', 'concat'):
+        if self.match_type not in ('xcorr_eff', 'concat', 'xcorr', 'xcorr-baseline'):
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
                                       "(shipped point configs use 'xcorr_eff'; the baseline uses 'concat')")
 
@@ -230,6 +230,9 @@ class ReIDNet(nn.Module):
                 e2 = K.cn_chanmax(_cn(h2))
                 cat = torch.cat([e1, e2], dim=1).t().contiguous().unsqueeze(0)
                 return self._head_cn(cat)
+            if self.match_type in ('xcorr', 'xcorr-baseline'):
+                ar = torch.arange(P, device=h1.device, dtype=torch.int32)
+                return self._xcorr_search_pairs(_cn(h1), xyz1.float().contiguous(), _cn(h2), xyz2.float().contiguous(), ar, ar)
             raise NotImplementedError
 
     # ------------------------------------------------------------------ all-pairs driver
@@ -250,6 +253,38 @@ class ReIDNet(nn.Module):
         o1 = X2.attend(a, X2.search_query(a), wkv_b, ks_b, N_d)
         o2 = X2.attend(b, X2.search_query(b), wkv_a, ks_a, N_t)
         return self._pairs_head(o1, o2)
+
+    def xcorr(self, search_feat, search_xyz, template_feat, template_xyz):
+        """ReIDNet.xcorr (ReIDNet.py:250-256): cross -> local -> cross -> local, the search side only."""
+        a = self.cross_stage1(search_feat, search_xyz, template_feat, template_xyz)
+        a = self.local_stage1(a, search_xyz)
+        a = self.cross_stage2(a, search_xyz, template_feat, template_xyz)
+        return self.local_stage2(a, search_xyz)
+
+    def xcorr_baseline(self, search_feat, search_xyz, template_feat, template_xyz):
+        """ReIDNet.xcorr_baseline (ReIDNet.py:258-264): the two cross stages only."""
+        a = self.cross_stage1(search_feat, search_xyz, template_feat, template_xyz)
+        return self.cross_stage2(a, search_xyz, template_feat, template_xyz)
+
+    def _xcorr_search_pairs(self, h_t, xyz_t, h_d, xyz_d, ti, dj):
+        """'xcorr' / 'xcorr-baseline' + pooling + head for the pairs (ti[p], dj[p]): the track is the search object, the
+        detection the template; BOTH cross stages attend the template's original features, so their key/value summaries
+        are per-object work; only the attention read-out (and the local stages) run per pair."""
+        X1, X2 = self.cross_stage1, self.cross_stage2
+        N_d = h_d.shape[2]
+        local = self.match_type == 'xcorr'
+        wkv1, ks1 = X1.template_summary(h_d, X1.position_code(xyz_d))
+        wkv2, ks2 = X2.template_summary(h_d, X2.position_code(xyz_d))
+        a = X1.attend(h_t, X1.search_query(h_t), wkv1, ks1, N_d, s_map=ti, t_map=dj)
+        if local:
+            xyz_s = xyz_t[ti.long()].contiguous()
+            a = self.local_stage1(a, xyz_s)
+        a = X2.attend(a, X2.search_query(a), wkv2, ks2, N_d, t_map=dj)
+        if local:
+            a = self.local_stage2(a, xyz_s)
+        if self.pool_type == 'both':
+            return self._head_cn(K.cn_pool(a, None, mode=0, transposed=True))
+        return self._head_cn(self.get_pooled_feats(a).t().contiguous().unsqueeze(0))
 
     def _pairs_head(self, o1, o2):
         if self.pool_type == 'both' and self.combine == 'point-cat':
@@ -301,8 +336,10 @@ class ReIDNet(nn.Module):
                     lin = ti * D + dj
                 if fused is not None:
                     flat[lin] = fused.match(pk_t, pk_d, ti, dj)
-                else:
+                elif self.match_type == 'xcorr_eff':
                     flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
+                else:
+                    flat[lin] = self._xcorr_search_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
             return out
 
     def pooled_embedding(self, h):

@@ -67,6 +67,57 @@ class corss_attention(PackedModule):
         return self.attend(search_feat, self.search_query(search_feat), wkv, ksum, template_feat.shape[2])
 
 
+class local_self_attention(PackedModule):
+    """mmdet3d/models/attention.py:221-296: every point attends its `knum` nearest neighbours in FEATURE space
+    (the 'xcorr' match type, reid_pts_point-transformer_baseline_orig.py)."""
+
+    def __init__(self, d_model, nhead, attention='linear', knum=32, pos_size=16):
+        super().__init__()
+        self.d_model = d_model
+        self.dim = d_model // nhead
+        self.nhead = nhead
+        self.knum = knum
+        self.pos_mlp_knn = nn.Sequential(nn.Linear(3, pos_size), nn.ReLU(True), nn.Linear(pos_size, pos_size))
+        self.q_proj_knn = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj_knn = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj_knn = nn.Linear(d_model, d_model, bias=False)
+        self.attention_knn = LinearAttention()
+        self.merge_knn = nn.Linear(d_model, d_model, bias=False)
+        self.mlp_knn = nn.Sequential(nn.Linear(d_model * 2, d_model * 2, bias=False), nn.ReLU(True),
+                                     nn.Linear(d_model * 2, d_model, bias=False))
+        self.norm1_knn = nn.LayerNorm(d_model)
+        self.norm2_knn = nn.LayerNorm(d_model)
+        if pos_size != d_model:
+            raise ValueError("local_self_attention adds pos_mlp_knn(xyz) to the features: pos_size must equal d_model "
+                             "(attention.py:277-278)")
+
+    def _pack(self):
+        d = self.d_model
+        m0 = self.mlp_knn[0].weight.detach()
+        f = lambda t: t.detach().float().contiguous()
+        return dict(
+            pos0=kmajor(self.pos_mlp_knn[0].weight), pos0b=f(self.pos_mlp_knn[0].bias),
+            pos2=kmajor(self.pos_mlp_knn[2].weight), pos2b=f(self.pos_mlp_knn[2].bias),
+            qkv=kmajor(torch.cat([self.q_proj_knn.weight, self.k_proj_knn.weight, self.v_proj_knn.weight], 0)),
+            merge=kmajor(self.merge_knn.weight), mlp0a=kmajor(m0[:, :d]), mlp0b=kmajor(m0[:, d:]), mlp2=kmajor(self.mlp_knn[2].weight),
+            n1w=f(self.norm1_knn.weight), n1b=f(self.norm1_knn.bias), n2w=f(self.norm2_knn.weight), n2b=f(self.norm2_knn.bias))
+
+    def forward(self, search_feat, search_xyz, mask=None):
+        """search_feat (B, C, N), search_xyz (B, N, 3) -> (B, C, N)."""
+        pk = self.packed()
+        feat = _cn_view(search_feat)
+        if not feat.is_contiguous():
+            feat = feat.contiguous()
+        xyz = search_xyz.contiguous().float()
+        kidx = K.knn_feature(feat, self.knum)                                   # (B, N, knum), includes the point itself
+        hid = K.cn_linear(xyz, pk["pos0"], bias=pk["pos0b"], act=K.ACT_RELU, x1_pm=True)
+        feat_pos = K.cn_linear(hid, pk["pos2"], bias=pk["pos2b"], res=feat)
+        qkv = K.cn_linear(feat_pos, pk["qkv"], y_pm=True)                       # (B, N, 3C) point-major rows
+        att = K.local_linattn(qkv, kidx, self.nhead)                            # (B, N, C) point-major
+        msg = K.cn_groupnorm(K.cn_linear(att, pk["merge"], x1_pm=True), pk["n1w"], pk["n1b"], 1)
+        return attention_ffn(feat, msg, pk, residual=True)
+
+
 def _cn_view(t):
     """accepts any (B, C, N) float tensor; copies only if the point axis is not unit-stride."""
     t = t.float()

@@ -107,6 +107,20 @@ def knn_feature(x, k):
     return torch.sort(pd, dim=-1, descending=True, stable=True)[1][..., :k].to(torch.int32).contiguous()
 
 
+def local_linattn(qkv_pm, idx, nhead):
+    """specification of pcreid_local_linattn: one query per point over its gathered neighbours."""
+    B, N, C3 = qkv_pm.shape
+    C, k = C3 // 3, idx.shape[2]
+    q = F.elu(qkv_pm[..., :C]) + 1
+    bidx = torch.arange(B).view(B, 1, 1).expand(B, N, k)
+    nb = qkv_pm[bidx, idx.long()]                                            # (B, N, k, 3C)
+    kf, v = F.elu(nb[..., C:2 * C]) + 1, nb[..., 2 * C:]
+    dh = C // nhead
+    w = (q.view(B, N, 1, nhead, dh) * kf.view(B, N, k, nhead, dh)).sum(-1)   # (B, N, k, H)
+    num = (w.unsqueeze(-1) * v.view(B, N, k, nhead, dh)).sum(2)              # (B, N, H, dh)
+    return (num / (w.sum(2).unsqueeze(-1) + 1e-6)).reshape(B, N, C).contiguous()
+
+
 def _gather_pts(p, idx):
     B, C, N = p.shape
     S, k = idx.shape[1], idx.shape[2]
@@ -155,7 +169,7 @@ def install(monkeypatch=None):
     """Replaces pcreid_b200.kernels' entry points by the emulations above (optionally via pytest's monkeypatch)."""
     import pcreid_b200.kernels as K
     names = ["cn_linear", "cn_groupnorm", "linattn_kv", "linattn_scale", "cn_pool", "cn_chanmax", "knn_point",
-             "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head"]
+             "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head", "local_linattn"]
     for n in names:
         if monkeypatch is not None:
             monkeypatch.setattr(K, n, globals()[n])

@@ -27,6 +27,13 @@ def model_cfg(kind="pt", backbone_list=(128, 64, 32)):
         c.update(match_type='concat', combine='cat', pool_type='max', cross_stage1=None, cross_stage2=None, local_stage1=None,
                  local_stage2=None, match_head=[dict(type='LinearRes', n_in=256, n_out=256, norm='GN', ng=32),
                                                 dict(type='Linear', in_features=256, out_features=1)])
+    elif kind in ("xcorr", "xcorr-baseline"):
+        # reid_pts_point-transformer_baseline_orig.py ('xcorr': local_self_attention stages, knum 48) /
+        # reid_pts_point-transformer_baseline_stnet.py ('xcorr-baseline')
+        c.update(match_type=kind)
+        if kind == "xcorr":
+            loc = dict(type='local_self_attention', d_model=64, nhead=2, attention='linear', knum=48, pos_size=64)
+            c.update(local_stage1=dict(loc), local_stage2=dict(loc))
     elif kind in ("pt15m", "pt7m"):
         # reid_pts_point-transformer-1.5M_point-cat.py (mul=2, width 64) / -7M_point-cat.py (mul=4, width 128)
         mul, w, ng = (2, 64, 8) if kind == "pt15m" else (4, 128, 16)
@@ -49,6 +56,8 @@ ORACLE_KW = {
     "concat": dict(backbone='Pointnet_Backbone', match_type='concat', pool_type='max', combine='cat', head_ng=32),
     "dgcnn": dict(backbone='dgcnn', head_ng=16),
     "pointnet": dict(backbone='PointNet', head_ng=8),
+    "xcorr": dict(backbone='Pointnet_Backbone', match_type='xcorr', knum=48),
+    "xcorr-baseline": dict(backbone='Pointnet_Backbone', match_type='xcorr-baseline'),
     "pt15m": dict(backbone='Pointnet_Backbone', head_ng=8),
     "pt7m": dict(backbone='Pointnet_Backbone', head_ng=16),
 }

@@ -14,7 +14,8 @@ DEV = "cuda"
 TOL = 1e-4
 
 
-@pytest.mark.parametrize("name,kind", [("reid_pt", "pt"), ("reid_pt256", "pt"), ("reid_dgcnn", "dgcnn"), ("reid_pointnet", "pointnet")])
+@pytest.mark.parametrize("name,kind", [("reid_pt", "pt"), ("reid_pt256", "pt"), ("reid_dgcnn", "dgcnn"), ("reid_pointnet", "pointnet"),
+                                       ("reid_xcorr", "xcorr"), ("reid_xcorr-baseline", "xcorr-baseline")])
 def test_golden_vectors(name, kind):
     g = helpers.golden(name)
     m, _ = helpers.build_pair(kind, tuple(int(v) for v in g["backbone_list"]), device=DEV)
@@ -35,7 +36,8 @@ def test_golden_vectors(name, kind):
 @pytest.mark.parametrize("kind,N,blist", [("pt", 128, (128, 64, 32)), ("pt", 256, (256, 128, 64)), ("pt", 160, (160, 80, 40)),
                                           ("concat", 128, (128, 64, 32)), ("dgcnn", 256, (128, 64, 32)),
                                           ("pointnet", 128, (128, 64, 32)),
-                                          ("pt15m", 128, (128, 64, 32)), ("pt7m", 128, (128, 64, 32))])
+                                          ("pt15m", 128, (128, 64, 32)), ("pt7m", 128, (128, 64, 32)),
+                                          ("xcorr", 128, (128, 64, 32)), ("xcorr-baseline", 256, (256, 128, 64))])
 @pytest.mark.parametrize("dup", [False, True])
 def test_model_vs_oracle(kind, N, blist, dup):
     m, orc = helpers.build_pair(kind, blist, device=DEV)

@@ -14,7 +14,7 @@ def fake(monkeypatch):
     fake_kernels.install(monkeypatch)
 
 
-@pytest.mark.parametrize("kind", ["pt", "concat", "dgcnn", "pointnet", "pt15m", "pt7m"])
+@pytest.mark.parametrize("kind", ["pt", "concat", "dgcnn", "pointnet", "pt15m", "pt7m", "xcorr", "xcorr-baseline"])
 def test_model_vs_oracle_with_spec_kernels(fake, kind):
     m, orc = helpers.build_pair(kind)
     t, d = O.synth_objects(3, 128, 0), O.synth_objects(4, 128, 1)

@@ -73,6 +73,25 @@ def test_dgcnn_pointnet_heads_bit_exact_vs_reference():
 
 
 @needs_ref
+@pytest.mark.parametrize("canonical", [True, False])
+def test_local_self_attention_bit_exact_vs_reference(canonical):
+    """the 'xcorr' match type's local stage (attention.py:221-296) against the unmodified reference module"""
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    ls = R.local_self_attention(d_model=64, nhead=2, attention='linear', knum=48, pos_size=64).eval()
+    sd = O.perturb_norm_state({"local_stage1." + k: v for k, v in ls.state_dict().items()})
+    _load_ref_sd(ls, "local_stage1.", sd)
+    f, x = torch.randn(3, 64, 128), O.synth_objects(3, 128, 5)
+    with torch.no_grad():
+        ref = ls(f, x)
+        got = O.local_self_attention(sd, "local_stage1", f, x, 48, canonical=canonical)
+    if canonical:
+        assert (ref - got).abs().max() < 1e-6       # tie order of topk is the only freedom (none on random input)
+    else:
+        assert torch.equal(ref, got)
+
+
+@needs_ref
 def test_product_modules_reproduce_reference_init_and_keys():
     """seed-66 default init of the product's modules == the reference's, key for key (so goldens travel)."""
     R = ref_loader.load()
@@ -91,7 +110,8 @@ def test_product_modules_reproduce_reference_init_and_keys():
 
 
 @pytest.mark.parametrize("name,kind,tol", [("reid_pt", "pt", 2e-5), ("reid_pt256", "pt", 2e-5), ("reid_dgcnn", "dgcnn", 2e-5),
-                                           ("reid_pointnet", "pointnet", 2e-5)])
+                                           ("reid_pointnet", "pointnet", 2e-5), ("reid_xcorr", "xcorr", 2e-5),
+                                           ("reid_xcorr-baseline", "xcorr-baseline", 2e-5)])
 def test_oracle_matches_golden(name, kind, tol):
     """Goldens were produced by the reference modules (oracle/make_golden.py); tolerance covers BLAS/CPU differences
     between the generating machine and this one (bit-exact on the generating machine)."""
