@@ -1,0 +1,77 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the mmdet3d PointNet++ modules
+(mmdet3d/ops/pointnet_modules/point_sa_module.py:164-208 BasePointSAModule.forward, point_fp_module.py:39-79
+PointFPModule.forward) as plain torch over the op oracle (oracle/ops_oracle.py).
+
+PARITY UNPINNED for the module glue: the reference modules import mmcv (ConvModule, BaseModule), which is absent here,
+so they cannot be executed; the ops underneath (FPS, ball query, grouping, three_nn, three_interpolate) ARE pinned
+against the reference .cu files, and the glue is restated line by line: sample -> gather -> for each scale
+QueryAndGroup (group_points.py:49-83) -> Conv2d 1x1 / BatchNorm2d (eval) / ReLU -> max over the samples -> concat.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import ops_oracle as OP
+
+
+def conv_module(sd, p, x):
+    """mmcv ConvModule(1x1 Conv2d, BN2d, ReLU) in eval mode; x (B, C, S, k)."""
+    x = F.conv2d(x, sd[p + ".conv.weight"], sd.get(p + ".conv.bias"))
+    if (p + ".bn.weight") in sd:
+        x = F.batch_norm(x, sd[p + ".bn.running_mean"], sd[p + ".bn.running_var"], sd[p + ".bn.weight"], sd[p + ".bn.bias"],
+                         False, 0.0, 1e-5)
+    return F.relu(x)
+
+
+def _mlp(sd, p, x):
+    i = 0
+    while (f"{p}.layer{i}.conv.weight") in sd:
+        x = conv_module(sd, f"{p}.layer{i}", x)
+        i += 1
+    return x
+
+
+def query_and_group(points_xyz, center_xyz, features, max_radius, sample_num, min_radius=0, use_xyz=True, normalize_xyz=False):
+    idx = OP.ball_query(min_radius, max_radius, sample_num, points_xyz, center_xyz)
+    xyz_trans = points_xyz.transpose(1, 2).contiguous()
+    grouped_xyz = OP.grouping_operation(xyz_trans, idx)
+    diff = grouped_xyz - center_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        diff = diff / max_radius
+    if features is not None:
+        gf = OP.grouping_operation(features, idx)
+        return torch.cat([diff, gf], dim=1) if use_xyz else gf
+    return diff
+
+
+def sa_module_msg(sd, num_point, radii, sample_nums, points_xyz, features=None, indices=None, use_xyz=True, normalize_xyz=False,
+                  dilated_group=False, prefix=""):
+    """-> new_xyz, new_features, indices (D-FPS sampling)."""
+    xyz_flipped = points_xyz.transpose(1, 2).contiguous()
+    if num_point is None:
+        g = xyz_flipped.unsqueeze(2)
+        if features is not None:
+            g = torch.cat([g, features.unsqueeze(2)], dim=1) if use_xyz else features.unsqueeze(2)
+        x = _mlp(sd, prefix + "mlps.0", g)
+        return None, F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1), None
+    if indices is None:
+        indices = OP.furthest_point_sample(points_xyz, num_point)
+    new_xyz = OP.gather_points(xyz_flipped, indices).transpose(1, 2).contiguous()
+    outs = []
+    for i in range(len(radii)):
+        mn = radii[i - 1] if (dilated_group and i != 0) else 0
+        g = query_and_group(points_xyz, new_xyz, features, radii[i], sample_nums[i], mn, use_xyz, normalize_xyz)
+        x = _mlp(sd, f"{prefix}mlps.{i}", g)
+        outs.append(F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1))
+    return new_xyz, torch.cat(outs, dim=1), indices
+
+
+def fp_module(sd, target, source, target_feats, source_feats, prefix=""):
+    if source is not None:
+        dist, idx = OP.three_nn(target, source)
+        dr = 1.0 / (dist + 1e-8)
+        w = dr / torch.sum(dr, dim=2, keepdim=True)
+        interp = OP.three_interpolate(source_feats, idx, w)
+    else:
+        interp = source_feats.expand(*source_feats.size()[0:2], target.size(1))
+    x = torch.cat([interp, target_feats], dim=1) if target_feats is not None else interp
+    return _mlp(sd, prefix + "mlps", x.unsqueeze(-1)).squeeze(-1)

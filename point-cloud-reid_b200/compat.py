@@ -26,6 +26,6 @@ def install(force=False):
     sys.modules["mmdet3d"] = root
     sys.modules["mmdet3d.ops"] = ops
     sys.modules["mmdet3d.models"] = models
-    for sub in ("ball_query", "furthest_point_sample", "gather_points", "group_points", "knn"):
+    for sub in ("ball_query", "furthest_point_sample", "gather_points", "group_points", "knn", "interpolate", "pointnet_modules"):
         sys.modules[f"mmdet3d.ops.{sub}"] = importlib.import_module(f"{ops.__name__}.{sub}")
     return True

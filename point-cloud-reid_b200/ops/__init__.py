@@ -7,8 +7,11 @@ from .gather_points import GatherPoints, gather_points
 from .group_points import GroupAll, GroupingOperation, QueryAndGroup, grouping_operation
 from .interpolate import ThreeInterpolate, ThreeNN, three_interpolate, three_nn
 from .knn import KNN, knn
+from .pointnet_modules import (SA_MODULES, ConvModule, PointFPModule, PointSAModule, PointSAModuleMSG,
+                               build_sa_module)
 
 __all__ = ["ball_query", "BallQuery", "furthest_point_sample", "furthest_point_sample_with_dist", "Points_Sampler",
            "FurthestPointSampling", "FurthestPointSamplingWithDist", "gather_points", "GatherPoints", "GroupAll",
            "QueryAndGroup", "group_points", "grouping_operation", "GroupingOperation", "knn", "KNN",
-           "three_nn", "three_interpolate", "ThreeNN", "ThreeInterpolate"]
+           "three_nn", "three_interpolate", "ThreeNN", "ThreeInterpolate", "PointSAModule", "PointSAModuleMSG",
+           "PointFPModule", "build_sa_module", "SA_MODULES", "ConvModule"]

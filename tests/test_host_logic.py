@@ -107,3 +107,38 @@ def test_feature_bank_and_reidentifier_match_the_tracker_semantics(fake):
     xt, ht = bank.get_features(torch.arange(4))
     ref = orc.match_all_pairs(ht, xt, hd, xd, pair_mask=mask)
     assert (cost - ref).abs().max() < 2e-5 and (cost[~mask] == 0).all()
+
+
+def test_pointnet_module_family_keys_and_builder():
+    """state_dict keys follow mmcv's ConvModule naming so that mmdet3d checkpoints of these modules load unchanged
+    (point_sa_module.py:283-300, point_fp_module.py:24-37); builder errors as pointnet_modules/builder.py:6-38."""
+    from pcreid_b200.ops import PointFPModule, PointSAModule, PointSAModuleMSG, build_sa_module
+    m = PointSAModuleMSG(num_point=16, radii=[0.5, 1.0], sample_nums=[8, 16], mlp_channels=[[4, 16, 32], [4, 32, 64]])
+    keys = list(m.state_dict().keys())
+    assert keys[:6] == ['mlps.0.layer0.conv.weight', 'mlps.0.layer0.bn.weight', 'mlps.0.layer0.bn.bias',
+                        'mlps.0.layer0.bn.running_mean', 'mlps.0.layer0.bn.running_var', 'mlps.0.layer0.bn.num_batches_tracked']
+    assert m.mlps[0].layer0.conv.weight.shape == (16, 7, 1, 1) and m.mlps[0].layer0.conv.bias is None
+    f = PointFPModule([96, 64, 32])
+    assert list(f.state_dict().keys())[0] == 'mlps.layer0.conv.weight'
+    assert isinstance(build_sa_module(None, mlp_channels=[3, 8]), PointSAModule)
+    with pytest.raises(KeyError):
+        build_sa_module(dict(type="PAConvSAModule"))
+    with pytest.raises(TypeError):
+        build_sa_module([1, 2])
+    nobn = PointSAModule(mlp_channels=[3, 8], num_point=4, radius=1.0, num_sample=4, norm_cfg=None)
+    assert nobn.mlps[0].layer0.conv.bias is not None and not hasattr(nobn.mlps[0].layer0, "bn")
+
+
+def test_pointnet_module_oracle_is_self_consistent():
+    """CPU restatement: GroupAll pooling equals a plain max over per-point MLP outputs; FP module with a single source
+    point copies that point's features (weights 1, 0, 0 -> the reference kernel's first-three-slots rule)."""
+    from oracle import pointnet_modules_oracle as PO
+    from pcreid_b200.ops import PointSAModule
+    torch.manual_seed(0)
+    g = PointSAModule(mlp_channels=[5, 8, 16]).eval()
+    sd = g.state_dict()
+    xyz, feat = O.synth_objects(2, 30, 1), torch.randn(2, 5, 30)
+    _, gf, _ = PO.sa_module_msg(sd, None, [None], [None], xyz, feat)
+    x = torch.cat([xyz.transpose(1, 2), feat], 1).unsqueeze(2)
+    ref = PO._mlp(sd, "mlps.0", x).max(-1)[0]
+    assert torch.equal(gf, ref)
