@@ -129,6 +129,12 @@ typedef struct pcreid_norm_args {
 } pcreid_norm_args;
 int pcreid_cn_groupnorm(const pcreid_norm_args* args, void* stream);
 
+/* Second generation of pcreid_cn_linear_tc (csrc/cn_linear_tc2.cu): warp-specialised persistent tf32 GEMM (activation
+ * loader warps, bulk-TMA weight loader, MMA issuer, epilogue warps over a double-buffered TMEM accumulator).  Same
+ * contract; the weights are ALSO passed as operand images W*img[(k/4)][co][k%4] (fp32, K a multiple of 8).  Shared
+ * (not per-object) weights, channel-major inputs, no object maps; else PCREID_ERR_UNSUPPORTED. */
+int pcreid_cn_linear_tc2(const pcreid_linear_args* args, const float* W1img, const float* W2img, int n_sms, void* stream);
+
 /* LinearAttention (pointnet2_utils.py:14-47, attention.py:19-54), split in two kernels:
  * kv:    Wkv[b] (d x d, k-major, block diagonal per head) = sum_s (elu(k_s)+1) (x) (v_s / S);  ksum[b] (d)
  * scale: Qs[b,c,n] = (elu(q)+1) * S / ( (elu(q_h)+1) . ksum_h + 1e-6 )

@@ -63,6 +63,24 @@ def _map(m):
     return m
 
 
+_W_IMAGES = {}
+
+
+def _weight_image(w):
+    """k-major (K, CO) weight -> cached tf32 operand image [(k/4)][co][k%4] for pcreid_cn_linear_tc2.  The cache holds the
+    source tensor itself: its storage cannot be recycled for another weight while the entry lives, so (data_ptr, version)
+    identifies it."""
+    key = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+    ent = _W_IMAGES.get(key)
+    if ent is None or ent[0] is not w:
+        if len(_W_IMAGES) >= 256:
+            _W_IMAGES.clear()
+        Kd, CO = w.shape
+        ent = (w, w.detach().reshape(Kd // 4, 4, CO).permute(0, 2, 1).contiguous())
+        _W_IMAGES[key] = ent
+    return ent[1]
+
+
 def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_after_act=False, rows=None,
               x1_map=None, x2_map=None, w1_map=None, r_map=None, x1_pm=False, x2_pm=False, out=None, B=None,
               y_pm=False):
@@ -119,10 +137,18 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
             out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
         a.y_bs, a.ldy = _cn(out, "out")
     a.Y = _p(out)
-    # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernel wins from K >= 256 (2.2x at 512x1024);
-    # below that the FFMA kernel (up to 48 TFLOP/s) is faster
+    # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernels win from K >= 256; below that the FFMA kernel
+    # (up to 48 TFLOP/s) is faster
     if (_TC_LINEAR["on"] and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None
             and r_map is None and not x1_pm and not x2_pm):
+        # gen 2 (warp-specialised, cn_linear_tc2.cu) wins from K >= 512: 127-141 vs 100-107 TFLOP/s on the DGCNN / PointNet heads
+        if (_TC_LINEAR.get("gen", 2 if K1 + a.K2 >= 512 else 1) == 2 and w1.dim() == 2 and (w2 is None or w2.dim() == 2) and K1 % 8 == 0 and a.K2 % 8 == 0):
+            n_sms = torch.cuda.get_device_properties(x1.device).multi_processor_count
+            rc = _lib.lib().pcreid_cn_linear_tc2(ctypes.byref(a), _p(_weight_image(w1)), _p(_weight_image(w2) if w2 is not None else None),
+                                                 n_sms, _stream())
+            if rc != 3:
+                _lib.check(rc, "pcreid_cn_linear_tc2")
+                return out
         rc = _lib.lib().pcreid_cn_linear_tc(ctypes.byref(a), _stream())
         if rc != 3:                      # 3 == PCREID_ERR_UNSUPPORTED: shape stays on the FFMA kernel
             _lib.check(rc, "pcreid_cn_linear_tc")

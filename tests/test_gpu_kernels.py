@@ -56,16 +56,31 @@ def test_cn_linear_two_inputs_residual_maps_strides():
 
 @pytest.mark.parametrize("B,K1,CO,N", [(3, 64, 64, 256), (2, 128, 192, 132), (2, 1024, 512, 256), (5, 72, 12, 36), (1, 512, 1024, 100)])
 @pytest.mark.parametrize("act", [0, 2])
-def test_cn_linear_tensor_core(B, K1, CO, N, act):
-    """tcgen05 kind::tf32 GEMM against the fp32 specification (tf32 operands: 10-bit mantissa)."""
+@pytest.mark.parametrize("gen", [1, 2])
+def test_cn_linear_tensor_core(B, K1, CO, N, act, gen):
+    """tcgen05 kind::tf32 GEMMs (gen 1: cn_linear_tc.cu, gen 2: warp-specialised cn_linear_tc2.cu) against the fp32
+    specification (tf32 operands: 10-bit mantissa)."""
     x, w, b = rnd(B, K1, N, seed=1), rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
     K._TC_LINEAR["min_k"] = 8            # force the tensor-core kernel for every shape under test
+    K._TC_LINEAR["gen"] = gen
     try:
         with K.tensor_core_linear(True):
             got = K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act)
     finally:
         K._TC_LINEAR.pop("min_k")
+        K._TC_LINEAR.pop("gen")
     close(got, F.cn_linear(x, w, bias=b, act=act), 3e-3)
+
+
+def test_cn_linear_tc2_many_tiles_per_cta():
+    """persistent loop: several tiles per CTA, both accumulator buffers and every ring slot reused many times"""
+    B, K1, K2, CO, N = 700, 256, 64, 320, 200
+    x1, x2 = rnd(B, K1, N, seed=1), rnd(B, K2, N, seed=2)
+    w1, w2, b = rnd(K1, CO, seed=3) / 16, rnd(K2, CO, seed=4) / 8, rnd(CO, seed=5)
+    res = rnd(B, CO, N, seed=6)
+    with K.tensor_core_linear(True):
+        got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), bias=b.to(DEV), act=1, res=res.to(DEV))
+    close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, bias=b, act=1, res=res), 3e-3)
 
 
 def test_cn_linear_tensor_core_options():
