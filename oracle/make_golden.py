@@ -110,11 +110,55 @@ def main_xcorr(R):
         print(kind, "logits std", float(logits.std()), "checksum", checksum(sd))
 
 
+def build_image_reference(R, dim=192, dd=64):
+    """Reference modules in ImageReIDNet.__init__ construction order (cross_stage1, cross_stage2, cls_head, match_head,
+    vis_head, fp_head, downsample; ReIDNet.py:852-859), config reid_image_deit-tiny_point-cat.py."""
+    torch.manual_seed(66)
+    hp = 2 * dim
+    aux = lambda n: torch.nn.Sequential(R.LinearRes(hp, hp, norm='GN', ng=64), torch.nn.Linear(hp, n))
+    mods = {}
+    mods["cross_stage1"] = R.cross_lin_attn(d_model=dd, nhead=2, attention='linear')
+    mods["cross_stage2"] = R.cross_lin_attn(d_model=dd, nhead=2, attention='linear')
+    mods["cls_head"] = aux(20)
+    mods["match_head"] = torch.nn.Sequential(R.LinearRes(2 * dd, 2 * dd, norm='GN', ng=16), torch.nn.Linear(2 * dd, 1))
+    mods["vis_head"] = aux(4)
+    mods["fp_head"] = aux(1)
+    mods["downsample"] = torch.nn.Sequential(R.LinearRes(dim, 256, norm='GN', ng=32), R.LinearRes(256, 128, norm='GN', ng=16),
+                                             torch.nn.Linear(128, dd))
+    net = torch.nn.ModuleDict(mods).eval()
+    sd = O.perturb_norm_state(net.state_dict())
+    net.load_state_dict(sd)
+    return net, sd
+
+
+@torch.no_grad()
+def main_image(R):
+    """token side of ImageReIDNet: downsample (ReIDNet.py:1276-1277), xcorr_eff with cross_lin_attn (896-912), pooling
+    'both' (1147-1155), match head (1057-1066); 198 tokens = DeiT-distilled @224."""
+    net, sd = build_image_reference(R)
+    dim, dd, S, T, D = 192, 64, 198, 3, 4
+    raw = O.synth_tokens(2, dim, S, 0)
+    b, c, s = raw.shape
+    h_raw = net["downsample"](raw.reshape(-1, c)).reshape(b, dd, s)
+    h_t, h_d = O.synth_tokens(T, dd, S, 1), O.synth_tokens(D, dd, S, 2)
+    pairs = torch.cartesian_prod(torch.arange(T), torch.arange(D))
+    o1, o2 = h_t[pairs[:, 0]], h_d[pairs[:, 1]]
+    a, bb = net["cross_stage1"](o1, o2), net["cross_stage1"](o2, o1)
+    out = torch.cat([net["cross_stage2"](a, bb), net["cross_stage2"](bb, a)], dim=2)
+    pooled = torch.cat((F.adaptive_max_pool1d(out, 1).view(out.size(0), -1), F.adaptive_avg_pool1d(out, 1).view(out.size(0), -1)), 1)
+    logits = net["match_head"](pooled).squeeze(1).reshape(T, D)
+    np.savez_compressed(os.path.join(OUT, "reid_image_tokens.npz"), raw=raw.numpy(), h_raw=h_raw.numpy(), h_t=h_t.numpy(),
+                        h_d=h_d.numpy(), logits=logits.numpy(), weight_checksum=np.float64(checksum(sd)))
+    print("image tokens: logits std", float(logits.std()), "checksum", checksum(sd))
+
+
 def main():
     R = ref_loader.load()
     os.makedirs(OUT, exist_ok=True)
     if "--xcorr-only" in sys.argv:
         return main_xcorr(R)
+    if "--image-only" in sys.argv:
+        return main_image(R)
     for kind, N, blist, T, D in (("pt", 128, [128, 64, 32], 4, 5), ("pt256", 256, [256, 128, 64], 2, 3),
                                  ("dgcnn", 128, [128, 64, 32], 3, 4), ("pointnet", 128, [128, 64, 32], 4, 4)):
         base = "pt" if kind.startswith("pt") else kind
@@ -139,6 +183,7 @@ def main():
                         feat=xf.numpy(), idx_feat=idx_f.numpy().astype(np.int32))
     print("knn golden written")
     main_xcorr(R)
+    main_image(R)
 
 
 if __name__ == "__main__":

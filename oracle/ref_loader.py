@@ -82,5 +82,6 @@ def load():
         pointnet2_utils=p2, backbone_net=bb, dgcnn_orig=dg, pointnet=pn, attention=at, lanegcn_nets=lg,
         Pointnet_Backbone=bb.Pointnet_Backbone, DGCNN=dg.DGCNN, PointNet=pn.PointNet,
         corss_attention=at.corss_attention, LinearRes=lg.LinearRes, local_self_attention=at.local_self_attention,
+        cross_lin_attn=at.cross_lin_attn,
     )
     return ns

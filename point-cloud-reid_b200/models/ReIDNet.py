@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from .. import kernels as K
-from .attention import corss_attention, local_self_attention
+from .attention import corss_attention, cross_lin_attn, local_self_attention
 from .backbone_net import Pointnet_Backbone
 from .builder import FUSIONMODELS
 from .dgcnn_orig import DGCNN
@@ -25,8 +25,9 @@ module_obj = {
     'LayerNorm': nn.LayerNorm, 'LinearRes': LinearRes, 'Pointnet_Backbone': Pointnet_Backbone,
     'corss_attention': corss_attention, 'Conv1d': nn.Conv1d, 'Conv2d': nn.Conv2d, 'BatchNorm1d': nn.BatchNorm1d,
     'Sigmoid': nn.Sigmoid, 'dgcnn': DGCNN, 'PointNet': PointNet, 'local_self_attention': local_self_attention,
+    'cross_lin_attn': cross_lin_attn,
 }
-_OUT_OF_SCOPE = ('PostRes', 'cross_lin_attn')   # image-token matcher
+_OUT_OF_SCOPE = ('PostRes',)   # lanegcn residual block no shipped ReID config instantiates
 
 
 def build_module(cfg):

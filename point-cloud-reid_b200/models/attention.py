@@ -1,5 +1,6 @@
 """corss_attention -- the pair cross-attention block of the xcorr_eff match head
-(mmdet3d/models/attention.py:156-219; the reference's spelling is kept because configs name it)."""
+(mmdet3d/models/attention.py:156-219; the reference's spelling is kept because configs name it), its image-token
+variant cross_lin_attn (attention.py:312-372) and local_self_attention (attention.py:221-296)."""
 import torch
 from torch import nn
 
@@ -64,6 +65,26 @@ class corss_attention(PackedModule):
         search_feat = _cn_view(search_feat)
         template_feat = _cn_view(template_feat)
         wkv, ksum = self.template_summary(template_feat, self.position_code(template_xyz.contiguous().float()))
+        return self.attend(search_feat, self.search_query(search_feat), wkv, ksum, template_feat.shape[2])
+
+
+class cross_lin_attn(corss_attention):
+    """mmdet3d/models/attention.py:312-372 -- the image-token matcher's cross block: corss_attention without the position
+    code (`pos_mlp` is constructed, and therefore part of the state_dict, but never used by the reference forward)."""
+
+    def position_code(self, xyz):
+        return None
+
+    def template_summary(self, feat, pos=None, pos_map=None):
+        """-> (Wkv (B, C, C), ksum (B, C)) of a template token set: k = Wk f, v = Wv f."""
+        pk = self.packed()
+        return K.linattn_kv(K.cn_linear(feat, pk["k"]), K.cn_linear(feat, pk["v"]), self.nhead)
+
+    def forward(self, search_feat, template_feat, mask=None):
+        """search_feat (B, C, Ns), template_feat (B, C, Nt) -> (B, C, Ns)."""
+        search_feat = _cn_view(search_feat)
+        template_feat = _cn_view(template_feat)
+        wkv, ksum = self.template_summary(template_feat)
         return self.attend(search_feat, self.search_query(search_feat), wkv, ksum, template_feat.shape[2])
 
 

@@ -141,7 +141,7 @@ class FusedXcorr:
         return out
 
     def prepare(self, h, xyz):
-        """h (B, 64, N) fp32 channel-major, xyz (B, N, 3) -> ObjectPack."""
+        """h (B, 64, N) fp32 channel-major, xyz (B, N, 3) (None for token sets without coordinates) -> ObjectPack."""
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
         pk1, pk2 = X1.packed(), X2.packed()
         self._weights()
@@ -157,7 +157,11 @@ class FusedXcorr:
         else:
             o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"]))
             o.H = self._pack_image(h)
-        o.PV = self._pack_image(K.cn_linear(X2.position_code(xyz), pk2["v"]))
+        pos2 = X2.position_code(xyz)
+        if pos2 is None:            # cross_lin_attn (image tokens, attention.py:312-372): no position code -> Wv.pos == 0
+            o.PV = torch.zeros((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
+        else:
+            o.PV = self._pack_image(K.cn_linear(pos2, pk2["v"]))
         wkv, ksum = X1.template_summary(h, X1.position_code(xyz))          # (B, 64, 64) [d][v] block diagonal, (B, 64)
         M = K.cn_linear(wkv, self._merge1c if self.gen2 else pk1["merge"], x1_pm=True, y_pm=True)   # (B, d, out) = blockdiag(KV) Wm^T
         M.mul_(float(N))                                                    # undo the reference's values / S (attention.py:47)

@@ -34,14 +34,17 @@ class LinearRes(PackedModule):
             pk.update(wt=kmajor(self.transform[0].weight), gt=f(self.transform[1].weight), bt=f(self.transform[1].bias))
         return pk
 
-    def forward_cn(self, x):
-        """channel-major core: x (B, n_in, R) -> (B, n_out, R); every column (point / pair) is one row of the reference."""
+    def forward_cn(self, x, x_pm=False):
+        """channel-major core: x (B, n_in, R) -> (B, n_out, R); every column (point / pair) is one row of the reference.
+        x_pm: x is point-major (B, R, n_in) -- the reference's own row layout -- and is read in place."""
         pk = self.packed()
-        h = K.cn_groupnorm(K.cn_linear(x, pk["w1"]), pk["g1"], pk["b1"], self.groups, act=K.ACT_RELU)
+        h = K.cn_groupnorm(K.cn_linear(x, pk["w1"], x1_pm=x_pm), pk["g1"], pk["b1"], self.groups, act=K.ACT_RELU)
         h = K.cn_linear(h, pk["w2"])
         if self.transform is not None:
-            t = K.cn_groupnorm(K.cn_linear(x, pk["wt"]), pk["gt"], pk["bt"], self.groups)
+            t = K.cn_groupnorm(K.cn_linear(x, pk["wt"], x1_pm=x_pm), pk["gt"], pk["bt"], self.groups)
             return K.cn_groupnorm(h, pk["g2"], pk["b2"], self.groups, res=t, act=K.ACT_RELU)
+        if x_pm:
+            x = x.transpose(1, 2).contiguous()          # the identity shortcut is read channel-major
         return K.cn_groupnorm(h, pk["g2"], pk["b2"], self.groups, res=x, act=K.ACT_RELU)
 
     def forward(self, x):

@@ -76,6 +76,34 @@ def build_pair(kind="pt", backbone_list=(128, 64, 32), device="cpu", perturb=Tru
     return m.to(device), orc
 
 
+def image_cfg(dim=192, downsample_dim=64):
+    """reid_image_deit-tiny_point-cat.py (dim 192) / reid_image_deit-base_point-cat.py (dim 768); aux heads as shipped."""
+    hp = dim * 2
+    aux = lambda n_out: [dict(type='LinearRes', n_in=hp, n_out=hp, norm='GN', ng=64), dict(type='Linear', in_features=hp, out_features=n_out)]
+    return dict(type='ImageReIDNet', dim=dim, backbone='deit-tiny', downsample_dim=downsample_dim, combine='point-cat',
+                match_type='xcorr_eff', pool_type='both',
+                losses_to_use=dict(kl=False, match=True, cls=True, fp=True, triplet=False, vis=True),
+                downsample=[dict(type='LinearRes', n_in=dim, n_out=256, norm='GN', ng=32), dict(type='LinearRes', n_in=256, n_out=128, norm='GN', ng=16),
+                            dict(type='Linear', in_features=128, out_features=downsample_dim)],
+                cross_lin_attn=dict(type='cross_lin_attn', d_model=downsample_dim, nhead=2, attention='linear'),
+                cls_head=aux(20), fp_head=aux(1), vis_head=aux(4),
+                match_head=[dict(type='LinearRes', n_in=2 * downsample_dim, n_out=2 * downsample_dim, norm='GN', ng=16),
+                            dict(type='Linear', in_features=2 * downsample_dim, out_features=1)])
+
+
+def build_image_pair(dim=192, downsample_dim=64, device="cpu", perturb=True):
+    """-> (ImageReIDNet on `device`, oracle.ImageReIDOracle) sharing seed-66 weights."""
+    from pcreid_b200.models import build_model
+    torch.manual_seed(66)
+    m = build_model(image_cfg(dim, downsample_dim)).eval()
+    sd = m.state_dict()
+    if perturb:
+        sd = O.perturb_norm_state(sd)
+        m.load_state_dict(sd)
+    orc = O.ImageReIDOracle(sd, downsample_dim=downsample_dim, downsample_ng=(32, 16), head_ng=16)
+    return m.to(device), orc
+
+
 def weight_checksum(sd):
     return float(sum(v.double().abs().sum() for k, v in sorted(sd.items()) if v.dtype.is_floating_point))
 

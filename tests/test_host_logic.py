@@ -142,3 +142,75 @@ def test_pointnet_module_oracle_is_self_consistent():
     x = torch.cat([xyz.transpose(1, 2), feat], 1).unsqueeze(2)
     ref = PO._mlp(sd, "mlps.0", x).max(-1)[0]
     assert torch.equal(gf, ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# image-token matcher: cross_lin_attn + the token side of ImageReIDNet
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("S", [198, 64])
+def test_image_token_matcher_vs_oracle_with_spec_kernels(fake, S):
+    m, orc = helpers.build_image_pair()
+    raw_t, raw_d = O.synth_tokens(3, 192, S, 0), O.synth_tokens(4, 192, S, 1)
+    h_t, h_d = m.downsample_tokens(raw_t), m.downsample_tokens(raw_d)
+    assert h_t.shape == (3, 64, S)
+    assert (h_t - orc.downsample_tokens(raw_t)).abs().max() < 2e-5       # incl. the reference's un-permuted reshape
+    assert (h_d - orc.downsample_tokens(raw_d)).abs().max() < 2e-5
+    o_t, o_d = orc.downsample_tokens(raw_t), orc.downsample_tokens(raw_d)
+    lg = m.match_forward_inference(h_t, h_d[:3])
+    assert (lg - orc.match_forward_inference(o_t, o_d[:3])).abs().max() < 2e-5
+    out = m.xcorr_eff(h_t, h_d[:3])
+    assert out.shape == (3, 64, 2 * S) and (out - O.image_xcorr_eff(orc.sd, o_t, o_d[:3])).abs().max() < 2e-5
+    assert (m.get_pooled_feats(out) - orc.pooled(O.image_xcorr_eff(orc.sd, o_t, o_d[:3]))).abs().max() < 2e-5
+    L = m.match_all_pairs(h_t, h_d, chunk=5)
+    Lo = orc.match_all_pairs(o_t, o_d)
+    assert (L - Lo).abs().max() < 2e-5
+    mask = torch.rand(3, 4, generator=torch.Generator().manual_seed(0)) > 0.4
+    Lm = m.match_all_pairs(h_t, h_d, pair_mask=mask, chunk=5)
+    assert (Lm - orc.match_all_pairs(o_t, o_d, pair_mask=mask)).abs().max() < 2e-5 and (Lm[~mask] == 0).all()
+
+
+def test_image_reid_api_surface(fake):
+    """registry name, state_dict keys of the reference (unused pos_mlp of cross_lin_attn included), forward_test with an
+    attached token backbone, loud failure without one."""
+    from pcreid_b200.models import FUSIONMODELS, ImageReIDNet
+    assert "ImageReIDNet" in FUSIONMODELS
+    m, orc = helpers.build_image_pair()
+    keys = set(m.state_dict())
+    assert {"cross_stage1.pos_mlp.0.weight", "cross_stage2.merge.weight", "downsample.2.bias", "vis_head.1.weight",
+            "match_head.0.norm1.weight"} <= keys
+    imgs = torch.randn(3, 3, 8, 8)
+    with pytest.raises(RuntimeError):
+        m.siamese_forward(imgs, imgs)
+
+    class Out:
+        def __init__(self, t):
+            self.hidden_states = (None, t)
+
+    class ToyBackbone(torch.nn.Module):            # stands in for DeiT: (B, 3, 8, 8) -> 198 tokens x 192
+        def __init__(self):
+            super().__init__()
+            self.proj = torch.nn.Linear(192, 198 * 192)
+
+        def forward(self, pixel_values):
+            return Out(self.proj(pixel_values.reshape(pixel_values.shape[0], -1)).reshape(-1, 198, 192))
+
+    torch.manual_seed(1)
+    m.set_backbone(ToyBackbone(), name="deit-toy")
+    s1, s2 = torch.randn(3, 3, 8, 8), torch.randn(3, 3, 8, 8)
+    h1, h2 = m.siamese_forward(s1, s2)
+    assert h1.shape == (3, 192, 198)
+    one = lambda v: [torch.tensor([x]) for x in v]
+    res = m(return_loss=False, sparse_1=list(s1), sparse_2=list(s2), label_1=one([1, 2, 12]), label_2=one([1, 2, 3]),
+            vis_1=one([0, 1, -1]), vis_2=one([2, 3, 1]), id_1=one([5, 6, 7]), id_2=one([5, 9, 7]), size_1=one([4, 4, 4]),
+            size_2=one([4, 4, 4]))[0]
+    h_cat = torch.cat([h1, h2], 0)
+    temp = orc.downsample_tokens(h_cat)
+    assert (res['val_match_preds'] - orc.match_forward_inference(temp[:3], temp[3:])).abs().max() < 2e-5
+    assert res['val_match_gt'].tolist() == [1., 0., 1.]
+    assert res['val_cls_preds'].shape == (6, 20) and res['val_fp_preds'].shape == (6,) and res['val_vis_preds'].shape == (5, 4)
+    sd = orc.sd
+    cls_ref = O._lin(sd, "cls_head.1", O.linear_res(sd, "cls_head.0", orc.pooled(h_cat), 64))
+    assert (res['val_cls_preds'] - cls_ref).abs().max() < 2e-5
+    assert res['val_fp_gt'].tolist() == [0., 0., 1., 0., 0., 0.]
+    with pytest.raises(NotImplementedError):
+        m(return_loss=True)

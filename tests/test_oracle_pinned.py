@@ -150,3 +150,37 @@ def test_class_gate_matches_tracker_semantics():
     ld = torch.tensor([1, 1, 3, 9]); nd = torch.tensor([4, 0, 2, 8])
     m = O.class_gated_pairs(lt, nt, ld, nd)
     assert m.tolist() == [[False] * 4, [False] * 4, [True, False, False, False], [False] * 4, [False, False, True, False]]
+
+
+@needs_ref
+def test_cross_lin_attn_bit_exact_vs_reference():
+    """image-token cross block (attention.py:312-372) against the unmodified reference module, 198 tokens"""
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    ca = R.cross_lin_attn(d_model=64, nhead=2).eval()
+    sd = O.perturb_norm_state({"cross_stage1." + k: v for k, v in ca.state_dict().items()})
+    _load_ref_sd(ca, "cross_stage1.", sd)
+    a, b = O.synth_tokens(3, 64, 198, 0), O.synth_tokens(3, 64, 77, 1)
+    with torch.no_grad():
+        assert torch.equal(ca(a, b), O.cross_lin_attention(sd, "cross_stage1", a, b))
+
+
+@needs_ref
+def test_image_modules_reproduce_reference_init_and_keys():
+    from pcreid_b200.models import cross_lin_attn
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    a = cross_lin_attn(64, 2).state_dict()
+    torch.manual_seed(66)
+    b = R.cross_lin_attn(64, 2).state_dict()
+    assert list(a.keys()) == list(b.keys()) and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_image_oracle_matches_golden():
+    """golden = reference cross_lin_attn / LinearRes / nn.Linear modules assembled as ImageReIDNet does (oracle/make_golden.py)"""
+    g = helpers.golden("reid_image_tokens")
+    _, orc = helpers.build_image_pair()
+    assert abs(helpers.weight_checksum(orc.sd) - float(g["weight_checksum"])) < 1e-6 * float(g["weight_checksum"])
+    assert (orc.downsample_tokens(torch.from_numpy(g["raw"])) - torch.from_numpy(g["h_raw"])).abs().max() < 2e-5
+    L = orc.match_all_pairs(torch.from_numpy(g["h_t"]), torch.from_numpy(g["h_d"]))
+    assert (L - torch.from_numpy(g["logits"])).abs().max() < 2e-5
