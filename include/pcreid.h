@@ -35,6 +35,11 @@ int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, voi
 /* replaces furthest_point_sampling_with_dist_kernel_launcher (same file :333-400): dist (b,n,n). */
 int pcreid_fps_with_dist(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
 int pcreid_fps_block_size(int n); /* host helper: opt_n_threads(n), same file :11-15 */
+/* replaces calc_square_dist (ops/furthest_point_sample/utils.py:4-31; torch sum / matmul / sqrt there): the (b,n,m) feature
+ * distance matrix the F-FPS / FS samplers (points_sampler.py:124-157) pass to furthest_point_sample_with_dist.
+ * a (b,n,c), b (b,m,c) point-major; out[b,i,j] = |a_i|^2 + |b_j|^2 - 2 a_i.b_j (fma chains over c ascending);
+ * norm != 0: sqrt(.) / c. */
+int pcreid_pairwise_sqdist(int b, int n, int m, int c, const float* a, const float* bm, float* out, int norm, void* stream);
 
 /* replaces knn_kernel_launcher(b,n,m,nsample,xyz,new_xyz,idx,dist2,stream) (ops/knn/src/knn_cuda.cu:97-116;
  * python knn.py:7-71).  xyz (b,n,3), new_xyz (b,m,3), idx/dist2 (b,m,nsample); nsample <= 100.
@@ -173,6 +178,9 @@ int pcreid_sa_edge_mlp(int B, int C, int N, int S, int k, const float* P1, const
  *   seg_max:    out[i] = max_j x[i*k + j]  (rows = B*C*S).  pointnet2_utils.py:353-357. */
 int pcreid_edge_build(int B, int C, int N, int S, int k, const float* P1, const float* Cc, const int* idx, float* out, void* stream);
 int pcreid_seg_max(long long rows, int k, const float* x, float* out, void* stream);
+/* pool_mod='avg' of the mmdet3d SA modules (ops/pointnet_modules/point_sa_module.py:158-160, F.avg_pool2d over the k
+ * samples): out[i] = (sum_j x[i*k + j]) / k, summed in sample order. */
+int pcreid_seg_mean(long long rows, int k, const float* x, float* out, void* stream);
 
 /* EdgeConv gather-max (dgcnn_orig.py:31-54,129-147 with the bias-free conv factorised):
  *   out[b,c,i] = act( max_j P[b,c,idx[b,i,j]] + Q[b,c,i] ),  element (b,c,i) at out + b*o_bs + c*ldo + i */

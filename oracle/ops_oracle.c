@@ -89,6 +89,27 @@ static void fps_impl(int b, int n, int m, const float *dataset, float *temp, int
 void oracle_fps(int b, int n, int m, const float *xyz, float *temp, int *idx) { fps_impl(b, n, m, xyz, temp, idx, 0); }
 void oracle_fps_with_dist(int b, int n, int m, const float *dist, float *temp, int *idx) { fps_impl(b, n, m, dist, temp, idx, 1); }
 
+/* ---- calc_square_dist (ops/furthest_point_sample/utils.py:4-31) in the arithmetic of pcreid_pairwise_sqdist:
+ * fma chains over the channels in ascending order, d = fma(-2, dot, |a|^2 + |b|^2); norm: sqrt(d) / c.  The reference
+ * computes the same quantity with torch.sum / torch.matmul (library reduction order), so it agrees to rounding only;
+ * tests/test_ops_oracle.py checks that both give the same F-FPS indices on the seeded inputs. ---- */
+void oracle_pairwise_sqdist(int b, int n, int m, int c, const float *a, const float *bm, float *out, int norm) {
+  for (int bi = 0; bi < b; ++bi)
+    for (int i = 0; i < n; ++i) {
+      const float *ai = a + ((size_t)bi * n + i) * c;
+      float a2 = 0.f;
+      for (int ch = 0; ch < c; ++ch) a2 = fmaf(ai[ch], ai[ch], a2);
+      for (int j = 0; j < m; ++j) {
+        const float *bj = bm + ((size_t)bi * m + j) * c;
+        float b2 = 0.f, dot = 0.f;
+        for (int ch = 0; ch < c; ++ch) { b2 = fmaf(bj[ch], bj[ch], b2); dot = fmaf(ai[ch], bj[ch], dot); }
+        float d = fmaf(-2.f, dot, a2 + b2);
+        if (norm) d = sqrtf(d) / (float)c;
+        out[((size_t)bi * n + i) * m + j] = d;
+      }
+    }
+}
+
 /* ---- kNN: knn_cuda.cu:26-94 ---- */
 static void reheap(float *dist, int *idx, int k) {
   int root = 0, child = 1;

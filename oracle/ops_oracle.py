@@ -72,6 +72,16 @@ def furthest_point_sample_with_dist(dist, m):
     return torch.from_numpy(idx)
 
 
+def pairwise_sqdist(a, b, norm=False):
+    """calc_square_dist (furthest_point_sample/utils.py:4-31) in the kernel's arithmetic: a (B,N,C), b (B,M,C) -> (B,N,M)."""
+    x, y = _c(a, np.float32), _c(b, np.float32)
+    B, N, C = x.shape
+    M = y.shape[1]
+    out = np.zeros((B, N, M), np.float32)
+    _cpu().oracle_pairwise_sqdist(B, N, M, C, _fp(x), _fp(y), _fp(out), int(bool(norm)))
+    return torch.from_numpy(out)
+
+
 def knn(k, xyz, center_xyz=None, transposed=False, return_dist=False):
     """-> int32 [B,k,S] (knn.py:62 transposes the kernel's [B,S,k])."""
     if center_xyz is None:

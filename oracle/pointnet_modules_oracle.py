@@ -5,7 +5,8 @@ PointFPModule.forward) as plain torch over the op oracle (oracle/ops_oracle.py).
 PARITY UNPINNED for the module glue: the reference modules import mmcv (ConvModule, BaseModule), which is absent here,
 so they cannot be executed; the ops underneath (FPS, ball query, grouping, three_nn, three_interpolate) ARE pinned
 against the reference .cu files, and the glue is restated line by line: sample -> gather -> for each scale
-QueryAndGroup (group_points.py:49-83) -> Conv2d 1x1 / BatchNorm2d (eval) / ReLU -> max over the samples -> concat.
+QueryAndGroup (group_points.py:49-83) -> Conv2d 1x1 / BatchNorm2d (eval) / ReLU -> max (or mean) over the samples -> concat;
+samplers D-FPS / F-FPS / FS (furthest_point_sample/points_sampler.py:67-157, utils.py:4-31).
 """
 import torch
 import torch.nn.functional as F
@@ -43,25 +44,72 @@ def query_and_group(points_xyz, center_xyz, features, max_radius, sample_num, mi
     return diff
 
 
+def calc_square_dist_ref(a, b, norm=True):
+    """furthest_point_sample/utils.py:4-31 verbatim (torch sum / matmul): what the reference feeds to F-FPS."""
+    length_a, length_b, num_channel = a.shape[1], b.shape[1], a.shape[-1]
+    a_square = torch.sum(a.unsqueeze(dim=2).pow(2), dim=-1).repeat((1, 1, length_b))
+    b_square = torch.sum(b.unsqueeze(dim=1).pow(2), dim=-1).repeat((1, length_a, 1))
+    dist = a_square + b_square - 2 * torch.matmul(a, b.transpose(1, 2))
+    if norm:
+        dist = torch.sqrt(dist) / num_channel
+    return dist
+
+
+def _sample(mod, points, features, npoint, sqdist):
+    """DFPS / FFPS / FS samplers (points_sampler.py:107-157)."""
+    if mod == "D-FPS":
+        return OP.furthest_point_sample(points.contiguous(), npoint)
+    f = torch.cat([points, features.transpose(1, 2)], dim=2)
+    ffps = OP.furthest_point_sample_with_dist(sqdist(f, f, norm=False).contiguous(), npoint)
+    if mod == "F-FPS":
+        return ffps
+    if mod == "FS":
+        return torch.cat([ffps, OP.furthest_point_sample(points.contiguous(), npoint)], dim=1)
+    raise ValueError(mod)
+
+
+def points_sampler(points_xyz, features, num_point, fps_mod_list=("D-FPS",), fps_sample_range_list=(-1,), sqdist=None):
+    """Points_Sampler.forward (points_sampler.py:67-104).  sqdist: OP.pairwise_sqdist (the kernel's arithmetic, default) or
+    calc_square_dist_ref (the reference's torch ops)."""
+    sqdist = sqdist or OP.pairwise_sqdist
+    indices, last = [], 0
+    for rng, mod, npoint in zip(fps_sample_range_list, fps_mod_list, num_point):
+        assert rng < points_xyz.shape[1]
+        if rng == -1:
+            xyz, feats = points_xyz[:, last:], (features[:, :, last:] if features is not None else None)
+        else:
+            xyz, feats = points_xyz[:, last:rng], (features[:, :, last:rng] if features is not None else None)
+        indices.append(_sample(mod, xyz.contiguous(), feats, npoint, sqdist) + last)
+        last += rng
+    return torch.cat(indices, dim=1)
+
+
+def _pool(x, pool_mod):
+    """BasePointSAModule._pool_features (point_sa_module.py:144-164)."""
+    fn = F.max_pool2d if pool_mod == "max" else F.avg_pool2d
+    return fn(x, kernel_size=[1, x.size(3)]).squeeze(-1)
+
+
 def sa_module_msg(sd, num_point, radii, sample_nums, points_xyz, features=None, indices=None, use_xyz=True, normalize_xyz=False,
-                  dilated_group=False, prefix=""):
-    """-> new_xyz, new_features, indices (D-FPS sampling)."""
+                  dilated_group=False, prefix="", pool_mod="max", fps_mod=("D-FPS",), fps_sample_range_list=(-1,)):
+    """-> new_xyz, new_features, indices."""
     xyz_flipped = points_xyz.transpose(1, 2).contiguous()
     if num_point is None:
         g = xyz_flipped.unsqueeze(2)
         if features is not None:
             g = torch.cat([g, features.unsqueeze(2)], dim=1) if use_xyz else features.unsqueeze(2)
         x = _mlp(sd, prefix + "mlps.0", g)
-        return None, F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1), None
+        return None, _pool(x, pool_mod), None
     if indices is None:
-        indices = OP.furthest_point_sample(points_xyz, num_point)
+        npts = [num_point] if isinstance(num_point, int) else list(num_point)
+        indices = points_sampler(points_xyz, features, npts, fps_mod, fps_sample_range_list)
     new_xyz = OP.gather_points(xyz_flipped, indices).transpose(1, 2).contiguous()
     outs = []
     for i in range(len(radii)):
         mn = radii[i - 1] if (dilated_group and i != 0) else 0
         g = query_and_group(points_xyz, new_xyz, features, radii[i], sample_nums[i], mn, use_xyz, normalize_xyz)
         x = _mlp(sd, f"{prefix}mlps.{i}", g)
-        outs.append(F.max_pool2d(x, kernel_size=[1, x.size(3)]).squeeze(-1))
+        outs.append(_pool(x, pool_mod))
     return new_xyz, torch.cat(outs, dim=1), indices
 
 

@@ -45,6 +45,7 @@ _SIGS = {
     "pcreid_fps": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_fps_with_dist": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_fps_block_size": [c_int],
+    "pcreid_pairwise_sqdist": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "pcreid_knn": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_t": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_point": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
@@ -77,6 +78,7 @@ _SIGS = {
     "pcreid_sa_edge_mlp": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_edge_build": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_seg_max": [c_ll, c_int, c_vp, c_vp, c_vp],
+    "pcreid_seg_mean": [c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_edge_gather_max": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_ll, c_int, c_vp],
     "pcreid_pair_tc_smem_bytes": [c_int],
     "pcreid_pair_tc_set_trace": [c_vp],

@@ -629,7 +629,73 @@ __global__ void __launch_bounds__(256) three_interpolate_kernel(int c, int m, in
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// pairwise squared feature distance (calc_square_dist, ops/furthest_point_sample/utils.py:4-31): the N x M matrix the
+// F-FPS / FS samplers hand to furthest_point_sample_with_dist.  a (B, N, C), b (B, M, C) point-major; out (B, N, M).
+//   dot = fma chain over c ascending;  |a|^2, |b|^2 likewise;  d = fma(-2, dot, |a|^2 + |b|^2);  norm: sqrt(d) / C
+// 64 x 64 output tile per CTA (16 x 16 threads, 4 x 4 outputs each), channels staged through shared memory 16 at a time;
+// output-write bound (4 N M bytes per object against 4 C (N + M) read).
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pairwise_sqdist_kernel(int N, int M, int C, const float* __restrict__ A,
+                                                              const float* __restrict__ Bm, float* __restrict__ out, int norm) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int b = blockIdx.z, i0 = blockIdx.y * 64, j0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const float* a = A + (size_t)b * N * C;
+  const float* bb = Bm + (size_t)b * M * C;
+  float dot[4][4], a2[4], b2[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    a2[r] = 0.f; b2[r] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dot[r][q] = 0.f;
+  }
+  for (int c0 = 0; c0 < C; c0 += 16) {
+    for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c = e & 15;                         // consecutive threads read consecutive channels of a row
+      As[c][r] = (i0 + r < N && c0 + c < C) ? __ldg(a + (size_t)(i0 + r) * C + c0 + c) : 0.f;
+      Bs[c][r] = (j0 + r < M && c0 + c < C) ? __ldg(bb + (size_t)(j0 + r) * C + c0 + c) : 0.f;
+    }
+    __syncthreads();
+    const int cn = min(16, C - c0);
+    for (int c = 0; c < cn; ++c) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { av[r] = As[c][ty + 16 * r]; bv[r] = Bs[c][tx + 16 * r]; }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        a2[r] = __fmaf_rn(av[r], av[r], a2[r]);
+        b2[r] = __fmaf_rn(bv[r], bv[r], b2[r]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) dot[r][q] = __fmaf_rn(av[r], bv[q], dot[r][q]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int i = i0 + ty + 16 * r;
+    if (i >= N) continue;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = j0 + tx + 16 * q;
+      if (j >= M) continue;
+      float d = __fmaf_rn(-2.f, dot[r][q], __fadd_rn(a2[r], b2[q]));
+      if (norm) d = __fdiv_rn(__fsqrt_rn(d), (float)C);
+      out[((size_t)b * N + i) * M + j] = d;
+    }
+  }
+}
+
 extern "C" {
+
+int pcreid_pairwise_sqdist(int B, int N, int M, int C, const float* a, const float* b, float* out, int norm, void* stream) {
+  if (B <= 0 || N <= 0 || M <= 0) return PCREID_OK;
+  if (!a || !b || !out || C <= 0) return PCREID_ERR_ARG;
+  if (B > 65535 || ceil_div(N, 64) > 65535) return PCREID_ERR_UNSUPPORTED;
+  pairwise_sqdist_kernel<<<dim3(ceil_div(M, 64), ceil_div(N, 64), B), 256, 0, (cudaStream_t)stream>>>(N, M, C, a, b, out, norm);
+  return pcreid_launch_status();
+}
 
 int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, void* stream) {
   return fps_launch(b, n, m, xyz, temp, idx, 0, (cudaStream_t)stream);

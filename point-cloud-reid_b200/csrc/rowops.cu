@@ -473,6 +473,16 @@ __global__ void __launch_bounds__(256) seg_max_kernel(long long rows, int k, con
   out[i] = mx;
 }
 
+// pool_mod='avg' of the mmdet3d SA modules (point_sa_module.py:158-160): mean over the k samples of a group
+__global__ void __launch_bounds__(256) seg_mean_kernel(long long rows, int k, const float* __restrict__ x, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  const float* r = x + i * k;
+  float s = r[0];
+  for (int j = 1; j < k; ++j) s += r[j];
+  out[i] = s / (float)k;
+}
+
 // ------------------------------------------------------------------------------------------------
 // pooling
 // ------------------------------------------------------------------------------------------------
@@ -885,6 +895,13 @@ int pcreid_seg_max(long long rows, int k, const float* x, float* out, void* stre
   if (rows <= 0) return PCREID_OK;
   if (!x || !out || k <= 0) return PCREID_ERR_ARG;
   seg_max_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, k, x, out);
+  return pcreid_launch_status();
+}
+
+int pcreid_seg_mean(long long rows, int k, const float* x, float* out, void* stream) {
+  if (rows <= 0) return PCREID_OK;
+  if (!x || !out || k <= 0) return PCREID_ERR_ARG;
+  seg_mean_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rows, k, x, out);
   return pcreid_launch_status();
 }
 

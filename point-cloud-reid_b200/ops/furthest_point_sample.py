@@ -46,18 +46,19 @@ furthest_point_sample_with_dist = FurthestPointSamplingWithDist.apply
 
 
 def calc_square_dist(point_feat_a, point_feat_b, norm=True):
-    """furthest_point_sample/utils.py: pairwise squared distance of (B, N, C) / (B, M, C) features."""
-    length_a = point_feat_a.shape[1]
-    length_b = point_feat_b.shape[1]
-    num_channel = point_feat_a.shape[-1]
-    a_square = torch.sum(point_feat_a.unsqueeze(dim=2).pow(2), dim=-1)
-    b_square = torch.sum(point_feat_b.unsqueeze(dim=1).pow(2), dim=-1)
-    a_square = a_square.repeat((1, 1, length_b))
-    b_square = b_square.repeat((1, length_a, 1))
-    coor = torch.matmul(point_feat_a, point_feat_b.transpose(1, 2))
-    dist = a_square + b_square - 2 * coor
-    if norm:
-        dist = torch.sqrt(dist) / num_channel
+    """furthest_point_sample/utils.py:4-31: pairwise squared distance of (B, N, C) / (B, M, C) features -> (B, N, M), one
+    kernel (pcreid_pairwise_sqdist) instead of the reference's sum / repeat / matmul / sqrt chain of torch ops."""
+    a = point_feat_a.contiguous().float()
+    b = point_feat_b.contiguous().float()
+    require(a, "point_feat_a")
+    require(b, "point_feat_b")
+    assert a.dim() == 3 and b.dim() == 3 and a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2]
+    B, N, C = a.shape
+    M = b.shape[1]
+    with torch.cuda.device(a.device):
+        dist = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
+        check(lib().pcreid_pairwise_sqdist(B, N, M, C, ptr(a), ptr(b), ptr(dist), int(bool(norm)), stream()),
+              "pcreid_pairwise_sqdist")
     return dist
 
 

@@ -74,8 +74,6 @@ class BasePointSAModule(_PackedMLPs):
         assert pool_mod in ["max", "avg"]
         assert isinstance(fps_mod, (list, tuple)) and isinstance(fps_sample_range_list, (list, tuple))
         assert len(fps_mod) == len(fps_sample_range_list)
-        if pool_mod != "max":
-            raise NotImplementedError("pool_mod='avg' is not built (every shipped config pools with max)")
         if isinstance(mlp_channels, tuple):
             mlp_channels = list(map(list, mlp_channels))
         self.mlp_channels = [list(m) for m in mlp_channels]
@@ -137,7 +135,9 @@ class BasePointSAModule(_PackedMLPs):
                 raise NotImplementedError("first ConvModule without ReLU")
             if new_xyz is None:                                  # GroupAll: one group holding every point, absolute xyz
                 h = self._first_conv_points(points_xyz, features, sc, bias=sc["b1"], act=K.ACT_RELU)
-                outs.append(K.cn_pool(_mlp_tail(h, sc["tail"]), mode=1).unsqueeze(-1))
+                h = _mlp_tail(h, sc["tail"])
+                pooled = K.cn_pool(h, mode=1) if self.pool_mod == "max" else K.cn_pool(h, mode=0)[:, h.shape[1]:].contiguous()
+                outs.append(pooled.unsqueeze(-1))
                 continue
             idx = ball_query(self.min_radii[i], self.radii[i], self.sample_nums[i], points_xyz, new_xyz)
             p1 = self._first_conv_points(points_xyz, features, sc)                        # (B, C1, N)
@@ -145,7 +145,7 @@ class BasePointSAModule(_PackedMLPs):
                 cc = K.cn_linear(new_xyz, sc["nwa"], bias=sc["b1"], x1_pm=True)           # (B, C1, S)
             else:
                 cc = sc["b1"].view(1, -1, 1).expand(p1.shape[0], -1, new_xyz.shape[1]).contiguous()
-            outs.append(self._edge_mlp_max(p1, cc, idx, sc["tail"]))
+            outs.append(self._edge_mlp_pool(p1, cc, idx, sc["tail"], self.pool_mod))
         return new_xyz, torch.cat(outs, dim=1), indices
 
     @staticmethod
@@ -158,11 +158,12 @@ class BasePointSAModule(_PackedMLPs):
         return K.cn_linear(features.contiguous().float(), sc["wf"], bias=bias, act=act)
 
     @staticmethod
-    def _edge_mlp_max(p1, cc, idx, tail):
+    def _edge_mlp_pool(p1, cc, idx, tail, pool_mod="max"):
+        """relu(P1[idx] + Cc) -> remaining ConvModules -> max (or mean, point_sa_module.py:144-164) over the k samples."""
         B, C, N = p1.shape
         S, k = idx.shape[1], idx.shape[2]
         same = len(tail) == 2 and all(w.shape == (C, C) and act == K.ACT_RELU for w, _, act in tail)
-        if same and C % 16 == 0 and C <= 128 and k <= 128:
+        if pool_mod == "max" and same and C % 16 == 0 and C <= 128 and k <= 128:
             (w2, b2, _), (w3, b3, _) = tail
             return K.sa_edge_mlp(p1, cc, idx, w2.t().contiguous(), b2, w3.t().contiguous(), b3)
         Co = tail[-1][0].shape[0] if tail else C
@@ -176,7 +177,8 @@ class BasePointSAModule(_PackedMLPs):
             check(lib().pcreid_edge_build(nb, C, N, S, k, ptr(p1[b0:b1]), ptr(cc[b0:b1]), ptr(idx[b0:b1]), ptr(h), stream()),
                   "pcreid_edge_build")
             h = _mlp_tail(h, tail)
-            check(lib().pcreid_seg_max(nb * Co * S, k, ptr(h), ptr(out[b0:b1]), stream()), "pcreid_seg_max")
+            seg_pool = lib().pcreid_seg_max if pool_mod == "max" else lib().pcreid_seg_mean
+            check(seg_pool(nb * Co * S, k, ptr(h), ptr(out[b0:b1]), stream()), "pcreid_seg_pool")
         return out
 
 

@@ -88,3 +88,58 @@ def test_training_mode_is_rejected():
     m = PointFPModule([8, 8]).to(DEV).train()
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 4, 3, device=DEV), torch.zeros(1, 4, 3, device=DEV), None, torch.zeros(1, 8, 4, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F-FPS / FS samplers and pool_mod='avg' (points_sampler.py:107-157, point_sa_module.py:144-164)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,C,norm", [(96, 96, 3, False), (130, 70, 35, False), (64, 200, 131, True), (257, 65, 16, True)])
+def test_calc_square_dist_bit_exact_vs_oracle(N, M, C, norm):
+    from oracle import ops_oracle as P
+    from pcreid_b200.ops.furthest_point_sample import calc_square_dist
+    g = torch.Generator().manual_seed(C)
+    a, b = torch.randn(2, N, C, generator=g), torch.randn(2, M, C, generator=g)
+    got = calc_square_dist(a.to(DEV), b.to(DEV), norm=norm).cpu()
+    ref = P.pairwise_sqdist(a, b, norm=norm)
+    assert torch.equal(got.isnan(), ref.isnan())
+    ok = ~ref.isnan()                                   # norm=True takes sqrt of a rounded difference that may be < 0
+    assert torch.equal(got[ok], ref[ok])
+    assert (got[ok] - PO.calc_square_dist_ref(a, b, norm=norm)[ok]).abs().max() < 1e-4 * max(1.0, float(ref[ok].abs().max()))
+
+
+@pytest.mark.parametrize("mods,ranges,npts", [(["F-FPS"], [-1], [32]), (["FS"], [-1], [24]), (["D-FPS", "F-FPS"], [64, -1], [16, 16])])
+def test_points_sampler_ffps_fs(mods, ranges, npts):
+    from pcreid_b200.ops import Points_Sampler
+    xyz = O.synth_objects(3, 160, 11)
+    feat = torch.randn(3, 32, 160, generator=torch.Generator().manual_seed(5))
+    got = Points_Sampler(npts, mods, ranges)(xyz.to(DEV), feat.to(DEV)).cpu()
+    assert got.dtype == torch.int32
+    assert torch.equal(got, PO.points_sampler(xyz, feat, npts, mods, ranges))                                  # kernel arithmetic
+    assert torch.equal(got, PO.points_sampler(xyz, feat, npts, mods, ranges, sqdist=PO.calc_square_dist_ref))  # reference formula
+
+
+@pytest.mark.parametrize("fps_mod,equal_width", [(["D-FPS"], True), (["F-FPS"], False), (["FS"], False)])
+def test_point_sa_module_avg_pool_and_feature_samplers(fps_mod, equal_width):
+    from pcreid_b200.ops import PointSAModuleMSG
+    torch.manual_seed(5)
+    npt = 20 if fps_mod == ["FS"] else 40
+    chans = [[29, 32, 32, 32], [29, 16, 48]] if equal_width else [[29, 24, 40], [29, 16, 48]]
+    m = _randomise_bn(PointSAModuleMSG(num_point=npt, radii=[0.7, 1.3], sample_nums=[12, 24], mlp_channels=chans,
+                                       fps_mod=fps_mod, fps_sample_range_list=[-1], pool_mod="avg"), 4).eval()
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    xyz, feat = O.synth_objects(2, 150, 9), torch.randn(2, 29, 150)
+    with torch.no_grad():
+        nx, nf, idx = m.to(DEV)(xyz.to(DEV), feat.to(DEV))
+    ox, of, oidx = PO.sa_module_msg(sd, npt, [0.7, 1.3], [12, 24], xyz, feat, pool_mod="avg", fps_mod=fps_mod)
+    S = 2 * npt if fps_mod == ["FS"] else npt
+    assert idx.shape == (2, S) and torch.equal(idx.cpu().long(), oidx.long())
+    assert torch.equal(nx.cpu(), ox)
+    assert nf.shape == of.shape and (nf.cpu() - of).abs().max() < TOL
+    # GroupAll with mean pooling
+    from pcreid_b200.ops import PointSAModule
+    g = _randomise_bn(PointSAModule(mlp_channels=[29, 64, 128], pool_mod="avg"), 3).eval()
+    sdg = {k: v.clone() for k, v in g.state_dict().items()}
+    with torch.no_grad():
+        _, gf, _ = g.to(DEV)(xyz.to(DEV), feat.to(DEV))
+    _, ogf, _ = PO.sa_module_msg(sdg, None, [None], [None], xyz, feat, pool_mod="avg")
+    assert gf.shape == (2, 128, 1) and (gf.cpu() - ogf).abs().max() < TOL

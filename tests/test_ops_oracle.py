@@ -120,3 +120,35 @@ def test_three_interpolate_oracle():
     out = P.three_interpolate(f, idx, w)
     ref = (torch.gather(f[:, :, None, :].expand(2, 5, 9, 20), 3, idx.long()[:, None].expand(2, 5, 9, 3)) * w[:, None]).sum(-1)
     assert torch.allclose(out, ref, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# F-FPS / FS samplers (points_sampler.py:107-157): the kernel-arithmetic distance matrix against the reference's torch formula
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,M,C", [(96, 96, 3), (130, 70, 35), (64, 200, 131)])
+def test_pairwise_sqdist_oracle_vs_reference_formula(N, M, C):
+    from oracle import pointnet_modules_oracle as PO
+    g = torch.Generator().manual_seed(C)
+    a, b = torch.randn(2, N, C, generator=g), torch.randn(2, M, C, generator=g)
+    d = P.pairwise_sqdist(a, b, norm=False)
+    ref = PO.calc_square_dist_ref(a, b, norm=False)
+    assert d.shape == (2, N, M)
+    assert (d - ref).abs().max() <= 2e-5 * ref.abs().max()               # same quantity, different summation order
+    dn = P.pairwise_sqdist(a, b, norm=True)
+    assert (dn - PO.calc_square_dist_ref(a, b, norm=True)).abs().max() < 1e-5
+    # exact properties of the fma-chain arithmetic: zero diagonal and symmetry of the self-distance matrix
+    s = P.pairwise_sqdist(a, a, norm=False)
+    assert torch.equal(s, s.transpose(1, 2)) and (torch.diagonal(s, dim1=1, dim2=2) == 0).all()
+
+
+@pytest.mark.parametrize("mods,ranges,npts", [(["F-FPS"], [-1], [32]), (["FS"], [-1], [24]), (["D-FPS", "F-FPS"], [64, -1], [16, 16])])
+def test_samplers_same_indices_with_kernel_and_reference_distance(mods, ranges, npts):
+    """F-FPS picks arg-maxes of the distance matrix: the fma-chain matrix and the reference's matmul matrix differ in the last
+    bits only and select the same points on the seeded (continuous) inputs."""
+    from oracle import pointnet_modules_oracle as PO
+    xyz = O.synth_objects(3, 160, 11)
+    feat = torch.randn(3, 32, 160, generator=torch.Generator().manual_seed(5))
+    got = PO.points_sampler(xyz, feat, npts, mods, ranges)
+    ref = PO.points_sampler(xyz, feat, npts, mods, ranges, sqdist=PO.calc_square_dist_ref)
+    assert got.shape == (3, sum(n * (2 if m == "FS" else 1) for n, m in zip(npts, mods)))
+    assert torch.equal(got, ref)
