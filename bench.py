@@ -19,7 +19,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import torch  # noqa: E402
 
@@ -75,7 +74,8 @@ def cpu_reference_sample(n_obj=32, n_pairs=2048, threads=None):
     """The reference's PyTorch path (oracle restatement, bit-exact vs the reference modules) on host cores, on a
     bounded sample of the same workload: encode n_obj+n_obj objects, score n_pairs pairs; extrapolated to the
     step's composition (objects and pairs per step)."""
-    import helpers
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers                                  # oracle builder shared with the parity tests
     from oracle import reid_oracle as O
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
@@ -133,9 +133,7 @@ def main():
         return run_reference(args)
 
     import torch.distributed as dist
-    import helpers
-    from oracle import reid_oracle as O            # synthetic input generator + cpu_baseline leg only
-    from pcreid_b200 import _lib
+    from pcreid_b200 import _lib, synthetic as S   # the measured legs never import oracle/ or tests/ (cpu_baseline leg only)
     from pcreid_b200.parallel import encode_and_gather, match_all_pairs_sharded, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -151,10 +149,10 @@ def main():
 
     torch.manual_seed(66)
     from pcreid_b200.models import build_model
-    model = build_model(helpers.model_cfg("pt", BLIST)).eval().to(dev)
+    model = build_model(S.point_transformer_cfg(BLIST)).eval().to(dev)
     model.set_mode(args.mode)
-    tracks_h = O.synth_objects(T_loc, NPTS, 1000 + rank).pin_memory()
-    dets_h = O.synth_objects(D, NPTS, 1)[d0:d1].contiguous().pin_memory()
+    tracks_h = S.synth_objects(T_loc, NPTS, 1000 + rank).pin_memory()
+    dets_h = S.synth_objects(D, NPTS, 1)[d0:d1].contiguous().pin_memory()
     tracks_d, dets_d = tracks_h.to(dev), dets_h.to(dev)
     out_h = torch.empty((T_loc, D), dtype=torch.float32).pin_memory()
 

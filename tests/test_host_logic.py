@@ -214,3 +214,12 @@ def test_image_reid_api_surface(fake):
     assert res['val_fp_gt'].tolist() == [0., 0., 1., 0., 0., 0.]
     with pytest.raises(NotImplementedError):
         m(return_loss=True)
+
+
+def test_product_synthetic_module_matches_the_oracle_generators():
+    """bench.py's measured legs draw inputs / configs from pcreid_b200.synthetic (never from oracle/ or tests/)"""
+    from pcreid_b200 import synthetic as S
+    for dup in (False, True):
+        assert torch.equal(S.synth_objects(3, 64, 5, dup=dup), O.synth_objects(3, 64, 5, dup=dup))
+    assert torch.equal(S.synth_tokens(2, 8, 9, 1), O.synth_tokens(2, 8, 9, 1))
+    assert S.point_transformer_cfg((256, 128, 64)) == helpers.model_cfg("pt", (256, 128, 64))
