@@ -53,6 +53,12 @@ int pcreid_knn_t(int b, int n, int m, int nsample, const float* xyz, const float
  * zero-filled by the caller (ball_query.py:41); rows without a hit are left untouched. */
 int pcreid_ball_query(int b, int n, int m, float min_radius, float max_radius, int nsample,
                       const float* new_xyz, const float* xyz, int* idx, void* stream);
+/* replaces the torch-path query_ball_point (models/pointnet2_utils.py:218-240; arange / square_distance / sort / mask there),
+ * the grouping of the ReID backbone's SA layers when use_knn=False: expansion-form distance of square_distance op for op,
+ * a point is kept unless d2 > r2 (r2 = fp32(radius ** 2)), first nsample kept indices in ascending order, padded with the
+ * first; idx (b,m,nsample) int32; a row without any kept point is filled with n (as the reference's sort leaves it). */
+int pcreid_query_ball_point(int b, int n, int m, float r2, int nsample, const float* new_xyz, const float* xyz, int* idx,
+                            void* stream);
 
 /* replaces group_points_kernel_launcher(b,c,n,npoints,nsample,points,idx,out,stream)
  * (ops/group_points/src/group_points_cuda.cu:81-100): out[b,c,s,j] = points[b,c,idx[b,s,j]]. */

@@ -52,6 +52,7 @@ _SIGS = {
     "pcreid_knn_point_set": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_feature": [c_int, c_int, c_int, c_int, c_vp, c_ll, c_vp, c_vp],
     "pcreid_ball_query": [c_int, c_int, c_int, c_float, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_query_ball_point": [c_int, c_int, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_crop_tiles": [c_int],

@@ -481,6 +481,13 @@ static int fps_launch(int b, int n, int m, const float* data, float* temp, int* 
 // ------------------------------------------------------------------------------------------------
 // ball query
 // ------------------------------------------------------------------------------------------------
+// MODE 0: the mmdet3d op (ball_query_cuda.cu:11-54): direct-form distance, hit = d2 == 0 || (min_r2 <= d2 < max_r2), rows
+//         without a hit keep the caller's zeros.
+// MODE 1: the torch-path query_ball_point of the ReID backbone (models/pointnet2_utils.py:218-240, use_knn=False):
+//         expansion-form distance of square_distance (op for op, as knn_kernel<1>), hit = !(d2 > r2), the first nsample hits
+//         in index order, padded with the first hit; a row without any hit is filled with N exactly like the reference's
+//         sort-based formulation (which then fails in index_points).
+template <int MODE>
 __global__ void __launch_bounds__(256) ball_query_kernel(int N, int M, int k, float min_r2, float max_r2,
                                                          const float* __restrict__ qxyz, const float* __restrict__ xyz,
                                                          int* __restrict__ idx) {
@@ -490,18 +497,24 @@ __global__ void __launch_bounds__(256) ball_query_kernel(int N, int M, int k, fl
   const float* P = xyz + (size_t)b * N * 3;
   const float* Q = qxyz + ((size_t)b * M + q) * 3;
   const float qx = Q[0], qy = Q[1], qz = Q[2];
+  const float qn = MODE == 1 ? sqnorm3(qx, qy, qz) : 0.f;
   int* o = idx + ((size_t)b * M + q) * k;
   int cnt = 0;
   for (int base = 0; base < N && cnt < k; base += 32) {
     int i = base + lane;
     bool hit = false;
     if (i < N) {
-      float d2 = dist_direct(qx, qy, qz, __ldg(P + i * 3), __ldg(P + i * 3 + 1), __ldg(P + i * 3 + 2));
-      hit = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+      const float px = __ldg(P + i * 3), py = __ldg(P + i * 3 + 1), pz = __ldg(P + i * 3 + 2);
+      if (MODE == 0) {
+        float d2 = dist_direct(qx, qy, qz, px, py, pz);
+        hit = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+      } else {
+        hit = !(dist_expand(qx, qy, qz, qn, px, py, pz) > max_r2);
+      }
     }
     uint32_t mask = __ballot_sync(FULL_MASK, hit);
     if (mask == 0) continue;
-    if (cnt == 0) {   // first hit is broadcast to every slot (ball_query_cuda.cu:44-48)
+    if (cnt == 0) {   // first hit is broadcast to every slot (ball_query_cuda.cu:44-48 / pointnet2_utils.py:237-239)
       int first = base + __ffs(mask) - 1;
       for (int l = lane; l < k; l += 32) o[l] = first;
       __syncwarp();
@@ -510,6 +523,8 @@ __global__ void __launch_bounds__(256) ball_query_kernel(int N, int M, int k, fl
     if (hit && pos < k) o[pos] = i;
     cnt += __popc(mask);
   }
+  if (MODE == 1 && cnt == 0)
+    for (int l = lane; l < k; l += 32) o[l] = N;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -758,8 +773,18 @@ int pcreid_ball_query(int b, int n, int m, float min_radius, float max_radius, i
   if (b <= 0 || m <= 0 || nsample <= 0) return PCREID_OK;
   if (n <= 0 || !new_xyz || !xyz || !idx) return PCREID_ERR_ARG;
   dim3 grid(ceil_div(m, 8), b);
-  ball_query_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, nsample, min_radius * min_radius,
-                                                            max_radius * max_radius, new_xyz, xyz, idx);
+  ball_query_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, nsample, min_radius * min_radius,
+                                                               max_radius * max_radius, new_xyz, xyz, idx);
+  return pcreid_launch_status();
+}
+
+// torch-path query_ball_point (models/pointnet2_utils.py:218-240): r2 = fp32(radius ** 2) as torch compares it.
+int pcreid_query_ball_point(int b, int n, int m, float r2, int nsample, const float* new_xyz, const float* xyz, int* idx,
+                            void* stream) {
+  if (b <= 0 || m <= 0 || nsample <= 0) return PCREID_OK;
+  if (n <= 0 || !new_xyz || !xyz || !idx) return PCREID_ERR_ARG;
+  if (b > 65535) return PCREID_ERR_UNSUPPORTED;
+  ball_query_kernel<1><<<dim3(ceil_div(m, 8), b), 256, 0, (cudaStream_t)stream>>>(n, m, nsample, 0.f, r2, new_xyz, xyz, idx);
   return pcreid_launch_status();
 }
 

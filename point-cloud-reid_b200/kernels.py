@@ -272,6 +272,21 @@ def knn_point_set(k, xyz, new_xyz):
     return idx
 
 
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """torch-path ball query of the backbones (pointnet2_utils.py:218-240): int32 (B, S, nsample), indices of the first
+    nsample points with d <= radius^2 in ascending order, padded with the first."""
+    _need_cuda(xyz, new_xyz)
+    if not (xyz.is_contiguous() and new_xyz.is_contiguous()):
+        raise ValueError("xyz / new_xyz must be contiguous")
+    B, N, _ = xyz.shape
+    S = new_xyz.shape[1]
+    r2 = float(torch.tensor(radius ** 2, dtype=torch.float32))          # the fp32 value torch compares the distances with
+    idx = torch.empty((B, S, nsample), device=xyz.device, dtype=torch.int32)
+    _lib.check(_lib.lib().pcreid_query_ball_point(B, N, S, r2, nsample, _p(new_xyz), _p(xyz), _p(idx), _stream()),
+               "pcreid_query_ball_point")
+    return idx
+
+
 def knn_feature(x, k):
     """DGCNN kNN in feature space: x (B, C, N) contiguous -> int32 (B, N, k)."""
     _need_cuda(x)

@@ -111,9 +111,10 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         self.group_all = group_all
         self.self_attention = Self_Attention(last_channel, 2, 'linear')
         self.tc_mode = False      # True: shared MLP on the tensor cores (tcgen05 kind::tf32), "fast" encoder mode
-        if group_all or not use_knn or sampling != "RANDOM" or not use_xyz or len(mlp) != 4:
-            raise NotImplementedError("only the configuration the reference backbone instantiates is built: "
-                                      "sampling='RANDOM', use_knn=True, use_xyz=True, 3-layer MLP (backbone_net.py:49-81)")
+        if group_all or sampling != "RANDOM" or not use_xyz or len(mlp) != 4:
+            raise NotImplementedError("built: sampling='RANDOM', use_xyz=True, 3-layer MLP, kNN or ball-query grouping "
+                                      "(backbone_net.py:49-81; sampling='FPS' starts from torch.randint and is unreachable "
+                                      "from the shipped backbone)")
 
     def _pack(self):
         # first conv acts on [xyz_j - xyz_c (3), f_c (D), f_j - f_c (D)] (pointnet2_utils.py:279-282):
@@ -140,7 +141,10 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         new_xyz = xyz[:, :S, :].contiguous()              # sampling == "RANDOM": the first S points
         tc = self.tc_mode and "w2img" in pk          # tensor-core kernel gathers point-major rows
         # (B, S, k) int32; the max over the k edges does not depend on their order: fast mode asks for the set only
-        idx = K.knn_point_set(self.nsample, xyz, new_xyz) if tc else K.knn_point(self.nsample, xyz, new_xyz)
+        if not self.use_knn:                          # query_ball_point (pointnet2_utils.py:218-240)
+            idx = K.query_ball_point(self.radius, self.nsample, xyz, new_xyz)
+        else:
+            idx = K.knn_point_set(self.nsample, xyz, new_xyz) if tc else K.knn_point(self.nsample, xyz, new_xyz)
         if pk["D"] > 0:
             p1 = K.cn_linear(xyz, pk["pa"], x2=points, w2=pk["pc"], x1_pm=True, y_pm=tc)
             cc = K.cn_linear(xyz, pk["ca"], x2=points, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)

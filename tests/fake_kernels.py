@@ -100,6 +100,19 @@ def knn_point(k, xyz, new_xyz):
     return torch.sort(d, dim=-1, stable=True)[1][..., :k].to(torch.int32).contiguous()
 
 
+def query_ball_point(radius, nsample, xyz, new_xyz):
+    """specification of pcreid_query_ball_point: first nsample indices with d <= r^2 (fp32), padded with the first; N if none."""
+    B, N, _ = xyz.shape
+    d = -2 * torch.matmul(new_xyz, xyz.permute(0, 2, 1))
+    d += torch.sum(new_xyz ** 2, -1).unsqueeze(-1)
+    d += torch.sum(xyz ** 2, -1).unsqueeze(1)
+    keep = ~(d > float(torch.tensor(radius ** 2, dtype=torch.float32)))
+    ar = torch.arange(N).view(1, 1, N).expand_as(d)
+    cand = torch.where(keep, ar, torch.full_like(ar, N)).sort(-1)[0][..., :nsample]
+    first = cand[..., :1].expand_as(cand)
+    return torch.where(cand == N, first, cand).to(torch.int32).contiguous()
+
+
 def knn_feature(x, k):
     inner = -2 * torch.matmul(x.transpose(2, 1), x)
     xx = torch.sum(x ** 2, dim=1, keepdim=True)
@@ -169,7 +182,7 @@ def install(monkeypatch=None):
     """Replaces pcreid_b200.kernels' entry points by the emulations above (optionally via pytest's monkeypatch)."""
     import pcreid_b200.kernels as K
     names = ["cn_linear", "cn_groupnorm", "linattn_kv", "linattn_scale", "cn_pool", "cn_chanmax", "knn_point",
-             "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head", "local_linattn"]
+             "query_ball_point", "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head", "local_linattn"]
     for n in names:
         if monkeypatch is not None:
             monkeypatch.setattr(K, n, globals()[n])

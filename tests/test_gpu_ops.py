@@ -212,3 +212,36 @@ def test_three_interpolate_bit_exact(C, M, N):
     assert torch.equal(out.cpu(), P.three_interpolate(f, idx.cpu(), w.cpu()))
     if P.ref_available():
         assert torch.equal(out, P.ref_three_interpolate(f.to(DEV), idx, w))
+
+
+@pytest.mark.parametrize("radius,nsample,dup", [(0.7, 16, False), (2.5, 48, False), (0.05, 8, True), (1e-4, 4, False)])
+def test_query_ball_point_torch_path_exact(radius, nsample, dup):
+    """pointnet2_utils.query_ball_point (use_knn=False): indices exact, expansion-form distance, d <= r^2"""
+    import pcreid_b200.kernels as K
+    from oracle import reid_oracle as RO
+    x = RO.synth_objects(3, 160, 4, dup=dup)
+    q = x[:, :80].contiguous()
+    got = K.query_ball_point(radius, nsample, x.to(DEV), q.to(DEV)).cpu()
+    assert got.dtype == torch.int32 and torch.equal(got.long(), RO.query_ball_point(radius, nsample, x, q))
+    far = (q + 100.0).contiguous()                      # no point within the radius: the reference leaves N in every slot
+    assert (K.query_ball_point(radius, nsample, x.to(DEV), far.to(DEV)).cpu() == 160).all()
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_sa_layer_with_ball_query_grouping(fast):
+    from pcreid_b200.models.pointnet2_utils import PointNetSetAbstractionEdgeSA
+    from oracle import reid_oracle as RO
+    torch.manual_seed(66)
+    sa = PointNetSetAbstractionEdgeSA(npoint=None, radius=1.2, nsample=24, mlp=[0, 32, 32, 32], sampling="RANDOM", use_xyz=True,
+                                      use_knn=False).eval()
+    sd = RO.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    sa.load_state_dict({k[3:]: v for k, v in sd.items()})
+    sa = sa.to(DEV)
+    sa.tc_mode = fast
+    sa.self_attention.tc_mode = fast
+    x = RO.synth_objects(2, 128, 3)
+    with torch.no_grad():
+        nx, nf = sa(x.to(DEV), None, 64)
+    ox, of = RO.sa_layer(sd, "sa", x, None, 64, 24, radius=1.2)
+    assert torch.equal(nx.cpu(), ox)
+    assert (nf.cpu() - of).abs().max() < (2e-2 if fast else 1e-4)

@@ -223,3 +223,21 @@ def test_product_synthetic_module_matches_the_oracle_generators():
         assert torch.equal(S.synth_objects(3, 64, 5, dup=dup), O.synth_objects(3, 64, 5, dup=dup))
     assert torch.equal(S.synth_tokens(2, 8, 9, 1), O.synth_tokens(2, 8, 9, 1))
     assert S.point_transformer_cfg((256, 128, 64)) == helpers.model_cfg("pt", (256, 128, 64))
+
+
+def test_sa_layer_ball_query_grouping_vs_oracle_with_spec_kernels(fake):
+    """PointNetSetAbstractionEdgeSA(use_knn=False) groups with query_ball_point (pointnet2_utils.py:218-240)"""
+    from pcreid_b200.models.pointnet2_utils import PointNetSetAbstractionEdgeSA
+    torch.manual_seed(66)
+    sa = PointNetSetAbstractionEdgeSA(npoint=None, radius=1.2, nsample=24, mlp=[0, 32, 32, 32], sampling="RANDOM", use_xyz=True,
+                                      use_knn=False).eval()
+    sd = O.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    sa.load_state_dict({k[3:]: v for k, v in sd.items()})
+    x = O.synth_objects(2, 128, 3)
+    with torch.no_grad():
+        nx, nf = sa(x, None, 64)
+    ox, of = O.sa_layer(sd, "sa", x, None, 64, 24, radius=1.2)
+    assert torch.equal(nx, ox) and (nf - of).abs().max() < 2e-5
+    import fake_kernels
+    q = x[:, :64].contiguous()
+    assert torch.equal(fake_kernels.query_ball_point(0.7, 16, x, q).long(), O.query_ball_point(0.7, 16, x, q))

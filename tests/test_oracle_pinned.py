@@ -184,3 +184,28 @@ def test_image_oracle_matches_golden():
     assert (orc.downsample_tokens(torch.from_numpy(g["raw"])) - torch.from_numpy(g["h_raw"])).abs().max() < 2e-5
     L = orc.match_all_pairs(torch.from_numpy(g["h_t"]), torch.from_numpy(g["h_d"]))
     assert (L - torch.from_numpy(g["logits"])).abs().max() < 2e-5
+
+
+@needs_ref
+@pytest.mark.parametrize("radius,nsample", [(0.7, 16), (2.5, 48), (0.05, 8)])
+def test_query_ball_point_bit_exact_vs_reference(radius, nsample):
+    """the torch-path ball query (pointnet2_utils.py:218-240), reachable with use_knn=False"""
+    R = ref_loader.load()
+    x = O.synth_objects(3, 160, 4, dup=(nsample == 8))
+    ref = R.pointnet2_utils.query_ball_point(radius, nsample, x, x[:, :80].contiguous())
+    assert torch.equal(ref, O.query_ball_point(radius, nsample, x, x[:, :80].contiguous()))
+
+
+@needs_ref
+def test_sa_layer_with_ball_query_bit_exact_vs_reference():
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    sa = R.pointnet2_utils.PointNetSetAbstractionEdgeSA(npoint=None, radius=1.2, nsample=24, mlp=[0, 32, 32, 32], sampling="RANDOM",
+                                                        use_xyz=True, use_knn=False).eval()
+    sd = O.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    _load_ref_sd(sa, "sa.", sd)
+    x = O.synth_objects(2, 128, 3)
+    with torch.no_grad():
+        rx, rf = sa(x, None, 64)
+    ox, of = O.sa_layer(sd, "sa", x, None, 64, 24, radius=1.2)
+    assert torch.equal(rx, ox) and torch.equal(rf, of)
