@@ -33,6 +33,25 @@ def run(name, kind, N, blist, T, D, mode, check=8, reps=2):
     return r
 
 
+def run_image(name, S, T, D, mode, check=6):
+    """token side of ImageReIDNet (reid_image_deit-tiny_point-cat.py): downsample of (T + D) x S tokens x 192 + all-pairs match"""
+    m, orc = helpers.build_image_pair(device=dev, perturb=False)
+    m.set_mode(mode)
+    raw = O.synth_tokens(T + D, 192, S, 0)
+    rd = raw.to(dev)
+    for _ in range(2):
+        e0 = ev(); h = m.downsample_tokens(rd); e1 = ev()
+        L = m.match_all_pairs(h[:T], h[T:]); e2 = ev(); torch.cuda.synchronize()
+    enc, mat = e0.elapsed_time(e1), e1.elapsed_time(e2)
+    ho = orc.downsample_tokens(raw)
+    Lo = orc.match_all_pairs(ho[:check], ho[T:T + check])
+    err = float((L[:check, :check].cpu() - Lo).abs().max())
+    print(json.dumps({"config": name, "backbone": "image tokens (DeiT-tiny shape)", "tokens": S, "tracks": T, "dets": D, "mode": mode,
+                      "downsample_ms": enc, "match_ms": mat, "pairs_per_s": T * D / mat * 1e3,
+                      "max_abs_dlogit_vs_oracle_on_sample": err, "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}), flush=True)
+    torch.cuda.reset_peak_memory_stats()
+
+
 only = os.environ.get("ONLY", "")
 jobs = [
     ("c1", lambda: run("C1 PointNet 64x64 @128", "pointnet", 128, (128, 64, 32), 64, 64, "parity")),
@@ -49,6 +68,10 @@ jobs = [
     ("concat", lambda: run("C5 concat head PT 4096x4096 @128 (tensor-core head)", "concat", 128, (128, 64, 32), 4096, 4096, "fast")),
     ("concat", lambda: run("target shape: concat head PT 16384x16384 @128 (tensor-core head)", "concat", 128, (128, 64, 32), 16384, 16384, "fast", reps=1)),
     ("concat", lambda: run("target shape: concat head PT 4096x4096 @128, 16384x16384", "concat", 128, (128, 64, 32), 16384, 16384, "parity", reps=1)),
+]
+jobs += [
+    ("image", lambda: run_image("image-token matcher 256x256 @198 tokens", 198, 256, 256, "parity")),
+    ("image", lambda: run_image("image-token matcher 1024x1024 @198 tokens", 198, 1024, 1024, "fast")),
 ]
 for tag, job in jobs:
     if not only or tag in only.split(","):
