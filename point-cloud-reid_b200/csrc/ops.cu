@@ -183,22 +183,28 @@ static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, co
 // per bit instead of k rounds of two REDUX.MIN + rescan), then the members are emitted by ballot / prefix popcount.
 // Same distance arithmetic as knn_kernel<1> (torch path, pointnet2_utils.py:169-216).
 // ------------------------------------------------------------------------------------------------
-template <int KPL>
+// STAGED (large N): the candidates live in shared memory (one float4 per point, loaded once per CTA) instead of 3 x KPL
+// registers per lane, so that 32 keys per lane still leave room for full occupancy.
+template <int KPL, bool STAGED>
 __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int qpw, const float* __restrict__ xyz,
                                                       const float* __restrict__ qxyz, int* __restrict__ idx) {
+  __shared__ float4 cand[STAGED ? KPL * 32 : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int q0 = (blockIdx.x * 8 + warp) * qpw;
-  if (q0 >= M) return;
   const float* P = xyz + (size_t)b * N * 3;
-  float px[KPL], py[KPL], pz[KPL], pn[KPL];
+  if (STAGED) {
+    for (int i = threadIdx.x; i < N; i += 256) cand[i] = make_float4(__ldg(P + i * 3), __ldg(P + i * 3 + 1), __ldg(P + i * 3 + 2), 0.f);
+    __syncthreads();
+  }
+  if (q0 >= M) return;
+  float px[STAGED ? 1 : KPL], py[STAGED ? 1 : KPL], pz[STAGED ? 1 : KPL];
+  if (!STAGED) {
 #pragma unroll
-  for (int j = 0; j < KPL; ++j) {
-    const int i = lane + 32 * j;
-    px[j] = py[j] = pz[j] = pn[j] = 0.f;
-    if (i < N) {
-      px[j] = __ldg(P + i * 3); py[j] = __ldg(P + i * 3 + 1); pz[j] = __ldg(P + i * 3 + 2);
-      pn[j] = sqnorm3(px[j], py[j], pz[j]);
+    for (int j = 0; j < KPL; ++j) {
+      const int i = lane + 32 * j;
+      px[j] = py[j] = pz[j] = 0.f;
+      if (i < N) { px[j] = __ldg(P + i * 3); py[j] = __ldg(P + i * 3 + 1); pz[j] = __ldg(P + i * 3 + 2); }
     }
   }
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -213,7 +219,12 @@ __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int q
     for (int j = 0; j < KPL; ++j) {
       key[j] = 0xffffffffu;
       if (lane + 32 * j < N) {
-        key[j] = f32_to_ordered(dist_expand(qx, qy, qz, qn, px[j], py[j], pz[j]));
+        if (STAGED) {
+          const float4 c = cand[lane + 32 * j];
+          key[j] = f32_to_ordered(dist_expand(qx, qy, qz, qn, c.x, c.y, c.z));
+        } else {
+          key[j] = f32_to_ordered(dist_expand(qx, qy, qz, qn, px[j], py[j], pz[j]));
+        }
         lmin = min(lmin, key[j]);
         lmax = max(lmax, key[j]);
       }
@@ -221,6 +232,7 @@ __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int q
     const uint32_t kmin = __reduce_min_sync(FULL_MASK, lmin), kmax = __reduce_max_sync(FULL_MASK, lmax);
     // T = k-th smallest key: largest T with count(key < T) < k; bits above the highest differing bit are common
     uint32_t T = kmin;
+    bool exact = false;         // a threshold with exactly k keys below it: the member set is known, no tie to break
     if (kmin != kmax) {
       const int top = 31 - __clz(kmin ^ kmax);
       T = top == 31 ? 0u : (kmin & ~((2u << top) - 1u));
@@ -230,6 +242,8 @@ __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int q
 #pragma unroll
         for (int j = 0; j < KPL; ++j) c += key[j] < t ? 1 : 0;
         c = __reduce_add_sync(FULL_MASK, c);
+        // distinct keys: the search interval isolates the gap between the k-th and (k+1)-th key after ~log2(N) bits
+        if (c == k) { T = t; exact = true; break; }
         if (c < k) T = t;
       }
     }
@@ -242,6 +256,7 @@ __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int q
       if (in) oi[base + __popc(bal & lt_mask)] = lane + 32 * j;
       base += __popc(bal);
     }
+    if (exact) continue;
 #pragma unroll
     for (int j = 0; j < KPL; ++j) {
       const bool eq = key[j] == T && lane + 32 * j < N;
@@ -253,10 +268,10 @@ __global__ void __launch_bounds__(256) knn_set_kernel(int N, int M, int k, int q
   }
 }
 
-template <int KPL>
+template <int KPL, bool STAGED>
 static int knn_set_launch(int b, int n, int m, int k, const float* xyz, const float* q, int* idx, cudaStream_t st) {
   const int qpw = m >= 64 ? 8 : (m >= 16 ? 2 : 1);
-  knn_set_kernel<KPL><<<dim3(ceil_div(m, 8 * qpw), b), 256, 0, st>>>(n, m, k, qpw, xyz, q, idx);
+  knn_set_kernel<KPL, STAGED><<<dim3(ceil_div(m, 8 * qpw), b), 256, 0, st>>>(n, m, k, qpw, xyz, q, idx);
   return pcreid_launch_status();
 }
 
@@ -739,10 +754,13 @@ int pcreid_knn_point_set(int b, int n, int m, int k, const float* xyz, const flo
   if (!xyz || !new_xyz || !idx || n <= 0) return PCREID_ERR_ARG;
   if (k > n || n > 1024 || b > 65535) return PCREID_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
-  if (n <= 128) return knn_set_launch<4>(b, n, m, k, xyz, new_xyz, idx, st);
-  if (n <= 256) return knn_set_launch<8>(b, n, m, k, xyz, new_xyz, idx, st);
-  if (n <= 512) return knn_set_launch<16>(b, n, m, k, xyz, new_xyz, idx, st);
-  return knn_set_launch<32>(b, n, m, k, xyz, new_xyz, idx, st);
+  static const int staged_from = getenv("PCREID_KNN_STAGED_FROM") ? atoi(getenv("PCREID_KNN_STAGED_FROM")) : 257;   // A/B knob
+  if (n <= 128) return knn_set_launch<4, false>(b, n, m, k, xyz, new_xyz, idx, st);
+  if (n <= 256) return knn_set_launch<8, false>(b, n, m, k, xyz, new_xyz, idx, st);
+  if (n <= 512) return n >= staged_from ? knn_set_launch<16, true>(b, n, m, k, xyz, new_xyz, idx, st)
+                                        : knn_set_launch<16, false>(b, n, m, k, xyz, new_xyz, idx, st);
+  return n >= staged_from ? knn_set_launch<32, true>(b, n, m, k, xyz, new_xyz, idx, st)
+                          : knn_set_launch<32, false>(b, n, m, k, xyz, new_xyz, idx, st);
 }
 
 int pcreid_knn_feature(int b, int c, int n, int k, const float* x, long long x_bs, int* idx, void* stream) {

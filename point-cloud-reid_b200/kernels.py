@@ -265,7 +265,7 @@ def knn_point_set(k, xyz, new_xyz):
         raise ValueError("xyz / new_xyz must be contiguous")
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
-    if k > N or N > 512 or B > 65535:       # measured: above 512 candidates the ordered kernel is as fast (register pressure)
+    if k > N or N > 1024 or B > 65535:
         return knn_point(k, xyz, new_xyz)
     idx = torch.empty((B, S, k), device=xyz.device, dtype=torch.int32)
     _lib.check(_lib.lib().pcreid_knn_point_set(B, N, S, k, _p(xyz), _p(new_xyz), _p(idx), _stream()), "pcreid_knn_point_set")
