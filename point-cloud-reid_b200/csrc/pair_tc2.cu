@@ -477,14 +477,27 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
 #undef TR
 
 // pool_part (P, 2, 128) [max | sum of (o - beta2)] -> pooled^T (128, P): max over both directions | mean over the 2*npts points
+// One CTA = 32 pairs x 128 channels through a padded shared-memory tile: rows of `part` are read coalesced (a warp reads one
+// pair's 128 floats per direction), columns of the (128, P) output are written coalesced (32 consecutive pairs per channel).
 __global__ void __launch_bounds__(256) pool_finish2_kernel(int P, int npts, const float* __restrict__ part, const float* __restrict__ bias,
                                                            float* __restrict__ out) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 128LL * P) return;
-  const int c = (int)(idx / P), p = (int)(idx % P);
-  const float x0 = part[((size_t)p * 2) * 128 + c], x1 = part[((size_t)p * 2 + 1) * 128 + c];
-  const float b = bias ? bias[c & 63] : 0.f;
-  out[idx] = (c < 64 ? fmaxf(x0, x1) : (x0 + x1) / (float)(2 * npts)) + b;
+  __shared__ float tile[32][129];
+  const int p0 = blockIdx.x * 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < 32; r += 8) {
+    const int p = p0 + r;
+    if (p >= P) break;
+    const float* row = part + (size_t)p * 256;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = lane + 32 * j;
+      const float x0 = row[c], x1 = row[128 + c];
+      const float b = bias ? bias[c & 63] : 0.f;
+      tile[r][c] = (c < 64 ? fmaxf(x0, x1) : (x0 + x1) / (float)(2 * npts)) + b;
+    }
+  }
+  __syncthreads();
+  if (p0 + lane < P)
+    for (int c = warp; c < 128; c += 8) out[(size_t)c * P + p0 + lane] = tile[lane][c];
 }
 
 // src (B, C, N) channel-major fp32 + per-channel bias -> dst [B][N/128][C/8][128][8] bf16
@@ -530,7 +543,7 @@ int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs
 int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias, float* out, void* stream) {
   if (P <= 0) return PCREID_OK;
   if (!part || !out) return PCREID_ERR_ARG;
-  pool_finish2_kernel<<<(unsigned)((128LL * P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(P, npts, part, bias, out);
+  pool_finish2_kernel<<<(unsigned)((P + 31) / 32), 256, 0, (cudaStream_t)stream>>>(P, npts, part, bias, out);
   return pcreid_launch_status();
 }
 

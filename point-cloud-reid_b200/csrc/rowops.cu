@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(NTHR) cn_linear_kernel(const pcreid_linear_arg
 // ------------------------------------------------------------------------------------------------
 // cn_groupnorm: one thread per (object, point); channels strided by ld (coalesced across points)
 // ------------------------------------------------------------------------------------------------
+// CG > 0: channels per group known at compile time -> the group is read ONCE into registers (the generic CG = 0 path reads it
+// three times: sum, centred squares, normalise); same operations in the same order, bit-identical results.
+template <int CG>
 __global__ void __launch_bounds__(128) cn_groupnorm_kernel(const pcreid_norm_args a) {
   // one thread per (object, point), flattened so that objects with few points still fill the CTAs
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -308,8 +311,29 @@ __global__ void __launch_bounds__(128) cn_groupnorm_kernel(const pcreid_norm_arg
   const float* X = a.X + (size_t)b * a.x_bs + n;
   const float* R = a.R ? a.R + (size_t)(a.r_map ? a.r_map[b] : b) * a.r_bs + n : nullptr;
   float* Y = a.Y + (size_t)b * a.y_bs + n;
-  const int cg = a.C / a.G;
+  const int cg = CG > 0 ? CG : a.C / a.G;
   for (int g = 0; g < a.G; ++g) {
+    if (CG > 0) {
+      float x[CG > 0 ? CG : 1];
+#pragma unroll
+      for (int i = 0; i < CG; ++i) x[i] = X[(size_t)(g * CG + i) * a.ldx];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CG; ++i) s += x[i];
+      const float mean = s / (float)CG;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < CG; ++i) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+      const float rstd = rsqrtf(v / (float)CG + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < CG; ++i) {
+        const int c = g * CG + i;
+        float y = (x[i] - mean) * rstd * __ldg(a.gamma + c) + __ldg(a.beta + c);
+        if (R) y += R[(size_t)c * a.ldr];
+        Y[(size_t)c * a.ldy] = apply_act(y, a.act);
+      }
+      continue;
+    }
     float s = 0.f;
     for (int c = g * cg; c < (g + 1) * cg; ++c) s += X[(size_t)c * a.ldx];
     const float mean = s / (float)cg;
@@ -778,7 +802,16 @@ int pcreid_cn_groupnorm(const pcreid_norm_args* p, void* stream) {
     s.X += (size_t)b0 * s.x_bs;
     s.Y += (size_t)b0 * s.y_bs;
     if (s.R) { if (s.r_map) s.r_map += b0; else s.R += (size_t)b0 * s.r_bs; }
-    cn_groupnorm_kernel<<<(unsigned)(((long long)s.B * a.rows + 127) / 128), 128, 0, st>>>(s);
+    const unsigned grid = (unsigned)(((long long)s.B * a.rows + 127) / 128);
+    switch (a.C / a.G) {
+      case 4: cn_groupnorm_kernel<4><<<grid, 128, 0, st>>>(s); break;
+      case 8: cn_groupnorm_kernel<8><<<grid, 128, 0, st>>>(s); break;
+      case 16: cn_groupnorm_kernel<16><<<grid, 128, 0, st>>>(s); break;
+      case 32: cn_groupnorm_kernel<32><<<grid, 128, 0, st>>>(s); break;
+      case 64: cn_groupnorm_kernel<64><<<grid, 128, 0, st>>>(s); break;
+      case 128: cn_groupnorm_kernel<128><<<grid, 128, 0, st>>>(s); break;
+      default: cn_groupnorm_kernel<0><<<grid, 128, 0, st>>>(s); break;
+    }
   }
   return pcreid_launch_status();
 }
