@@ -116,3 +116,31 @@ def test_concat_head_tensor_core_matches_parity_and_oracle(T, D, masked):
     if T > 8:
         ok, agree, n = helpers.margin_aware_top1(Lo, Lf, err)
         assert ok, f"top-1 changed on a decisive row (agreement {agree}, {n} decisive rows)"
+
+
+def test_full_size_config_properties():
+    """BASELINE configs[1] at its full size (1024 tracks x 1024 detections x 256 points, fast mode): size-independent
+    properties instead of an oracle pass -- (1) the dense row-chunked driver and the pair-list driver give the same logit for
+    the same pair, (2) scoring a row block on its own equals the rows of the full matrix (what the row-sharded multi-GPU
+    driver relies on), (3) swapping the roles of the two sets transposes the matrix (xcorr_eff + 'both' pooling is symmetric),
+    (4) a sampled 6 x 6 block agrees with the oracle within the fast-mode tolerance."""
+    T = D = 1024
+    m, orc = helpers.build_pair("pt", (256, 128, 64), device=DEV, perturb=False)
+    m.set_mode('fast')
+    t, d = O.synth_objects(T, 256, 0), O.synth_objects(D, 256, 1)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    L = m.match_all_pairs(ht, xt, hd, xd)
+    assert L.shape == (T, D) and torch.isfinite(L).all()
+    mask = torch.rand(T, D, generator=torch.Generator().manual_seed(1)) < 2e-3
+    Lm = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.to(DEV))
+    assert int(mask.sum()) > 1000 and torch.equal(Lm[mask.to(DEV)], L[mask.to(DEV)]) and (Lm[~mask.to(DEV)] == 0).all()
+    rows = slice(384, 512)
+    assert torch.equal(m.match_all_pairs(ht[rows], xt[rows], hd, xd), L[rows])
+    Lt = m.match_all_pairs(hd[:256], xd[:256], ht[:256], xt[:256])
+    assert (Lt - L[:256, :256].t()).abs().max() < TOL_FAST
+    ti, di = torch.tensor([0, 1, 511, 512, 1022, 1023]), torch.tensor([3, 64, 65, 700, 1000, 1023])
+    oxt, oht = orc.encode(t[ti])
+    oxd, ohd = orc.encode(d[di])
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    assert (L[ti][:, di].cpu() - Lo).abs().max() < TOL_FAST
