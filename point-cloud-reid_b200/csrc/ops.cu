@@ -16,6 +16,8 @@
 //                                                        ops/gather_points/src/gather_points_cuda.cu:8-26)
 #include "common.cuh"
 #include <math.h>
+#include <stdlib.h>
+#include <string.h>
 
 // ------------------------------------------------------------------------------------------------
 // distance arithmetic (must match the reference bit for bit; never let nvcc re-contract)
@@ -52,6 +54,29 @@ __device__ void heap_reheap(float* dist, int* idx, int k) {
     int ti = idx[root]; idx[root] = idx[child]; idx[child] = ti;
     root = child;
     child = root * 2 + 1;
+  }
+}
+
+// the reference's sequential max-heap over all candidates + heap_sort (knn_cuda.cu:26-94), run by ONE lane for the rare
+// queries with an exact tie among the selected k / at the k-th boundary (which tied candidates survive, and in which
+// order, depends on the heap's internal structure).
+template <int MODE>
+__device__ void heap_replay(const float* __restrict__ P, int N, int k, float qx, float qy, float qz, float qn, float* hd, int* hi,
+                            int* oi, float* od, long long sk) {
+  for (int i = 0; i < k; ++i) { hd[i] = 1e10f; hi[i] = 0; }
+  for (int i = 0; i < N; ++i) {
+    float px = __ldg(P + i * 3), py = __ldg(P + i * 3 + 1), pz = __ldg(P + i * 3 + 2);
+    float d = MODE == 0 ? dist_direct(qx, qy, qz, px, py, pz) : dist_expand(qx, qy, qz, qn, px, py, pz);
+    if (d < hd[0]) { hd[0] = d; hi[0] = i; heap_reheap(hd, hi, k); }
+  }
+  for (int i = k - 1; i > 0; --i) {   // heap_sort (knn_cuda.cu:45-54)
+    float tf = hd[0]; hd[0] = hd[i]; hd[i] = tf;
+    int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
+    heap_reheap(hd, hi, i);
+  }
+  for (int i = 0; i < k; ++i) {
+    oi[(size_t)i * sk] = hi[i];
+    if (od) od[(size_t)i * sk] = hd[i];
   }
 }
 
@@ -128,25 +153,148 @@ __global__ void __launch_bounds__(256) knn_kernel(int N, int M, int k, const flo
       // order depend on the heap's internal structure -> replay the reference heap (one lane).
       float* hd = reinterpret_cast<float*>(smem_u32 + (size_t)warps * npad) + (size_t)warp * 2 * k;
       int* hi = reinterpret_cast<int*>(hd + k);
-      if (lane == 0) {
-        for (int i = 0; i < k; ++i) { hd[i] = 1e10f; hi[i] = 0; }
-        for (int i = 0; i < N; ++i) {
-          float px = __ldg(P + i * 3), py = __ldg(P + i * 3 + 1), pz = __ldg(P + i * 3 + 2);
-          float d = MODE == 0 ? dist_direct(qx, qy, qz, px, py, pz) : dist_expand(qx, qy, qz, qn, px, py, pz);
-          if (d < hd[0]) { hd[0] = d; hi[0] = i; heap_reheap(hd, hi, k); }
-        }
-        for (int i = k - 1; i > 0; --i) {   // heap_sort (knn_cuda.cu:45-54)
-          float tf = hd[0]; hd[0] = hd[i]; hd[i] = tf;
-          int ti = hi[0]; hi[0] = hi[i]; hi[i] = ti;
-          heap_reheap(hd, hi, i);
-        }
-        for (int i = 0; i < k; ++i) {
-          oi[(size_t)i * sk] = hi[i];
-          if (od) od[(size_t)i * sk] = hd[i];
-        }
-      }
+      if (lane == 0) heap_replay<MODE>(P, N, k, qx, qy, qz, qn, hd, hi, oi, od, sk);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ordered kNN by SELECT + SORT (N <= 1024, k <= min(N, 128)): instead of k rounds of warp arg-min over all N keys, the
+// k-th smallest key is found by the early-exit radix search of knn_set_kernel (below), the k members are collected by
+// ballot / prefix popcount into a warp-private list of (key << 32 | index) words, and the list is rank-sorted (k words,
+// each lane counts the smaller words for its own) into the canonical ascending (distance, index) order -- the same output
+// as knn_kernel, bit for bit.  heap_ties (the mmdet3d op): a query with equal keys among its k members, a tie at the k-th
+// boundary or a distance >= 1e10 is replayed through the reference heap exactly as in knn_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int KPL, bool STAGED>
+__global__ void __launch_bounds__(256) knn_sel_kernel(int N, int M, int k, int qpw, const float* __restrict__ xyz,
+                                                      const float* __restrict__ qxyz, int* __restrict__ idx,
+                                                      float* __restrict__ dist2, long long sq, long long sk, int heap_ties) {
+  extern __shared__ unsigned long long sel_smem[];            // [8][kpad] member words, then [8][2k] heap scratch
+  __shared__ float4 cand[STAGED ? KPL * 32 : 1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int q0 = (blockIdx.x * 8 + warp) * qpw;
+  const int kpad = (k + 31) & ~31;
+  const float* P = xyz + (size_t)b * N * 3;
+  if (STAGED) {
+    for (int i = threadIdx.x; i < N; i += 256) cand[i] = make_float4(__ldg(P + i * 3), __ldg(P + i * 3 + 1), __ldg(P + i * 3 + 2), 0.f);
+    __syncthreads();
+  }
+  if (q0 >= M) return;
+  unsigned long long* sel = sel_smem + (size_t)warp * kpad;
+  float px[STAGED ? 1 : KPL], py[STAGED ? 1 : KPL], pz[STAGED ? 1 : KPL];
+  if (!STAGED) {
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const int i = lane + 32 * j;
+      px[j] = py[j] = pz[j] = 0.f;
+      if (i < N) { px[j] = __ldg(P + i * 3); py[j] = __ldg(P + i * 3 + 1); pz[j] = __ldg(P + i * 3 + 2); }
+    }
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int qend = min(q0 + qpw, M);
+  for (int q = q0; q < qend; ++q) {
+    const float* Q = qxyz + ((size_t)b * M + q) * 3;
+    const float qx = __ldg(Q), qy = __ldg(Q + 1), qz = __ldg(Q + 2);
+    const float qn = sqnorm3(qx, qy, qz);
+    uint32_t key[KPL];
+    uint32_t lmin = 0xffffffffu, lmax = 0u;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      key[j] = 0xffffffffu;
+      if (lane + 32 * j < N) {
+        float cx, cy, cz;
+        if (STAGED) { const float4 c = cand[lane + 32 * j]; cx = c.x; cy = c.y; cz = c.z; }
+        else { cx = px[j]; cy = py[j]; cz = pz[j]; }
+        key[j] = f32_to_ordered(MODE == 0 ? dist_direct(qx, qy, qz, cx, cy, cz) : dist_expand(qx, qy, qz, qn, cx, cy, cz));
+        lmin = min(lmin, key[j]);
+        lmax = max(lmax, key[j]);
+      }
+    }
+    const uint32_t kmin = __reduce_min_sync(FULL_MASK, lmin), kmax = __reduce_max_sync(FULL_MASK, lmax);
+    uint32_t T = kmin;
+    bool exact = false;
+    if (kmin != kmax) {
+      const int top = 31 - __clz(kmin ^ kmax);
+      T = top == 31 ? 0u : (kmin & ~((2u << top) - 1u));
+      for (int bit = top; bit >= 0; --bit) {
+        const uint32_t t = T | (1u << bit);
+        int c = 0;
+#pragma unroll
+        for (int j = 0; j < KPL; ++j) c += key[j] < t ? 1 : 0;
+        c = __reduce_add_sync(FULL_MASK, c);
+        if (c == k) { T = t; exact = true; break; }
+        if (c < k) T = t;
+      }
+    }
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < KPL; ++j) {
+      const bool in = key[j] < T;
+      const uint32_t bal = __ballot_sync(FULL_MASK, in);
+      if (in) sel[base + __popc(bal & lt_mask)] = ((unsigned long long)key[j] << 32) | (uint32_t)(lane + 32 * j);
+      base += __popc(bal);
+    }
+    if (!exact) {     // keys equal to the k-th smallest, in ascending index order, until k members
+#pragma unroll
+      for (int j = 0; j < KPL; ++j) {
+        const bool eq = key[j] == T && lane + 32 * j < N;
+        const uint32_t bal = __ballot_sync(FULL_MASK, eq);
+        const int pos = base + __popc(bal & lt_mask);
+        if (eq && pos < k) sel[pos] = ((unsigned long long)key[j] << 32) | (uint32_t)(lane + 32 * j);
+        base += __popc(bal);
+      }
+    }
+    const bool boundary_tie = base > k;          // more keys equal to the k-th one than slots left for them
+    __syncwarp();
+    int* oi = idx + (size_t)b * M * k + (size_t)q * sq;
+    float* od = dist2 ? dist2 + (size_t)b * M * k + (size_t)q * sq : nullptr;
+    bool bad = false;
+    for (int e = lane; e < k; e += 32) {
+      const unsigned long long v = sel[e];
+      int rank = 0;
+      bool dup = false;
+      for (int j = 0; j < k; ++j) {
+        const unsigned long long w = sel[j];
+        rank += w < v ? 1 : 0;
+        dup |= (j != e) && ((uint32_t)(w >> 32) == (uint32_t)(v >> 32));
+      }
+      const float dv = ordered_to_f32((uint32_t)(v >> 32));
+      bad |= dup || !(dv < 1e10f);
+      oi[(size_t)rank * sk] = (int)(uint32_t)v;
+      if (od) od[(size_t)rank * sk] = dv;
+    }
+    if (heap_ties) {
+      const bool slow = __any_sync(FULL_MASK, bad) || boundary_tie;
+      __syncwarp();
+      if (slow && lane == 0) {
+        float* hd = reinterpret_cast<float*>(sel_smem + (size_t)8 * kpad) + (size_t)warp * 2 * k;
+        heap_replay<MODE>(P, N, k, qx, qy, qz, qn, hd, reinterpret_cast<int*>(hd + k), oi, od, sk);
+      }
+    }
+    __syncwarp();      // the member list is reused by the next query
+  }
+}
+
+template <int MODE, int KPL, bool STAGED>
+static int knn_sel_launch(int b, int n, int m, int k, const float* xyz, const float* q, int* idx, float* dist2, long long sq,
+                          long long sk, int heap_ties, cudaStream_t st) {
+  const int qpw = m >= 64 ? 8 : (m >= 16 ? 2 : 1);
+  const int kpad = (k + 31) & ~31;
+  const size_t smem = (size_t)8 * kpad * 8 + (heap_ties ? (size_t)8 * 2 * k * 4 : 0);
+  knn_sel_kernel<MODE, KPL, STAGED><<<dim3(ceil_div(m, 8 * qpw), b), 256, smem, st>>>(n, m, k, qpw, xyz, q, idx, dist2, sq, sk,
+                                                                                      heap_ties);
+  return pcreid_launch_status();
+}
+
+template <int MODE>
+static int knn_sel_dispatch(int b, int n, int m, int k, const float* xyz, const float* q, int* idx, float* dist2, long long sq,
+                            long long sk, int heap_ties, cudaStream_t st) {
+  if (n <= 128) return knn_sel_launch<MODE, 4, false>(b, n, m, k, xyz, q, idx, dist2, sq, sk, heap_ties, st);
+  if (n <= 256) return knn_sel_launch<MODE, 8, false>(b, n, m, k, xyz, q, idx, dist2, sq, sk, heap_ties, st);
+  if (n <= 512) return knn_sel_launch<MODE, 16, true>(b, n, m, k, xyz, q, idx, dist2, sq, sk, heap_ties, st);
+  return knn_sel_launch<MODE, 32, true>(b, n, m, k, xyz, q, idx, dist2, sq, sk, heap_ties, st);
 }
 
 static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, const float* qxyz, int* idx,
@@ -155,6 +303,10 @@ static int knn_launch(int mode, int b, int n, int m, int k, const float* xyz, co
   if (n <= 0 || !xyz || !qxyz || !idx) return PCREID_ERR_ARG;
   if (heap_ties && k > 100) return PCREID_ERR_ARG;   // reference limit (knn.py:30)
   if (!heap_ties && k > n) return PCREID_ERR_ARG;
+  static const bool use_rounds = getenv("PCREID_KNN_ORDERED") && !strcmp(getenv("PCREID_KNN_ORDERED"), "rounds");   // A/B knob
+  if (!use_rounds && n <= 1024 && k <= n && k <= 128 && b <= 65535)
+    return mode == 0 ? knn_sel_dispatch<0>(b, n, m, k, xyz, qxyz, idx, dist2, sq, sk, heap_ties, st)
+                     : knn_sel_dispatch<1>(b, n, m, k, xyz, qxyz, idx, dist2, sq, sk, heap_ties, st);
   int npad = (n + 31) & ~31;
   int warps = 8;
   const size_t budget = 200 * 1024;
