@@ -2,9 +2,12 @@
 (mmdet3d/ops/pointnet_modules/point_sa_module.py:164-208 BasePointSAModule.forward, point_fp_module.py:39-79
 PointFPModule.forward) as plain torch over the op oracle (oracle/ops_oracle.py).
 
-PARITY UNPINNED for the module glue: the reference modules import mmcv (ConvModule, BaseModule), which is absent here,
-so they cannot be executed; the ops underneath (FPS, ball query, grouping, three_nn, three_interpolate) ARE pinned
-against the reference .cu files, and the glue is restated line by line: sample -> gather -> for each scale
+PINNED (tests/test_pointnet_modules_pinned.py, wherever /root/reference exists): bit-exact against the reference's own module
+files imported unmodified by path (oracle/ref_loader.load_pointnet_modules) -- BasePointSAModule / PointSAModuleMSG /
+PointSAModule / build_sa_module, PointFPModule, QueryAndGroup / GroupAll, Points_Sampler / calc_square_dist -- run on CPU with
+(a) the compiled CUDA ops replaced by oracle/ops_oracle.py, which is pinned to the reference .cu files on the GPU box, and
+(b) mmcv's ConvModule (a third-party dependency that is absent here) replaced by a torch stand-in with mmcv's documented
+conv -> norm -> activation order.  The glue restated here: sample -> gather -> for each scale
 QueryAndGroup (group_points.py:49-83) -> Conv2d 1x1 / BatchNorm2d (eval) / ReLU -> max (or mean) over the samples -> concat;
 samplers D-FPS / F-FPS / FS (furthest_point_sample/points_sampler.py:67-157, utils.py:4-31).
 """
@@ -91,8 +94,8 @@ def _pool(x, pool_mod):
 
 
 def sa_module_msg(sd, num_point, radii, sample_nums, points_xyz, features=None, indices=None, use_xyz=True, normalize_xyz=False,
-                  dilated_group=False, prefix="", pool_mod="max", fps_mod=("D-FPS",), fps_sample_range_list=(-1,)):
-    """-> new_xyz, new_features, indices."""
+                  dilated_group=False, prefix="", pool_mod="max", fps_mod=("D-FPS",), fps_sample_range_list=(-1,), sqdist=None):
+    """-> new_xyz, new_features, indices.  sqdist: distance function of the F-FPS / FS samplers (see points_sampler)."""
     xyz_flipped = points_xyz.transpose(1, 2).contiguous()
     if num_point is None:
         g = xyz_flipped.unsqueeze(2)
@@ -102,7 +105,7 @@ def sa_module_msg(sd, num_point, radii, sample_nums, points_xyz, features=None, 
         return None, _pool(x, pool_mod), None
     if indices is None:
         npts = [num_point] if isinstance(num_point, int) else list(num_point)
-        indices = points_sampler(points_xyz, features, npts, fps_mod, fps_sample_range_list)
+        indices = points_sampler(points_xyz, features, npts, fps_mod, fps_sample_range_list, sqdist=sqdist)
     new_xyz = OP.gather_points(xyz_flipped, indices).transpose(1, 2).contiguous()
     outs = []
     for i in range(len(radii)):

@@ -85,3 +85,158 @@ def load():
         cross_lin_attn=at.cross_lin_attn,
     )
     return ns
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# mmdet3d PointNet++ module family: the reference's own module glue on CPU
+# ------------------------------------------------------------------------------------------------------------------
+_OPS = os.path.join(REF_ROOT, "mmdet3d", "ops")
+_OPS_PKG = "_pcreid_ref_ops"
+
+
+def pointnet_modules_available():
+    return os.path.isdir(os.path.join(_OPS, "pointnet_modules"))
+
+
+def load_pointnet_modules():
+    """Loads the *unmodified* reference files ops/pointnet_modules/{builder,point_sa_module,point_fp_module}.py,
+    ops/group_points/group_points.py (QueryAndGroup, GroupAll) and ops/furthest_point_sample/{points_sampler,utils}.py by path
+    and runs their Python glue on CPU.  What is NOT the reference's code underneath, and why:
+      * the compiled CUDA ops (`*_ext` pybind modules: FPS, ball query, grouping, gather, three_nn, three_interpolate) are
+        replaced by the CPU restatements of oracle/ops_oracle.py, themselves pinned bit-exact against the reference .cu
+        files on the GPU box (tests/test_gpu_ops.py);
+      * mmcv is absent: `mmcv.cnn.ConvModule` is a torch stand-in with mmcv's documented order conv -> norm -> activation and
+        its `conv` / `bn` attribute names, `mmcv.runner.BaseModule` is `nn.Module` + a stored `init_cfg`, `force_fp32` an identity decorator,
+        `mmcv.utils.Registry` a dict-backed registry; PAConv is a placeholder class (never instantiated).
+    Nothing is written into the reference tree; the temporary `mmcv` / `mmdet3d` entries in sys.modules are removed again."""
+    import torch
+    from torch import nn
+    from . import ops_oracle as OP
+
+    class ConvModule(nn.Module):
+        def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, conv_cfg=None, norm_cfg=None,
+                     act_cfg=dict(type="ReLU"), bias="auto", **kw):
+            super().__init__()
+            conv = {"Conv2d": nn.Conv2d, "Conv1d": nn.Conv1d}[(conv_cfg or dict(type="Conv2d"))["type"]]
+            self.with_norm, self.with_activation = norm_cfg is not None, act_cfg is not None
+            if bias == "auto":
+                bias = not self.with_norm
+            self.conv = conv(in_channels, out_channels, kernel_size, stride=stride, bias=bias)
+            if self.with_norm:
+                self.bn = {"BN2d": nn.BatchNorm2d, "BN1d": nn.BatchNorm1d, "BN": nn.BatchNorm2d}[norm_cfg["type"]](out_channels)
+            if self.with_activation:
+                self.activate = nn.ReLU(inplace=True)
+
+        def forward(self, x):
+            x = self.conv(x)
+            if self.with_norm:
+                x = self.bn(x)
+            return self.activate(x) if self.with_activation else x
+
+    class Registry:
+        def __init__(self, name):
+            self.name, self.module_dict = name, {}
+
+        def register_module(self, name=None, **kw):
+            def deco(cls):
+                self.module_dict[name or cls.__name__] = cls
+                return cls
+            return deco
+
+        def get(self, key):
+            return self.module_dict.get(key)
+
+        def __contains__(self, key):
+            return key in self.module_dict
+
+    class BaseModule(nn.Module):          # mmcv.runner.BaseModule: nn.Module + an init_cfg it only stores
+        def __init__(self, init_cfg=None):
+            super().__init__()
+            self.init_cfg = init_cfg
+
+    def force_fp32(*a, **k):
+        return lambda fn: fn
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    def load(full, path, package=None):
+        spec = importlib.util.spec_from_file_location(full, path)
+        m = importlib.util.module_from_spec(spec)
+        if package:
+            m.__package__ = package
+        sys.modules[full] = m
+        spec.loader.exec_module(m)
+        return m
+
+    saved = {k: sys.modules.get(k) for k in ("mmcv", "mmcv.cnn", "mmcv.runner", "mmcv.utils", "mmdet3d", "mmdet3d.ops")}
+    created = []
+    try:
+        sys.modules["mmcv"] = mod("mmcv")
+        sys.modules["mmcv.cnn"] = mod("mmcv.cnn", ConvModule=ConvModule)
+        sys.modules["mmcv.runner"] = mod("mmcv.runner", BaseModule=BaseModule, force_fp32=force_fp32)
+        sys.modules["mmcv.utils"] = mod("mmcv.utils", Registry=Registry)
+
+        def pkg(name, path):
+            p = types.ModuleType(name)
+            p.__path__ = [path]
+            sys.modules[name] = p
+            created.append(name)
+            return p
+
+        pkg(_OPS_PKG, _OPS)
+        i32 = lambda t: t.to(torch.int32)
+        # the compiled ops -> CPU restatements with the reference wrappers' signatures
+        bq = pkg(f"{_OPS_PKG}.ball_query", os.path.join(_OPS, "ball_query"))
+        bq.ball_query = lambda mn, mx, ns, xyz, cen: i32(OP.ball_query(mn, mx, ns, xyz, cen))
+        kn = pkg(f"{_OPS_PKG}.knn", os.path.join(_OPS, "knn"))
+        kn.knn = lambda k, xyz, cen=None, transposed=False: i32(OP.knn(k, xyz, cen, transposed))
+        gp = pkg(f"{_OPS_PKG}.group_points", os.path.join(_OPS, "group_points"))
+        sys.modules[f"{_OPS_PKG}.group_points.group_points_ext"] = mod("group_points_ext")
+        created.append(f"{_OPS_PKG}.group_points.group_points_ext")
+        gpm = load(f"{_OPS_PKG}.group_points.group_points", os.path.join(_OPS, "group_points", "group_points.py"),
+                   f"{_OPS_PKG}.group_points")
+        created.append(f"{_OPS_PKG}.group_points.group_points")
+        gpm.grouping_operation = lambda feats, idx: OP.grouping_operation(feats, idx)     # module global used by QueryAndGroup
+        fps = pkg(f"{_OPS_PKG}.furthest_point_sample", os.path.join(_OPS, "furthest_point_sample"))
+        sys.modules[f"{_OPS_PKG}.furthest_point_sample.furthest_point_sample"] = mod(
+            "furthest_point_sample", furthest_point_sample=lambda p, n: i32(OP.furthest_point_sample(p, n)),
+            furthest_point_sample_with_dist=lambda d, n: i32(OP.furthest_point_sample_with_dist(d, n)))
+        created.append(f"{_OPS_PKG}.furthest_point_sample.furthest_point_sample")
+        utils = load(f"{_OPS_PKG}.furthest_point_sample.utils", os.path.join(_OPS, "furthest_point_sample", "utils.py"),
+                     f"{_OPS_PKG}.furthest_point_sample")
+        created.append(f"{_OPS_PKG}.furthest_point_sample.utils")
+        ps = load(f"{_OPS_PKG}.furthest_point_sample.points_sampler", os.path.join(_OPS, "furthest_point_sample", "points_sampler.py"),
+                  f"{_OPS_PKG}.furthest_point_sample")
+        created.append(f"{_OPS_PKG}.furthest_point_sample.points_sampler")
+
+        class PAConv(nn.Module):          # placeholder: only isinstance-checked by the SA module
+            pass
+
+        gather = lambda feats, idx: OP.gather_points(feats, idx)
+        sys.modules["mmdet3d"] = mod("mmdet3d")
+        sys.modules["mmdet3d.ops"] = mod(
+            "mmdet3d.ops", GroupAll=gpm.GroupAll, QueryAndGroup=gpm.QueryAndGroup, PAConv=PAConv, Points_Sampler=ps.Points_Sampler,
+            gather_points=gather, three_nn=lambda t, s: OP.three_nn(t, s),
+            three_interpolate=lambda f, i, w: OP.three_interpolate(f, i, w))
+        pm = pkg(f"{_OPS_PKG}.pointnet_modules", os.path.join(_OPS, "pointnet_modules"))
+        builder = load(f"{_OPS_PKG}.pointnet_modules.builder", os.path.join(_OPS, "pointnet_modules", "builder.py"),
+                       f"{_OPS_PKG}.pointnet_modules")
+        sa = load(f"{_OPS_PKG}.pointnet_modules.point_sa_module", os.path.join(_OPS, "pointnet_modules", "point_sa_module.py"),
+                  f"{_OPS_PKG}.pointnet_modules")
+        fp = load(f"{_OPS_PKG}.pointnet_modules.point_fp_module", os.path.join(_OPS, "pointnet_modules", "point_fp_module.py"),
+                  f"{_OPS_PKG}.pointnet_modules")
+        created += [f"{_OPS_PKG}.pointnet_modules.builder", f"{_OPS_PKG}.pointnet_modules.point_sa_module",
+                    f"{_OPS_PKG}.pointnet_modules.point_fp_module"]
+        return types.SimpleNamespace(PointSAModuleMSG=sa.PointSAModuleMSG, PointSAModule=sa.PointSAModule,
+                                     PointFPModule=fp.PointFPModule, build_sa_module=builder.build_sa_module,
+                                     Points_Sampler=ps.Points_Sampler, calc_square_dist=utils.calc_square_dist,
+                                     QueryAndGroup=gpm.QueryAndGroup, GroupAll=gpm.GroupAll)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
