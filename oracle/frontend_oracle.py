@@ -7,8 +7,12 @@ Follows, line by line:
   mmdet3d/core/bbox/structures/depth_box3d.py:256-282   depth -> LiDAR frame for points and boxes
   mmdet3d/core/bbox/structures/box_3d_mode.py:125-148   DEPTH -> LIDAR box conversion (rt_mat, size swap)
   mmdet3d/ops/roiaware_pool3d/src/points_in_boxes_cuda.cu:24-49, 79-105   the in-box test
-PARITY UNPINNED against the reference python (mmcv / pytorch3d are not importable here); the in-box test is pinned on
-the GPU box against the reference's own points_in_boxes_cuda.cu when oracle/_ref/libref_pib.so could be built."""
+PINNED (tests/test_frontend_pinned.py, wherever /root/reference exists) against the reference's own pc_utils.py and
+core/bbox/structures/*.py imported unmodified by path (oracle/ref_loader.load_frontend): box origin / frame conversion and
+crop order exactly, centred coordinates within 2e-5 (fp32 torch there, fp64 numpy here), sampling with the same torch.randint
+draws.  Stand-ins there: pytorch3d (absent; Pointclouds.points_padded and axis_angle_to_matrix restated from pytorch3d 0.7)
+and the compiled points_in_boxes_batch op (-> pib_kernel_lidar below, which is pinned on the GPU box against the
+reference's own points_in_boxes_cuda.cu when oracle/_ref/libref_pib.so could be built)."""
 import ctypes
 import os
 
@@ -19,15 +23,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 f32, f64 = np.float32, np.float64
 
 
-def points_in_boxes(bboxes, pts):
-    """-> bool (B, P), plus the margin (B, P) = distance of the decisive coordinate to the nearest box face (for
-    margin-aware comparisons: cosf / sinf differ in the last bit between libm and CUDA)."""
-    b = np.asarray(bboxes, f32)
-    p = np.asarray(pts, f32)[:, :3]
-    zb = (b[:, 2] + b[:, 5] * f32(-0.5)).astype(f32)                       # base_box3d.py:61-64
-    cx, cy = b[:, 1], -b[:, 0]                                             # box_3d_mode.py:127 rt_mat
-    w, l, h, rz = b[:, 4], b[:, 3], b[:, 5], b[:, 6]                        # sizes swapped (y_size, x_size, z_size)
-    xl, yl, zl = p[:, 1], -p[:, 0], p[:, 2]                                # depth_box3d.py:270-272
+def pib_kernel_lidar(boxes_lidar, pts_lidar):
+    """points_in_boxes_cuda.cu:24-49, 79-105 (check_pt_in_box3d + lidar_to_local_coords) on boxes (T, 7) = (x, y, z_bottom, w, l,
+    h, rz) and points (M, 3), both already in the LiDAR frame -> (inside bool (T, M), margin (T, M))."""
+    b = np.asarray(boxes_lidar, f32)
+    p = np.asarray(pts_lidar, f32)
+    cx, cy, zb, w, l, h, rz = (b[:, i] for i in range(7))
+    xl, yl, zl = p[:, 0], p[:, 1], p[:, 2]
     hh = h.astype(f64) / 2.0
     cz = (zb.astype(f64) + hh).astype(f32)                                  # points_in_boxes_cuda.cu:42
     dz = np.abs((zl[None, :] - cz[:, None]).astype(f32)).astype(f64)
@@ -42,6 +44,22 @@ def points_in_boxes(bboxes, pts):
     inside = (dz <= hh[:, None]) & (lx > -hl[:, None]) & (lx < hl[:, None]) & (ly > -hw[:, None]) & (ly < hw[:, None])
     margin = np.minimum(np.minimum(np.abs(hh[:, None] - dz), np.abs(hl[:, None] - np.abs(lx))), np.abs(hw[:, None] - np.abs(ly)))
     return inside, margin
+
+
+def depth_boxes_to_lidar(bboxes):
+    """DepthInstance3DBoxes(bboxes, origin=(0.5, 0.5, 0.5)).convert_to(LIDAR).tensor (base_box3d.py:61-64,
+    box_3d_mode.py:125-148): (x, y, z_centre, dx, dy, dz, yaw) -> (y, -x, z_bottom, dy, dx, dz, yaw)."""
+    b = np.asarray(bboxes, f32)
+    zb = (b[:, 2] + b[:, 5] * f32(-0.5)).astype(f32)                       # base_box3d.py:61-64
+    return np.stack([b[:, 1], -b[:, 0], zb, b[:, 4], b[:, 3], b[:, 5], b[:, 6]], 1).astype(f32)
+
+
+def points_in_boxes(bboxes, pts):
+    """-> bool (B, P), plus the margin (B, P) = distance of the decisive coordinate to the nearest box face (for
+    margin-aware comparisons: cosf / sinf differ in the last bit between libm and CUDA)."""
+    p = np.asarray(pts, f32)[:, :3]
+    pl = np.stack([p[:, 1], -p[:, 0], p[:, 2]], 1)                          # depth_box3d.py:270-272
+    return pib_kernel_lidar(depth_boxes_to_lidar(bboxes), pl)
 
 
 def crop_center_resample(bboxes, pts, subsample_number, sample_rank, inside=None):

@@ -240,3 +240,112 @@ def load_pointnet_modules():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# crop -> centre -> resample front-end: the reference's own pc_utils.py + box structures on CPU
+# ------------------------------------------------------------------------------------------------------------------
+_STRUCTS = os.path.join(REF_ROOT, "mmdet3d", "core", "bbox", "structures")
+_PC_UTILS = os.path.join(_MODELS, "trackers", "deprecated", "pc_utils.py")
+
+
+def frontend_available():
+    return os.path.isdir(_STRUCTS) and os.path.exists(_PC_UTILS)
+
+
+def load_frontend():
+    """Loads the *unmodified* reference files models/trackers/deprecated/pc_utils.py (interpolate_per_frame,
+    get_input_batch, get_affine_torch) and core/bbox/structures/{base_box3d,utils,depth_box3d,lidar_box3d,cam_box3d,
+    box_3d_mode}.py (DepthInstance3DBoxes, Box3DMode.convert) by path and runs them on CPU.  Stand-ins, none of which touches
+    the reference tree:
+      * pytorch3d (absent; the reference pins no version): `Pointclouds(list).points_padded()` = zero padding to the longest
+        cloud, `transforms.axis_angle_to_matrix` = quaternion_to_matrix(axis_angle_to_quaternion(.)) as published in
+        pytorch3d 0.7 (rotation_conversions.py);
+      * the compiled ops: `mmdet3d.ops.points_in_boxes_batch` -> oracle.frontend_oracle.pib_kernel_lidar (restatement of
+        points_in_boxes_cuda.cu, pinned against that .cu on the GPU box); iou3d / roiaware extensions and BasePoints are
+        placeholders (never called on this path)."""
+    import importlib
+    import torch
+    from . import frontend_oracle as FO
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    class Pointclouds:
+        def __init__(self, points):
+            self._p = list(points)
+
+        def points_padded(self):
+            n = max([x.shape[0] for x in self._p] + [0])
+            out = torch.zeros((len(self._p), n, 3), dtype=torch.float32)
+            for i, x in enumerate(self._p):
+                out[i, :x.shape[0]] = x
+            return out
+
+    def quaternion_to_matrix(quaternions):
+        r, i, j, k = torch.unbind(quaternions, -1)
+        two_s = 2.0 / (quaternions * quaternions).sum(-1)
+        o = torch.stack((1 - two_s * (j * j + k * k), two_s * (i * j - k * r), two_s * (i * k + j * r),
+                         two_s * (i * j + k * r), 1 - two_s * (i * i + k * k), two_s * (j * k - i * r),
+                         two_s * (i * k - j * r), two_s * (j * k + i * r), 1 - two_s * (i * i + j * j)), -1)
+        return o.reshape(quaternions.shape[:-1] + (3, 3))
+
+    def axis_angle_to_quaternion(axis_angle):
+        angles = torch.norm(axis_angle, p=2, dim=-1, keepdim=True)
+        half_angles = angles * 0.5
+        small = angles.abs() < 1e-6
+        k = torch.empty_like(angles)
+        k[~small] = torch.sin(half_angles[~small]) / angles[~small]
+        k[small] = 0.5 - (angles[small] * angles[small]) / 48
+        return torch.cat([torch.cos(half_angles), axis_angle * k], dim=-1)
+
+    def points_in_boxes_batch(points, boxes):
+        assert points.shape[0] == boxes.shape[0] == 1
+        inside, _ = FO.pib_kernel_lidar(boxes[0].numpy(), points[0].numpy())
+        return torch.from_numpy(inside.T.astype("int32")).unsqueeze(0)             # (B, M, T)
+
+    names = ("pytorch3d", "pytorch3d.transforms", "pytorch3d.structures", "pytorch3d.structures.pointclouds", "mmdet3d",
+             "mmdet3d.core", "mmdet3d.core.points", "mmdet3d.ops", "mmdet3d.ops.iou3d", "mmdet3d.ops.roiaware_pool3d",
+             "nuscenes", "nuscenes.utils", "nuscenes.utils.geometry_utils", "torchvision", "torchvision.transforms")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        sys.modules["pytorch3d"] = mod("pytorch3d")
+        sys.modules["pytorch3d.transforms"] = mod("pytorch3d.transforms", quaternion_to_matrix=quaternion_to_matrix,
+                                                  axis_angle_to_matrix=lambda aa: quaternion_to_matrix(axis_angle_to_quaternion(aa)))
+        sys.modules["pytorch3d"].transforms = sys.modules["pytorch3d.transforms"]
+        sys.modules["pytorch3d.structures"] = mod("pytorch3d.structures")
+        sys.modules["pytorch3d.structures.pointclouds"] = mod("pytorch3d.structures.pointclouds", Pointclouds=Pointclouds)
+        # module-level imports of the image-crop half of pc_utils.py (lines 112-122), unused on this path
+        for n, attrs in (("nuscenes", {}), ("nuscenes.utils", {}), ("nuscenes.utils.geometry_utils", dict(BoxVisibility=type("BoxVisibility", (), dict(ANY=1, ALL=0, NONE=2))))):
+            sys.modules[n] = mod(n, **attrs)
+        try:
+            import torchvision.transforms  # noqa: F401
+        except Exception:
+            sys.modules["torchvision"] = mod("torchvision")
+            sys.modules["torchvision.transforms"] = mod("torchvision.transforms", ToTensor=None)
+        sys.modules["mmdet3d"] = mod("mmdet3d")
+        sys.modules["mmdet3d.core.points"] = mod("mmdet3d.core.points", BasePoints=type("BasePoints", (), {}))
+        sys.modules["mmdet3d.ops"] = mod("mmdet3d.ops", points_in_boxes_batch=points_in_boxes_batch)
+        sys.modules["mmdet3d.ops.iou3d"] = mod("mmdet3d.ops.iou3d", iou3d_cuda=None)
+        sys.modules["mmdet3d.ops.roiaware_pool3d"] = mod("mmdet3d.ops.roiaware_pool3d", points_in_boxes_gpu=None)
+        pkg = "_pcreid_ref_structs"
+        if pkg not in sys.modules:
+            p = types.ModuleType(pkg)
+            p.__path__ = [_STRUCTS]                 # a bare package: the reference __init__.py (which pulls in mmcv) is not run
+            sys.modules[pkg] = p
+        depth = importlib.import_module(f"{pkg}.depth_box3d")
+        b3d = importlib.import_module(f"{pkg}.box_3d_mode")
+        sys.modules["mmdet3d.core"] = mod("mmdet3d.core", DepthInstance3DBoxes=depth.DepthInstance3DBoxes)
+        spec = importlib.util.spec_from_file_location("_pcreid_ref_pc_utils", _PC_UTILS)
+        pcu = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(pcu)
+        return types.SimpleNamespace(pc_utils=pcu, DepthInstance3DBoxes=depth.DepthInstance3DBoxes, Box3DMode=b3d.Box3DMode,
+                                     interpolate_per_frame=pcu.interpolate_per_frame, get_input_batch=pcu.get_input_batch)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
