@@ -349,3 +349,65 @@ def load_frontend():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# all-pairs driver + feature bank: the reference's own deprecated tracker files on CPU
+# ------------------------------------------------------------------------------------------------------------------
+_TRK = os.path.join(_MODELS, "trackers", "deprecated")
+
+
+def tracker_available():
+    return os.path.exists(os.path.join(_TRK, "tracking_point_reid.py")) and os.path.exists(os.path.join(_TRK, "tracking_feature_set.py"))
+
+
+def load_tracker():
+    """Loads the *unmodified* reference files trackers/deprecated/tracking_point_reid.py (get_labels_to_compare,
+    PointReidentifier) and tracking_feature_set.py (PointFeatureSet) by path.  Stand-ins: the mmcv-backed `TRACKERS` registry and
+    `builder.build_tracker` of mmdet3d.models (a dict-backed registry), `mmdet3d.models.trackers.pc_utils` (placeholders: the
+    crop helpers are pinned separately by load_frontend) and `mmdet3d.datasets.utils.MatchingEval` (a placeholder, unused)."""
+    reg = {}
+
+    class _Registry:
+        def register_module(self, name=None, **kw):
+            def deco(cls):
+                reg[name or cls.__name__] = cls
+                return cls
+            return deco
+
+    def build_tracker(cfg):
+        cfg = dict(cfg)
+        return reg[cfg.pop("type")](**cfg)
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    names = ("mmdet3d", "mmdet3d.models", "mmdet3d.models.trackers", "mmdet3d.models.trackers.pc_utils", "mmdet3d.datasets",
+             "mmdet3d.datasets.utils")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        builder = mod("mmdet3d.models.builder", build_tracker=build_tracker)
+        sys.modules["mmdet3d"] = mod("mmdet3d")
+        sys.modules["mmdet3d.models"] = mod("mmdet3d.models", TRACKERS=_Registry(), builder=builder)
+        sys.modules["mmdet3d.models.trackers"] = mod("mmdet3d.models.trackers")
+        sys.modules["mmdet3d.models.trackers.pc_utils"] = mod("mmdet3d.models.trackers.pc_utils", get_crops_per_image=None,
+                                                              interpolate_per_frame=None, get_input_batch=None)
+        sys.modules["mmdet3d.datasets"] = mod("mmdet3d.datasets")
+        sys.modules["mmdet3d.datasets.utils"] = mod("mmdet3d.datasets.utils", MatchingEval=None)
+        out = {}
+        for name in ("tracking_feature_set", "tracking_point_reid"):
+            spec = importlib.util.spec_from_file_location(f"_pcreid_ref_{name}", os.path.join(_TRK, name + ".py"))
+            m = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(m)
+            out[name] = m
+        return types.SimpleNamespace(get_labels_to_compare=out["tracking_point_reid"].get_labels_to_compare,
+                                     PointReidentifier=out["tracking_point_reid"].PointReidentifier,
+                                     PointFeatureSet=out["tracking_feature_set"].PointFeatureSet)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
