@@ -5,9 +5,10 @@ Only usable where ``/root/reference`` exists (the build container).  It is used 
   (2) generate the committed golden vectors under ``tests/golden/`` (``oracle/make_golden.py``).
 Nothing in the product package, ``bench.py`` or the ``-m gpu`` tests may import this file.
 
-The reference's ``mmdet3d/models/ReIDNet.py`` cannot be imported (needs mmcv / mmdet / pytorch3d,
-SURVEY.md section 8c) but every leaf file holding the arithmetic of the path can, with three
-non-invasive shims, none of which touches the reference tree:
+``load()`` imports every leaf file holding the arithmetic of the path; ``load_reidnet()`` adds
+``mmdet3d/models/ReIDNet.py`` itself (the real ReIDNet / ImageReIDNet classes; mmcv / mmdet / pytorch3d are
+absent, so their registry / base class / chamfer loss are stand-ins -- see its docstring).  The leaf files
+need three non-invasive shims, none of which touches the reference tree:
   * ``fractions.gcd`` (removed in py3.9) is aliased to ``math.gcd`` before ``lanegcn_nets.py`` loads
     (``lanegcn_nets.py:6``);
   * the module-global ``torch`` of ``dgcnn_orig`` / ``attention`` is replaced by a proxy whose
@@ -405,6 +406,64 @@ def load_tracker():
         return types.SimpleNamespace(get_labels_to_compare=out["tracking_point_reid"].get_labels_to_compare,
                                      PointReidentifier=out["tracking_point_reid"].PointReidentifier,
                                      PointFeatureSet=out["tracking_feature_set"].PointFeatureSet)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the reference's ReIDNet / ImageReIDNet classes themselves (mmdet3d/models/ReIDNet.py), on CPU
+# ------------------------------------------------------------------------------------------------------------------
+def load_reidnet():
+    """Loads the *unmodified* reference file mmdet3d/models/ReIDNet.py by path (after load(), which provides the leaf modules of
+    its relative imports under the fake parent package) and returns its classes: ReIDNet, ReIDNetCosine, ImageReIDNet and the
+    module factory (module_obj, build_module, build_sequential).  Stand-ins for what is absent here, none of which carries
+    arithmetic of the path:
+      * `mmdet3d.models.FUSIONMODELS` (an mmcv Registry)  -> a dict-backed registry with `register_module()`;
+      * `mmdet.models.BaseDetector`                      -> `nn.Module` (the reference only inherits forward dispatch from it);
+      * `pytorch3d.loss.chamfer_distance`                -> a placeholder (training-only shape loss);
+      * `transformers` is installed and imported for real (HuggingFace checkpoints are NOT downloaded: ImageReIDNet's
+        `get_image_model` must be monkey-patched by the caller)."""
+    import torch
+    from torch import nn
+    ns = load()
+
+    class _Registry:
+        def __init__(self):
+            self.module_dict = {}
+
+        def register_module(self, name=None, **kw):
+            def deco(cls):
+                self.module_dict[name or cls.__name__] = cls
+                return cls
+            return deco
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    names = ("mmdet3d", "mmdet3d.models", "mmdet", "mmdet.models", "pytorch3d", "pytorch3d.loss")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        reg = _Registry()
+        sys.modules["mmdet3d"] = mod("mmdet3d")
+        sys.modules["mmdet3d.models"] = mod("mmdet3d.models", FUSIONMODELS=reg)
+        sys.modules["mmdet"] = mod("mmdet")
+        sys.modules["mmdet.models"] = mod("mmdet.models", BaseDetector=nn.Module)
+        sys.modules["pytorch3d"] = mod("pytorch3d")
+        sys.modules["pytorch3d.loss"] = mod("pytorch3d.loss", chamfer_distance=None)
+        m = _load("ReIDNet")
+        proxy = _TorchProxy(torch)
+        m.torch = proxy                   # torch.device('cuda') literals -> CPU, as for dgcnn_orig / attention
+        ns.ReIDNet_module = m
+        ns.ReIDNet, ns.ReIDNetCosine, ns.ImageReIDNet = m.ReIDNet, m.ReIDNetCosine, m.ImageReIDNet
+        ns.module_obj, ns.build_module, ns.build_sequential = m.module_obj, m.build_module, m.build_sequential
+        ns.FUSIONMODELS = reg
+        return ns
     finally:
         for k, v in saved.items():
             if v is None:
