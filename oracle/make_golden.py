@@ -8,9 +8,9 @@ the CUDA path on machines where the reference tree is absent (the GPU box).  Wei
 modules' default init under torch.manual_seed(66) (reference `seed`, reidentification_runtime.py:16)
 followed by oracle.reid_oracle.perturb_norm_state (deterministic de-trivialisation of norm statistics);
 the product's modules reproduce them bit-for-bit from the same seed (asserted by a checksum).
-The only non-reference code on the path is the ReIDNet glue (ReIDNet.py:311-332, 231-247, 526-534,
-444-462), which cannot be imported (mmcv / mmdet / pytorch3d absent) and is restated below on top of
-the reference's own corss_attention / LinearRes / nn.Linear modules.
+The ReIDNet glue (ReIDNet.py:311-332, 231-247, 526-534, 444-462) is restated below on top of the reference's own
+corss_attention / LinearRes / nn.Linear modules; tests/test_reidnet_pinned.py verifies that the committed vectors are the
+outputs of the reference's real ReIDNet class (imported by oracle/ref_loader.load_reidnet) on the stored inputs.
 """
 import os
 import sys
