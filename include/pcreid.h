@@ -35,6 +35,11 @@ int pcreid_fps(int b, int n, int m, const float* xyz, float* temp, int* idx, voi
 /* replaces furthest_point_sampling_with_dist_kernel_launcher (same file :333-400): dist (b,n,n). */
 int pcreid_fps_with_dist(int b, int n, int m, const float* dist, float* temp, int* idx, void* stream);
 int pcreid_fps_block_size(int n); /* host helper: opt_n_threads(n), same file :11-15 */
+/* replaces the torch-path farthest_point_sample (models/pointnet2_utils.py:116-137; a Python loop of npoint steps over
+ * index / sub / pow / sum / masked assignment / max there), the SA sampling with sampling="FPS": idx[b,0] = start[b] (the
+ * reference draws it with torch.randint on the host), distance (dx*dx + dy*dy) + dz*dz without contraction, running minimum
+ * initialised to 1e10, arg-max with the lowest index among tied maxima (torch.max on the CPU).  idx (b,m) int32. */
+int pcreid_fps_torch(int b, int n, int m, const float* xyz, const int* start, int* idx, void* stream);
 /* replaces calc_square_dist (ops/furthest_point_sample/utils.py:4-31; torch sum / matmul / sqrt there): the (b,n,m) feature
  * distance matrix the F-FPS / FS samplers (points_sampler.py:124-157) pass to furthest_point_sample_with_dist.
  * a (b,n,c), b (b,m,c) point-major; out[b,i,j] = |a_i|^2 + |b_j|^2 - 2 a_i.b_j (fma chains over c ascending);

@@ -45,6 +45,7 @@ _SIGS = {
     "pcreid_fps": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_fps_with_dist": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_fps_block_size": [c_int],
+    "pcreid_fps_torch": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pairwise_sqdist": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp],
     "pcreid_knn": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],
     "pcreid_knn_t": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp],

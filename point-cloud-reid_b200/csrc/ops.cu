@@ -29,6 +29,12 @@ __device__ __forceinline__ float dist_direct(float ax, float ay, float az, float
   t = __fmaf_rn(dx, dx, t);
   return __fmaf_rn(dz, dz, t);
 }
+// torch-path FPS (models/pointnet2_utils.py:116-137): dist = torch.sum((xyz - centroid) ** 2, -1) = (dx*dx + dy*dy) + dz*dz,
+// separate multiplies and adds (no contraction)
+__device__ __forceinline__ float dist_sum_sq(float ax, float ay, float az, float bx, float by, float bz) {
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
 // mode 1: torch path square_distance (models/pointnet2_utils.py:169-188):
 //   m = q.p as a sequential fma chain, |v|^2 = (x*x + y*y) + z*z, d = (-2*m + |q|^2) + |p|^2
 __device__ __forceinline__ float sqnorm3(float x, float y, float z) {
@@ -546,12 +552,15 @@ __device__ __forceinline__ int fps_untie32(uint32_t t, int log2bs) {
 
 template <int PPT, int MAXT>
 __global__ void __launch_bounds__(MAXT) fps_kernel(int N, int M, int log2bs, const float* __restrict__ data,
-                                                   float* __restrict__ temp, int* __restrict__ idxs, int with_dist) {
+                                                   float* __restrict__ temp, int* __restrict__ idxs, int with_dist,
+                                                   const int* __restrict__ start) {
+  // with_dist: 0 = xyz, the op's distance fma(dz,dz,fma(dx,dx,dy*dy)); 1 = precomputed (b,n,n) distances; 2 = xyz, the torch
+  // path's (dx*dx + dy*dy) + dz*dz (then log2bs = 0: ties go to the lowest index, and the first sample is start[b])
   if (M <= 0) return;
   __shared__ uint32_t s_hi[2][32], s_lo[2][32];
   const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
   const int b = blockIdx.x;
-  const float* ds = data + (size_t)b * N * (with_dist ? (size_t)N : 3);
+  const float* ds = data + (size_t)b * N * (with_dist == 1 ? (size_t)N : 3);
   float* tp = temp ? temp + (size_t)b * N : nullptr;
   int* out = idxs + (size_t)b * M;
 
@@ -564,23 +573,24 @@ __global__ void __launch_bounds__(MAXT) fps_kernel(int N, int M, int log2bs, con
     t[j] = 1e10f;
     tie[j] = 0;
     if (k < N) {
-      if (!with_dist) { x[j] = ds[k * 3]; y[j] = ds[k * 3 + 1]; z[j] = ds[k * 3 + 2]; }
+      if (with_dist != 1) { x[j] = ds[k * 3]; y[j] = ds[k * 3 + 1]; z[j] = ds[k * 3 + 2]; }
       if (tp) t[j] = tp[k];
       tie[j] = ~fps_tie32(k, log2bs);
     }
   }
-  int old = 0;
-  if (tid == 0) out[0] = 0;
+  int old = start ? start[b] : 0;
+  if (tid == 0) out[0] = old;
   for (int s = 1; s < M; ++s) {
     float x1 = 0.f, y1 = 0.f, z1 = 0.f;
-    if (!with_dist) { x1 = __ldg(ds + old * 3); y1 = __ldg(ds + old * 3 + 1); z1 = __ldg(ds + old * 3 + 2); }
+    if (with_dist != 1) { x1 = __ldg(ds + old * 3); y1 = __ldg(ds + old * 3 + 1); z1 = __ldg(ds + old * 3 + 2); }
     uint32_t bhi = 0, blo = 0;
     bool have = false;
 #pragma unroll
     for (int j = 0; j < PPT; ++j) {
       int k = tid + T * j;
       if (k < N) {
-        float d = with_dist ? __ldg(ds + (size_t)old * N + k) : dist_direct(x[j], y[j], z[j], x1, y1, z1);
+        float d = with_dist == 1 ? __ldg(ds + (size_t)old * N + k)
+                                 : (with_dist == 2 ? dist_sum_sq(x[j], y[j], z[j], x1, y1, z1) : dist_direct(x[j], y[j], z[j], x1, y1, z1));
         float d2 = fminf(d, t[j]);
         t[j] = d2;
         uint32_t hi = f32_to_ordered(d2);
@@ -618,13 +628,15 @@ static int fps_block_size_ref(int n) {   // opt_n_threads, furthest_point_sample
   return t;
 }
 
-static int fps_launch(int b, int n, int m, const float* data, float* temp, int* idxs, int with_dist, cudaStream_t st) {
+static int fps_launch(int b, int n, int m, const float* data, float* temp, int* idxs, int with_dist, cudaStream_t st,
+                      const int* start = nullptr) {
   if (b <= 0 || m <= 0) return PCREID_OK;
   if (n <= 0 || !data || !idxs) return PCREID_ERR_ARG;
   int bs = fps_block_size_ref(n), log2bs = 0;
   while ((1 << log2bs) < bs) ++log2bs;
+  if (with_dist == 2) log2bs = 0;                           // torch.max: the first index among tied maxima
   int T;
-  if (b >= 592 && n <= 1024 && !with_dist) T = 32;          // many small objects: one warp each, no barriers
+  if (b >= 592 && n <= 1024 && with_dist != 1) T = 32;      // many small objects: one warp each, no barriers
   else {
     T = 32;
     while (T < 1024 && T * 4 < n) T <<= 1;                  // ~4 points per thread, latency bound otherwise
@@ -635,8 +647,8 @@ static int fps_launch(int b, int n, int m, const float* data, float* temp, int* 
   if (p2 > 32) return PCREID_ERR_UNSUPPORTED;               // n > 32768
 #define FPS_CASE(P)                                                                              \
   case P:                                                                                        \
-    if (T == 32) fps_kernel<P, 32><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist);   \
-    else fps_kernel<P, 1024><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist);         \
+    if (T == 32) fps_kernel<P, 32><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist, start);   \
+    else fps_kernel<P, 1024><<<b, T, 0, st>>>(n, m, log2bs, data, temp, idxs, with_dist, start);         \
     break;
   switch (p2) {
     FPS_CASE(1) FPS_CASE(2) FPS_CASE(4) FPS_CASE(8) FPS_CASE(16) FPS_CASE(32)
@@ -886,6 +898,10 @@ int pcreid_fps_with_dist(int b, int n, int m, const float* dist, float* temp, in
   return fps_launch(b, n, m, dist, temp, idx, 1, (cudaStream_t)stream);
 }
 int pcreid_fps_block_size(int n) { return n > 0 ? fps_block_size_ref(n) : 1; }
+int pcreid_fps_torch(int b, int n, int m, const float* xyz, const int* start, int* idx, void* stream) {
+  if (b > 0 && m > 0 && !start) return PCREID_ERR_ARG;
+  return fps_launch(b, n, m, xyz, nullptr, idx, 2, (cudaStream_t)stream, start);
+}
 
 // mmdet3d op: idx/dist2 laid out [b, m, k] exactly like knn_kernel_launcher's outputs.
 int pcreid_knn(int b, int n, int m, int k, const float* xyz, const float* new_xyz, int* idx, float* dist2, void* stream) {

@@ -272,6 +272,32 @@ def knn_point_set(k, xyz, new_xyz):
     return idx
 
 
+def farthest_point_sample(xyz, npoint, start=None):
+    """torch-path FPS of the backbones (pointnet2_utils.py:116-137): int32 (B, npoint); start (B,) = the first sample of each
+    object, drawn like the reference (torch.randint on the host RNG) when not given."""
+    _need_cuda(xyz)
+    if not xyz.is_contiguous():
+        raise ValueError("xyz must be contiguous")
+    B, N, _ = xyz.shape
+    if start is None:
+        start = torch.randint(0, N, (B,), dtype=torch.long)
+    start = start.to(device=xyz.device, dtype=torch.int32).contiguous()
+    idx = torch.empty((B, npoint), device=xyz.device, dtype=torch.int32)
+    _lib.check(_lib.lib().pcreid_fps_torch(B, N, npoint, _p(xyz), _p(start), _p(idx), _stream()), "pcreid_fps_torch")
+    return idx
+
+
+def gather_points(features, idx):
+    """features (B, C, N), idx int32 (B, M) -> (B, C, M) (pcreid_gather_points)."""
+    _need_cuda(features, idx)
+    features, idx = features.contiguous(), idx.contiguous()
+    B, C, N = features.shape
+    M = idx.shape[1]
+    out = torch.empty((B, C, M), device=features.device, dtype=torch.float32)
+    _lib.check(_lib.lib().pcreid_gather_points(B, C, N, M, _p(features), _p(idx), _p(out), _stream()), "pcreid_gather_points")
+    return out
+
+
 def query_ball_point(radius, nsample, xyz, new_xyz):
     """torch-path ball query of the backbones (pointnet2_utils.py:218-240): int32 (B, S, nsample), indices of the first
     nsample points with d <= radius^2 in ascending order, padded with the first."""

@@ -111,10 +111,9 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         self.group_all = group_all
         self.self_attention = Self_Attention(last_channel, 2, 'linear')
         self.tc_mode = False      # True: shared MLP on the tensor cores (tcgen05 kind::tf32), "fast" encoder mode
-        if group_all or sampling != "RANDOM" or not use_xyz or len(mlp) != 4:
-            raise NotImplementedError("built: sampling='RANDOM', use_xyz=True, 3-layer MLP, kNN or ball-query grouping "
-                                      "(backbone_net.py:49-81; sampling='FPS' starts from torch.randint and is unreachable "
-                                      "from the shipped backbone)")
+        if group_all or sampling not in ("RANDOM", "FPS") or not use_xyz or len(mlp) != 4:
+            raise NotImplementedError("built: sampling 'RANDOM' / 'FPS', use_xyz=True, 3-layer MLP, kNN or ball-query grouping "
+                                      "(sample_and_group_edge, pointnet2_utils.py:242-288; backbone_net.py:49-81)")
 
     def _pack(self):
         # first conv acts on [xyz_j - xyz_c (3), f_c (D), f_j - f_c (D)] (pointnet2_utils.py:279-282):
@@ -138,19 +137,26 @@ class PointNetSetAbstractionEdgeSA(PackedModule):
         self._inference_only()
         pk = self.packed()
         S = int(numpoints)
-        new_xyz = xyz[:, :S, :].contiguous()              # sampling == "RANDOM": the first S points
+        centres = None
+        if self.sampling == "FPS":                        # farthest_point_sample (pointnet2_utils.py:116-137), random start
+            fps_idx = K.farthest_point_sample(xyz, S)
+            new_xyz = torch.gather(xyz, 1, fps_idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+            centres = K.gather_points(points, fps_idx) if points is not None else None
+        else:
+            new_xyz = xyz[:, :S, :].contiguous()          # sampling == "RANDOM": the first S points
         tc = self.tc_mode and "w2img" in pk          # tensor-core kernel gathers point-major rows
         # (B, S, k) int32; the max over the k edges does not depend on their order: fast mode asks for the set only
         if not self.use_knn:                          # query_ball_point (pointnet2_utils.py:218-240)
             idx = K.query_ball_point(self.radius, self.nsample, xyz, new_xyz)
         else:
             idx = K.knn_point_set(self.nsample, xyz, new_xyz) if tc else K.knn_point(self.nsample, xyz, new_xyz)
+        cxyz, cpts = (new_xyz, centres) if self.sampling == "FPS" else (xyz, points)      # centre rows: gathered / the first S
         if pk["D"] > 0:
             p1 = K.cn_linear(xyz, pk["pa"], x2=points, w2=pk["pc"], x1_pm=True, y_pm=tc)
-            cc = K.cn_linear(xyz, pk["ca"], x2=points, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
+            cc = K.cn_linear(cxyz, pk["ca"], x2=cpts, w2=pk["cb"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
         else:
             p1 = K.cn_linear(xyz, pk["pa"], x1_pm=True, y_pm=tc)
-            cc = K.cn_linear(xyz, pk["ca"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
+            cc = K.cn_linear(cxyz, pk["ca"], bias=pk["cbias"], x1_pm=True, rows=S, y_pm=tc)
         if tc:
             feat = K.sa_edge_mlp_tc(p1, cc, idx, pk["w2img"], pk["b2"], pk["w3img"], pk["b3"])
         else:

@@ -100,6 +100,25 @@ def knn_point(k, xyz, new_xyz):
     return torch.sort(d, dim=-1, stable=True)[1][..., :k].to(torch.int32).contiguous()
 
 
+def farthest_point_sample(xyz, npoint, start=None):
+    """specification of pcreid_fps_torch: running minimum of (dx*dx + dy*dy) + dz*dz, first index among tied maxima."""
+    B, N, _ = xyz.shape
+    far = torch.randint(0, N, (B,), dtype=torch.long) if start is None else start.long().clone()
+    dist = torch.full((B, N), 1e10)
+    out = torch.zeros(B, npoint, dtype=torch.int32)
+    for i in range(npoint):
+        out[:, i] = far.to(torch.int32)
+        c = xyz[torch.arange(B), far].view(B, 1, 3)
+        d = xyz - c
+        dist = torch.minimum(dist, (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2])
+        far = (dist == dist.max(-1, keepdim=True)[0]).float().argmax(-1)
+    return out
+
+
+def gather_points(features, idx):
+    return torch.gather(features, 2, idx.long().unsqueeze(1).expand(-1, features.shape[1], -1)).contiguous()
+
+
 def query_ball_point(radius, nsample, xyz, new_xyz):
     """specification of pcreid_query_ball_point: first nsample indices with d <= r^2 (fp32), padded with the first; N if none."""
     B, N, _ = xyz.shape
@@ -182,7 +201,7 @@ def install(monkeypatch=None):
     """Replaces pcreid_b200.kernels' entry points by the emulations above (optionally via pytest's monkeypatch)."""
     import pcreid_b200.kernels as K
     names = ["cn_linear", "cn_groupnorm", "linattn_kv", "linattn_scale", "cn_pool", "cn_chanmax", "knn_point",
-             "query_ball_point", "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head", "local_linattn"]
+             "query_ball_point", "farthest_point_sample", "gather_points", "knn_feature", "sa_edge_mlp", "sa_edge_mlp_tc", "tf32_image", "edge_gather_max", "pair_concat_head", "local_linattn"]
     for n in names:
         if monkeypatch is not None:
             monkeypatch.setattr(K, n, globals()[n])

@@ -245,3 +245,42 @@ def test_sa_layer_with_ball_query_grouping(fast):
     ox, of = RO.sa_layer(sd, "sa", x, None, 64, 24, radius=1.2)
     assert torch.equal(nx.cpu(), ox)
     assert (nf.cpu() - of).abs().max() < (2e-2 if fast else 1e-4)
+
+
+@pytest.mark.parametrize("B,N,M,dup", [(4, 96, 40, False), (4, 96, 40, True), (3, 1000, 128, False), (600, 128, 32, True), (2, 5000, 64, False)])
+def test_farthest_point_sample_torch_path_exact(B, N, M, dup):
+    """pointnet2_utils.farthest_point_sample (sampling='FPS'): given start indices, (dx*dx + dy*dy) + dz*dz distance,
+    lowest index among tied maxima -- indices exact against the oracle (itself bit-exact against the reference function)"""
+    import pcreid_b200.kernels as K
+    from oracle import reid_oracle as RO
+    x = RO.synth_objects(B, N, 3, dup=dup)
+    start = torch.randint(0, N, (B,), generator=torch.Generator().manual_seed(1))
+    got = K.farthest_point_sample(x.to(DEV), M, start=start).cpu()
+    assert got.dtype == torch.int32 and torch.equal(got.long(), RO.farthest_point_sample(x, M, start))
+    torch.manual_seed(9)                                  # default start: the reference's host-RNG draw
+    got = K.farthest_point_sample(x.to(DEV), M).cpu()
+    torch.manual_seed(9)
+    assert torch.equal(got.long(), RO.farthest_point_sample(x, M))
+
+
+@pytest.mark.parametrize("fast,use_knn", [(False, True), (False, False), (True, True)])
+def test_sa_layer_with_fps_sampling(fast, use_knn):
+    from pcreid_b200.models.pointnet2_utils import PointNetSetAbstractionEdgeSA
+    from oracle import reid_oracle as RO
+    torch.manual_seed(66)
+    sa = PointNetSetAbstractionEdgeSA(npoint=None, radius=1.5, nsample=24, mlp=[64, 64, 64, 64], sampling="FPS", use_xyz=True,
+                                      use_knn=use_knn).eval()
+    sd = RO.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    sa.load_state_dict({k[3:]: v for k, v in sd.items()})
+    sa = sa.to(DEV)
+    sa.tc_mode = fast
+    sa.self_attention.tc_mode = fast
+    x, f = RO.synth_objects(2, 128, 3), torch.randn(2, 32, 128)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        nx, nf = sa(x.to(DEV), f.to(DEV), 64)
+    torch.manual_seed(5)
+    start = torch.randint(0, 128, (2,), dtype=torch.long)
+    ox, of = RO.sa_layer(sd, "sa", x, f, 64, 24, radius=None if use_knn else 1.5, fps_start=start)
+    assert torch.equal(nx.cpu(), ox)
+    assert (nf.cpu() - of).abs().max() < (2e-2 if fast else 1e-4)

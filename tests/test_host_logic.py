@@ -241,3 +241,22 @@ def test_sa_layer_ball_query_grouping_vs_oracle_with_spec_kernels(fake):
     import fake_kernels
     q = x[:, :64].contiguous()
     assert torch.equal(fake_kernels.query_ball_point(0.7, 16, x, q).long(), O.query_ball_point(0.7, 16, x, q))
+
+
+@pytest.mark.parametrize("use_knn", [True, False])
+def test_sa_layer_fps_sampling_vs_oracle_with_spec_kernels(fake, use_knn):
+    """PointNetSetAbstractionEdgeSA(sampling='FPS'): centres gathered by the sampled indices"""
+    from pcreid_b200.models.pointnet2_utils import PointNetSetAbstractionEdgeSA
+    torch.manual_seed(66)
+    sa = PointNetSetAbstractionEdgeSA(npoint=None, radius=1.5, nsample=24, mlp=[64, 64, 64, 64], sampling="FPS", use_xyz=True,
+                                      use_knn=use_knn).eval()
+    sd = O.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    sa.load_state_dict({k[3:]: v for k, v in sd.items()})
+    x, f = O.synth_objects(2, 128, 3), torch.randn(2, 32, 128)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        nx, nf = sa(x, f, 64)                       # draws the start indices from the host RNG like the reference
+    torch.manual_seed(5)
+    start = torch.randint(0, 128, (2,), dtype=torch.long)
+    ox, of = O.sa_layer(sd, "sa", x, f, 64, 24, radius=None if use_knn else 1.5, fps_start=start)
+    assert torch.equal(nx, ox) and (nf - of).abs().max() < 2e-5

@@ -209,3 +209,37 @@ def test_sa_layer_with_ball_query_bit_exact_vs_reference():
         rx, rf = sa(x, None, 64)
     ox, of = O.sa_layer(sd, "sa", x, None, 64, 24, radius=1.2)
     assert torch.equal(rx, ox) and torch.equal(rf, of)
+
+
+@needs_ref
+@pytest.mark.parametrize("dup", [False, True])
+def test_farthest_point_sample_bit_exact_vs_reference(dup):
+    """the torch-path FPS (pointnet2_utils.py:116-137) incl. its host-RNG start and torch.max tie behaviour"""
+    R = ref_loader.load()
+    x = O.synth_objects(4, 96, 3, dup=dup)
+    torch.manual_seed(11)
+    ref = R.pointnet2_utils.farthest_point_sample(x, 40)
+    torch.manual_seed(11)
+    assert torch.equal(ref, O.farthest_point_sample(x, 40))
+    torch.manual_seed(11)
+    start = torch.randint(0, 96, (4,), dtype=torch.long)
+    assert torch.equal(ref, O.farthest_point_sample(x, 40, start))
+
+
+@needs_ref
+@pytest.mark.parametrize("use_knn", [True, False])
+def test_sa_layer_with_fps_sampling_bit_exact_vs_reference(use_knn):
+    R = ref_loader.load()
+    torch.manual_seed(66)
+    sa = R.pointnet2_utils.PointNetSetAbstractionEdgeSA(npoint=None, radius=1.5, nsample=24, mlp=[64, 64, 64, 64], sampling="FPS",
+                                                        use_xyz=True, use_knn=use_knn).eval()
+    sd = O.perturb_norm_state({"sa." + k: v for k, v in sa.state_dict().items()})
+    _load_ref_sd(sa, "sa.", sd)
+    x, f = O.synth_objects(2, 128, 3), torch.randn(2, 32, 128)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        rx, rf = sa(x, f, 64)
+    torch.manual_seed(5)
+    start = torch.randint(0, 128, (2,), dtype=torch.long)
+    ox, of = O.sa_layer(sd, "sa", x, f, 64, 24, radius=None if use_knn else 1.5, fps_start=start)
+    assert torch.equal(rx, ox) and torch.equal(rf, of)
