@@ -48,3 +48,27 @@ def test_host_helpers_without_gpu():
     # argument validation happens before any CUDA call
     assert L.pcreid_knn(1, 8, 4, 101, None, None, None, None, None) == 1
     assert L.pcreid_cn_linear(None, None) == 1
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: no file of the product package (nor bench.py's measured legs) imports it, and importing
+    every product module in a fresh interpreter leaves `oracle` / `tests` helpers unloaded."""
+    import glob
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "point-cloud-reid_b200")
+    pat = re.compile(r"^\s*(from|import)\s+(oracle|fake_kernels|helpers)\b", re.M)
+    for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
+        assert not pat.search(open(path).read()), path
+    code = ("import sys; sys.path.insert(0, %r); import pcreid_b200, pcreid_b200.ops, pcreid_b200.models, pcreid_b200.parallel, "
+            "pcreid_b200.synthetic, pcreid_b200.compat, pcreid_b200.models.tracking, pcreid_b200.models.frontend, "
+            "pcreid_b200.models.image_reid; bad = [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.') or "
+            "m in ('fake_kernels', 'helpers')]; assert not bad, bad; print('clean')") % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-1500:]
+    # bench.py: oracle / tests helpers only inside the cpu_baseline / reference-arm function
+    src = open(os.path.join(root, "bench.py")).read()
+    body = src[src.index("def main():"):]
+    assert "from oracle" not in body and "import helpers" not in body
