@@ -72,3 +72,16 @@ def test_product_package_never_touches_the_oracle():
     src = open(os.path.join(root, "bench.py")).read()
     body = src[src.index("def main():"):]
     assert "from oracle" not in body and "import helpers" not in body
+
+
+def test_header_is_plain_c_and_cpp():
+    """include/pcreid.h is the FFI contract: it must compile as C99 and as C++ with nothing but the standard headers (no torch,
+    no CUDA types in the signatures)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = os.path.join(root, "include", "pcreid.h")
+    for cmd in (["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror", hdr], ["g++", "-fsyntax-only", "-x", "c++", "-Wall", hdr]):
+        out = subprocess.run(cmd, capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    src = open(hdr).read()
+    assert "#include <torch" not in src and "#include <cuda" not in src and "at::Tensor" not in src
