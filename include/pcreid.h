@@ -214,45 +214,38 @@ int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const fl
                             const float* w, float b0, const unsigned char* mask, float* out, void* stream);
 
 /* ------------------------------------------------------------------ B'. fused tensor-core match path --- */
-/* "fast" mode of the xcorr_eff head (csrc/pair_tc.cu): bf16 tcgen05 GEMMs, fp32 accumulation / norms.
- * Operand "images" are bf16 [k/8][row][8] tiles of 128 points x 64 channels (16 KB); d_model = 64, 2 heads,
- * points per object a multiple of 128.  See point-cloud-reid_b200/models/fused_pairs.py for the host side. */
-int pcreid_pair_tc_smem_bytes(int phase);
-int pcreid_pair_tc_set_trace(void* dev_buffer);   /* debug: int64[2048] cycle trace of one group of pair_p2, NULL = off */
-/* (B, C, N) channel-major fp32 -> [B][N/128][C/8][128][8] bf16 (act: PCREID_ACT_NONE or PCREID_ACT_ELU1) */
-int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, void* dst, void* stream);
-/* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 18432 bytes) */
-int pcreid_pack_b7(int B, const float* M, const float* ksum, void* dst, void* stream);
-/* phase 1: cross_stage1 both ways + stage-2 key/value summaries; phase 2: cross_stage2 + pooling partials */
-int pcreid_pair_p1(int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
-                   const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out, void* B7_out,
-                   int n_ctas, void* stream);
-/* three-tiles-in-flight split of phase 1: which = 0 (attention + MLP -> stage-1 outputs a; W = [W0b | W2 | LN] blob) or
- * which = 1 (key/value summaries -> B7; W = [Wkv | Wm] blob; reads A_out of which = 0) */
-int pcreid_pair_p1ab(int which, int n_units, int NT, int role, const int* u_search, const int* u_templ, const int* u_slot,
-                     const void* QF1, const void* U, const void* H, const void* PV, const void* MK1, const void* W, void* A_out,
-                     void* B7_out, int n_ctas, void* stream);
-int pcreid_pair_p2(int n_units, int NT, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
-                   float* pool_part, int n_ctas, void* stream);
-/* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor */
-int pcreid_pool_finish(int P, int npts, const float* part, float* out, void* stream);
-
-/* Second generation of the phase-1a / phase-2 kernels (csrc/pair_tc2.cu): same operand images and GEMM chain, epilogues
- * with less than half the instructions.  The host folds LayerNorm1's affine into the following Linear, centres the
- * merge / mlp[2] weights over their output channels (LayerNorm inputs become zero-mean), pre-scales q_proj by
- * 1/bf16(ln 2), adds LayerNorm2's beta to the residual image (stage 1: pcreid_pack_image_bias) or after the pooling
- * (stage 2: pcreid_pool_finish2).  Weight blob layouts: see pair_tc2.cu (Q1A_*, Q2_*) and models/fused_pairs.py. */
-int pcreid_pair_tc2_set_trace(void* dev_buffer);   /* debug: int64[2048] cycle trace of one group of pair_p2y, NULL = off */
-int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst,
+/* Tensor-core modes of the xcorr_eff head (csrc/pair_tc.cu, csrc/pair_tc2.cu): tcgen05 kind::f16 GEMMs with fp32
+ * accumulation and fp32 norms.  `fmt` selects the 16-bit operand format of EVERY operand image of a call chain:
+ *   PCREID_FMT_BF16  "fast" mode      (8-bit significand;  |dlogit| <= 3e-2)
+ *   PCREID_FMT_F16   "parity_tc" mode (11-bit significand = tf32's; |dlogit| <= 5e-3; operands are O(1): key/value sums are
+ *                    stored scaled by 1/points -- kv_scale / att_eps below -- and conversions saturate)
+ * Operand "images" are [k/8][row][8] tiles of 128 points x 64 channels (16 KB); d_model = 64, 2 heads.  Reference
+ * arithmetic: corss_attention.forward (mmdet3d/models/attention.py:192-219), ReIDNet.xcorr_eff (ReIDNet.py:231-247),
+ * get_pooled_feats (ReIDNet.py:526-534).  Host side: point-cloud-reid_b200/models/fused_pairs.py.
+ * The host folds LayerNorm1's affine into the following Linear, centres the merge / mlp[2] weights over their output
+ * channels (LayerNorm inputs become zero-mean), pre-scales q_proj by 1/ln 2 (bf16: 1/bf16(ln 2)), adds LayerNorm2's beta
+ * to the residual image (stage 1: pcreid_pack_image_bias) or after the pooling (stage 2: pcreid_pool_finish2).
+ * Weight blob layouts: pair_tc.cu (P1B_*), pair_tc2.cu (Q1A_*, Q2_*). */
+#define PCREID_FMT_BF16 0
+#define PCREID_FMT_F16 1
+/* (B, C, N) channel-major fp32 -> [B][N/128][C/8][128][8] 16-bit (act: PCREID_ACT_NONE or PCREID_ACT_ELU1) */
+int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, int fmt, void* dst, void* stream);
+int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, int fmt, void* dst,
                            void* stream);
+/* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 18432 bytes) */
+int pcreid_pack_b7(int B, const float* M, const float* ksum, int fmt, void* dst, void* stream);
+/* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor (+ beta2) */
 int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /* (64) or NULL */, float* out, void* stream);
-/* npts = points per object (any value >= 1; objects are zero-padded to a multiple of 128 rows inside the operand images) */
-int pcreid_pair_p1a2(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
-                     const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream);
-int pcreid_pair_p1b_n(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* PV,
-                      const void* W, void* A_out, void* B7_out, int n_ctas, void* stream);
-int pcreid_pair_p2y(int n_units, int npts, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
-                    float* pool_part, int n_ctas, void* stream);
+/* npts = points per object (any value >= 1; objects are zero-padded to a multiple of 128 rows inside the operand images).
+ * att_eps = LinearAttention.eps (1e-6, attention.py:21) times the scale the template's key/value sums carry
+ * (MK1 of pcreid_pack_b7 for phase 1a; kv_scale of phase 1b for phase 2). */
+int pcreid_pair_p1a2(int n_units, int npts, int role, int fmt, float att_eps, const int* u_search, const int* u_templ,
+                     const int* u_slot, const void* QF1, const void* U, const void* H, const void* MK1, const void* W, void* A_out,
+                     int n_ctas, void* stream);
+int pcreid_pair_p1b_n(int n_units, int npts, int role, int fmt, float kv_scale, const int* u_search, const int* u_templ,
+                      const int* u_slot, const void* PV, const void* W, void* A_out, void* B7_out, int n_ctas, void* stream);
+int pcreid_pair_p2y(int n_units, int npts, int role, int fmt, float att_eps, const int* u_slot, const void* A_in, const void* B7_in,
+                    const void* W, float* pool_part, int n_ctas, void* stream);
 
 /* tensor-core (tcgen05 kind::tf32, fp32 accumulate) version of pcreid_sa_edge_mlp: same arguments except that the
  * two weight matrices are fp32 operand images [k/4][n][4] of the (C_out, C_in) BatchNorm-folded weights and that P1 / Cc
@@ -296,12 +289,6 @@ int pcreid_attn_back(int B, int rows, int D, int H, int C1, int CO, int res, int
                      int ldf1, const float* q, long long q_bs, int ldq, const float* ksum, const float* kvimg, const float* g1,
                      const float* b1, const float* g2, const float* b2, const void* blob, float* out, long long o_bs, int ldo,
                      void* stream);
-
-/* ------------------------------------------------------------------ C. tcgen05 self-test ------- */
-/* One 128 x n x k GEMM on the 5th-gen tensor cores in each operand configuration the fused kernels use
- * (mode 0: bf16 K-major smem operands, 1: bf16 MN-major, 2: tf32 K-major, 3: bf16 A operand from TMEM, 5: tf32 A operand from TMEM);
- * d (128, n) f32 = a (128, k) * b (n, k)^T.  Modes 0/2/3 take row-major a, b; mode 1 takes a^T (k,128), b^T (k,n). */
-int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream);
 
 #ifdef __cplusplus
 }

@@ -82,23 +82,15 @@ _SIGS = {
     "pcreid_seg_max": [c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_seg_mean": [c_ll, c_int, c_vp, c_vp, c_vp],
     "pcreid_edge_gather_max": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_ll, c_int, c_vp],
-    "pcreid_pair_tc_smem_bytes": [c_int],
-    "pcreid_pair_tc_set_trace": [c_vp],
-    "pcreid_pack_image": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp, c_vp],
-    "pcreid_pack_b7": [c_int, c_vp, c_vp, c_vp, c_vp],
-    "pcreid_pair_p1": [c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],
-    "pcreid_pair_p1ab": [c_int, c_int, c_int, c_int] + [c_vp] * 11 + [c_int, c_vp],
-    "pcreid_pair_p2": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
-    "pcreid_pool_finish": [c_int, c_int, c_vp, c_vp, c_vp],
-    "pcreid_pack_image_bias": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_vp],
+    "pcreid_pack_image": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_int, c_int, c_vp, c_vp],
+    "pcreid_pack_image_bias": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_int, c_vp, c_vp],
+    "pcreid_pack_b7": [c_int, c_vp, c_vp, c_int, c_vp, c_vp],
     "pcreid_pool_finish2": [c_int, c_int, c_vp, c_vp, c_vp, c_vp],
-    "pcreid_pair_tc2_set_trace": [c_vp],
-    "pcreid_pair_p1a2": [c_int, c_int, c_int] + [c_vp] * 9 + [c_int, c_vp],
-    "pcreid_pair_p1b_n": [c_int, c_int, c_int] + [c_vp] * 7 + [c_int, c_vp],
-    "pcreid_pair_p2y": [c_int, c_int, c_int] + [c_vp] * 5 + [c_int, c_vp],
+    "pcreid_pair_p1a2": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 9 + [c_int, c_vp],
+    "pcreid_pair_p1b_n": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 7 + [c_int, c_vp],
+    "pcreid_pair_p2y": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 5 + [c_int, c_vp],
     "pcreid_sa_edge_mlp_tc": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_vp],
     "pcreid_sa_edge_mlp_tc2": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_int, c_vp],
-    "pcreid_tc_probe": [c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_pair_concat_head_tc": [c_int, c_int, c_int, c_int] + [c_vp] * 10 + [c_float, c_vp, c_vp, c_int, c_vp],
     "pcreid_pair_concat_head": [c_int, c_int, c_int, c_int] + [c_vp] * 10 + [c_float, c_vp, c_vp, c_vp],
 }

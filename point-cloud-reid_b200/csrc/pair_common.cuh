@@ -9,36 +9,17 @@
 namespace {
 
 
-constexpr int GT = 256;                 // threads per group: 8 warps = 4 TMEM lane quadrants x 2 column halves
 constexpr int IMG = 16384;              // bytes of a 128 x 64 bf16 operand image  [k/8][row][8]
 constexpr int NB7 = 144;                // columns of the attention operand: 64 (head 0) | 64 (head 1) | 16 (2 dots + pad)
 constexpr int B7_BYTES = (NB7 / 8) * 64 * 16;   // [n/8][k][8] bf16 = 18432
 constexpr int ONES_BYTES = 2 * 2048;    // two extra 8-column chunks appended to V: column 64 == 1 (Ksum), rest 0
-constexpr int KV_COL = 144;             // TMEM columns [144, 224) of a group: KV / Ksum accumulator
-constexpr float LN_EPS = 1e-5f, ATT_EPS = 1e-6f;
-
-// weights blob of phase 1 (bytes)
-constexpr int P1_W0B = 0, P1_W2 = 16384, P1_WKV = 32768, P1_WM = 49152, P1_LN = 57344, P1_WBYTES = 57344 + 1024;
-// weights blob of phase 2
-constexpr int P2_WQ = 0, P2_W0 = 8192, P2_W2 = 40960, P2_LN = 57344, P2_WBYTES = 57344 + 1024;
-// per-group shared memory of phase 1: QXa (16K) | HdKV (32K) + ones (4K) | MK1 (18K) | LN exchange (2K)
-constexpr int P1_QXA = 0, P1_HDKV = IMG, P1_ONES = IMG + 2 * IMG, P1_MK1 = P1_ONES + ONES_BYTES, P1_XCH = P1_MK1 + B7_BYTES,
-              P1_GBYTES = P1_XCH + 2048;
-// per-group shared memory of phase 2: R1 (32K: a | Qf/X, later Hd, later fp32 transpose) | B7 x2 (36K) | exchange
-constexpr int P2_R1 = 0, P2_B7 = 2 * IMG, P2_XCH = P2_B7 + 2 * B7_BYTES, P2_GBYTES = P2_XCH + 2048;
-
-// optional cycle trace (debug): when set, thread 0 of group 0 in CTA 0 records clock64() at stage boundaries
-__device__ long long* g_trace = nullptr;
-__device__ __forceinline__ void trace_mark(int& n, int tag) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && n < 2040 && g_trace != nullptr) {
-    g_trace[n++] = clock64();
-    g_trace[n++] = tag;
-  }
-}
+constexpr float LN_EPS = 1e-5f;
 
 struct P1Args {
   int n_units, NT, role;
   int npts;                              // true points per object (<= 128 NT; rows beyond it are zero padding)
+  float att_eps;                         // LinearAttention eps times the scale the key/value sums were stored with
+  float kv_scale;                        // phase 1b: scale applied to KV / Ksum before they become the stage-2 operand
   const int *u_search, *u_templ, *u_slot;
   const uint8_t *QF1, *U, *H, *PV;      // search-side per-object images: [obj][NT][IMG] (U: [obj][NT][2*IMG])
   const uint8_t* MK1;                    // template-side per-object stage-1 attention operand [obj][B7_BYTES]
@@ -49,6 +30,7 @@ struct P1Args {
 struct P2Args {
   int n_units, NT, role;
   int npts;
+  float att_eps;
   const int* u_slot;
   const uint8_t* A_in;                   // == A_out of phase 1
   const uint8_t* B7_in;                  // == B7_out of phase 1
@@ -57,8 +39,6 @@ struct P2Args {
 };
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x + 1.f : __expf(x); }
-__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
-__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // 16-byte read-only global load that the compiler may NOT sink to its first use (plain __ldg of data consumed a whole
 // stage later was being moved next to the consumer, which exposed the full L2 latency there)
@@ -113,6 +93,7 @@ __device__ __forceinline__ void load_side(uint4 (&sd)[NCH], const uint8_t* __res
 
 // chunks [c_lo, c_hi) of row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]
 // (MN-major image [n/8][k=d][8]); M32 holds M[d][8*c_lo .. 8*c_hi)
+template <class F>
 __device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, float ksum, bool tail, int d, uint8_t* dst) {
   const int hd = d >> 5;
   const uint4 zero = make_uint4(0, 0, 0, 0);
@@ -120,14 +101,14 @@ __device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, 
   for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = tc::pack_bf16(M32[c * 8 + 2 * j], M32[c * 8 + 2 * j + 1]);
+    for (int j = 0; j < 4; ++j) w[j] = F::pack(M32[c * 8 + 2 * j], M32[c * 8 + 2 * j + 1]);
     const uint4 val = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4*>(dst + (c_lo + c) * 1024 + d * 16) = hd == 0 ? val : zero;
     *reinterpret_cast<uint4*>(dst + (8 + c_lo + c) * 1024 + d * 16) = hd == 1 ? val : zero;
   }
   if (tail) {
     *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) =
-        make_uint4(hd == 0 ? tc::pack_bf16(ksum, 0.f) : tc::pack_bf16(0.f, ksum), 0, 0, 0);
+        make_uint4(hd == 0 ? F::pack(ksum, 0.f) : F::pack(0.f, ksum), 0, 0, 0);
     *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
   }
 }
@@ -162,12 +143,13 @@ __device__ __forceinline__ void ld32_stats(uint32_t taddr, float (&o)[32], float
 }
 
 // row d of the stage operand (used by the per-object packer): all 64 columns at once
+template <class F>
 __device__ __forceinline__ void write_b7_row(const float (&M)[64], float ksum, int d, uint8_t* dst) {
   float lo[32], hi[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) { lo[j] = M[j]; hi[j] = M[32 + j]; }
-  write_b7_part(lo, 0, ksum, true, d, dst);
-  write_b7_part(hi, 4, ksum, false, d, dst);
+  write_b7_part<F>(lo, 0, ksum, true, d, dst);
+  write_b7_part<F>(hi, 4, ksum, false, d, dst);
 }
 
 __device__ __forceinline__ void groupx_setup(GroupX& g, uint64_t* bars, uint32_t tmem_base) {

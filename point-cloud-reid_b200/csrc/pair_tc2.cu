@@ -30,13 +30,13 @@ constexpr int Q1A_QXA = 0, Q1A_MK1 = IMG, Q1A_GBYTES = IMG + B7_BYTES;          
 constexpr int Q2_WQ = 0, Q2_W0 = 8192, Q2_W2 = Q2_W0 + 18 * 2048, Q2_LN = Q2_W2 + 16384, Q2_WBYTES = Q2_LN + 256;   // 61696
 constexpr int Q2_ONES = Q2_WBYTES;                                                           // 4 KB: A chunk pair, k = 0 is 1.0
 constexpr int Q2_R1 = 0, Q2_B7 = 2 * IMG, Q2_GBYTES = Q2_B7 + B7_BYTES;                      // 51200 B per group
-constexpr uint32_t BF2_ONE = 0x3f803f80u;
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 
 // Attention accumulator (columns [0,64) head 0, [64,128) head 1, 128/129 the two Q.Ksum dots) -> LayerNorm1-normalised
 // merged message WITHOUT affine (folded into the next GEMM), packed to bf16 into this thread's row of an operand image.
-__device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row) {
+template <class F>
+__device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row, float att_eps) {
   uint32_t d8[8], a0[32], a1[32], b0[32], b1[32];
   tc::tmem_ld8(tl + 128, d8);
   tc::tmem_ld32(tl, a0);
@@ -44,7 +44,7 @@ __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row) {
   tc::tmem_ld_wait();
   tc::tmem_ld32(tl + 32, b0);                                   // in flight while the first half is processed
   tc::tmem_ld32(tl + 96, b1);
-  const float d0 = u2f(d8[0]) + ATT_EPS, d1 = u2f(d8[1]) + ATT_EPS;
+  const float d0 = u2f(d8[0]) + att_eps, d1 = u2f(d8[1]) + att_eps;
   const float r = __fdividef(d0, d1);
   float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
   float m0[32], m1[32];
@@ -69,8 +69,8 @@ __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row) {
     uint32_t w[4], v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      w[j] = tc::pack_bf16(m0[c * 8 + 2 * j] * rstd, m0[c * 8 + 2 * j + 1] * rstd);
-      v[j] = tc::pack_bf16(m1[c * 8 + 2 * j] * rstd, m1[c * 8 + 2 * j + 1] * rstd);
+      w[j] = F::pack(m0[c * 8 + 2 * j] * rstd, m0[c * 8 + 2 * j + 1] * rstd);
+      v[j] = F::pack(m1[c * 8 + 2 * j] * rstd, m1[c * 8 + 2 * j + 1] * rstd);
     }
     *reinterpret_cast<uint4*>(dst_row + c * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
     *reinterpret_cast<uint4*>(dst_row + (4 + c) * 2048) = make_uint4(v[0], v[1], v[2], v[3]);
@@ -96,6 +96,7 @@ __device__ __forceinline__ float ld64_sumsq(uint32_t tl, uint32_t (&x0)[32], uin
 // ---------------------------------------------------------------------------------------------------------------
 // phase 1a: G1 attention (Qf1_i x MK1_j) -> LN1 -> G2 (+U', ReLU, TMEM-resident) -> G3 -> LN2 + (h + beta2) -> a
 // ---------------------------------------------------------------------------------------------------------------
+template <class F>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
@@ -120,9 +121,9 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   uint8_t* QXa = G + Q1A_QXA;
   uint8_t* MK1 = G + Q1A_MK1;
   const uint32_t sQXa = tc::smem_u32(QXa), sW = tc::smem_u32(Wsm);
-  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
-  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
-  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id144 = tc::instr_desc(128, NB7, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const Opnd oQXa = A_IMG(sQXa), oMK1 = B7_IMG(tc::smem_u32(MK1)), oW0b = W_IMG(sW + Q1A_W0B, 128), oW2 = W_IMG(sW + Q1A_W2, 64);
   const int row = g.t;
   uint8_t* xrow = QXa + row * 16;
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
       const size_t ti = (size_t)so * a.NT + tile;
       if (u == u0 && tile == 0) start_tile(ti, te);                       // every later tile was started by its predecessor
       g.wait();
-      epi_attn_norm(g.tlane, xrow);                                       // X' over the query image
+      epi_attn_norm<F>(g.tlane, xrow, a.att_eps);                                       // X' over the query image
       g.publish();
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oW0b, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
       {   // Hd = relu(acc + U') -> bf16, written back IN PLACE to TMEM columns [0, 64): the A operand of G3
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
             const uint32_t sw0[4] = {s0.x, s0.y, s0.z, s0.w}, sw1[4] = {s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              w[c * 4 + j] = tc::bf2_fma_relu(tc::pack_bf16(u2f(r0[c * 8 + 2 * j]), u2f(r0[c * 8 + 2 * j + 1])), BF2_ONE, sw0[j]);
-              w[16 + c * 4 + j] = tc::bf2_fma_relu(tc::pack_bf16(u2f(r1[c * 8 + 2 * j]), u2f(r1[c * 8 + 2 * j + 1])), BF2_ONE, sw1[j]);
+              w[c * 4 + j] = F::add_relu(u2f(r0[c * 8 + 2 * j]), u2f(r0[c * 8 + 2 * j + 1]), sw0[j]);
+              w[16 + c * 4 + j] = F::add_relu(u2f(r1[c * 8 + 2 * j]), u2f(r1[c * 8 + 2 * j + 1]), sw1[j]);
             }
           }
           tc::tmem_st32(g.tlane + 32 * b, w);
@@ -215,10 +216,10 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
             const uint4 rs = sdH[4 * hh + c];
             const float4 ga = g2v[8 * hh + 2 * c], gb = g2v[8 * hh + 2 * c + 1];
             uint32_t w[4];
-            w[0] = tc::pack_bf16(fmaf(u2f(x[c * 8 + 0]) * rstd, ga.x, bf_lo(rs.x)), fmaf(u2f(x[c * 8 + 1]) * rstd, ga.y, bf_hi(rs.x)));
-            w[1] = tc::pack_bf16(fmaf(u2f(x[c * 8 + 2]) * rstd, ga.z, bf_lo(rs.y)), fmaf(u2f(x[c * 8 + 3]) * rstd, ga.w, bf_hi(rs.y)));
-            w[2] = tc::pack_bf16(fmaf(u2f(x[c * 8 + 4]) * rstd, gb.x, bf_lo(rs.z)), fmaf(u2f(x[c * 8 + 5]) * rstd, gb.y, bf_hi(rs.z)));
-            w[3] = tc::pack_bf16(fmaf(u2f(x[c * 8 + 6]) * rstd, gb.z, bf_lo(rs.w)), fmaf(u2f(x[c * 8 + 7]) * rstd, gb.w, bf_hi(rs.w)));
+            w[0] = F::pack(fmaf(u2f(x[c * 8 + 0]) * rstd, ga.x, F::lo(rs.x)), fmaf(u2f(x[c * 8 + 1]) * rstd, ga.y, F::hi(rs.x)));
+            w[1] = F::pack(fmaf(u2f(x[c * 8 + 2]) * rstd, ga.z, F::lo(rs.y)), fmaf(u2f(x[c * 8 + 3]) * rstd, ga.w, F::hi(rs.y)));
+            w[2] = F::pack(fmaf(u2f(x[c * 8 + 4]) * rstd, gb.x, F::lo(rs.z)), fmaf(u2f(x[c * 8 + 5]) * rstd, gb.y, F::hi(rs.z)));
+            w[3] = F::pack(fmaf(u2f(x[c * 8 + 6]) * rstd, gb.z, F::lo(rs.w)), fmaf(u2f(x[c * 8 + 7]) * rstd, gb.w, F::hi(rs.w)));
             *reinterpret_cast<uint4*>(orow + (4 * hh + c) * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
           }
         }
@@ -234,10 +235,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
 // ---------------------------------------------------------------------------------------------------------------
 // phase 2: q projection -> attention against B7 -> LN1 -> [a | X' | 1] W0'^T, ReLU (TMEM-resident) -> W2 -> LN2 + a -> pooling
 // ---------------------------------------------------------------------------------------------------------------
-#define TR(tag) do { if constexpr (TRACE) trace_mark(ntr, tag); } while (0)
-template <bool TRACE>
+template <class F>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
-  int ntr = 0;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
   __shared__ uint32_t tmem_base_s;
@@ -252,7 +251,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   copy_to_smem(Wsm, a.W, Q2_WBYTES, threadIdx.x, NGX * GX);
   cp_async_commit();
   if (threadIdx.x < 256)   // constant A chunk pair of the bias K-step: element k = 0 of every row is 1.0
-    reinterpret_cast<uint4*>(smem + Q2_ONES)[threadIdx.x] = threadIdx.x < 128 ? make_uint4(0x00003f80u, 0, 0, 0) : make_uint4(0, 0, 0, 0);
+    reinterpret_cast<uint4*>(smem + Q2_ONES)[threadIdx.x] = threadIdx.x < 128 ? make_uint4(F::ONE_LO, 0, 0, 0) : make_uint4(0, 0, 0, 0);
   cp_async_wait<0>();
   tc::fence_async_smem();
   tc::tc_fence_before();
@@ -265,9 +264,9 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   uint8_t* R1 = G + Q2_R1;
   uint8_t* B7 = G + Q2_B7;
   const uint32_t sR1 = tc::smem_u32(R1), sW = tc::smem_u32(Wsm);
-  const uint32_t id144 = tc::instr_desc(128, NB7, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_MN);
-  const uint32_t id128 = tc::instr_desc(128, 128, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
-  const uint32_t id64 = tc::instr_desc(128, 64, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id144 = tc::instr_desc(128, NB7, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id128 = tc::instr_desc(128, 128, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const Opnd oR1 = A_IMG(sR1), oQf = A_IMG(sR1 + IMG), oOnes = A_IMG(tc::smem_u32(smem + Q2_ONES)), oWq = W_IMG(sW + Q2_WQ, 64),
              oW0 = W_IMG(sW + Q2_W0, 128), oW2 = W_IMG(sW + Q2_W2, 64), oB7 = B7_IMG(tc::smem_u32(B7));
   const int row = g.t;
@@ -299,10 +298,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
     psm[0] = psm[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int tile = 0; tile < a.NT; ++tile) {
       const uint8_t* a_img = a.A_in + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG;
-      TR(0);
       if (u == u0 && tile == 0) start_tile();                             // every later tile was started by its predecessor
       else g.sync();              // the Qf image below overwrites the transpose buffer: every warp has finished its pooling reads
-      TR(1);
       {   // L2 prefetch of the next tile's `a` image (its shared-memory copy is issued after this tile's G8)
         int ns = slot, nt = tile + 1;
         if (nt == a.NT) { ns = slot_next; nt = 0; }
@@ -310,7 +307,6 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         if (tile == 0 && u + 1 < u1) prefetch_l2_16k(a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, g.t);
       }
       g.wait();
-      TR(2);
       {   // Qf = elu(q)+1 -> second half of R1
         uint32_t r0[32], r1[32];
         tc::tmem_ld32(g.tlane, r0);
@@ -321,27 +317,22 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
           uint32_t w[4], v[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            w[j] = tc::bf2_elu1s(tc::pack_bf16(u2f(r0[c * 8 + 2 * j]), u2f(r0[c * 8 + 2 * j + 1])));
-            v[j] = tc::bf2_elu1s(tc::pack_bf16(u2f(r1[c * 8 + 2 * j]), u2f(r1[c * 8 + 2 * j + 1])));
+            w[j] = F::elu1_scaled(u2f(r0[c * 8 + 2 * j]), u2f(r0[c * 8 + 2 * j + 1]));
+            v[j] = F::elu1_scaled(u2f(r1[c * 8 + 2 * j]), u2f(r1[c * 8 + 2 * j + 1]));
           }
           *reinterpret_cast<uint4*>(arow + IMG + c * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
           *reinterpret_cast<uint4*>(arow + IMG + (4 + c) * 2048) = make_uint4(v[0], v[1], v[2], v[3]);
         }
       }
-      TR(3);
       g.publish();
-      TR(4);
       if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
-      TR(5);
       if (tile + 1 == a.NT && u + 1 < u1) {   // last attention GEMM of the unit is done: next unit's B7 streams in
         copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
         cp_async_commit();
       }
-      epi_attn_norm(g.tlane, arow + IMG);                                 // X' next to a: [a | X' | 1] is the K = 144 operand
-      TR(6);
+      epi_attn_norm<F>(g.tlane, arow + IMG, a.att_eps);                                 // X' next to a: [a | X' | 1] is the K = 144 operand
       g.publish();
-      TR(7);
       if (g.issuer) {
         if (tc::elect_one()) {
           issue_gemm<8>(g.tmem, oR1, oW0, id128, false);
@@ -353,7 +344,6 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
       uint4 sdA[8];
       load_side<8>(sdA, a_img, 0, row);                                   // residual a (this tile), consumed after G9
       g.wait();
-      TR(8);
       {   // G8 has consumed [a | X']: the next tile's `a` image streams into R1 behind the rest of this tile
         int nu = u, nt = tile + 1;
         if (nt == a.NT) { nu = u + 1; nt = 0; }
@@ -370,17 +360,15 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         tc::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          w[j] = tc::pack_bf16_relu(u2f(r0[2 * j]), u2f(r0[2 * j + 1]));
-          w[16 + j] = tc::pack_bf16_relu(u2f(r1[2 * j]), u2f(r1[2 * j + 1]));
+          w[j] = F::pack_relu(u2f(r0[2 * j]), u2f(r0[2 * j + 1]));
+          w[16 + j] = F::pack_relu(u2f(r1[2 * j]), u2f(r1[2 * j + 1]));
         }
         tc::tmem_st32(g.tlane + 32 * b, w);
       }
       tc::tmem_st_wait();
-      TR(9);
       tc::tc_fence_before();
       g.sync();
       tc::tc_fence_after();
-      TR(10);
       if (g.issuer) {
         if (tc::elect_one()) {
 #pragma unroll
@@ -391,7 +379,6 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         __syncwarp();
       }
       g.wait();
-      TR(11);
       {   // o - beta2 = a + gamma2 * acc * rstd ; pooled over the points, 32 channels per pass
         uint32_t x0[32], x1[32];
         const float rstd = rsqrtf(ld64_sumsq(g.tlane + 64, x0, x1) * (1.f / 64.f) + LN_EPS);
@@ -406,14 +393,14 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
             const uint4 rs = sdA[4 * hh + c];
             const float4 ga = g2v[8 * hh + 2 * c], gb = g2v[8 * hh + 2 * c + 1];
             float4 oa, ob;
-            oa.x = fmaf(u2f(x[c * 8 + 0]) * rstd, ga.x, bf_lo(rs.x));
-            oa.y = fmaf(u2f(x[c * 8 + 1]) * rstd, ga.y, bf_hi(rs.x));
-            oa.z = fmaf(u2f(x[c * 8 + 2]) * rstd, ga.z, bf_lo(rs.y));
-            oa.w = fmaf(u2f(x[c * 8 + 3]) * rstd, ga.w, bf_hi(rs.y));
-            ob.x = fmaf(u2f(x[c * 8 + 4]) * rstd, gb.x, bf_lo(rs.z));
-            ob.y = fmaf(u2f(x[c * 8 + 5]) * rstd, gb.y, bf_hi(rs.z));
-            ob.z = fmaf(u2f(x[c * 8 + 6]) * rstd, gb.z, bf_lo(rs.w));
-            ob.w = fmaf(u2f(x[c * 8 + 7]) * rstd, gb.w, bf_hi(rs.w));
+            oa.x = fmaf(u2f(x[c * 8 + 0]) * rstd, ga.x, F::lo(rs.x));
+            oa.y = fmaf(u2f(x[c * 8 + 1]) * rstd, ga.y, F::hi(rs.x));
+            oa.z = fmaf(u2f(x[c * 8 + 2]) * rstd, ga.z, F::lo(rs.y));
+            oa.w = fmaf(u2f(x[c * 8 + 3]) * rstd, ga.w, F::hi(rs.y));
+            ob.x = fmaf(u2f(x[c * 8 + 4]) * rstd, gb.x, F::lo(rs.z));
+            ob.y = fmaf(u2f(x[c * 8 + 5]) * rstd, gb.y, F::hi(rs.z));
+            ob.z = fmaf(u2f(x[c * 8 + 6]) * rstd, gb.z, F::lo(rs.w));
+            ob.w = fmaf(u2f(x[c * 8 + 7]) * rstd, gb.w, F::hi(rs.w));
             Tb[row * 8 + ((2 * c) ^ (row & 7))] = oa;
             Tb[row * 8 + ((2 * c + 1) ^ (row & 7))] = ob;
           }
@@ -439,7 +426,6 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
           }
         }
       }
-      TR(12);
       tc::tc_fence_before();      // the next tile's publish() orders these TMEM / transpose-buffer reads before its writes
     }
     // unit done: combine the row blocks (lanes with equal jg inside a warp, then the 4 warps through shared memory)
@@ -474,8 +460,6 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
-#undef TR
-
 // pool_part (P, 2, 128) [max | sum of (o - beta2)] -> pooled^T (128, P): max over both directions | mean over the 2*npts points
 // One CTA = 32 pairs x 128 channels through a padded shared-memory tile: rows of `part` are read coalesced (a warp reads one
 // pair's 128 floats per direction), columns of the (128, P) output are written coalesced (32 consecutive pairs per channel).
@@ -501,6 +485,7 @@ __global__ void __launch_bounds__(256) pool_finish2_kernel(int P, int npts, cons
 }
 
 // src (B, C, N) channel-major fp32 + per-channel bias -> dst [B][N/128][C/8][128][8] bf16
+template <class F>
 __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int N, const float* __restrict__ src, long long s_bs,
                                                               int lds, const float* __restrict__ bias, uint8_t* __restrict__ dst) {
   const int nt = (N + 127) / 128, nch = C / 8;
@@ -515,28 +500,41 @@ __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int 
   if (tile * 128 + row < N) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      w[j] = tc::pack_bf16(s[(size_t)(2 * j) * lds] + bias[chunk * 8 + 2 * j], s[(size_t)(2 * j + 1) * lds] + bias[chunk * 8 + 2 * j + 1]);
+      w[j] = F::pack(s[(size_t)(2 * j) * lds] + bias[chunk * 8 + 2 * j], s[(size_t)(2 * j + 1) * lds] + bias[chunk * 8 + 2 * j + 1]);
   }
   *reinterpret_cast<uint4*>(dst + (((size_t)b * nt + tile) * nch + chunk) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 }  // namespace
 
-static bool g_trace_host = false;
+template <class F>
+static int launch_p1a2(const P1Args& a, int grid, cudaStream_t st) {
+  const int smem = Q1A_WBYTES + NGX * Q1A_GBYTES;
+  cudaFuncSetAttribute(pair_p1a2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p1a2_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
+  return pcreid_launch_status();
+}
+
+template <class F>
+static int launch_p2y(const P2Args& a, int grid, cudaStream_t st) {
+  const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;
+  cudaFuncSetAttribute(pair_p2y_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p2y_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
+  return pcreid_launch_status();
+}
 
 extern "C" {
 
-int pcreid_pair_tc2_set_trace(void* dev_buffer) {   /* debug: int64[2048] cycle trace of group 0 / CTA 0 of pair_p2y, NULL = off */
-  long long* p = (long long*)dev_buffer;
-  g_trace_host = p != nullptr;
-  return cudaMemcpyToSymbol(g_trace, &p, sizeof(p)) == cudaSuccess ? PCREID_OK : PCREID_ERR_LAUNCH;
-}
-
-int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, void* dst, void* stream) {
+int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, int fmt, void* dst,
+                           void* stream) {
   if (B <= 0) return PCREID_OK;
-  if (!src || !dst || !bias || C % 8 || N <= 0) return PCREID_ERR_ARG;
+  if (!src || !dst || !bias || C % 8 || N <= 0 || (fmt != PCREID_FMT_BF16 && fmt != PCREID_FMT_F16)) return PCREID_ERR_ARG;
   const long long per = 128LL * (C / 8) * ((N + 127) / 128);
-  pack_image_bias_kernel<<<(unsigned)((per * B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, bias, (uint8_t*)dst);
+  const unsigned grid = (unsigned)((per * B + 255) / 256);
+  if (fmt == PCREID_FMT_F16)
+    pack_image_bias_kernel<tc::OpF16><<<grid, 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, bias, (uint8_t*)dst);
+  else
+    pack_image_bias_kernel<tc::OpBF16><<<grid, 256, 0, (cudaStream_t)stream>>>(B, C, N, src, s_bs, lds, bias, (uint8_t*)dst);
   return pcreid_launch_status();
 }
 
@@ -547,38 +545,29 @@ int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias, f
   return pcreid_launch_status();
 }
 
-int pcreid_pair_p1a2(int n_units, int npts, int role, const int* u_search, const int* u_templ, const int* u_slot, const void* QF1,
-                     const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream) {
+int pcreid_pair_p1a2(int n_units, int npts, int role, int fmt, float att_eps, const int* u_search, const int* u_templ, const int* u_slot,
+                     const void* QF1, const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
-  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !MK1 || !W || !A_out || npts <= 0) return PCREID_ERR_ARG;
+  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !MK1 || !W || !A_out || npts <= 0 ||
+      (fmt != PCREID_FMT_BF16 && fmt != PCREID_FMT_F16))
+    return PCREID_ERR_ARG;
   const int NT = (npts + 127) / 128;
-  P1Args a{n_units, NT, role, npts, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+  P1Args a{n_units, NT, role, npts, att_eps, 1.f, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
            nullptr, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, nullptr};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
-  const int smem = Q1A_WBYTES + NGX * Q1A_GBYTES;
-  cudaFuncSetAttribute(pair_p1a2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p1a2_kernel<<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
-  return pcreid_launch_status();
+  return fmt == PCREID_FMT_F16 ? launch_p1a2<tc::OpF16>(a, grid, (cudaStream_t)stream) : launch_p1a2<tc::OpBF16>(a, grid, (cudaStream_t)stream);
 }
 
-int pcreid_pair_p2y(int n_units, int npts, int role, const int* u_slot, const void* A_in, const void* B7_in, const void* W,
-                    float* pool_part, int n_ctas, void* stream) {
+int pcreid_pair_p2y(int n_units, int npts, int role, int fmt, float att_eps, const int* u_slot, const void* A_in, const void* B7_in,
+                    const void* W, float* pool_part, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
-  if (!u_slot || !A_in || !B7_in || !W || !pool_part || npts <= 0) return PCREID_ERR_ARG;
+  if (!u_slot || !A_in || !B7_in || !W || !pool_part || npts <= 0 || (fmt != PCREID_FMT_BF16 && fmt != PCREID_FMT_F16)) return PCREID_ERR_ARG;
   const int NT = (npts + 127) / 128;
-  P2Args a{n_units, NT, role, npts, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
+  P2Args a{n_units, NT, role, npts, att_eps, u_slot, (const uint8_t*)A_in, (const uint8_t*)B7_in, (const uint8_t*)W, pool_part};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;
-  const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;
-  if (g_trace_host) {
-    cudaFuncSetAttribute(pair_p2y_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    pair_p2y_kernel<true><<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
-    return pcreid_launch_status();
-  }
-  cudaFuncSetAttribute(pair_p2y_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p2y_kernel<false><<<grid, NGX * GX, smem, (cudaStream_t)stream>>>(a);
-  return pcreid_launch_status();
+  return fmt == PCREID_FMT_F16 ? launch_p2y<tc::OpF16>(a, grid, (cudaStream_t)stream) : launch_p2y<tc::OpBF16>(a, grid, (cudaStream_t)stream);
 }
 
 }  // extern "C"

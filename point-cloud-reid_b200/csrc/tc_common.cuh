@@ -181,6 +181,63 @@ __device__ __forceinline__ uint32_t bf2_elu1s(uint32_t x) {
   return bf2_fma(bf2_max(x, 0u), LN2B, bf2_ex2(bf2_min(x, 0u)));
 }
 
+// ---- operand element formats of the kind::f16 MMAs ----------------------------------------------------------------
+// The fused matcher kernels are templated on one of these.  Both are 16-bit operands with fp32 accumulation, i.e. the same
+// tensor-pipe rate and the same operand bytes; they differ in where the 16 bits go:
+//   OpBF16: 8-bit significand (rel. rounding error 2^-9), fp32 exponent range           -> "fast" mode, |dlogit| <= 3e-2
+//   OpF16 : 11-bit significand (rel. rounding error 2^-12, the significand of tf32), 5-bit exponent -> "parity_tc" mode.
+//           Every operand of the matcher is O(1) by construction (LayerNorm outputs, elu+1 features, key/value sums
+//           pre-scaled by 1/points); conversions saturate to +-65504 instead of producing inf.
+// Epilogue arithmetic whose result is rounded to the operand format anyway runs packed (2 elements per instruction) for
+// OpBF16; OpF16 keeps it in fp32 and rounds ONCE (the parity mode pays ~10 % more epilogue instructions for that).
+struct OpBF16 {
+  static constexpr int FMT = FMT_BF16;
+  static constexpr uint32_t ONE_LO = 0x00003f80u;     // packed pair (1.0, 0.0)
+  static constexpr bool PACKED_MATH = true;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) { return pack_bf16(lo, hi); }
+  static __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) { return pack_bf16_relu(lo, hi); }
+  static __device__ __forceinline__ float lo(uint32_t w) { return __uint_as_float(w << 16); }
+  static __device__ __forceinline__ float hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+  // relu(acc + side) -> packed
+  static __device__ __forceinline__ uint32_t add_relu(float a, float b, uint32_t side) {
+    return bf2_fma_relu(pack_bf16(a, b), 0x3f803f80u, side);
+  }
+  // acc + side -> packed
+  static __device__ __forceinline__ uint32_t add(float a, float b, uint32_t side) { return bf2_add(pack_bf16(a, b), side); }
+  // elu(x)+1 of accumulators produced by weights pre-scaled by 1/bf16(ln 2) -> packed
+  static __device__ __forceinline__ uint32_t elu1_scaled(float a, float b) { return bf2_elu1s(pack_bf16(a, b)); }
+  // elu(x)+1 of plain accumulators -> packed
+  static __device__ __forceinline__ uint32_t elu1(float a, float b) { return bf2_elu1(pack_bf16(a, b)); }
+};
+struct OpF16 {
+  static constexpr int FMT = FMT_F16;
+  static constexpr uint32_t ONE_LO = 0x00003c00u;
+  static constexpr bool PACKED_MATH = false;
+  static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
+    uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+  }
+  static __device__ __forceinline__ uint32_t pack_relu(float lo, float hi) {
+    uint32_t r; asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
+  }
+  static __device__ __forceinline__ float lo(uint32_t w) {
+    float f; asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}\n" : "=f"(f) : "r"(w)); return f;
+  }
+  static __device__ __forceinline__ float hi(uint32_t w) {
+    float f; asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}\n" : "=f"(f) : "r"(w)); return f;
+  }
+  static __device__ __forceinline__ uint32_t add_relu(float a, float b, uint32_t side) { return pack_relu(a + lo(side), b + hi(side)); }
+  static __device__ __forceinline__ uint32_t add(float a, float b, uint32_t side) { return pack(a + lo(side), b + hi(side)); }
+  // weights pre-scaled by 1/ln 2 (fp32-exact constant here: the multiply happens in fp32)
+  static __device__ __forceinline__ float elu1s_f(float x) {
+    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f)));
+    return fmaf(fmaxf(x, 0.f), 0.69314718056f, e);
+  }
+  static __device__ __forceinline__ uint32_t elu1_scaled(float a, float b) { return pack(elu1s_f(a), elu1s_f(b)); }
+  static __device__ __forceinline__ uint32_t elu1(float a, float b) {
+    return pack(a > 0.f ? a + 1.f : __expf(a), b > 0.f ? b + 1.f : __expf(b));
+  }
+};
+
 // warp-uniform helpers: values produced through these are known to be warp-uniform by the compiler, so descriptor
 // arithmetic and tcgen05.mma operands stay on the uniform datapath (no per-MMA R2UR moves)
 __device__ __forceinline__ uint32_t uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }

@@ -90,11 +90,11 @@ class ReIDNet(nn.Module):
         self.compute_summary = compute_summary
         self.use_dgcnn = use_dgcnn
         self.combine = combine
-        # 'parity': fp32 kernels (logits within 1e-4 of the reference); 'fast': fused bf16 tcgen05 matcher where the
-        # configuration allows it (d_model 64, 2 heads, point-cat + both pooling, points a multiple of 128)
+        # 'parity': fp32 kernels (logits within 1e-4 of the reference); 'parity_tc' / 'fast': fused tcgen05 matcher with
+        # fp16 / bf16 operands where the configuration allows it (d_model 64, 2 heads, point-cat + both pooling)
         self.match_mode = 'parity'
-        self.tc_encoder = True      # in 'fast' mode the encoder's 1x1 convs / Linears run as tf32 tcgen05 GEMMs
-        self._fused = None
+        self.tc_encoder = True      # in the tensor-core modes the encoder's 1x1 convs / Linears run as tf32 tcgen05 GEMMs
+        self._fused = {}
         # encode() replays a captured CUDA graph per (shape, mode, weights version): the ~90 launches of one encoder pass
         # are issued by the GPU front-end instead of by ~90 Python -> ctypes -> cudaLaunchKernel round trips
         self.cuda_graphs = False
@@ -103,15 +103,28 @@ class ReIDNet(nn.Module):
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
                                       "(shipped point configs use 'xcorr_eff'; the baseline uses 'concat')")
 
+    TC_MODES = ('parity_tc', 'fast')
+
     def set_mode(self, mode):
-        """'parity': fp32 kernels everywhere (1e-4).  'fast': fused bf16 tcgen05 matcher + tf32 tensor-core shared MLPs in
-        the Point Transformer set-abstraction layers (|dlogit| <= 3e-2)."""
-        assert mode in ('parity', 'fast')
+        """'parity': fp32 FFMA kernels everywhere (|dlogit| <= 1e-4).
+        'parity_tc': every contraction on the tensor cores at an 11-bit significand -- tcgen05 kind::tf32 shared MLPs /
+        attention blocks in the encoder, fused tcgen05 matcher with fp16 operands -- fp32 accumulation and norms
+        (|dlogit| <= 5e-3, the tf32 gate of SURVEY.md 8d).
+        'fast': the same kernels with bf16 matcher operands (|dlogit| <= 3e-2)."""
+        assert mode in ('parity',) + self.TC_MODES
         self.match_mode = mode
         for m in self.modules():
             if hasattr(m, 'tc_mode'):
-                m.tc_mode = (mode == 'fast')
+                m.tc_mode = mode in self.TC_MODES
         return self
+
+    def fused_matcher(self):
+        """the fused tcgen05 matcher of the current tensor-core mode (one per operand format)"""
+        from . import fused_pairs
+        fmt = fused_pairs.FMT_F16 if self.match_mode == 'parity_tc' else fused_pairs.FMT_BF16
+        if fmt not in self._fused:
+            self._fused[fmt] = fused_pairs.FusedXcorr(self, fmt)
+        return self._fused[fmt]
 
     # ------------------------------------------------------------------ encoders
     def _encode(self, pts):
@@ -133,7 +146,7 @@ class ReIDNet(nn.Module):
 
     def encode(self, pts):
         """public inference entry: pts (B, N, 3) -> (xyz (B, N, 3), per-point embedding (B, C, N))."""
-        with torch.no_grad(), K.tensor_core_linear(self.match_mode == 'fast' and self.tc_encoder):
+        with torch.no_grad(), K.tensor_core_linear(self.match_mode in self.TC_MODES and self.tc_encoder):
             if self.cuda_graphs and pts.is_cuda and pts.shape[0] > 0:
                 return self._encode_graphed(pts)
             return self._encode(pts)
@@ -306,12 +319,10 @@ class ReIDNet(nn.Module):
                 return self._concat_all_pairs(h_t, h_d, pair_mask)
             out = torch.zeros((T, D), device=dev, dtype=torch.float32)
             fused = None
-            if self.match_mode == 'fast':
+            if self.match_mode in self.TC_MODES:
                 from . import fused_pairs
                 if fused_pairs.supported(self, h_t.shape[2]) and h_t.shape[2] == h_d.shape[2]:
-                    if self._fused is None:
-                        self._fused = fused_pairs.FusedXcorr(self)
-                    fused = self._fused
+                    fused = self.fused_matcher()
                     pk_t, pk_d = fused.prepare(h_t, xyz_t), fused.prepare(h_d, xyz_d)
                     chunk = max(chunk, 65536 * 256 // h_t.shape[2])
             if pair_mask is None:

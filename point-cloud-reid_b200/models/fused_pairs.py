@@ -1,15 +1,21 @@
-"""Host side of the fused tensor-core `xcorr_eff` matcher (csrc/pair_tc.cu) -- the "fast" mode of
-ReIDNet.match_all_pairs / match_forward_inference.
+"""Host side of the fused tensor-core `xcorr_eff` matcher (csrc/pair_tc.cu, csrc/pair_tc2.cu) -- the tensor-core
+modes of ReIDNet.match_all_pairs / match_forward_inference:
 
-Everything that depends on one object only is computed once per object with the fp32 kernels and packed to
-bf16 operand images (stage-1 queries elu(Wq1 h)+1, U = W0a1 h, h, Wv2 pos2(xyz), and the stage-1 attention
-operand MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the two fused kernels then score pairs without
-writing any per-pair activation except the bf16 stage-1 outputs (64 KB / pair at 256 points) and the stage-2
-attention operands (36 KB / pair).
+  'fast'      bf16 operand images (8-bit significand), |dlogit| <= 3e-2
+  'parity_tc' fp16 operand images (11-bit significand, the precision of tf32 at the tensor-pipe rate and operand bytes of
+              bf16), |dlogit| <= 5e-3.  fp16's narrow exponent is safe here because every operand is O(1) by construction:
+              LayerNorm outputs, elu+1 features, projections of those, and key/value sums that are stored divided by the
+              point count (the attention read-out is a ratio, so the scale cancels; LinearAttention's eps is scaled
+              with it).  Conversions saturate instead of overflowing.
+
+Everything that depends on one object only is computed once per object with the fp32 kernels and packed to 16-bit
+operand images (stage-1 queries elu(Wq1 h)+1, U = W0a1 h, h, Wv2 pos2(xyz), and the stage-1 attention operand
+MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the three fused kernels then score pairs without writing any per-pair
+activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and the stage-2 attention operands (36 KB / pair).
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
 """
 import ctypes
-import os
+import math
 
 import torch
 
@@ -19,7 +25,9 @@ from ._packing import kmajor
 
 IMG = 16384
 B7_BYTES = 18432
-LN2B = 0.69140625          # bf16(ln 2): the packed elu epilogue of pair_tc2.cu multiplies by this constant
+FMT_BF16, FMT_F16 = 0, 1
+LN2B = 0.69140625          # bf16(ln 2): the packed elu epilogue of the bf16 kernels multiplies by this constant
+ATT_EPS = 1e-6             # LinearAttention.eps (attention.py:21)
 
 
 def _center_out(w):
@@ -37,10 +45,10 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def _w_image(w):
-    """torch weight (N, K) -> bf16 K-major operand image [K/8][N][8] as bytes."""
+def _w_image(w, dtype):
+    """torch weight (N, K) -> 16-bit K-major operand image [K/8][N][8] as bytes."""
     N, Kd = w.shape
-    return w.detach().to(torch.bfloat16).view(N, Kd // 8, 8).permute(1, 0, 2).contiguous().view(torch.uint8).flatten()
+    return w.detach().to(dtype).view(N, Kd // 8, 8).permute(1, 0, 2).contiguous().view(torch.uint8).flatten()
 
 
 def _f32_bytes(*ts):
@@ -49,75 +57,54 @@ def _f32_bytes(*ts):
 
 def supported(model, n_points):
     X1, X2 = model.cross_stage1, model.cross_stage2
-    ok = (model.match_type == 'xcorr_eff' and model.combine == 'point-cat' and model.pool_type == 'both'
-          and X1 is not None and X2 is not None and X1.q_proj.weight.shape == (64, 64) and X1.nhead == 2
-          and X2.q_proj.weight.shape == (64, 64) and X2.nhead == 2 and n_points >= 1)
-    if ok and n_points % 128:
-        # ragged point counts (160 / 192 / 224 in the reference's ablation configs) are zero-padded to 128-row tiles by
-        # the second-generation kernels only
-        ok = os.environ.get("PCREID_PAIR_GEN", "2") == "2"
-    return ok
+    return (model.match_type == 'xcorr_eff' and model.combine == 'point-cat' and model.pool_type == 'both'
+            and X1 is not None and X2 is not None and X1.q_proj.weight.shape == (64, 64) and X1.nhead == 2
+            and X2.q_proj.weight.shape == (64, 64) and X2.nhead == 2 and n_points >= 1)
 
 
 class ObjectPack:
     """per-object operand images of a set of objects (tracks or detections)."""
-    __slots__ = ("n", "npts", "QF1", "U", "H", "PV", "MK1")
+    __slots__ = ("n", "npts", "fmt", "QF1", "U", "H", "PV", "MK1")
 
 
 class FusedXcorr:
-    def __init__(self, model):
+    def __init__(self, model, fmt=FMT_BF16):
         self.model = model
+        self.fmt = fmt
+        self.dtype = torch.float16 if fmt == FMT_F16 else torch.bfloat16
         self._key = None
-        self._w1 = self._w2 = None
-        self.n_ctas = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        self.n_ctas = None
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
-        self.p2_three_tiles = os.environ.get("PCREID_P2_VARIANT", "3") == "3"   # 3 groups x 4 warps (default) or 2 x 8
-        self.p1_split = os.environ.get("PCREID_P1_VARIANT", "split") == "split"   # p1a + p1b (3 tiles in flight) or monolithic
-        self.gen2 = os.environ.get("PCREID_PAIR_GEN", "2") == "2"       # pair_tc2.cu kernels (default) or the first generation
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
         key = tuple((t.data_ptr(), t._version) for t in list(X1.parameters()) + list(X2.parameters()))
         if key != self._key:
             with torch.no_grad():
-                d = 64
-                self._w1 = torch.cat([
-                    _w_image(X1.mlp[0].weight[:, d:]), _w_image(X1.mlp[2].weight),
-                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)), _w_image(X2.merge.weight),
-                    _f32_bytes(X1.norm1.weight, X1.norm1.bias, X1.norm2.weight, X1.norm2.bias)]).contiguous()
-                self._w2 = torch.cat([
-                    _w_image(X2.q_proj.weight), _w_image(X2.mlp[0].weight), _w_image(X2.mlp[2].weight),
-                    _f32_bytes(X2.norm1.weight, X2.norm1.bias, X2.norm2.weight, X2.norm2.bias)]).contiguous()
-                self._w1a = torch.cat([
-                    _w_image(X1.mlp[0].weight[:, d:]), _w_image(X1.mlp[2].weight),
-                    _f32_bytes(X1.norm1.weight, X1.norm1.bias, X1.norm2.weight, X1.norm2.bias)]).contiguous()
-                self._w1b = torch.cat([
-                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)), _w_image(X2.merge.weight)]).contiguous()
-                assert self._w1.numel() == 58368 and self._w2.numel() == 58368
-                assert self._w1a.numel() == 33792 and self._w1b.numel() == 24576
-                # ---- second generation (pair_tc2.cu): LN1 affine folded forward, centred merge / mlp[2], scaled q_proj
+                d, dt = 64, self.dtype
+                # LN1 affine folded forward, centred merge / mlp[2], q_proj scaled for the exp2-based elu epilogue
                 f = lambda t: t.detach().float()
                 W0_1, W0_2 = f(X1.mlp[0].weight), f(X2.mlp[0].weight)
                 self._w1a2 = torch.cat([
-                    _w_image(W0_1[:, d:] * f(X1.norm1.weight)[None, :]), _w_image(_center_out(X1.mlp[2].weight)),
+                    _w_image(W0_1[:, d:] * f(X1.norm1.weight)[None, :], dt), _w_image(_center_out(X1.mlp[2].weight), dt),
                     _f32_bytes(X1.norm2.weight)]).contiguous()
                 self._c1 = (W0_1[:, d:] @ f(X1.norm1.bias)).contiguous()           # W0b.beta1 -> bias of the per-object term U
                 self._b2_1 = f(X1.norm2.bias).contiguous()                         # added to the residual image H
                 self._merge1c = kmajor(_center_out(X1.merge.weight))
                 self._w1b2 = torch.cat([
-                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0)),
-                    _w_image(_center_out(X2.merge.weight))]).contiguous()
+                    _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0), dt),
+                    _w_image(_center_out(X2.merge.weight), dt)]).contiguous()
                 W0ext = torch.zeros((2 * d, 2 * d + 16), device=W0_2.device)
                 W0ext[:, :d] = W0_2[:, :d]
                 W0ext[:, d:2 * d] = W0_2[:, d:] * f(X2.norm1.weight)[None, :]
                 W0ext[:, 2 * d] = W0_2[:, d:] @ f(X2.norm1.bias)
+                ln2 = math.log(2.0) if self.fmt == FMT_F16 else LN2B
                 self._w2y = torch.cat([
-                    _w_image(f(X2.q_proj.weight) / LN2B), _w_image(W0ext), _w_image(_center_out(X2.mlp[2].weight)),
+                    _w_image(f(X2.q_proj.weight) / ln2, dt), _w_image(W0ext, dt), _w_image(_center_out(X2.mlp[2].weight), dt),
                     _f32_bytes(X2.norm2.weight)]).contiguous()
                 self._b2_2 = f(X2.norm2.bias).contiguous()                         # added after the pooling
                 assert self._w1a2.numel() == 33024 and self._w2y.numel() == 61696 and self._w1b2.numel() == 24576
             self._key = key
-        return self._w1, self._w2
 
     def _tick(self):
         if self.timing is None:
@@ -132,13 +119,16 @@ class FusedXcorr:
             e1.record()
             self.timing.append((name, e0, e1, units))
 
-    @staticmethod
-    def _pack_image(x, act=K.ACT_NONE):
+    def _pack_image(self, x, act=K.ACT_NONE):
         B, C, N = x.shape
         out = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=x.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().pcreid_pack_image(B, C, N, _p(x), x.stride(0), x.stride(1), act, _p(out), _stream()),
+        _lib.check(_lib.lib().pcreid_pack_image(B, C, N, _p(x), x.stride(0), x.stride(1), act, self.fmt, _p(out), _stream()),
                    "pcreid_pack_image")
         return out
+
+    def kv_scale(self, npts):
+        """scale the key/value sums of a template with `npts` points are stored with (fp16: 1/points keeps them O(1))."""
+        return 1.0 / npts if self.fmt == FMT_F16 else 1.0
 
     def prepare(self, h, xyz):
         """h (B, 64, N) fp32 channel-major, xyz (B, N, 3) (None for token sets without coordinates) -> ObjectPack."""
@@ -147,26 +137,26 @@ class FusedXcorr:
         self._weights()
         B, C, N = h.shape
         o = ObjectPack()
-        o.n, o.npts = B, N
+        o.n, o.npts, o.fmt = B, N, self.fmt
         o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
-        if self.gen2:
-            o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
-            o.H = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
-            _lib.check(_lib.lib().pcreid_pack_image_bias(B, C, N, _p(h), h.stride(0), h.stride(1), _p(self._b2_1), _p(o.H),
-                                                         _stream()), "pcreid_pack_image_bias")   # h + beta2
-        else:
-            o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"]))
-            o.H = self._pack_image(h)
+        o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
+        o.H = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
+        _lib.check(_lib.lib().pcreid_pack_image_bias(B, C, N, _p(h), h.stride(0), h.stride(1), _p(self._b2_1), self.fmt, _p(o.H),
+                                                     _stream()), "pcreid_pack_image_bias")   # h + beta2
         pos2 = X2.position_code(xyz)
         if pos2 is None:            # cross_lin_attn (image tokens, attention.py:312-372): no position code -> Wv.pos == 0
             o.PV = torch.zeros((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
         else:
             o.PV = self._pack_image(K.cn_linear(pos2, pk2["v"]))
         wkv, ksum = X1.template_summary(h, X1.position_code(xyz))          # (B, 64, 64) [d][v] block diagonal, (B, 64)
-        M = K.cn_linear(wkv, self._merge1c if self.gen2 else pk1["merge"], x1_pm=True, y_pm=True)   # (B, d, out) = blockdiag(KV) Wm^T
-        M.mul_(float(N))                                                    # undo the reference's values / S (attention.py:47)
+        M = K.cn_linear(wkv, self._merge1c, x1_pm=True, y_pm=True)          # (B, d, out) = blockdiag(KV) Wm^T
+        # template_summary follows the reference's values / S (attention.py:47): M carries 1/N, ksum does not
+        sc = self.kv_scale(N)
+        M.mul_(float(N) * sc)
+        if sc != 1.0:
+            ksum = ksum * sc
         o.MK1 = torch.empty((B, B7_BYTES), device=h.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), _p(o.MK1), _stream()), "pcreid_pack_b7")
+        _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), self.fmt, _p(o.MK1), _stream()), "pcreid_pack_b7")
         return o
 
     def match(self, pt, pd, ti, dj, debug=None, dense=None):
@@ -174,8 +164,11 @@ class FusedXcorr:
         dense=(r0, nrows, D): the pairs are the full row block [r0, r0+nrows) x [0, D) in row-major order (ti, dj may be
         None) -- the unit lists are then generated arithmetically instead of by a stable argsort over the templates."""
         assert pt.npts == pd.npts, "fused matcher expects equal point counts on both sides"
-        w1, w2 = self._weights()
+        assert pt.fmt == self.fmt and pd.fmt == self.fmt, "object packs were prepared for another operand format"
+        self._weights()
         dev = pt.H.device
+        if self.n_ctas is None:
+            self.n_ctas = torch.cuda.get_device_properties(dev).multi_processor_count
         if dense is not None:
             r0, nrows, Dn = dense
             P = nrows * Dn
@@ -188,70 +181,45 @@ class FusedXcorr:
             ti, dj = ti.long(), dj.long()
             unit_lists = None
         NT, N = (pt.npts + 127) // 128, pt.npts
-        assert N % 128 == 0 or self.gen2, "ragged point counts need the second-generation kernels"
         A = torch.empty((P, 2, NT, IMG), device=dev, dtype=torch.uint8)
         B7 = torch.empty((P, 2, B7_BYTES), device=dev, dtype=torch.uint8)
         part = torch.empty((P, 2, 128), device=dev, dtype=torch.float32)
         L = _lib.lib()
+        sc = self.kv_scale(N)
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             if unit_lists is not None:
                 us, ut, sl = (x.contiguous() for x in unit_lists[role])
             else:
                 order = torch.argsort(tmpl, stable=True)                    # runs of units share the template operand
                 us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
-            if self.gen2:
-                e0 = self._tick()
-                _lib.check(L.pcreid_pair_p1a2(P, N, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(pm.MK1),
-                                              _p(self._w1a2), _p(A), self.n_ctas, _stream()), "pcreid_pair_p1a2")
-                self._tock("pair_p1a2_kernel", e0, P)
-                e0 = self._tick()
-                _lib.check(L.pcreid_pair_p1b_n(P, N, role, _p(us), _p(ut), _p(sl), _p(ps.PV), _p(self._w1b2), _p(A), _p(B7),
-                                               self.n_ctas, _stream()), "pcreid_pair_p1b_n")
-                self._tock("pair_p1b_kernel", e0, P)
-                continue
-            if self.p1_split:
-                for which, blob, name in ((0, self._w1a, "pair_p1a_kernel"), (1, self._w1b, "pair_p1b_kernel")):
-                    e0 = self._tick()
-                    _lib.check(L.pcreid_pair_p1ab(which, P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H),
-                                                  _p(ps.PV), _p(pm.MK1), _p(blob), _p(A), _p(B7), self.n_ctas, _stream()),
-                               "pcreid_pair_p1ab")
-                    self._tock(name, e0, P)
-                continue
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p1(P, NT, role, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U), _p(ps.H), _p(ps.PV),
-                                        _p(pm.MK1), _p(w1), _p(A), _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1")
-            self._tock("pair_p1_kernel", e0, P)
+            _lib.check(L.pcreid_pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U),
+                                          _p(ps.H), _p(pm.MK1), _p(self._w1a2), _p(A), self.n_ctas, _stream()), "pcreid_pair_p1a2")
+            self._tock("pair_p1a2_kernel", e0, P)
+            e0 = self._tick()
+            _lib.check(L.pcreid_pair_p1b_n(P, N, role, self.fmt, sc, _p(us), _p(ut), _p(sl), _p(ps.PV), _p(self._w1b2), _p(A),
+                                           _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1b_n")
+            self._tock("pair_p1b_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
-        if self.gen2:
-            for role in (0, 1):
-                e0 = self._tick()
-                _lib.check(L.pcreid_pair_p2y(P, N, role, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part), self.n_ctas,
-                                             _stream()), "pcreid_pair_p2y")
-                self._tock("pair_p2y_kernel", e0, P)
-            _lib.check(L.pcreid_pool_finish2(P, N, _p(part), _p(self._b2_2), _p(pooled), _stream()), "pcreid_pool_finish2")
-            if debug is not None:
-                debug.update(A=A, B7=B7, part=part, pooled=pooled)
-            return self.model._head_cn(pooled)
         for role in (0, 1):
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p2(P, NT, role, _p(slots), _p(A), _p(B7), _p(w2), _p(part),
-                                        -self.n_ctas if self.p2_three_tiles else self.n_ctas, _stream()),
-                       "pcreid_pair_p2")
-            self._tock("pair_p2_kernel", e0, P)
-        _lib.check(L.pcreid_pool_finish(P, N, _p(part), _p(pooled), _stream()), "pcreid_pool_finish")
+            _lib.check(L.pcreid_pair_p2y(P, N, role, self.fmt, ATT_EPS * sc, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part),
+                                         self.n_ctas, _stream()), "pcreid_pair_p2y")
+            self._tock("pair_p2y_kernel", e0, P)
+        _lib.check(L.pcreid_pool_finish2(P, N, _p(part), _p(self._b2_2), _p(pooled), _stream()), "pcreid_pool_finish2")
         if debug is not None:
             debug.update(A=A, B7=B7, part=part, pooled=pooled)
         return self.model._head_cn(pooled)
 
 
-def decode_image(img):
+def decode_image(img, dtype=torch.bfloat16):
     """(..., C/8, 128, 16) uint8 operand image -> (..., C, 128) fp32 (debug / tests)."""
-    x = img.contiguous().view(torch.bfloat16).float().transpose(-1, -2)     # (..., C/8, 8, 128)
+    x = img.contiguous().view(dtype).float().transpose(-1, -2)     # (..., C/8, 8, 128)
     return x.reshape(*x.shape[:-3], x.shape[-3] * 8, 128)
 
 
-def decode_b7(img):
+def decode_b7(img, dtype=torch.bfloat16):
     """(..., 18432) uint8 attention operand -> (..., 64 k, 144 n) fp32 (debug / tests)."""
-    x = img.contiguous().view(torch.bfloat16).float().reshape(*img.shape[:-1], 18, 64, 8)   # [n/8][k][8]
+    x = img.contiguous().view(dtype).float().reshape(*img.shape[:-1], 18, 64, 8)   # [n/8][k][8]
     return x.permute(*range(x.dim() - 3), x.dim() - 2, x.dim() - 3, x.dim() - 1).reshape(*img.shape[:-1], 64, 144)

@@ -68,16 +68,24 @@ class ImageReIDNet(nn.Module):
         self.verbose = False
         self.sampling = None
         self.match_mode = 'parity'
-        self._fused = None
+        self._fused = {}
         if self.match_type != 'xcorr_eff':
             raise NotImplementedError(f"match_type '{match_type}' is outside the accelerated hot path "
                                       "(every shipped image config uses 'xcorr_eff')")
 
     def set_mode(self, mode):
-        """'parity': fp32 kernels (1e-4).  'fast': fused bf16 tcgen05 matcher (|dlogit| <= 3e-2)."""
-        assert mode in ('parity', 'fast')
+        """'parity': fp32 kernels (1e-4).  'parity_tc' / 'fast': fused tcgen05 matcher with fp16 / bf16 operands
+        (|dlogit| <= 5e-3 / 3e-2)."""
+        assert mode in ('parity', 'parity_tc', 'fast')
         self.match_mode = mode
         return self
+
+    def fused_matcher(self):
+        from . import fused_pairs
+        fmt = fused_pairs.FMT_F16 if self.match_mode == 'parity_tc' else fused_pairs.FMT_BF16
+        if fmt not in self._fused:
+            self._fused[fmt] = fused_pairs.FusedXcorr(self, fmt)
+        return self._fused[fmt]
 
     def set_backbone(self, module, name=None):
         """attach an image backbone (any module whose output has `.hidden_states` / `.last_hidden_state`, ReIDNet.py:914-941)."""
@@ -189,12 +197,10 @@ class ImageReIDNet(nn.Module):
             dev = h_t.device
             out = torch.zeros((T, D), device=dev, dtype=torch.float32)
             fused = None
-            if self.match_mode == 'fast':
+            if self.match_mode in ('parity_tc', 'fast'):
                 from . import fused_pairs
                 if fused_pairs.supported(self, h_t.shape[2]) and h_t.shape[2] == h_d.shape[2]:
-                    if self._fused is None:
-                        self._fused = fused_pairs.FusedXcorr(self)
-                    fused = self._fused
+                    fused = self.fused_matcher()
                     pk_t, pk_d = fused.prepare(h_t, None), fused.prepare(h_d, None)
                     chunk = max(chunk, 65536 * 256 // h_t.shape[2])
             pairs = None if pair_mask is None else pair_mask.nonzero()

@@ -7,15 +7,19 @@
 //   mode 3: bf16, A from tensor memory (tcgen05.st by the row-owning threads), B K-major in shared memory
 //   mode 4: tf32, A and B MN-major in shared memory  ([mn/4][k][4] fp32; global holds A^T (K x 128), B^T (K x N))
 //   mode 5: tf32, A from tensor memory (one fp32 element per 32-bit column), B K-major in shared memory
+//   modes 6 / 7 / 8: modes 0 / 1 / 3 with fp16 instead of bf16 operands (the parity_tc mode of the fused matcher)
+// Test-only library (tests/native/libpcreid_tcprobe.so, built by __graft_entry__.build()); not part of the product .so.
 // D (128 x N, fp32, row-major) = A (128 x K) * B (N x K)^T.
 #include "../../include/pcreid.h"
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "../../point-cloud-reid_b200/csrc/common.cuh"
+#include "../../point-cloud-reid_b200/csrc/tc_common.cuh"
 
 namespace {
 
 __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, const void* __restrict__ Ag,
                                                        const void* __restrict__ Bg, float* __restrict__ D) {
+  const int fmt16 = mode >= 6 ? tc::FMT_F16 : tc::FMT_BF16;
+  if (mode >= 6) mode = mode == 6 ? 0 : (mode == 7 ? 1 : 3);
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -112,7 +116,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
   if (tid == 0) {
     const uint32_t a0 = tc::smem_u32(As), b0 = tc::smem_u32(Bs);
     if (mode == 0 || mode == 3) {
-      const uint32_t idesc = tc::instr_desc(128, N, tc::FMT_BF16, tc::MAJOR_K, tc::MAJOR_K);
+      const uint32_t idesc = tc::instr_desc(128, N, fmt16, tc::MAJOR_K, tc::MAJOR_K);
       for (int ks = 0; ks < K / 16; ++ks) {
         uint64_t bd = tc::smem_desc(b0 + ks * 2 * (N * 16), N * 16, 128, tc::LAYOUT_NONE);
         if (mode == 0) {
@@ -123,7 +127,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
         }
       }
     } else if (mode == 1) {
-      const uint32_t idesc = tc::instr_desc(128, N, tc::FMT_BF16, tc::MAJOR_MN, tc::MAJOR_MN);
+      const uint32_t idesc = tc::instr_desc(128, N, fmt16, tc::MAJOR_MN, tc::MAJOR_MN);
       for (int ks = 0; ks < K / 16; ++ks) {
         uint64_t ad = tc::smem_desc(a0 + ks * 2 * 128, 128, K * 16, tc::LAYOUT_NONE);
         uint64_t bd = tc::smem_desc(b0 + ks * 2 * 128, 128, K * 16, tc::LAYOUT_NONE);
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(int mode, int N, int K, c
 }  // namespace
 
 extern "C" int pcreid_tc_probe(int mode, int n, int k, const void* a, const void* b, float* d, void* stream) {
-  if (!a || !b || !d || mode < 0 || mode > 5) return PCREID_ERR_ARG;
+  if (!a || !b || !d || mode < 0 || mode > 8) return PCREID_ERR_ARG;
   if (n < 16 || n > 256 || n % 16 || k < 16 || k > 256 || k % 16) return PCREID_ERR_UNSUPPORTED;
   const int esz = (mode == 2 || mode == 4 || mode == 5) ? 4 : 2;
   size_t smem = (size_t)(128 + n) * k * esz;
