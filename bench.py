@@ -7,9 +7,16 @@ A step = encode the step's tracks and detections (PT backbone) + score every tra
 At N GPUs the track rows are sharded (weak scaling: 1024 tracks per rank, the 1024 detections are
 split for encoding and all-gathered once).  Prints ONE JSON line (rank 0).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode parity]
+The headline mode is 'parity_tc' -- every contraction on the tensor cores at an 11-bit significand (tf32 encoder GEMMs,
+fp16 matcher operands), the mode that passes the parity gates of SURVEY.md 8d; the line carries the measured parity
+(`parity`: max |dlogit| and RAW top-1 agreement on a 256 x 256 block of the workload against the CPU oracle), the bf16
+'fast' mode beside it (`fast_mode`), an encoder roofline (`encoder`), and a fixed-size strong-scaling leg (`strong`: 4096 x 4096
+pairs row-sharded over the N ranks INCLUDING the all-gather of the score rows).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode parity_tc|fast|parity]
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -24,10 +31,20 @@ import torch  # noqa: E402
 
 T_PER_GPU, D_TOTAL, NPTS = 1024, 1024, 256
 BLIST = (256, 128, 64)
+STRONG_T = STRONG_D = 4096
 # algorithmic work of the reference formulation (torch.utils.flop_counter on the reference)
 FLOP_PER_OBJECT = 592e6          # Pointnet_Backbone @256 pts
 FLOP_PER_PAIR = 101.25e6         # xcorr_eff + pool + head @256 pts
 METRIC = "pair scores/sec (PT-256 encode + all-pairs xcorr_eff match)"
+CPU_SAMPLE = (64, 8192)          # objects per side, pairs: the bounded CPU sample, identical in both arms
+MODE_TEXT = {
+    "parity_tc": "parity_tc: tcgen05 everywhere at an 11-bit significand -- kind::tf32 SA shared MLPs / attention blocks in the "
+                 "encoder, fused kind::f16 matcher with fp16 operands (pair_tc.cu, pair_tc2.cu) -- fp32 accumulate / norms; "
+                 "gate |dlogit| <= 5e-3, raw top-1 >= 0.97",
+    "fast": "fast: the same kernels with bf16 matcher operands; gate |dlogit| <= 3e-2",
+    "parity": "parity: fp32 FFMA kernels, logits within 1e-4 of the reference",
+}
+DTYPE = {"parity_tc": "f16", "fast": "bf16", "parity": "f32"}
 
 
 def peaks():
@@ -36,6 +53,19 @@ def peaks():
         d = json.load(open(p))
         return d, "measured"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def ncu_traffic(mode):
+    """per-unit DRAM bytes of the fused kernels from the newest ncu --set full capture (profiles/rNN_ncu_traffic.json, written by
+    scripts/ncu_traffic.py from the capture itself) -> ({kernel: bytes per (pair, direction) unit}, source) or (None, None)."""
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    ent = d.get("modes", {}).get(mode) or d.get("modes", {}).get("parity_tc") or d.get("modes", {}).get("fast")
+    if not ent:
+        return None, None
+    return {k: v["dram_bytes_per_unit"] for k, v in ent["kernels"].items()}, os.path.relpath(files[-1], ROOT)
 
 
 class ClockSampler:
@@ -70,16 +100,32 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_sample(n_obj=32, n_pairs=2048, threads=None):
-    """The reference's PyTorch path (oracle restatement, bit-exact vs the reference modules) on host cores, on a
-    bounded sample of the same workload: encode n_obj+n_obj objects, score n_pairs pairs; extrapolated to the
-    step's composition (objects and pairs per step)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import helpers                                  # oracle builder shared with the parity tests
-    from oracle import reid_oracle as O
+_ORACLE = {}
+
+
+def _oracle():
+    """the CPU checker: oracle restatement of the reference's PyTorch path (bit-exact vs the reference modules,
+    tests/test_reidnet_pinned.py) with the weights of the benchmarked model (seed 66, default init)."""
+    if "orc" not in _ORACLE:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import helpers                                  # oracle builder shared with the parity tests
+        from oracle import reid_oracle as O
+        _ORACLE["orc"] = helpers.build_pair("pt", BLIST, device="cpu", perturb=False)[1]
+        _ORACLE["O"] = O
+    return _ORACLE["orc"], _ORACLE["O"]
+
+
+def cpu_reference_sample(n_obj=CPU_SAMPLE[0], n_pairs=CPU_SAMPLE[1], threads=None, warm=True):
+    """The reference's PyTorch path (oracle port) on host cores, on a bounded sample of the same workload: encode
+    n_obj+n_obj objects, score n_pairs pairs; extrapolated to the step's composition (objects and pairs per step).
+    warm: one small untimed pass first (thread pool, allocator, lazy module state), so a single call is not a cold number."""
+    orc, O = _oracle()
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    _, orc = helpers.build_pair("pt", BLIST, device="cpu", perturb=False)
+    if warm:
+        w = O.synth_objects(4, NPTS, 7)
+        xw, hw = orc.encode(w)
+        orc.match_all_pairs(hw, xw, hw, xw, chunk=4096)
     t, d = O.synth_objects(n_obj, NPTS, 0), O.synth_objects(n_obj, NPTS, 1)
     t0 = time.perf_counter()
     xt, ht = orc.encode(t)
@@ -92,9 +138,36 @@ def cpu_reference_sample(n_obj=32, n_pairs=2048, threads=None):
     s_pair = (t2 - t1) / (rows * n_obj)
     step_s = s_obj * (T_PER_GPU + D_TOTAL) + s_pair * T_PER_GPU * D_TOTAL
     return {"value": T_PER_GPU * D_TOTAL / step_s, "unit": "pairs/s", "cores": threads, "kind": "port",
-            "sample": f"{2 * n_obj} objects encoded ({1 / s_obj:.1f} obj/s) + {rows * n_obj} pairs scored ({1 / s_pair:.1f} pairs/s), "
-                      f"extrapolated to {T_PER_GPU + D_TOTAL} objects + {T_PER_GPU * D_TOTAL} pairs per step",
+            "sample": f"{2 * n_obj} objects encoded ({1 / s_obj:.1f} obj/s) + {rows * n_obj} pairs scored ({1 / s_pair:.1f} pairs/s) "
+                      f"after one warm-up pass, extrapolated to {T_PER_GPU + D_TOTAL} objects + {T_PER_GPU * D_TOTAL} pairs per step",
             "objects_per_s": 1 / s_obj, "pairs_only_per_s": 1 / s_pair}
+
+
+def parity_block(model, dev, rows=256, cols=256):
+    """measured parity of the benchmarked mode: a rows x cols block of the workload (tracks seed 1000, detections seed 1 --
+    the step's own inputs) through the CUDA path end to end (encode + match) against the CPU oracle."""
+    orc, O = _oracle()
+    from pcreid_b200 import synthetic as S
+    t, d = S.synth_objects(rows, NPTS, 1000), S.synth_objects(cols, NPTS, 1)
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd, chunk=4096)
+    cpu_s = time.perf_counter() - t0
+    xt, ht = model.encode(t.to(dev))
+    xd, hd = model.encode(d.to(dev))
+    L = model.match_all_pairs(ht, xt, hd, xd).cpu()
+    err = (L - Lo).abs()
+    top2 = torch.topk(Lo, 2, dim=1)[0]
+    gap = top2[:, 0] - top2[:, 1]
+    same = Lo.argmax(1) == L.argmax(1)
+    mx = float(err.max())
+    dec = gap > 2 * mx
+    return {"mode": model.match_mode, "block": f"{rows}x{cols} pairs of the step's own inputs, encode + match end to end vs the CPU oracle",
+            "max_abs": mx, "mean_abs": float(err.mean()), "top1_raw": float(same.float().mean()), "decisive_rows": int(dec.sum()),
+            "decisive_rows_unchanged": bool(same[dec].all()), "oracle_logit_std": float(Lo.std()), "oracle_gap_median": float(gap.median()),
+            "embedding_max_abs": float((ht.cpu() - oht).abs().max()), "oracle_cpu_s": cpu_s}
 
 
 def run_reference(args):
@@ -104,7 +177,7 @@ def run_reference(args):
     vals = []
     last = None
     for i in range(args.warmup + args.steps):
-        last = cpu_reference_sample(32, 4096)
+        last = cpu_reference_sample(warm=(i == 0))
         if i >= args.warmup:
             vals.append(last["value"])
     v = sum(vals) / len(vals)
@@ -124,17 +197,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="fast", choices=["parity", "fast"])
+    ap.add_argument("--mode", default="parity_tc", choices=["parity", "parity_tc", "fast"])
     ap.add_argument("--tracks", type=int, default=T_PER_GPU)
     ap.add_argument("--dets", type=int, default=D_TOTAL)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU legs (cpu_baseline, parity)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the fast-mode and strong-scaling legs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch.distributed as dist
-    from pcreid_b200 import _lib, synthetic as S   # the measured legs never import oracle/ or tests/ (cpu_baseline leg only)
-    from pcreid_b200.parallel import encode_and_gather, match_all_pairs_sharded, shard_range
+    from pcreid_b200 import _lib, synthetic as S   # the measured legs never import oracle/ or tests/ (CPU checker legs only)
+    from pcreid_b200.parallel import encode_and_gather, gathered_bytes, match_all_pairs_sharded, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,19 +280,57 @@ def main():
     enc_ms, match_ms = e0.elapsed_time(e1), e0.elapsed_time(e2) - e0.elapsed_time(e1)
     # per-launch durations of the fused kernels (CUDA events on the launching stream), one more match pass
     kern = {}
-    if args.mode == "fast" and model._fused is not None:
-        model._fused.timing = []
+    if args.mode in model.TC_MODES:
+        fm = model.fused_matcher()
+        fm.timing = []
         model.match_all_pairs(ht, xt, hd, xd)
         torch.cuda.synchronize()
-        for name, a0, a1, units in model._fused.timing:
+        for name, a0, a1, units in fm.timing:
             k = kern.setdefault(name, {"launches": 0, "ms": 0.0, "units": 0})
             k["launches"] += 1
             k["ms"] += a0.elapsed_time(a1)
             k["units"] += units
-        model._fused.timing = None
+        fm.timing = None
+    del xt, ht, xd, hd
     for _ in range(1):
         step_e2e()
     e2e_ms, _ = timed(step_e2e, args.steps)
+
+    # ---- beside the headline: the bf16 'fast' mode on the same workload (same timing protocol, fewer steps)
+    fast = None
+    if not args.no_extra and args.mode != "fast":
+        model.set_mode("fast")
+        for _ in range(2):
+            step_device()
+        f_ms, _ = timed(step_device, min(args.steps, 5))
+        fast = {"value": T_loc * world * D / (f_ms / min(args.steps, 5) * 1e-3), "unit": "pairs/s", "ms_per_step": f_ms / min(args.steps, 5),
+                "dtype": "bf16", "mode": MODE_TEXT["fast"]}
+        model.set_mode(args.mode)
+
+    # ---- strong scaling: a FIXED 4096 x 4096 @256 matrix row-sharded over the ranks, score rows all-gathered inside the timed region
+    strong = None
+    if not args.no_extra:
+        Ts, Ds = STRONG_T, STRONG_D
+        s_t0, s_t1 = shard_range(Ts, rank, world)
+        s_d0, s_d1 = shard_range(Ds, rank, world)
+        s_tc = [shard_range(Ts, r, world)[1] - shard_range(Ts, r, world)[0] for r in range(world)]
+        s_dc = [shard_range(Ds, r, world)[1] - shard_range(Ds, r, world)[0] for r in range(world)]
+        s_tr = S.synth_objects(Ts, NPTS, 0)[s_t0:s_t1].contiguous().to(dev)
+        s_de = S.synth_objects(Ds, NPTS, 1)[s_d0:s_d1].contiguous().to(dev)
+
+        def step_strong():
+            return match_all_pairs_sharded(model, s_tr, s_de, s_dc, gather_scores=True, track_counts=s_tc)
+
+        step_strong()
+        n_s = 2
+        s_ms, _ = timed(step_strong, n_s)
+        gb = gathered_bytes(model, NPTS, s_dc, s_tc, gather_scores=True)
+        strong = {"workload": f"fixed {Ts}x{Ds} all-pairs xcorr_eff @ {NPTS} pts + encode of {Ts}+{Ds} objects, track rows and detections "
+                              f"sharded over {world} rank(s); timed region includes the all-gather of the detection embeddings (overlapped "
+                              "with scoring of the local detection block) AND the all-gather of the score rows",
+                  "scaling": "strong", "steps": n_s, "ms_per_step": s_ms / n_s, "value": Ts * Ds / (s_ms / n_s * 1e-3), "unit": "pairs/s",
+                  "bytes_received_per_rank": gb, "mode": args.mode}
+        del s_tr, s_de
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -229,26 +341,26 @@ def main():
         match_tflops = FLOP_PER_PAIR * T_loc * D / (match_ms * 1e-3) / 1e12 if match_ms > 0 else None
         peak_tf = pk["bf16_tflops_sustained"]
         roof_kernel = "match stage (cn_linear_kernel<*> dominates; unfused fp32 parity path)"
-        roof_extra, roof_traffic = {}, None
+        roof_extra, roof_traffic, traffic_src = {}, None, None
         if kern:
-            # dominant kernels: the two fused phases; algorithmic FLOPs of the reference formulation (101.25 MFLOP/pair:
+            # dominant kernels: the three fused phases; algorithmic FLOPs of the reference formulation (101.25 MFLOP/pair:
             # stage 1 both ways = 33.9 %, stage 2 + pool + head = 66.1 %) / their summed CUDA-event durations
             tot_ms = sum(k["ms"] for k in kern.values())
             match_tflops = FLOP_PER_PAIR * T_loc * D / (tot_ms * 1e-3) / 1e12
             roof_kernel = " + ".join(sorted(kern)) + " (fused tcgen05 xcorr_eff)"
-            # DRAM traffic per unit (pair, direction) from the ncu --set full capture in profiles/r01_ncu_pair_kernels.md
-            # (dram__bytes_read.sum + dram__bytes_write.sum per launch / units per launch): p1a2 31.4 KB, p1b 49.8 KB, p2y 52.0 KB
-            roof_traffic = 2 * T_loc * D * (31.4e3 + 49.8e3 + 52.0e3)
+            per_unit, traffic_src = ncu_traffic(args.mode)
+            if per_unit:
+                roof_traffic = sum(per_unit.get(n, 0.0) * k["units"] for n, k in kern.items())
             roof_extra = {"kernels": {n: {"launches": k["launches"], "avg_ms_per_launch": k["ms"] / k["launches"],
                                           "share_of_match": k["ms"] / match_ms} for n, k in kern.items()}}
+        enc_tflops = FLOP_PER_OBJECT * n_enc / (enc_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.mode == "fast" else "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[args.mode],
             "data": "synthetic",
             "config": {"workload": f"configs[1]: Point Transformer encode of {T_loc} tracks/GPU + {D} detections x {NPTS} pts "
                                    f"(backbone_list {list(BLIST)}), {T_loc}x{D} all-pairs xcorr_eff match per GPU",
-                       "mode": ("fast: fused bf16 tcgen05 matcher (pair_tc2.cu), fp32 accumulate/norms, tf32 tcgen05 SA shared MLPs, |dlogit| <= 3e-2"
-                                if args.mode == "fast" else "parity: fp32 FFMA kernels, logits within 1e-4 of the reference"),
+                       "mode": MODE_TEXT[args.mode],
                        "l2": "no flush needed: each step streams >1 GB of activations (>> 126 MB L2)",
                        "sharding": f"track rows over {world} rank(s), one all-gather of detection embeddings"},
             "objects_encoded_per_s": n_enc * world / (enc_ms * 1e-3),
@@ -259,12 +371,21 @@ def main():
             "e2e": {"value": pairs_total / (e2e_ms / args.steps * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": (tracks_h.numel() + dets_h.numel()) * 4, "d2h_bytes_per_step": out_h.numel() * 4},
             "roofline": {"bound": "tensor", "achieved": match_tflops, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": (match_tflops / peak_tf) if match_tflops else None, "traffic": roof_traffic if kern else None,
+                         "frac": (match_tflops / peak_tf) if match_tflops else None, "traffic": roof_traffic,
+                         "traffic_source": traffic_src,
                          "per": "all fused launches of one step (three kernels x both directions x pair chunks), rank 0",
                          "kernel": roof_kernel, "peak_source": pk_src + " bf16 sustained (MEASURED_PEAKS.json)", **roof_extra},
+            "encoder": {"bound": "tensor", "objects_per_s": n_enc / (enc_ms * 1e-3), "achieved": enc_tflops, "peak": peak_tf,
+                        "unit": "TFLOP/s", "frac": enc_tflops / peak_tf,
+                        "per": f"one encode of {n_enc} objects x {NPTS} pts on rank 0 (39 launches), {FLOP_PER_OBJECT / 1e6:.0f} MFLOP/object algorithmic"},
         }
+        if fast:
+            line["fast_mode"] = fast
+        if strong:
+            line["strong"] = strong
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference_sample(32, 2048)
+            line["parity"] = parity_block(model, dev)
+            line["cpu_baseline"] = cpu_reference_sample()
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
