@@ -68,6 +68,15 @@ int pcreid_query_ball_point(int b, int n, int m, float r2, int nsample, const fl
 /* replaces group_points_kernel_launcher(b,c,n,npoints,nsample,points,idx,out,stream)
  * (ops/group_points/src/group_points_cuda.cu:81-100): out[b,c,s,j] = points[b,c,idx[b,s,j]]. */
 int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const float* points, const int* idx, float* out, void* stream);
+
+/* the body of QueryAndGroup.forward (ops/group_points/group_points.py:93-118) after the index query, in one pass over the
+ * (b, c+3, npoints, nsample) result instead of the reference's grouping_operation x2 + transpose + sub + div + cat:
+ *   out[b, 0:3, s, j]  = (xyz[b, idx[b,s,j], :] - center_xyz[b, s, :]) (/ divide_by when divide_by != 0: normalize_xyz)   if use_xyz
+ *   out[b, 3*use_xyz + ch, s, j] = features[b, ch, idx[b,s,j]]                                   if features != NULL (b,c,n)
+ *   grouped_xyz[b, 0:3, s, j] = xyz[b, idx[b,s,j], :]                                             if grouped_xyz != NULL
+ * xyz (b,n,3), center_xyz (b,npoints,3), idx int32 (b,npoints,nsample).  Bit-identical to the reference's op chain. */
+int pcreid_query_group(int b, int c, int n, int npoints, int nsample, const float* xyz, const float* center_xyz, const float* features,
+                       const int* idx, int use_xyz, float divide_by, float* out, float* grouped_xyz, void* stream);
 /* replaces gather_points_kernel_launcher(b,c,n,npoints,points,idx,out,stream)
  * (ops/gather_points/src/gather_points_cuda.cu:28-49): out[b,c,m] = points[b,c,idx[b,m]]. */
 int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream);

@@ -47,6 +47,45 @@ def query_and_group(points_xyz, center_xyz, features, max_radius, sample_num, mi
     return diff
 
 
+def uniform_resample(idx, sample_num):
+    """uniform_sample branch of QueryAndGroup.forward (group_points.py:78-91) restated: per (batch, region) keep the distinct
+    indices (torch.unique: ascending) and fill up to sample_num with torch.randint picks among them (host default generator,
+    one call per region in (batch, region) order).  -> (idx, unique_cnt (B, S) float32)."""
+    idx = idx.clone()
+    cnt = torch.zeros((idx.shape[0], idx.shape[1]))
+    for b in range(idx.shape[0]):
+        for r in range(idx.shape[1]):
+            u = torch.unique(idx[b, r, :])
+            n = u.shape[0]
+            cnt[b, r] = n
+            fill = torch.randint(0, n, (sample_num - n,), dtype=torch.long)
+            idx[b, r, :] = torch.cat((u, u[fill]))
+    return idx, cnt
+
+
+def query_and_group_full(points_xyz, center_xyz, features, max_radius, sample_num, min_radius=0, use_xyz=True, normalize_xyz=False,
+                         uniform_sample=False):
+    """QueryAndGroup.forward (group_points.py:49-129) with every return it can be configured to give:
+    -> (new_features, grouped_xyz, unique_cnt or None, idx)."""
+    if max_radius is None:
+        idx = OP.knn(sample_num, points_xyz, center_xyz).transpose(1, 2).contiguous()
+    else:
+        idx = OP.ball_query(min_radius, max_radius, sample_num, points_xyz, center_xyz)
+    cnt = None
+    if uniform_sample:
+        idx, cnt = uniform_resample(idx, sample_num)
+    grouped_xyz = OP.grouping_operation(points_xyz.transpose(1, 2).contiguous(), idx)
+    diff = grouped_xyz - center_xyz.transpose(1, 2).unsqueeze(-1)
+    if normalize_xyz:
+        diff = diff / max_radius
+    if features is not None:
+        gf = OP.grouping_operation(features, idx)
+        nf = torch.cat([diff, gf], dim=1) if use_xyz else gf
+    else:
+        nf = diff
+    return nf, grouped_xyz, cnt, idx
+
+
 def calc_square_dist_ref(a, b, norm=True):
     """furthest_point_sample/utils.py:4-31 verbatim (torch sum / matmul): what the reference feeds to F-FPS."""
     length_a, length_b, num_channel = a.shape[1], b.shape[1], a.shape[-1]

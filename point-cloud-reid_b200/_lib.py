@@ -56,6 +56,7 @@ _SIGS = {
     "pcreid_query_ball_point": [c_int, c_int, c_int, c_float, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_group_points": [c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_gather_points": [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp],
+    "pcreid_query_group": [c_int] * 5 + [c_vp] * 4 + [c_int, c_float, c_vp, c_vp, c_vp],
     "pcreid_crop_tiles": [c_int],
     "pcreid_crop_mask": [c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp],
     "pcreid_crop_gather": [c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],

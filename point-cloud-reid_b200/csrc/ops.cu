@@ -752,6 +752,47 @@ static int group_launch(int b, int c, int n, int p, const float* points, const i
 }
 
 // ------------------------------------------------------------------------------------------------
+// query_group: the body of QueryAndGroup.forward (mmdet3d/ops/group_points/group_points.py:93-118) in ONE pass:
+//   out[b, 0:3, s, j]   = (xyz[b, idx[b,s,j], :] - center[b, s, :]) (/ radius when normalize_xyz)      (use_xyz)
+//   out[b, c0+c, s, j]  = features[b, c, idx[b,s,j]]                                                    (features given)
+//   gxyz[b, 0:3, s, j]  = xyz[b, idx[b,s,j], :]                                                         (return_grouped_xyz)
+// The reference runs two grouping kernels, a transpose, a subtraction, a division and a cat over the (B, C+3, S, k)
+// tensor; here the index is read once per position and every output element is written exactly once.  Same fp32
+// arithmetic (one subtraction, one IEEE division), so results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) query_group_kernel(int C, int N, int S, int k, const float* __restrict__ xyz,
+                                                          const float* __restrict__ center, const float* __restrict__ feats,
+                                                          const int* __restrict__ idx, int use_xyz, float inv_div, float* __restrict__ out,
+                                                          float* __restrict__ gxyz) {
+  const int b = blockIdx.z, e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int E = S * k;
+  if (e >= E) return;
+  const int s = e / k, src = idx[(size_t)b * E + e];
+  const int c_xyz = use_xyz ? 3 : 0, Ctot = c_xyz + (feats ? C : 0);
+  float* ob = out + (size_t)b * Ctot * E + e;
+  if (blockIdx.y == 0 && (use_xyz || gxyz)) {
+    const float* p = xyz + ((size_t)b * N + src) * 3;
+    const float* q = center + ((size_t)b * S + s) * 3;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float v = __ldg(p + a);
+      if (gxyz) gxyz[((size_t)b * 3 + a) * E + e] = v;
+      if (use_xyz) {
+        float d = v - __ldg(q + a);
+        if (inv_div != 0.f) d = __fdiv_rn(d, inv_div);
+        ob[(size_t)a * E] = d;
+      }
+    }
+  }
+  if (feats) {
+    const int c0 = blockIdx.y * 16;
+    const float* fb = feats + (size_t)b * C * N + src;
+#pragma unroll 4
+    for (int c = c0; c < min(c0 + 16, C); ++c) ob[(size_t)(c_xyz + c) * E] = __ldg(fb + (size_t)c * N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // C ABI (declared in include/pcreid.h)
 // ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
@@ -980,6 +1021,17 @@ int pcreid_group_points(int b, int c, int n, int npoints, int nsample, const flo
 }
 int pcreid_gather_points(int b, int c, int n, int npoints, const float* points, const int* idx, float* out, void* stream) {
   return group_launch(b, c, n, npoints, points, idx, out, (cudaStream_t)stream);
+}
+
+int pcreid_query_group(int b, int c, int n, int npoints, int nsample, const float* xyz, const float* center_xyz, const float* features,
+                       const int* idx, int use_xyz, float divide_by, float* out, float* grouped_xyz, void* stream) {
+  if (b <= 0 || npoints <= 0 || nsample <= 0) return PCREID_OK;
+  if (!xyz || !center_xyz || !idx || !out || n <= 0 || (!use_xyz && !features) || (features && c <= 0)) return PCREID_ERR_ARG;
+  if (b > 65535 || ceil_div(c, 16) > 65535) return PCREID_ERR_UNSUPPORTED;
+  const int cy = features ? ceil_div(c, 16) : 1;
+  query_group_kernel<<<dim3(ceil_div(npoints * nsample, 256), cy, b), 256, 0, (cudaStream_t)stream>>>(
+      c, n, npoints, nsample, xyz, center_xyz, features, idx, use_xyz, divide_by, out, grouped_xyz);
+  return pcreid_launch_status();
 }
 
 int pcreid_three_nn(int b, int n, int m, const float* unknown, const float* known, float* dist2, int* idx, void* stream) {

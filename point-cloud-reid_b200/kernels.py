@@ -9,6 +9,9 @@ import ctypes
 import torch
 
 from . import _lib
+from . import torch_ops as _T
+
+_OPS = _T.ops          # torch.ops.pcreid.*: one dispatcher op per compute entry point of include/pcreid.h
 
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_ELU1 = 0, 1, 2, 3
 
@@ -86,7 +89,7 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
               y_pm=False):
     """Y[b,:,n] = act(W1^T X1[b,:,n] + W2^T X2[b,:,n] + bias (+res)) (+res).  w*: k-major (K, CO) or (Bw, K, CO)."""
     _need_cuda(x1, w1, x2, w2, bias, res, out)
-    a = _lib.LinearArgs()
+    a = _T.linear_args()
     K1, CO = w1.shape[-2], w1.shape[-1]
     if x1_pm:
         if not x1.is_contiguous() or x1.shape[2] != K1:
@@ -101,10 +104,10 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
     if B is None:
         B = x1_map.numel() if x1_map is not None else x1.shape[0]
     a.B, a.rows, a.CO, a.K1 = B, rows, CO, K1
-    a.X1, a.x1_pm, a.x1_map = _p(x1), int(x1_pm), _p(_map(x1_map))
+    a.X1, a.x1_pm, a.x1_map = x1, int(x1_pm), _map(x1_map)
     if not w1.is_contiguous() or w1.dtype != torch.float32:
         raise ValueError("weights must be contiguous float32")
-    a.W1, a.w1_bs, a.w1_map = _p(w1), (w1.shape[-2] * w1.shape[-1] if w1.dim() == 3 else 0), _p(_map(w1_map))
+    a.W1, a.w1_bs, a.w1_map = w1, (w1.shape[-2] * w1.shape[-1] if w1.dim() == 3 else 0), _map(w1_map)
     if x2 is not None:
         K2 = w2.shape[-2]
         if w2.shape[-1] != CO or not w2.is_contiguous():
@@ -117,14 +120,14 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
             if x2.shape[1] != K2:
                 raise ValueError(f"x2 has {x2.shape[1]} channels, weight expects {K2}")
             a.x2_bs, a.ldx2 = _cn(x2, "x2")
-        a.K2, a.X2, a.x2_pm, a.x2_map = K2, _p(x2), int(x2_pm), _p(_map(x2_map))
-        a.W2, a.w2_bs = _p(w2), (w2.shape[-2] * w2.shape[-1] if w2.dim() == 3 else 0)
+        a.K2, a.X2, a.x2_pm, a.x2_map = K2, x2, int(x2_pm), _map(x2_map)
+        a.W2, a.w2_bs = w2, (w2.shape[-2] * w2.shape[-1] if w2.dim() == 3 else 0)
     else:
         a.K2 = 0
-    a.bias = _p(bias)
+    a.bias = bias
     if res is not None:
         a.r_bs, a.ldr = _cn(res, "res")
-        a.R, a.r_map, a.res_after_act = _p(res), _p(_map(r_map)), int(res_after_act)
+        a.R, a.r_map, a.res_after_act = res, _map(r_map), int(res_after_act)
     a.act = act
     if y_pm:
         if out is None:
@@ -136,7 +139,7 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
         if out is None:
             out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
         a.y_bs, a.ldy = _cn(out, "out")
-    a.Y = _p(out)
+    a.Y = out
     # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernels win from K >= 256; below that the FFMA kernel
     # (up to 48 TFLOP/s) is faster
     if (_TC_LINEAR["on"] and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None
@@ -144,35 +147,30 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
         # gen 2 (warp-specialised, cn_linear_tc2.cu) wins from K >= 512: 127-141 vs 100-107 TFLOP/s on the DGCNN / PointNet heads
         if (_TC_LINEAR.get("gen", 2 if K1 + a.K2 >= 512 else 1) == 2 and w1.dim() == 2 and (w2 is None or w2.dim() == 2) and K1 % 8 == 0 and a.K2 % 8 == 0):
             n_sms = torch.cuda.get_device_properties(x1.device).multi_processor_count
-            rc = _lib.lib().pcreid_cn_linear_tc2(ctypes.byref(a), _p(_weight_image(w1)), _p(_weight_image(w2) if w2 is not None else None),
-                                                 n_sms, _stream())
-            if rc != 3:
-                _lib.check(rc, "pcreid_cn_linear_tc2")
+            if _OPS.cn_linear_tc2(*a.astuple(), _weight_image(w1), _weight_image(w2) if w2 is not None else None, n_sms) != 3:
                 return out
-        rc = _lib.lib().pcreid_cn_linear_tc(ctypes.byref(a), _stream())
-        if rc != 3:                      # 3 == PCREID_ERR_UNSUPPORTED: shape stays on the FFMA kernel
-            _lib.check(rc, "pcreid_cn_linear_tc")
+        if _OPS.cn_linear_tc(*a.astuple()) != 3:     # 3 == PCREID_ERR_UNSUPPORTED: shape stays on the FFMA kernel
             return out
-    _lib.check(_lib.lib().pcreid_cn_linear(ctypes.byref(a), _stream()), "pcreid_cn_linear")
+    _OPS.cn_linear(*a.astuple())
     return out
 
 
 def cn_groupnorm(x, gamma, beta, groups=1, res=None, r_map=None, act=ACT_NONE, out=None):
     """Y = act(GroupNorm_G(X) * gamma + beta (+res)) per (object, point); LayerNorm is groups=1."""
     _need_cuda(x, gamma, beta, res)
-    a = _lib.NormArgs()
+    a = _T.norm_args()
     a.B, a.C, a.rows, a.G = x.shape[0], x.shape[1], x.shape[2], groups
     a.x_bs, a.ldx = _cn(x, "x")
-    a.X, a.gamma, a.beta = _p(x), _p(gamma), _p(beta)
+    a.X, a.gamma, a.beta = x, gamma, beta
     if res is not None:
         a.r_bs, a.ldr = _cn(res, "res")
-        a.R, a.r_map = _p(res), _p(_map(r_map))
+        a.R, a.r_map = res, _map(r_map)
     a.act = act
     if out is None:
         out = torch.empty(tuple(x.shape), device=x.device, dtype=torch.float32)
     a.y_bs, a.ldy = _cn(out, "out")
-    a.Y = _p(out)
-    _lib.check(_lib.lib().pcreid_cn_groupnorm(ctypes.byref(a), _stream()), "pcreid_cn_groupnorm")
+    a.Y = out
+    _OPS.cn_groupnorm(*a.astuple())
     return out
 
 
@@ -184,8 +182,7 @@ def linattn_kv(k, v, nhead):
     v_bs, ldv = _cn(v, "v")
     wkv = torch.empty((B, d, d), device=k.device, dtype=torch.float32)
     ksum = torch.empty((B, d), device=k.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_linattn_kv(B, S, d, nhead, _p(k), k_bs, ldk, _p(v), v_bs, ldv, _p(wkv), _p(ksum), _stream()),
-               "pcreid_linattn_kv")
+    _OPS.linattn_kv(B, S, d, nhead, k, k_bs, ldk, v, v_bs, ldv, wkv, ksum)
     return wkv, ksum
 
 
@@ -197,8 +194,7 @@ def linattn_scale(q, ksum, nhead, s_len, q_map=None, ksum_map=None, B=None):
     if B is None:
         B = q_map.numel() if q_map is not None else (ksum_map.numel() if ksum_map is not None else q.shape[0])
     out = torch.empty((B, d, rows), device=q.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_linattn_scale(B, rows, d, nhead, s_len, _p(q), q_bs, ldq, _p(_map(q_map)), _p(ksum),
-                                               _p(_map(ksum_map)), _p(out), d * rows, rows, _stream()), "pcreid_linattn_scale")
+    _OPS.linattn_scale(B, rows, d, nhead, s_len, q, q_bs, ldq, _map(q_map), ksum, _map(ksum_map), out, d * rows, rows)
     return out
 
 
@@ -211,8 +207,7 @@ def local_linattn(qkv_pm, idx, nhead):
     B, N, C3 = qkv_pm.shape
     C = C3 // 3
     out = torch.empty((B, N, C), device=qkv_pm.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_local_linattn(B, N, C, nhead, idx.shape[2], _p(qkv_pm), _p(idx), _p(out), _stream()),
-               "pcreid_local_linattn")
+    _OPS.local_linattn(B, N, C, nhead, idx.shape[2], qkv_pm, idx, out)
     return out
 
 
@@ -229,8 +224,7 @@ def cn_pool(x1, x2=None, mode=0, out=None, transposed=False):
     if out is None:
         out = torch.empty((1, Co, B) if transposed else (B, Co), device=x1.device, dtype=torch.float32)
     ob, oc = (1, B) if transposed else (Co, 1)
-    _lib.check(_lib.lib().pcreid_cn_pool(B, C, r1, _p(x1), bs1, ld1, r2, _p(x2), bs2, ld2, mode, _p(out), ob, oc, _stream()),
-               "pcreid_cn_pool")
+    _OPS.cn_pool(B, C, r1, x1, bs1, ld1, r2, x2, bs2, ld2, mode, out, ob, oc)
     return out
 
 
@@ -242,7 +236,7 @@ def cn_chanmax(x, out=None, transposed=False):
     if out is None:
         out = torch.empty((1, rows, B) if transposed else (B, rows), device=x.device, dtype=torch.float32)
     ob, on = (1, B) if transposed else (rows, 1)
-    _lib.check(_lib.lib().pcreid_cn_chanmax(B, C, rows, _p(x), bs, ld, _p(out), ob, on, _stream()), "pcreid_cn_chanmax")
+    _OPS.cn_chanmax(B, C, rows, x, bs, ld, out, ob, on)
     return out
 
 
@@ -254,7 +248,7 @@ def knn_point(k, xyz, new_xyz):
     B, N, _ = xyz.shape
     S = new_xyz.shape[1]
     idx = torch.empty((B, S, k), device=xyz.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_knn_point(B, N, S, k, _p(xyz), _p(new_xyz), _p(idx), _stream()), "pcreid_knn_point")
+    _OPS.knn_point(B, N, S, k, xyz, new_xyz, idx)
     return idx
 
 
@@ -268,7 +262,7 @@ def knn_point_set(k, xyz, new_xyz):
     if k > N or N > 1024 or B > 65535:
         return knn_point(k, xyz, new_xyz)
     idx = torch.empty((B, S, k), device=xyz.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_knn_point_set(B, N, S, k, _p(xyz), _p(new_xyz), _p(idx), _stream()), "pcreid_knn_point_set")
+    _OPS.knn_point_set(B, N, S, k, xyz, new_xyz, idx)
     return idx
 
 
@@ -283,7 +277,7 @@ def farthest_point_sample(xyz, npoint, start=None):
         start = torch.randint(0, N, (B,), dtype=torch.long)
     start = start.to(device=xyz.device, dtype=torch.int32).contiguous()
     idx = torch.empty((B, npoint), device=xyz.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_fps_torch(B, N, npoint, _p(xyz), _p(start), _p(idx), _stream()), "pcreid_fps_torch")
+    _OPS.fps_torch(B, N, npoint, xyz, start, idx)
     return idx
 
 
@@ -294,7 +288,7 @@ def gather_points(features, idx):
     B, C, N = features.shape
     M = idx.shape[1]
     out = torch.empty((B, C, M), device=features.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_gather_points(B, C, N, M, _p(features), _p(idx), _p(out), _stream()), "pcreid_gather_points")
+    _OPS.gather_points(B, C, N, M, features, idx, out)
     return out
 
 
@@ -308,8 +302,7 @@ def query_ball_point(radius, nsample, xyz, new_xyz):
     S = new_xyz.shape[1]
     r2 = float(torch.tensor(radius ** 2, dtype=torch.float32))          # the fp32 value torch compares the distances with
     idx = torch.empty((B, S, nsample), device=xyz.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_query_ball_point(B, N, S, r2, nsample, _p(new_xyz), _p(xyz), _p(idx), _stream()),
-               "pcreid_query_ball_point")
+    _OPS.query_ball_point(B, N, S, r2, nsample, new_xyz, xyz, idx)
     return idx
 
 
@@ -321,7 +314,7 @@ def knn_feature(x, k):
     if C > 1 and ld != N:
         raise ValueError("x must be dense in (C, N) per object")
     idx = torch.empty((B, N, k), device=x.device, dtype=torch.int32)
-    _lib.check(_lib.lib().pcreid_knn_feature(B, C, N, k, _p(x), x_bs, _p(idx), _stream()), "pcreid_knn_feature")
+    _OPS.knn_feature(B, C, N, k, x, x_bs, idx)
     return idx
 
 
@@ -340,13 +333,11 @@ def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
             b1 = min(B, b0 + step)
             nb = b1 - b0
             h1 = torch.empty((nb, C, S * k), device=p1.device, dtype=torch.float32)
-            _lib.check(L.pcreid_edge_build(nb, C, N, S, k, _p(p1[b0:b1]), _p(cc[b0:b1]), _p(idx[b0:b1]), _p(h1), _stream()),
-                       "pcreid_edge_build")
+            _OPS.edge_build(nb, C, N, S, k, p1[b0:b1], cc[b0:b1], idx[b0:b1], h1)
             h3 = cn_linear(cn_linear(h1, w2, bias=b2, act=ACT_RELU), w3, bias=b3, act=ACT_RELU)
-            _lib.check(L.pcreid_seg_max(nb * C * S, k, _p(h3), _p(out[b0:b1]), _stream()), "pcreid_seg_max")
+            _OPS.seg_max(nb * C * S, k, h3, out[b0:b1])
         return out
-    _lib.check(_lib.lib().pcreid_sa_edge_mlp(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2), _p(b2), _p(w3), _p(b3), _p(out),
-                                             _stream()), "pcreid_sa_edge_mlp")
+    _OPS.sa_edge_mlp(B, C, N, S, k, p1, cc, idx, w2, b2, w3, b3, out)
     return out
 
 
@@ -381,8 +372,7 @@ def attn_front(xyz, feat, wp0, bp0, bp2, blob, DP, NFP, NF):
     if blob.numel() * 4 != L.pcreid_attn_front_blob_bytes(C2, DP, NFP, NF):
         raise ValueError("attn_front: weight blob does not match the shapes")
     out = torch.empty((B, NFP + NF, S), device=feat.device, dtype=torch.float32)
-    _lib.check(L.pcreid_attn_front(B, S, C2, DP, NFP, NF, _p(xyz), _p(feat), f_bs, ldf, _p(wp0), _p(bp0), _p(bp2), _p(blob),
-                                   _p(out), out.stride(0), out.stride(1), _stream()), "pcreid_attn_front")
+    _OPS.attn_front(B, S, C2, DP, NFP, NF, xyz, feat, f_bs, ldf, wp0, bp0, bp2, blob, out, out.stride(0), out.stride(1))
     return out
 
 
@@ -398,8 +388,7 @@ def linattn_kv_img(k, v, nhead, rows_q):
     opt = L.pcreid_attn_back_objects_per_tile(rows_q, d)
     kvimg = torch.empty(((B + opt - 1) // opt * opt, d * (d // nhead)), device=k.device, dtype=torch.float32)
     ksum = torch.empty((B, d), device=k.device, dtype=torch.float32)
-    _lib.check(L.pcreid_linattn_kv_img(B, S, d, nhead, _p(k), k_bs, ldk, _p(v), v_bs, ldv, _p(kvimg), _p(ksum), _stream()),
-               "pcreid_linattn_kv_img")
+    _OPS.linattn_kv_img(B, S, d, nhead, k, k_bs, ldk, v, v_bs, ldv, kvimg, ksum)
     return kvimg, ksum
 
 
@@ -426,9 +415,7 @@ def attn_back(feat1, q, ksum, kvimg, g1, b1, g2, b2, blob, nhead, CO, residual, 
     if kvimg.shape[0] < (B + opt - 1) // opt * opt:
         raise ValueError("attn_back: kvimg must hold the objects of the last tile (use linattn_kv_img(..., rows_q=rows))")
     out = torch.empty((B, CO, rows), device=feat1.device, dtype=torch.float32)
-    _lib.check(L.pcreid_attn_back(B, rows, D, nhead, C1, CO, int(residual), int(feat1_pm), _p(feat1), f1_bs, ldf1, _p(q), q_bs,
-                                  ldq, _p(ksum), _p(kvimg), _p(g1), _p(b1), _p(g2), _p(b2), _p(blob), _p(out), out.stride(0),
-                                  out.stride(1), _stream()), "pcreid_attn_back")
+    _OPS.attn_back(B, rows, D, nhead, C1, CO, int(residual), int(feat1_pm), feat1, f1_bs, ldf1, q, q_bs, ldq, ksum, kvimg, g1, b1, g2, b2, blob, out, out.stride(0), out.stride(1))
     return out
 
 
@@ -444,13 +431,9 @@ def sa_edge_mlp_tc(p1, cc, idx, w2img, b2, w3img, b3, gen=2):
     out = torch.empty((B, C, S), device=p1.device, dtype=torch.float32)
     n_sms = torch.cuda.get_device_properties(p1.device).multi_processor_count
     if gen == 2:
-        rc = _lib.lib().pcreid_sa_edge_mlp_tc2(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2img), _p(b2), _p(w3img), _p(b3),
-                                               _p(out), 0, n_sms, _stream())
-        if rc != 3:
-            _lib.check(rc, "pcreid_sa_edge_mlp_tc2")
+        if _OPS.sa_edge_mlp_tc2(B, C, N, S, k, p1, cc, idx, w2img, b2, w3img, b3, out, 0, n_sms) != 3:
             return out
-    _lib.check(_lib.lib().pcreid_sa_edge_mlp_tc(B, C, N, S, k, _p(p1), _p(cc), _p(idx), _p(w2img), _p(b2), _p(w3img), _p(b3),
-                                                _p(out), n_sms, _stream()), "pcreid_sa_edge_mlp_tc")
+    _OPS.sa_edge_mlp_tc(B, C, N, S, k, p1, cc, idx, w2img, b2, w3img, b3, out, n_sms)
     return out
 
 
@@ -463,8 +446,7 @@ def edge_gather_max(p, q, idx, act, out=None):
     if out is None:
         out = torch.empty((B, C, N), device=p.device, dtype=torch.float32)
     o_bs, ldo = _cn(out, "out")
-    _lib.check(_lib.lib().pcreid_edge_gather_max(B, C, N, k, _p(p), _p(q), _p(idx), act, _p(out), o_bs, ldo, _stream()),
-               "pcreid_edge_gather_max")
+    _OPS.edge_gather_max(B, C, N, k, p, q, idx, act, out, o_bs, ldo)
     return out
 
 
@@ -472,9 +454,7 @@ def pair_concat_head(a, bv, et, ed, w2, g1, be1, g2, be2, w, b0, groups, mask=No
     _need_cuda(a, bv, et, ed)
     T, D, E = a.shape[0], bv.shape[0], et.shape[1]
     out = torch.empty((T, D), device=a.device, dtype=torch.float32)
-    _lib.check(_lib.lib().pcreid_pair_concat_head(T, D, E, groups, _p(a), _p(bv), _p(et), _p(ed), _p(w2), _p(g1), _p(be1),
-                                                  _p(g2), _p(be2), _p(w), float(b0), _p(mask), _p(out), _stream()),
-               "pcreid_pair_concat_head")
+    _OPS.pair_concat_head(T, D, E, groups, a, bv, et, ed, w2, g1, be1, g2, be2, w, float(b0), mask, out)
     return out
 
 
@@ -490,7 +470,5 @@ def pair_concat_head_tc(a, bv, et, ed, w2img, g1, be1, g2, be2, w, b0, groups, m
     T, D, E = a.shape[0], bv.shape[0], et.shape[1]
     out = torch.empty((T, D), device=a.device, dtype=torch.float32)
     n_ctas = torch.cuda.get_device_properties(a.device).multi_processor_count
-    _lib.check(_lib.lib().pcreid_pair_concat_head_tc(T, D, E, groups, _p(a), _p(bv), _p(et), _p(ed), _p(w2img), _p(g1), _p(be1),
-                                                     _p(g2), _p(be2), _p(w), float(b0), _p(mask), _p(out), n_ctas, _stream()),
-               "pcreid_pair_concat_head_tc")
+    _OPS.pair_concat_head_tc(T, D, E, groups, a, bv, et, ed, w2img, g1, be1, g2, be2, w, float(b0), mask, out, n_ctas)
     return out

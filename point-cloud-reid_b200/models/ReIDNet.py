@@ -118,6 +118,16 @@ class ReIDNet(nn.Module):
                 m.tc_mode = mode in self.TC_MODES
         return self
 
+    def invalidate_packed(self):
+        """forget every packed / BN-folded / operand-image weight copy and captured CUDA graph (see _packing.invalidate_packed:
+        needed only after parameters were written through `.data`, which no version counter records)."""
+        from ._packing import invalidate_packed
+        invalidate_packed(self)
+        self._fused.clear()
+        self._graphs.clear()
+        K._W_IMAGES.clear()
+        return self
+
     def fused_matcher(self):
         """the fused tcgen05 matcher of the current tensor-core mode (one per operand format)"""
         from . import fused_pairs
@@ -128,12 +138,14 @@ class ReIDNet(nn.Module):
 
     # ------------------------------------------------------------------ encoders
     def _encode(self, pts):
-        """pts (B, N, 3) -> (xyz (B, N, 3), h (B, C, N)); applies the per-point `downsample` for DGCNN / PointNet
-        exactly as siamese_forward does (ReIDNet.py:316-324)."""
+        """pts (B, N, 3) -> (xyz (B, N, 3), h (B, C, N)); applies the per-point `downsample` when use_dgcnn is set
+        (DGCNN and the shipped PointNet config), exactly as siamese_forward does (ReIDNet.py:316-328)."""
         pts = pts.float().contiguous()
         if self.use_dgcnn or isinstance(self.backbone, (DGCNN, PointNet)):
             _, h = self.backbone(pts.permute(0, 2, 1).contiguous(), self.backbone_list)
-            if self.downsample is not None:
+            # the reference applies `downsample` in its use_dgcnn branch only (ReIDNet.py:316-324); its
+            # `type(self.backbone) == PointNet` branch (:325-328) returns the backbone's raw channel map
+            if self.use_dgcnn and self.downsample is not None:
                 for m in self.downsample:
                     if isinstance(m, LinearRes):
                         h = m.forward_cn(h)
@@ -374,16 +386,14 @@ class ReIDNet(nn.Module):
         A = K.cn_linear(e_t.unsqueeze(0), w1a, x1_pm=True, y_pm=True)[0]     # (T, 2E)
         Bv = K.cn_linear(e_d.unsqueeze(0), w1b, x1_pm=True, y_pm=True)[0]    # (D, 2E)
         mask = None if pair_mask is None else pair_mask.to(torch.uint8).contiguous()
+        fin_w, fin_b = _final_cached(fin)          # weight vector + bias scalar, read back once per parameter version
         if self.match_mode == 'fast' and E == 128 and lr.groups * 8 == 2 * E:
             # tensor-core head (csrc/concat_tc.cu): bf16 operands for the 256 x 256 Linear, everything else fp32
             if "w2img" not in pk:
                 pk["w2img"] = K.bf16_kmajor_image(lr.linear2.weight)
-            return K.pair_concat_head_tc(A, Bv, e_t, e_d, pk["w2img"], pk["g1"], pk["b1"], pk["g2"], pk["b2"],
-                                         fin.weight.detach().float().reshape(-1).contiguous(), float(fin.bias.detach()[0]),
+            return K.pair_concat_head_tc(A, Bv, e_t, e_d, pk["w2img"], pk["g1"], pk["b1"], pk["g2"], pk["b2"], fin_w, fin_b,
                                          lr.groups, mask)
-        return K.pair_concat_head(A, Bv, e_t, e_d, pk["w2"], pk["g1"], pk["b1"], pk["g2"], pk["b2"],
-                                  fin.weight.detach().float().reshape(-1).contiguous(), float(fin.bias.detach()[0]),
-                                  lr.groups, mask)
+        return K.pair_concat_head(A, Bv, e_t, e_d, pk["w2"], pk["g1"], pk["b1"], pk["g2"], pk["b2"], fin_w, fin_b, lr.groups, mask)
 
     # ------------------------------------------------------------------ mmdet BaseDetector surface
     def forward(self, return_loss=True, **kwargs):
@@ -409,15 +419,35 @@ class ReIDNet(nn.Module):
         (sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2, size_1, size_2, vis_1, vis_2) = \
             self.preprocess_inputs_size_vis(sparse_1, sparse_2, dense_1, dense_2, label_1, label_2, id_1, id_2,
                                             size_1, size_2, vis_1, vis_2)
+        aux = [n for n, head in (("cls", self.cls_head), ("fp", self.fp_head), ("shape", self.shape_head))
+               if head is not None and self.losses_to_use.get(n)]
+        if self.losses_to_use.get("dense"):
+            aux.append("dense")
+        if aux:
+            raise NotImplementedError(f"forward_test: the auxiliary heads / losses {aux} are built AND enabled in this config; the "
+                                      "drop-in evaluates the match path (+ the kl term) only, ReIDNet.py:652-662 run the others "
+                                      "-- disable them in losses_to_use or validate with the reference")
+        if not self.losses_to_use.get("match", True):
+            raise NotImplementedError("forward_test with losses_to_use['match']=False (ReIDNet.py:572-575 returns no predictions)")
+        if self.match_type == 'concat' and self.pool_type != 'max':
+            raise NotImplementedError("forward_test: the reference's match_forward pools 'concat' inputs with get_pooled_feats "
+                                      "(ReIDNet.py:586-592); only pool_type='max' coincides with the channel max used here")
         xyz1, xyz2, h1, h2 = self.siamese_forward(sparse_1, sparse_2)
         h1, h2, xyz1, xyz2, match = self.get_match_supervision(h1, h2, xyz1, xyz2, id_1, id_2)
         match_preds = self.match_forward_inference(h1, h2, xyz1, xyz2)
         match_loss = self.bce(match_preds, match) * self.alpha['match']
+        kl_loss = 0.
+        if self.losses_to_use.get("kl"):           # get_kl_loss (ReIDNet.py:467-482): validation-only scalar over the embeddings
+            lsm = torch.nn.functional.log_softmax
+            kl = torch.nn.functional.kl_div(lsm(h1.reshape(h1.size(0), -1), dim=1), lsm(h2.reshape(h2.size(0), -1), dim=1),
+                                            reduction='none', log_target=True).mean(dim=1)
+            kl = torch.where(match == 0, -kl, kl)
+            kl_loss = (kl[match == 0].mean() + kl[match == 1].mean()) * self.alpha['kl']
         zero = torch.tensor([0.])
         labels = torch.cat([label_1, label_2], dim=0)
         results = {
             'val_dense_loss': zero, 'val_fp_loss': zero, 'val_match_loss': torch.tensor([match_loss]),
-            'val_shape_loss': zero, 'val_cls_loss': zero, 'val_kl_loss': zero,
+            'val_shape_loss': zero, 'val_cls_loss': zero, 'val_kl_loss': torch.tensor([kl_loss]),
             'val_match_preds': match_preds, 'val_match_gt': match, 'val_cls_preds': None, 'val_cls_gt': labels,
             'val_fp_preds': None, 'val_fp_gt': (labels > 9).float(),
             'match_classes': torch.cat([label_1.unsqueeze(1), label_2.unsqueeze(1)], dim=1),
@@ -446,6 +476,17 @@ def _kmajor_cached(m):
 def _bias_cached(m):
     _kmajor_cached(m)
     return m._pcreid_b
+
+
+def _final_cached(m):
+    """final Linear(2E, 1) of the concat head: (weight vector on the device, bias as a host float).  The bias read-back is a
+    device->host sync, so it happens once per parameter version instead of once per match call (and never inside a CUDA
+    graph capture of the head)."""
+    key = (m.weight.data_ptr(), m.weight._version, m.bias.data_ptr(), m.bias._version)
+    if getattr(m, "_pcreid_fin_key", None) != key:
+        m._pcreid_fin = (m.weight.detach().float().reshape(-1).contiguous(), float(m.bias.detach()[0]))
+        m._pcreid_fin_key = key
+    return m._pcreid_fin
 
 
 def _half_cached(lr, pk, E):

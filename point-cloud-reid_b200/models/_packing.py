@@ -1,6 +1,7 @@
 """Weight packing shared by the model modules: torch parameters stay in the reference's layout (so
 reference checkpoints load with strict=True); kernels consume k-major fp32 copies with eval-mode
-BatchNorm folded in.  Copies are cached and rebuilt when any parameter/buffer changes."""
+BatchNorm folded in.  Copies are cached and rebuilt when any parameter/buffer changes (as seen through the tensors'
+version counters; weights must not be mutated through `.data` -- see PackedModule.invalidate_packed)."""
 import torch
 from torch import nn
 
@@ -24,6 +25,17 @@ def fold_bn(w, b, bn):
     return w2, b2.contiguous()
 
 
+def invalidate_packed(root):
+    """drops the cached packed copies of every module below `root`.  The cache key is (data_ptr, _version, device) of every
+    parameter / buffer: load_state_dict, .to(), optimizer steps and in-place ops bump it, but writes that bypass the version
+    counter (`p.data.copy_()`, `p.data.mul_()`, storage-level edits as some EMA / quantisation utilities do) do NOT -- after
+    such a write call this (ReIDNet.invalidate_packed()), or the kernels keep using the old folded weights."""
+    for m in root.modules():
+        for attr in ("_pk_key", "_pcreid_key", "_pcreid_fin_key"):
+            if hasattr(m, attr):
+                object.__setattr__(m, attr, None)
+
+
 class PackedModule(nn.Module):
     """nn.Module whose forward runs on packed copies of its (and its plain children's) tensors."""
 
@@ -41,6 +53,13 @@ class PackedModule(nn.Module):
                 object.__setattr__(self, "_pk", self._pack())
             object.__setattr__(self, "_pk_key", key)
         return self._pk
+
+    def invalidate_packed(self):
+        invalidate_packed(self)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        object.__setattr__(self, "_pk_key", None)        # belt and braces: a checkpoint load always repacks
 
     def _inference_only(self):
         if self.training:

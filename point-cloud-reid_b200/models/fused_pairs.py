@@ -14,13 +14,12 @@ MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the three fused kernels then s
 activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and the stage-2 attention operands (36 KB / pair).
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
 """
-import ctypes
 import math
 
 import torch
 
-from .. import _lib
 from .. import kernels as K
+from .. import torch_ops as _T
 from ._packing import kmajor
 
 IMG = 16384
@@ -37,12 +36,7 @@ def _center_out(w):
     return w - w.mean(0, keepdim=True)
 
 
-def _p(t):
-    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
-
-
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+_OPS = _T.ops          # torch.ops.pcreid.*
 
 
 def _w_image(w, dtype):
@@ -74,6 +68,7 @@ class FusedXcorr:
         self.dtype = torch.float16 if fmt == FMT_F16 else torch.bfloat16
         self._key = None
         self.n_ctas = None
+        self._n_ctas_dev = None
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
 
     def _weights(self):
@@ -122,8 +117,7 @@ class FusedXcorr:
     def _pack_image(self, x, act=K.ACT_NONE):
         B, C, N = x.shape
         out = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=x.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().pcreid_pack_image(B, C, N, _p(x), x.stride(0), x.stride(1), act, self.fmt, _p(out), _stream()),
-                   "pcreid_pack_image")
+        _OPS.pack_image(B, C, N, x, x.stride(0), x.stride(1), act, self.fmt, out)
         return out
 
     def kv_scale(self, npts):
@@ -141,8 +135,7 @@ class FusedXcorr:
         o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
         o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
         o.H = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().pcreid_pack_image_bias(B, C, N, _p(h), h.stride(0), h.stride(1), _p(self._b2_1), self.fmt, _p(o.H),
-                                                     _stream()), "pcreid_pack_image_bias")   # h + beta2
+        _OPS.pack_image_bias(B, C, N, h, h.stride(0), h.stride(1), self._b2_1, self.fmt, o.H)   # h + beta2
         pos2 = X2.position_code(xyz)
         if pos2 is None:            # cross_lin_attn (image tokens, attention.py:312-372): no position code -> Wv.pos == 0
             o.PV = torch.zeros((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
@@ -156,7 +149,7 @@ class FusedXcorr:
         if sc != 1.0:
             ksum = ksum * sc
         o.MK1 = torch.empty((B, B7_BYTES), device=h.device, dtype=torch.uint8)
-        _lib.check(_lib.lib().pcreid_pack_b7(B, _p(M), _p(ksum), self.fmt, _p(o.MK1), _stream()), "pcreid_pack_b7")
+        _OPS.pack_b7(B, M, ksum, self.fmt, o.MK1)
         return o
 
     def match(self, pt, pd, ti, dj, debug=None, dense=None):
@@ -167,8 +160,8 @@ class FusedXcorr:
         assert pt.fmt == self.fmt and pd.fmt == self.fmt, "object packs were prepared for another operand format"
         self._weights()
         dev = pt.H.device
-        if self.n_ctas is None:
-            self.n_ctas = torch.cuda.get_device_properties(dev).multi_processor_count
+        if self.n_ctas is None or self._n_ctas_dev != dev:          # SM count of the device the operands live on
+            self.n_ctas, self._n_ctas_dev = torch.cuda.get_device_properties(dev).multi_processor_count, dev
         if dense is not None:
             r0, nrows, Dn = dense
             P = nrows * Dn
@@ -184,7 +177,6 @@ class FusedXcorr:
         A = torch.empty((P, 2, NT, IMG), device=dev, dtype=torch.uint8)
         B7 = torch.empty((P, 2, B7_BYTES), device=dev, dtype=torch.uint8)
         part = torch.empty((P, 2, 128), device=dev, dtype=torch.float32)
-        L = _lib.lib()
         sc = self.kv_scale(N)
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             if unit_lists is not None:
@@ -193,21 +185,18 @@ class FusedXcorr:
                 order = torch.argsort(tmpl, stable=True)                    # runs of units share the template operand
                 us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, _p(us), _p(ut), _p(sl), _p(ps.QF1), _p(ps.U),
-                                          _p(ps.H), _p(pm.MK1), _p(self._w1a2), _p(A), self.n_ctas, _stream()), "pcreid_pair_p1a2")
+            _OPS.pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, us, ut, sl, ps.QF1, ps.U, ps.H, pm.MK1, self._w1a2, A, self.n_ctas)
             self._tock("pair_p1a2_kernel", e0, P)
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p1b_n(P, N, role, self.fmt, sc, _p(us), _p(ut), _p(sl), _p(ps.PV), _p(self._w1b2), _p(A),
-                                           _p(B7), self.n_ctas, _stream()), "pcreid_pair_p1b_n")
+            _OPS.pair_p1b_n(P, N, role, self.fmt, sc, us, ut, sl, ps.PV, self._w1b2, A, B7, self.n_ctas)
             self._tock("pair_p1b_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
         for role in (0, 1):
             e0 = self._tick()
-            _lib.check(L.pcreid_pair_p2y(P, N, role, self.fmt, ATT_EPS * sc, _p(slots), _p(A), _p(B7), _p(self._w2y), _p(part),
-                                         self.n_ctas, _stream()), "pcreid_pair_p2y")
+            _OPS.pair_p2y(P, N, role, self.fmt, ATT_EPS * sc, slots, A, B7, self._w2y, part, self.n_ctas)
             self._tock("pair_p2y_kernel", e0, P)
-        _lib.check(L.pcreid_pool_finish2(P, N, _p(part), _p(self._b2_2), _p(pooled), _stream()), "pcreid_pool_finish2")
+        _OPS.pool_finish2(P, N, part, self._b2_2, pooled)
         if debug is not None:
             debug.update(A=A, B7=B7, part=part, pooled=pooled)
         return self.model._head_cn(pooled)

@@ -3,6 +3,7 @@ import ctypes
 import torch
 
 from .. import _lib
+from .. import torch_ops as _T
 
 
 def stream():
@@ -35,3 +36,4 @@ class _NoBackward(torch.autograd.Function):
 
 lib = _lib.lib
 check = _lib.check
+OPS = _T.ops            # torch.ops.pcreid.* (torch_ops.py): the op wrappers call the C ABI through the dispatcher

@@ -2,7 +2,7 @@
 Reference: mmdet3d/ops/ball_query/ball_query.py:7-54."""
 import torch
 
-from ._common import check, lib, ptr, require, stream
+from ._common import OPS, require
 
 
 class BallQuery:
@@ -13,10 +13,8 @@ class BallQuery:
         assert min_radius < max_radius
         B, N, _ = xyz.shape
         npoint = center_xyz.shape[1]
-        with torch.cuda.device(xyz.device):
-            idx = torch.zeros((B, npoint, sample_num), dtype=torch.int32, device=xyz.device)
-            check(lib().pcreid_ball_query(B, N, npoint, float(min_radius), float(max_radius), sample_num, ptr(center_xyz),
-                                          ptr(xyz), ptr(idx), stream()), "pcreid_ball_query")
+        idx = torch.zeros((B, npoint, sample_num), dtype=torch.int32, device=xyz.device)
+        OPS.ball_query(B, N, npoint, float(min_radius), float(max_radius), sample_num, center_xyz, xyz, idx)
         return idx
 
     forward = apply

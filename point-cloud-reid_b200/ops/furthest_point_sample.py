@@ -3,7 +3,7 @@ Reference: mmdet3d/ops/furthest_point_sample/furthest_point_sample.py:7-78, poin
 import torch
 from torch import nn
 
-from ._common import check, lib, ptr, require, stream
+from ._common import OPS, require
 
 
 def _fps(points_xyz, num_points, with_dist):
@@ -13,11 +13,9 @@ def _fps(points_xyz, num_points, with_dist):
         assert points_xyz.dim() == 3 and points_xyz.shape[2] == N, "points_dist must be (B, N, N)"
     else:
         assert points_xyz.dim() == 3 and points_xyz.shape[2] == 3, "points_xyz must be (B, N, 3)"
-    with torch.cuda.device(points_xyz.device):
-        output = torch.empty((B, num_points), dtype=torch.int32, device=points_xyz.device)
-        temp = torch.full((B, N), 1e10, dtype=torch.float32, device=points_xyz.device)
-        fn = lib().pcreid_fps_with_dist if with_dist else lib().pcreid_fps
-        check(fn(B, N, num_points, ptr(points_xyz), ptr(temp), ptr(output), stream()), "pcreid_fps")
+    output = torch.empty((B, num_points), dtype=torch.int32, device=points_xyz.device)
+    temp = torch.full((B, N), 1e10, dtype=torch.float32, device=points_xyz.device)
+    (OPS.fps_with_dist if with_dist else OPS.fps)(B, N, num_points, points_xyz, temp, output)
     return output
 
 
@@ -55,10 +53,8 @@ def calc_square_dist(point_feat_a, point_feat_b, norm=True):
     assert a.dim() == 3 and b.dim() == 3 and a.shape[0] == b.shape[0] and a.shape[2] == b.shape[2]
     B, N, C = a.shape
     M = b.shape[1]
-    with torch.cuda.device(a.device):
-        dist = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
-        check(lib().pcreid_pairwise_sqdist(B, N, M, C, ptr(a), ptr(b), ptr(dist), int(bool(norm)), stream()),
-              "pcreid_pairwise_sqdist")
+    dist = torch.empty((B, N, M), dtype=torch.float32, device=a.device)
+    OPS.pairwise_sqdist(B, N, M, C, a, b, dist, int(bool(norm)))
     return dist
 
 

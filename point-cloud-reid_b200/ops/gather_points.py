@@ -2,7 +2,7 @@
 Reference: mmdet3d/ops/gather_points/gather_points.py:7-50 (forward only)."""
 import torch
 
-from ._common import _NoBackward, check, lib, ptr, require, stream
+from ._common import OPS, _NoBackward, require
 
 
 class GatherPoints(_NoBackward):
@@ -12,10 +12,8 @@ class GatherPoints(_NoBackward):
         require(indices, "indices", torch.int32)
         B, npoint = indices.shape
         _, C, N = features.shape
-        with torch.cuda.device(features.device):
-            output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
-            check(lib().pcreid_gather_points(B, C, N, npoint, ptr(features), ptr(indices), ptr(output), stream()),
-                  "pcreid_gather_points")
+        output = torch.empty((B, C, npoint), dtype=torch.float32, device=features.device)
+        OPS.gather_points(B, C, N, npoint, features, indices, output)
         ctx.mark_non_differentiable(indices)
         return output
 

@@ -4,7 +4,7 @@ Reference: mmdet3d/ops/group_points/group_points.py:11-129 (QueryAndGroup), 132-
 import torch
 from torch import nn
 
-from ._common import _NoBackward, check, lib, ptr, require, stream
+from ._common import OPS, _NoBackward, require
 from .ball_query import ball_query
 from .knn import knn
 
@@ -16,10 +16,8 @@ class GroupingOperation(_NoBackward):
         require(indices, "indices", torch.int32)
         B, nfeatures, nsample = indices.shape
         _, C, N = features.shape
-        with torch.cuda.device(features.device):
-            output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
-            check(lib().pcreid_group_points(B, C, N, nfeatures, nsample, ptr(features), ptr(indices), ptr(output), stream()),
-                  "pcreid_group_points")
+        output = torch.empty((B, C, nfeatures, nsample), dtype=torch.float32, device=features.device)
+        OPS.group_points(B, C, N, nfeatures, nsample, features, indices, output)
         return output
 
 
@@ -47,39 +45,51 @@ class QueryAndGroup(nn.Module):
             assert not self.normalize_xyz, "can not normalize grouped xyz when max_radius is None"
 
     def forward(self, points_xyz, center_xyz, features=None):
+        """points_xyz (B, N, 3), center_xyz (B, S, 3), features (B, C, N) or None -> (B, 3 + C, S, k) [+ grouped xyz, unique
+        counts, indices as configured].  One index query + ONE fused kernel (pcreid_query_group) that writes the centred
+        (optionally radius-normalised) neighbour offsets and the gathered features straight into the concatenated result."""
+        require(points_xyz, "points_xyz")
+        require(center_xyz, "center_xyz")
+        if features is not None:
+            require(features, "features")
+        elif not self.use_xyz:
+            raise AssertionError("Cannot have not features and not use xyz as a feature!")
         if self.max_radius is None:
             idx = knn(self.sample_num, points_xyz, center_xyz, False).transpose(1, 2).contiguous()
         else:
             idx = ball_query(self.min_radius, self.max_radius, self.sample_num, points_xyz, center_xyz)
-        unique_cnt = None
+        counts = None
         if self.uniform_sample:
-            unique_cnt = torch.zeros((idx.shape[0], idx.shape[1]))
-            for i_batch in range(idx.shape[0]):
-                for i_region in range(idx.shape[1]):
-                    unique_ind = torch.unique(idx[i_batch, i_region, :])
-                    num_unique = unique_ind.shape[0]
-                    unique_cnt[i_batch, i_region] = num_unique
-                    sample_ind = torch.randint(0, num_unique, (self.sample_num - num_unique,), dtype=torch.long)
-                    idx[i_batch, i_region, :] = torch.cat((unique_ind, unique_ind[sample_ind]))
-        xyz_trans = points_xyz.transpose(1, 2).contiguous()
-        grouped_xyz = grouping_operation(xyz_trans, idx)
-        grouped_xyz_diff = grouped_xyz - center_xyz.transpose(1, 2).unsqueeze(-1)
-        if self.normalize_xyz:
-            grouped_xyz_diff /= self.max_radius
-        if features is not None:
-            grouped_features = grouping_operation(features, idx)
-            new_features = torch.cat([grouped_xyz_diff, grouped_features], dim=1) if self.use_xyz else grouped_features
-        else:
-            assert self.use_xyz, "Cannot have not features and not use xyz as a feature!"
-            new_features = grouped_xyz_diff
-        ret = [new_features]
-        if self.return_grouped_xyz:
-            ret.append(grouped_xyz)
-        if self.return_unique_cnt:
-            ret.append(unique_cnt)
-        if self.return_grouped_idx:
-            ret.append(idx)
-        return ret[0] if len(ret) == 1 else tuple(ret)
+            idx, counts = _spread_unique(idx)
+        B, S, k = idx.shape
+        n_feat = 0 if features is None else features.shape[1]
+        new_features = torch.empty((B, (3 if self.use_xyz else 0) + n_feat, S, k), dtype=torch.float32, device=points_xyz.device)
+        grouped_xyz = torch.empty((B, 3, S, k), dtype=torch.float32, device=points_xyz.device) if self.return_grouped_xyz else None
+        OPS.query_group(B, n_feat, points_xyz.shape[1], S, k, points_xyz, center_xyz, features, idx, int(self.use_xyz),
+                        float(self.max_radius) if self.normalize_xyz else 0.0, new_features, grouped_xyz)
+        extras = [t for t, wanted in ((grouped_xyz, self.return_grouped_xyz), (counts, self.return_unique_cnt),
+                                      (idx, self.return_grouped_idx)) if wanted]
+        return (new_features, *extras) if extras else new_features
+
+
+def _spread_unique(idx):
+    """uniform_sample of the reference (group_points.py:78-91): every region keeps its distinct indices (ascending, as
+    torch.unique returns them) and fills the remaining slots with random picks among them.  The distinct sets are found for
+    all regions at once on the device (sort, first-occurrence mask, stable compaction); only the random fill is drawn region
+    by region on the host generator, with the same call the reference makes, so a seeded run picks the same samples.
+    -> (idx (B, S, k) int32, distinct counts (B, S) float32 on the CPU like the reference's)."""
+    B, S, k = idx.shape
+    srt = idx.sort(dim=2).values
+    first = torch.ones_like(srt, dtype=torch.bool)
+    first[..., 1:] = srt[..., 1:] != srt[..., :-1]
+    distinct = srt.gather(2, (~first).to(torch.uint8).sort(dim=2, stable=True).indices)    # distinct values first, ascending
+    n_distinct = first.sum(2).cpu()
+    pick = torch.arange(k).repeat(B, S, 1)
+    for b, s in ((b, s) for b in range(B) for s in range(S)):
+        n = int(n_distinct[b, s])
+        if n < k:
+            pick[b, s, n:] = torch.randint(0, n, (k - n,), dtype=torch.long)
+    return distinct.gather(2, pick.to(idx.device)).to(torch.int32).contiguous(), n_distinct.to(torch.float32)
 
 
 class GroupAll(nn.Module):

@@ -2,7 +2,7 @@
 Reference: mmdet3d/ops/interpolate/three_nn.py:9-46, three_interpolate.py:9-63 (forward only)."""
 import torch
 
-from ._common import _NoBackward, check, lib, ptr, require, stream
+from ._common import OPS, _NoBackward, require
 
 
 class ThreeNN(_NoBackward):
@@ -13,10 +13,9 @@ class ThreeNN(_NoBackward):
         require(source, "source")
         B, N, _ = target.shape
         m = source.shape[1]
-        with torch.cuda.device(target.device):
-            dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=target.device)
-            idx = torch.empty((B, N, 3), dtype=torch.int32, device=target.device)
-            check(lib().pcreid_three_nn(B, N, m, ptr(target), ptr(source), ptr(dist2), ptr(idx), stream()), "pcreid_three_nn")
+        dist2 = torch.empty((B, N, 3), dtype=torch.float32, device=target.device)
+        idx = torch.empty((B, N, 3), dtype=torch.int32, device=target.device)
+        OPS.three_nn(B, N, m, target, source, dist2, idx)
         ctx.mark_non_differentiable(idx)
         return torch.sqrt(dist2), idx
 
@@ -30,10 +29,8 @@ class ThreeInterpolate(_NoBackward):
         require(weight, "weight")
         B, c, m = features.shape
         n = indices.shape[1]
-        with torch.cuda.device(features.device):
-            output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
-            check(lib().pcreid_three_interpolate(B, c, m, n, ptr(features), ptr(indices), ptr(weight), ptr(output), stream()),
-                  "pcreid_three_interpolate")
+        output = torch.empty((B, c, n), dtype=torch.float32, device=features.device)
+        OPS.three_interpolate(B, c, m, n, features, indices, weight, output)
         return output
 
 

@@ -2,7 +2,7 @@
 Reference: mmdet3d/ops/knn/knn.py:7-71 (heap kNN, k <= 100)."""
 import torch
 
-from ._common import check, lib, ptr, require, stream
+from ._common import OPS, require
 
 
 class KNN:
@@ -20,10 +20,9 @@ class KNN:
         assert k <= 100, "k should be no larger than 100 (knn.py:30)"
         B, npoint, _ = center_xyz.shape
         N = xyz.shape[1]
-        with torch.cuda.device(xyz.device):
-            idx = torch.zeros((B, k, npoint), dtype=torch.int32, device=xyz.device)
-            dist2 = torch.zeros((B, k, npoint), dtype=torch.float32, device=xyz.device)
-            check(lib().pcreid_knn_t(B, N, npoint, k, ptr(xyz), ptr(center_xyz), ptr(idx), ptr(dist2), stream()), "pcreid_knn")
+        idx = torch.zeros((B, k, npoint), dtype=torch.int32, device=xyz.device)
+        dist2 = torch.zeros((B, k, npoint), dtype=torch.float32, device=xyz.device)
+        OPS.knn_t(B, N, npoint, k, xyz, center_xyz, idx, dist2)
         return (idx, dist2) if return_dist else idx
 
     forward = apply

@@ -17,7 +17,7 @@ from .ball_query import ball_query
 from .furthest_point_sample import Points_Sampler
 from .gather_points import gather_points
 from .interpolate import three_interpolate, three_nn
-from ._common import check, lib, ptr, stream
+from ._common import OPS
 
 
 class ConvModule(nn.Module):
@@ -174,11 +174,9 @@ class BasePointSAModule(_PackedMLPs):
             b1 = min(B, b0 + step)
             nb = b1 - b0
             h = torch.empty((nb, C, S * k), device=p1.device, dtype=torch.float32)
-            check(lib().pcreid_edge_build(nb, C, N, S, k, ptr(p1[b0:b1]), ptr(cc[b0:b1]), ptr(idx[b0:b1]), ptr(h), stream()),
-                  "pcreid_edge_build")
+            OPS.edge_build(nb, C, N, S, k, p1[b0:b1], cc[b0:b1], idx[b0:b1], h)
             h = _mlp_tail(h, tail)
-            seg_pool = lib().pcreid_seg_max if pool_mod == "max" else lib().pcreid_seg_mean
-            check(seg_pool(nb * Co * S, k, ptr(h), ptr(out[b0:b1]), stream()), "pcreid_seg_pool")
+            (OPS.seg_max if pool_mod == "max" else OPS.seg_mean)(nb * Co * S, k, h, out[b0:b1])
         return out
 
 

@@ -53,6 +53,66 @@ def test_reference_api_surface(fake):
         m(return_loss=True)
 
 
+def test_forward_test_refuses_configs_it_does_not_evaluate(fake):
+    """auxiliary heads that are built and enabled, the dense loss, a disabled match loss: forward_test raises instead of
+    silently returning zeros / None where the reference would have run them (ReIDNet.py:652-662)."""
+    m, _ = helpers.build_pair("pt")
+    s1, s2 = O.synth_objects(2, 128, 2), O.synth_objects(2, 128, 3)
+    one = [torch.tensor([1]) for _ in range(2)]
+    kw = dict(sparse_1=list(s1), sparse_2=list(s2), dense_1=list(s1), dense_2=list(s2), label_1=one, label_2=one, id_1=one, id_2=one,
+              size_1=one, size_2=one, vis_1=one, vis_2=one)
+    m.losses_to_use.update(kl=False, cls=False, fp=False, shape=False, dense=False, match=True)
+    assert m(return_loss=False, **kw)[0]['val_kl_loss'].item() == 0.
+    m.losses_to_use["dense"] = True
+    with pytest.raises(NotImplementedError):
+        m(return_loss=False, **kw)
+    m.losses_to_use.update(dense=False, cls=True)
+    m.cls_head = torch.nn.Linear(128, 10)
+    with pytest.raises(NotImplementedError):
+        m(return_loss=False, **kw)
+    m.cls_head = None
+    m.losses_to_use["match"] = False
+    with pytest.raises(NotImplementedError):
+        m(return_loss=False, **kw)
+
+
+def test_packed_weight_cache_invalidation(fake):
+    """writes through .data bypass the version counter: invalidate_packed() is the documented way to repack"""
+    m, _ = helpers.build_pair("pt")
+    lr = m.cross_stage1
+    pk0 = lr.packed()
+    assert lr.packed() is pk0
+    p = next(lr.parameters())
+    p.data.mul_(2.0)                       # no version bump -> the cache cannot see it
+    assert lr.packed() is pk0
+    m.invalidate_packed()
+    assert lr.packed() is not pk0
+    pk1 = lr.packed()
+    with torch.no_grad():
+        p.mul_(0.5)                        # in-place op through the tensor: version bump -> repack
+    assert lr.packed() is not pk1
+
+
+def test_compat_registers_under_a_distinct_name_unless_overridden(monkeypatch):
+    import sys
+    import types
+    from pcreid_b200 import compat, models
+
+    class Reg(dict):
+        def register_module(self, name, force, module):
+            self[name] = module
+
+    fake_builder = types.ModuleType("mmdet3d.models.builder")
+    fake_builder.FUSIONMODELS = Reg(ReIDNet="the reference class")
+    for n in ("mmdet3d", "mmdet3d.models"):
+        monkeypatch.setitem(sys.modules, n, types.ModuleType(n))
+    monkeypatch.setitem(sys.modules, "mmdet3d.models.builder", fake_builder)
+    assert compat.install() is False
+    assert fake_builder.FUSIONMODELS["ReIDNet"] == "the reference class" and fake_builder.FUSIONMODELS["ReIDNetB200"] is models.ReIDNet
+    assert compat.install(override=True) is False
+    assert fake_builder.FUSIONMODELS["ReIDNet"] is models.ReIDNet
+
+
 def test_registry_and_state_dict_roundtrip():
     from pcreid_b200.models import FUSIONMODELS, build_model
     assert "ReIDNet" in FUSIONMODELS

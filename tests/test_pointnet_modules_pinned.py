@@ -90,6 +90,26 @@ def test_points_sampler_vs_reference(R, mods, ranges, npts):
     assert torch.equal(R.calc_square_dist(xyz, xyz, norm=False), PO.calc_square_dist_ref(xyz, xyz, norm=False))
 
 
+@pytest.mark.parametrize("max_r,normalize,uniform,use_xyz,use_feat", [
+    (None, False, False, True, True), (0.9, True, False, True, True), (0.9, False, True, True, True), (0.7, False, True, True, False),
+    (0.9, False, False, False, True)])
+def test_query_and_group_oracle_vs_reference_class(R, max_r, normalize, uniform, use_xyz, use_feat):
+    """oracle.query_and_group_full (what the GPU QueryAndGroup is compared with) equals the reference's own QueryAndGroup,
+    including the uniform_sample branch under the same host-generator seed."""
+    x = O.synth_objects(2, 96, 6)
+    f = torch.randn(2, 5, 96, generator=torch.Generator().manual_seed(1)) if use_feat else None
+    centers = x[:, :12].contiguous()
+    qg = R.QueryAndGroup(max_r, 8, use_xyz=use_xyz, normalize_xyz=normalize, uniform_sample=uniform, return_grouped_xyz=True,
+                         return_unique_cnt=uniform, return_grouped_idx=True)
+    torch.manual_seed(11)
+    ref = qg(x, centers, f)
+    torch.manual_seed(11)
+    nf, gx, cnt, idx = PO.query_and_group_full(x, centers, f, max_r, 8, use_xyz=use_xyz, normalize_xyz=normalize, uniform_sample=uniform)
+    assert torch.equal(ref[0], nf) and torch.equal(ref[1], gx) and torch.equal(ref[-1], idx)
+    if uniform:
+        assert torch.equal(ref[2], cnt)
+
+
 def test_product_modules_have_the_reference_state_dict_keys(R):
     from pcreid_b200.ops import PointFPModule, PointSAModuleMSG
     kw = dict(num_point=48, radii=[0.6, 1.2], sample_nums=[16, 32], mlp_channels=[[6, 16, 32], [6, 32, 32, 32]])

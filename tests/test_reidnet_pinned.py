@@ -87,12 +87,15 @@ def test_oracle_equals_the_real_reidnet_class(R, kind):
                     assert abs(float(L[i, j] - one)) < 1e-6
 
 
-@pytest.mark.parametrize("kind", ["pt", "concat", "dgcnn", "xcorr-baseline"])
-def test_product_forward_test_equals_the_real_class(R, fake, kind):
+@pytest.mark.parametrize("kind,kl", [("pt", False), ("concat", False), ("dgcnn", False), ("xcorr-baseline", False), ("pt", True)])
+def test_product_forward_test_equals_the_real_class(R, fake, kind, kl, monkeypatch):
     from pcreid_b200.models import build_model
+    shipped = copy.deepcopy(SHIPPED)
+    shipped["losses_to_use"]["kl"] = kl          # kl=True: the validation-only KL term over the embeddings (ReIDNet.py:467-482)
+    monkeypatch.setitem(globals(), "SHIPPED", shipped)
     net, sd = _build_ref(R, kind)
     cfg = copy.deepcopy(helpers.model_cfg(kind, (128, 64, 32)))
-    cfg.update(copy.deepcopy(SHIPPED))
+    cfg.update(copy.deepcopy(shipped))
     mine = build_model(cfg).eval()
     mine.load_state_dict(net.state_dict(), strict=True)              # the real class's checkpoint loads unchanged
     assert list(mine.state_dict().keys()) == list(net.state_dict().keys())
