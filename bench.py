@@ -38,9 +38,10 @@ FLOP_PER_PAIR = 101.25e6         # xcorr_eff + pool + head @256 pts
 METRIC = "pair scores/sec (PT-256 encode + all-pairs xcorr_eff match)"
 CPU_SAMPLE = (64, 8192)          # objects per side, pairs: the bounded CPU sample, identical in both arms
 MODE_TEXT = {
-    "parity_tc": "parity_tc: tcgen05 everywhere at an 11-bit significand -- kind::tf32 SA shared MLPs / attention blocks in the "
-                 "encoder, fused kind::f16 matcher with fp16 operands (pair_tc.cu, pair_tc2.cu) -- fp32 accumulate / norms; "
-                 "gate |dlogit| <= 5e-3, raw top-1 >= 0.97",
+    "parity_tc": "parity_tc: tensor cores at an 11-bit significand -- tcgen05 kind::tf32 SA shared MLPs / Self_Attention blocks in the "
+                 "encoder with operands pre-rounded to tf32 (the three FP_SA blocks that emit the embedding stay fp32: they cost ~1 % "
+                 "raw top-1, profiles/r02_parity_error_budget.md), fused kind::f16 matcher with fp16 operands (pair_tc.cu, pair_tc2.cu) "
+                 "-- fp32 accumulate / norms; gate |dlogit| <= 5e-3, raw top-1 >= 0.97",
     "fast": "fast: the same kernels with bf16 matcher operands; gate |dlogit| <= 3e-2",
     "parity": "parity: fp32 FFMA kernels, logits within 1e-4 of the reference",
 }
@@ -143,7 +144,7 @@ def cpu_reference_sample(n_obj=CPU_SAMPLE[0], n_pairs=CPU_SAMPLE[1], threads=Non
             "objects_per_s": 1 / s_obj, "pairs_only_per_s": 1 / s_pair}
 
 
-def parity_block(model, dev, rows=256, cols=256):
+def parity_block(model, dev, rows=384, cols=256):
     """measured parity of the benchmarked mode: a rows x cols block of the workload (tracks seed 1000, detections seed 1 --
     the step's own inputs) through the CUDA path end to end (encode + match) against the CPU oracle."""
     orc, O = _oracle()
@@ -377,7 +378,7 @@ def main():
                          "kernel": roof_kernel, "peak_source": pk_src + " bf16 sustained (MEASURED_PEAKS.json)", **roof_extra},
             "encoder": {"bound": "tensor", "objects_per_s": n_enc / (enc_ms * 1e-3), "achieved": enc_tflops, "peak": peak_tf,
                         "unit": "TFLOP/s", "frac": enc_tflops / peak_tf,
-                        "per": f"one encode of {n_enc} objects x {NPTS} pts on rank 0 (39 launches), {FLOP_PER_OBJECT / 1e6:.0f} MFLOP/object algorithmic"},
+                        "per": f"one encode of {n_enc} objects x {NPTS} pts on rank 0, {FLOP_PER_OBJECT / 1e6:.0f} MFLOP/object algorithmic"},
         }
         if fast:
             line["fast_mode"] = fast

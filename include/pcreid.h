@@ -248,8 +248,11 @@ int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /*
 /* npts = points per object (any value >= 1; objects are zero-padded to a multiple of 128 rows inside the operand images).
  * att_eps = LinearAttention.eps (1e-6, attention.py:21) times the scale the template's key/value sums carry
  * (MK1 of pcreid_pack_b7 for phase 1a; kv_scale of phase 1b for phase 2). */
+/* phase 1a: per (pair, direction) unit and 128-point tile of the search object: QF1 = elu(Wq h)+1 image, H = h + beta2 image
+ * (both per object), MK1 = the template's stage-1 attention operand; W = [W0b.diag(g1) | W0a | W0b.beta1 - W0a.beta2] (N=128,
+ * K=144) | centred W2 | LN2 gamma.  The search object's own term W0a.h is part of the K = 144 GEMM (no precomputed U image). */
 int pcreid_pair_p1a2(int n_units, int npts, int role, int fmt, float att_eps, const int* u_search, const int* u_templ,
-                     const int* u_slot, const void* QF1, const void* U, const void* H, const void* MK1, const void* W, void* A_out,
+                     const int* u_slot, const void* QF1, const void* H, const void* MK1, const void* W, void* A_out,
                      int n_ctas, void* stream);
 int pcreid_pair_p1b_n(int n_units, int npts, int role, int fmt, float kv_scale, const int* u_search, const int* u_templ,
                       const int* u_slot, const void* PV, const void* W, void* A_out, void* B7_out, int n_ctas, void* stream);

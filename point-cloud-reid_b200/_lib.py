@@ -87,7 +87,7 @@ _SIGS = {
     "pcreid_pack_image_bias": [c_int, c_int, c_int, c_vp, c_ll, c_int, c_vp, c_int, c_vp, c_vp],
     "pcreid_pack_b7": [c_int, c_vp, c_vp, c_int, c_vp, c_vp],
     "pcreid_pool_finish2": [c_int, c_int, c_vp, c_vp, c_vp, c_vp],
-    "pcreid_pair_p1a2": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 9 + [c_int, c_vp],
+    "pcreid_pair_p1a2": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 8 + [c_int, c_vp],
     "pcreid_pair_p1b_n": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 7 + [c_int, c_vp],
     "pcreid_pair_p2y": [c_int, c_int, c_int, c_int, c_float] + [c_vp] * 5 + [c_int, c_vp],
     "pcreid_sa_edge_mlp_tc": [c_int, c_int, c_int, c_int, c_int] + [c_vp] * 8 + [c_int, c_vp],

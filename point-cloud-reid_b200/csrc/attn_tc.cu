@@ -109,6 +109,8 @@ __device__ __forceinline__ float elu1(float v) { return v > 0.f ? v + 1.f : __ex
 // channel-major source -> operand image, zero outside (c < C, valid); Xr points at (channel 0, this thread's row), ld is the
 // channel stride.  32 channels are fetched per batch so that the loads of a batch are all in flight before the first
 // shared-memory store needs its data.
+// RNA: the image is a pure MMA operand -> values are rounded to tf32 here (tc::tf32_rna) instead of truncated by the tensor core.
+template <bool RNA>
 __device__ __forceinline__ void load_image_cm(uint8_t* img, const float* __restrict__ Xr, int ld, int C, int CP, bool valid, int tid) {
   for (int c0 = 0; c0 < CP; c0 += 32) {
     float v[32];
@@ -117,10 +119,12 @@ __device__ __forceinline__ void load_image_cm(uint8_t* img, const float* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (c0 + 4 * j < CP)
-        *reinterpret_cast<float4*>(img + ((c0 >> 2) + j) * 2048 + tid * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(img + ((c0 >> 2) + j) * 2048 + tid * 16) =
+            RNA ? tc::tf32_rna4(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])) : make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 }
 // point-major source (x = this thread's row of C floats) -> operand image
+template <bool RNA>
 __device__ __forceinline__ void load_image_pm(uint8_t* img, const float* __restrict__ x, int C, int CP, bool valid, int tid) {
   for (int c0 = 0; c0 < CP; c0 += 32) {
     float v[32];
@@ -129,7 +133,8 @@ __device__ __forceinline__ void load_image_pm(uint8_t* img, const float* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j)
       if (c0 + 4 * j < CP)
-        *reinterpret_cast<float4*>(img + ((c0 >> 2) + j) * 2048 + tid * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(img + ((c0 >> 2) + j) * 2048 + tid * 16) =
+            RNA ? tc::tf32_rna4(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3])) : make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   }
 }
 
@@ -217,7 +222,7 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
   const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t par = 0;
   // ---- operand images: feat, relu(Wp0 xyz + bp0)
-  load_image_cm(imgF, a.feat + (size_t)b * a.f_bs + row, a.ldf, a.C2, a.C2, valid, tid);
+  load_image_cm<false>(imgF, a.feat + (size_t)b * a.f_bs + row, a.ldf, a.C2, a.C2, valid, tid);   // exact: feat + pos reads it back
   {
     float x = 0.f, y = 0.f, z = 0.f;
     if (valid) {
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
         const int c = 4 * c4 + j;
         h[j] = fmaxf(fmaf(x, wp0_s[c], fmaf(y, wp0_s[a.DP + c], fmaf(z, wp0_s[2 * a.DP + c], bp0_s[c]))), 0.f);
       }
-      *reinterpret_cast<float4*>(imgA + c4 * 2048 + tid * 16) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(imgA + c4 * 2048 + tid * 16) = tc::tf32_rna4(make_float4(h[0], h[1], h[2], h[3]));
     }
   }
   stage_sync();
@@ -258,7 +263,9 @@ __global__ void __launch_bounds__(NTH) attn_front_kernel(const __grid_constant__
       v.y = __uint_as_float(r[j + 1]) + bp2_s[c + 1] + f.y;
       v.z = __uint_as_float(r[j + 2]) + bp2_s[c + 2] + f.z;
       v.w = __uint_as_float(r[j + 3]) + bp2_s[c + 3] + f.w;
-      *reinterpret_cast<float4*>(imgA + (c / 4) * 2048 + tid * 16) = v;
+      *reinterpret_cast<float4*>(imgA + (c / 4) * 2048 + tid * 16) = tc::tf32_rna4(v);
+      // the exact feat value has been consumed: from here on imgF is only the A operand of the feat projections
+      *reinterpret_cast<float4*>(imgF + (c / 4) * 2048 + tid * 16) = tc::tf32_rna4(f);
     }
   }
   stage_sync();
@@ -391,7 +398,7 @@ __global__ void __launch_bounds__(256, 3) linattn_kv_img_kernel(int S, int d, in
       float* ih = img + (size_t)h * dh * dh;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(ih + ((size_t)ti * dh + 4 * tj + j) * 4) = make_float4(acc[u][0][j], acc[u][1][j], acc[u][2][j], acc[u][3][j]);
+        *reinterpret_cast<float4*>(ih + ((size_t)ti * dh + 4 * tj + j) * 4) = tc::tf32_rna4(make_float4(acc[u][0][j], acc[u][1][j], acc[u][2][j], acc[u][3][j]));
     }
   }
 }
@@ -467,8 +474,8 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
   const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
   uint32_t par = 0;
   const float* F1 = a.feat1 + (size_t)b * a.f1_bs;
-  if (a.f1_pm) load_image_pm(imgF, F1 + (size_t)row * a.C1, a.C1, a.C1P, valid, tid);
-  else load_image_cm(imgF, F1 + row, a.ldf1, a.C1, a.C1P, valid, tid);
+  if (a.f1_pm) load_image_pm<true>(imgF, F1 + (size_t)row * a.C1, a.C1, a.C1P, valid, tid);     // residual is re-read from global
+  else load_image_cm<true>(imgF, F1 + row, a.ldf1, a.C1, a.C1P, valid, tid);
   const float* ksr = ksum_s + ob * D;
 
   float z[4] = {0.f, 0.f, 0.f, 0.f};        // per-head 1 / (Q.Ksum + eps)   (H <= 4)
@@ -491,7 +498,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
       for (int hh = 0; hh < 4; ++hh) dot[hh] += (hh == h) ? dd : 0.f;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<float4*>(imgQ + ((c0 >> 2) + j) * 2048 + tid * 16) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        *reinterpret_cast<float4*>(imgQ + ((c0 >> 2) + j) * 2048 + tid * 16) = tc::tf32_rna4(make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
     }
 #pragma unroll
     for (int hh = 0; hh < 4; ++hh) z[hh] = 1.f / (dot[hh] + 1e-6f);
@@ -525,7 +532,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
       for (int hh = 0; hh < 4; ++hh) dot[hh] += (hh == h) ? dd : 0.f;
 #pragma unroll
       for (int j = 0; j < 16; j += 4)
-        *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) = tc::tf32_rna4(make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
     }
 #pragma unroll
     for (int hh = 0; hh < 4; ++hh) z[hh] = 1.f / (dot[hh] + 1e-6f);
@@ -554,7 +561,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < 16; j += 4)
       *reinterpret_cast<float4*>(imgQ + ((16 * q + j) / 4) * 2048 + tid * 16) =
-          make_float4(__uint_as_float(r[j]) * zz, __uint_as_float(r[j + 1]) * zz, __uint_as_float(r[j + 2]) * zz, __uint_as_float(r[j + 3]) * zz);
+          tc::tf32_rna4(make_float4(__uint_as_float(r[j]) * zz, __uint_as_float(r[j + 1]) * zz, __uint_as_float(r[j + 2]) * zz, __uint_as_float(r[j + 3]) * zz));
   }
   stage_sync();
   // ---- GEMM 1b: merge projection, LayerNorm1
@@ -582,7 +589,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
         v.y = (__uint_as_float(r[j + 1]) - mean) * rstd * g1_s[c + 1] + b1_s[c + 1];
         v.z = (__uint_as_float(r[j + 2]) - mean) * rstd * g1_s[c + 2] + b1_s[c + 2];
         v.w = (__uint_as_float(r[j + 3]) - mean) * rstd * g1_s[c + 3] + b1_s[c + 3];
-        *reinterpret_cast<float4*>(imgQ + (c / 4) * 2048 + tid * 16) = v;
+        *reinterpret_cast<float4*>(imgQ + (c / 4) * 2048 + tid * 16) = tc::tf32_rna4(v);
       }
     }
   }
@@ -609,7 +616,7 @@ __global__ void __launch_bounds__(NTH) attn_back_kernel(const __grid_constant__ 
       v.y = fmaxf(__uint_as_float(r[j + 1]), 0.f);
       v.z = fmaxf(__uint_as_float(r[j + 2]), 0.f);
       v.w = fmaxf(__uint_as_float(r[j + 3]), 0.f);
-      *reinterpret_cast<float4*>(imgH + ((16 * q + j) / 4) * 2048 + tid * 16) = v;
+      *reinterpret_cast<float4*>(imgH + ((16 * q + j) / 4) * 2048 + tid * 16) = tc::tf32_rna4(v);
     }
   }
   stage_sync();

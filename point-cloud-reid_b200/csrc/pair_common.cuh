@@ -21,7 +21,7 @@ struct P1Args {
   float att_eps;                         // LinearAttention eps times the scale the key/value sums were stored with
   float kv_scale;                        // phase 1b: scale applied to KV / Ksum before they become the stage-2 operand
   const int *u_search, *u_templ, *u_slot;
-  const uint8_t *QF1, *U, *H, *PV;      // search-side per-object images: [obj][NT][IMG] (U: [obj][NT][2*IMG])
+  const uint8_t *QF1, *H, *PV;          // search-side per-object images: [obj][NT][IMG]
   const uint8_t* MK1;                    // template-side per-object stage-1 attention operand [obj][B7_BYTES]
   const uint8_t* W;                      // P1 weights blob
   uint8_t* A_out;                        // [slot][2][NT][IMG]   stage-1 outputs (bf16 operand images)

@@ -283,7 +283,7 @@ int pcreid_pair_p1b_n(int n_units, int npts, int role, int fmt, float kv_scale, 
       (fmt != PCREID_FMT_BF16 && fmt != PCREID_FMT_F16))
     return PCREID_ERR_ARG;
   const int NT = (npts + 127) / 128;
-  P1Args a{n_units, NT, role, npts, 0.f, kv_scale, u_search, u_templ, u_slot, nullptr, nullptr, nullptr, (const uint8_t*)PV, nullptr,
+  P1Args a{n_units, NT, role, npts, 0.f, kv_scale, u_search, u_templ, u_slot, nullptr, nullptr, (const uint8_t*)PV, nullptr,
            (const uint8_t*)W, (uint8_t*)A_out, (uint8_t*)B7_out};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;

@@ -22,9 +22,13 @@
 
 namespace {
 
-// weights blob of phase 1a (bytes): W0b.diag(g1) image (N=128, K=64) | centred W2 image (N=64, K=128) | LN2 gamma (64 fp32)
-constexpr int Q1A_W0B = 0, Q1A_W2 = 16384, Q1A_LN = 32768, Q1A_WBYTES = 32768 + 256;
-constexpr int Q1A_QXA = 0, Q1A_MK1 = IMG, Q1A_GBYTES = IMG + B7_BYTES;                       // 34816 B per group
+// weights blob of phase 1a (bytes): [W0b.diag(g1) | W0a | W0b.beta1 - W0a.beta2 | 0] image (N=128, K=144) | centred W2 image
+// (N=64, K=128) | LN2 gamma (64 fp32).  The search object's own term W0a.h rides on the tensor core as four more K steps of G2
+// against the (h + beta2) image that the residual needs anyway, instead of a per-object precomputed image U that every tile had
+// to read (32 KB) and add in the epilogue (the constant W0a.beta2 this adds is taken back out through the bias K step).
+constexpr int Q1A_W0 = 0, Q1A_W2 = 18 * 2048, Q1A_LN = Q1A_W2 + 16384, Q1A_WBYTES = Q1A_LN + 256;   // 53504
+constexpr int Q1A_ONES = Q1A_WBYTES;                                                         // 4 KB: A chunk pair, k = 0 is 1.0
+constexpr int Q1A_QXA = 0, Q1A_H = IMG, Q1A_MK1 = 2 * IMG, Q1A_GBYTES = 2 * IMG + B7_BYTES;  // 51200 B per group
 // weights blob of phase 2: Wq/bf16(ln2) image (N=64, K=64) | [W0a | W0b.diag(g1) | W0b.beta1 | 0] image (N=128, K=144) |
 // centred W2 image (N=64, K=128) | LN2 gamma (64 fp32)
 constexpr int Q2_WQ = 0, Q2_W0 = 8192, Q2_W2 = Q2_W0 + 18 * 2048, Q2_LN = Q2_W2 + 16384, Q2_WBYTES = Q2_LN + 256;   // 61696
@@ -94,7 +98,7 @@ __device__ __forceinline__ float ld64_sumsq(uint32_t tl, uint32_t (&x0)[32], uin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// phase 1a: G1 attention (Qf1_i x MK1_j) -> LN1 -> G2 (+U', ReLU, TMEM-resident) -> G3 -> LN2 + (h + beta2) -> a
+// phase 1a: G1 attention (Qf1_i x MK1_j) -> LN1 -> G2 = [X' | h + beta2 | 1] W0'^T, ReLU (TMEM-resident) -> G3 -> LN2 + (h + beta2) -> a
 // ---------------------------------------------------------------------------------------------------------------
 template <class F>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) {
@@ -110,6 +114,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
   copy_to_smem(Wsm, a.W, Q1A_WBYTES, threadIdx.x, NGX * GX);
   cp_async_commit();
+  if (threadIdx.x < 256)   // constant A chunk pair of the bias K-step: element k = 0 of every row is 1.0
+    reinterpret_cast<uint4*>(smem + Q1A_ONES)[threadIdx.x] = threadIdx.x < 128 ? make_uint4(F::ONE_LO, 0, 0, 0) : make_uint4(0, 0, 0, 0);
   cp_async_wait<0>();
   tc::fence_async_smem();
   tc::tc_fence_before();
@@ -117,14 +123,17 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   tc::tc_fence_after();
   GroupX g;
   groupx_setup(g, bars, tmem_base_s);
-  uint8_t* G = smem + Q1A_WBYTES + g.gid * Q1A_GBYTES;
+  uint8_t* G = smem + Q1A_ONES + 4096 + g.gid * Q1A_GBYTES;
   uint8_t* QXa = G + Q1A_QXA;
+  uint8_t* Hs = G + Q1A_H;
   uint8_t* MK1 = G + Q1A_MK1;
   const uint32_t sQXa = tc::smem_u32(QXa), sW = tc::smem_u32(Wsm);
   const uint32_t id144 = tc::instr_desc(128, NB7, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
   const uint32_t id128 = tc::instr_desc(128, 128, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
-  const Opnd oQXa = A_IMG(sQXa), oMK1 = B7_IMG(tc::smem_u32(MK1)), oW0b = W_IMG(sW + Q1A_W0B, 128), oW2 = W_IMG(sW + Q1A_W2, 64);
+  // QXa and Hs are adjacent: one K-major A operand of 8 K steps [X' | h + beta2]
+  const Opnd oQXa = A_IMG(sQXa), oOnes = A_IMG(tc::smem_u32(smem + Q1A_ONES)), oMK1 = B7_IMG(tc::smem_u32(MK1)),
+             oW0 = W_IMG(sW + Q1A_W0, 128), oW2 = W_IMG(sW + Q1A_W2, 64);
   const int row = g.t;
   uint8_t* xrow = QXa + row * 16;
 
@@ -136,7 +145,10 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   // attention GEMM of a tile (query image ti against the template operand te).  Called for tile n+1 as soon as tile n's
   // last accumulator has been read into registers, so that it runs behind tile n's LayerNorm2 epilogue.
   auto start_tile = [&](size_t ti_, int te_) {
-    if (!prefetched) copy_to_smem(QXa, a.QF1 + ti_ * IMG, IMG, g.t, GX);   // first tile of this group only
+    if (!prefetched) {                                                      // first tile of this group only
+      copy_to_smem(QXa, a.QF1 + ti_ * IMG, IMG, g.t, GX);
+      copy_to_smem(Hs, a.H + ti_ * IMG, IMG, g.t, GX);
+    }
     prefetched = false;
     if (te_ != cur_templ) { copy_to_smem(MK1, a.MK1 + (size_t)te_ * B7_BYTES, B7_BYTES, g.t, GX); cur_templ = te_; }
     cp_async_commit();
@@ -153,40 +165,40 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
       g.wait();
       epi_attn_norm<F>(g.tlane, xrow, a.att_eps);                                       // X' over the query image
       g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oW0b, id128, false); tc::umma_commit(g.bar); } __syncwarp(); }
-      {   // Hd = relu(acc + U') -> bf16, written back IN PLACE to TMEM columns [0, 64): the A operand of G3
-        uint4 sdU[16];
-        load_side<16>(sdU, a.U + ti * 2 * IMG, 0, row);
-        g.wait();
-        {   // G2 has consumed X': the query image of the next (unit, tile) streams into QXa behind the rest of this tile
-          int nu = u, nt = tile + 1;
-          if (nt == a.NT) { nu = u + 1; nt = 0; }
-          if (nu < u1) {
-            copy_to_smem(QXa, a.QF1 + ((size_t)(nt == 0 ? so_next : so) * a.NT + nt) * IMG, IMG, g.t, GX);
-            cp_async_commit();
-            prefetched = true;
-          }
+      if (g.issuer) {
+        if (tc::elect_one()) {
+          issue_gemm<8>(g.tmem, oQXa, oW0, id128, false);                                            // [X' | h + beta2]
+          tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);         // + W0b.beta1 - W0a.beta2
+          tc::umma_commit(g.bar);
         }
-#pragma unroll
-        for (int b = 0; b < 2; ++b) {
-          uint32_t r0[32], r1[32], w[32];
-          tc::tmem_ld32(g.tlane + 64 * b, r0);
-          tc::tmem_ld32(g.tlane + 64 * b + 32, r1);
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 s0 = sdU[8 * b + c], s1 = sdU[8 * b + 4 + c];
-            const uint32_t sw0[4] = {s0.x, s0.y, s0.z, s0.w}, sw1[4] = {s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              w[c * 4 + j] = F::add_relu(u2f(r0[c * 8 + 2 * j]), u2f(r0[c * 8 + 2 * j + 1]), sw0[j]);
-              w[16 + c * 4 + j] = F::add_relu(u2f(r1[c * 8 + 2 * j]), u2f(r1[c * 8 + 2 * j + 1]), sw1[j]);
-            }
-          }
-          tc::tmem_st32(g.tlane + 32 * b, w);
-        }
-        tc::tmem_st_wait();
+        __syncwarp();
       }
+      g.wait();
+      {   // G2 has consumed [X' | h]: the images of the next (unit, tile) stream into QXa / Hs behind the rest of this tile
+        int nu = u, nt = tile + 1;
+        if (nt == a.NT) { nu = u + 1; nt = 0; }
+        if (nu < u1) {
+          const size_t tn = (size_t)(nt == 0 ? so_next : so) * a.NT + nt;
+          copy_to_smem(QXa, a.QF1 + tn * IMG, IMG, g.t, GX);
+          copy_to_smem(Hs, a.H + tn * IMG, IMG, g.t, GX);
+          cp_async_commit();
+          prefetched = true;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {   // Hd = relu(acc) -> 16 bit, written back IN PLACE to TMEM columns [0, 64): the A operand of G3
+        uint32_t r0[32], r1[32], w[32];
+        tc::tmem_ld32(g.tlane + 64 * b, r0);
+        tc::tmem_ld32(g.tlane + 64 * b + 32, r1);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          w[j] = F::pack_relu(u2f(r0[2 * j]), u2f(r0[2 * j + 1]));
+          w[16 + j] = F::pack_relu(u2f(r1[2 * j]), u2f(r1[2 * j + 1]));
+        }
+        tc::tmem_st32(g.tlane + 32 * b, w);
+      }
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       g.sync();
       tc::tc_fence_after();
@@ -199,7 +211,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
         }
         __syncwarp();
       }
-      {   // a = (h + beta2) + gamma2 * acc * rstd -> global bf16 image (stage-1 output)
+      {   // a = (h + beta2) + gamma2 * acc * rstd -> global 16-bit image (stage-1 output)
         uint4 sdH[8];
         load_side<8>(sdH, a.H + ti * IMG, 0, row);
         g.wait();
@@ -227,6 +239,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
       tc::tc_fence_before();                                              // TMEM reads done before the next tile's G1 overwrites
     }
   }
+  cp_async_wait<0>();
   tc::tc_fence_before();
   __syncthreads();
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
@@ -509,7 +522,7 @@ __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int 
 
 template <class F>
 static int launch_p1a2(const P1Args& a, int grid, cudaStream_t st) {
-  const int smem = Q1A_WBYTES + NGX * Q1A_GBYTES;
+  const int smem = Q1A_ONES + 4096 + NGX * Q1A_GBYTES;
   cudaFuncSetAttribute(pair_p1a2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   pair_p1a2_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
   return pcreid_launch_status();
@@ -546,13 +559,13 @@ int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias, f
 }
 
 int pcreid_pair_p1a2(int n_units, int npts, int role, int fmt, float att_eps, const int* u_search, const int* u_templ, const int* u_slot,
-                     const void* QF1, const void* U, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream) {
+                     const void* QF1, const void* H, const void* MK1, const void* W, void* A_out, int n_ctas, void* stream) {
   if (n_units <= 0) return PCREID_OK;
-  if (!u_search || !u_templ || !u_slot || !QF1 || !U || !H || !MK1 || !W || !A_out || npts <= 0 ||
+  if (!u_search || !u_templ || !u_slot || !QF1 || !H || !MK1 || !W || !A_out || npts <= 0 ||
       (fmt != PCREID_FMT_BF16 && fmt != PCREID_FMT_F16))
     return PCREID_ERR_ARG;
   const int NT = (npts + 127) / 128;
-  P1Args a{n_units, NT, role, npts, att_eps, 1.f, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)U, (const uint8_t*)H,
+  P1Args a{n_units, NT, role, npts, att_eps, 1.f, u_search, u_templ, u_slot, (const uint8_t*)QF1, (const uint8_t*)H,
            nullptr, (const uint8_t*)MK1, (const uint8_t*)W, (uint8_t*)A_out, nullptr};
   int grid = n_ctas > 0 ? n_ctas : 148;
   if (grid * NGX > n_units) grid = (n_units + NGX - 1) / NGX;

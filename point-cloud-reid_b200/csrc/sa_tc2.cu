@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256 * CS, (C == 32 ? 4 : (C == 64 ? (CS == 2 ?
               const float4 q = *reinterpret_cast<const float4*>(crow + c0 + j);
               v = make_float4(fmaxf(p.x + q.x, 0.f), fmaxf(p.y + q.y, 0.f), fmaxf(p.z + q.z, 0.f), fmaxf(p.w + q.w, 0.f));
             }
+            v = tc::tf32_rna4(v);                                        // A operand of GEMM 1: round, do not let the MMA truncate
             r[j] = __float_as_uint(v.x); r[j + 1] = __float_as_uint(v.y); r[j + 2] = __float_as_uint(v.z); r[j + 3] = __float_as_uint(v.w);
           }
           tc::tmem_st16(tA1 + lane_off + cb + c0, r);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(256 * CS, (C == 32 ? 4 : (C == 64 ? (CS == 2 ?
           tc::tmem_ld16(d1 + lane_off + cb + c0, r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(fmaxf(__uint_as_float(r[j]), 0.f));
+          for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(tc::tf32_rna(fmaxf(__uint_as_float(r[j]), 0.f)));   // A operand of GEMM 2
           tc::tmem_st16(d1 + lane_off + cb + c0, r);
         }
         tc::tmem_st_wait();

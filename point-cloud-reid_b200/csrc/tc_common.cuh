@@ -233,10 +233,25 @@ struct OpF16 {
     return fmaf(fmaxf(x, 0.f), 0.69314718056f, e);
   }
   static __device__ __forceinline__ uint32_t elu1_scaled(float a, float b) { return pack(elu1s_f(a), elu1s_f(b)); }
-  static __device__ __forceinline__ uint32_t elu1(float a, float b) {
-    return pack(a > 0.f ? a + 1.f : __expf(a), b > 0.f ? b + 1.f : __expf(b));
+  // elu(x)+1 = max(x,0) + exp(min(x,0)), branch-free: 5 instructions per element (the select form `x > 0 ? x + 1 : __expf(x)`
+  // compiled to divergent regions around a non-ftz exp with denormal scaling: 12+ instructions and BSSY/BSYNC pairs)
+  static __device__ __forceinline__ float elu1_f(float x) {
+    float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
+    return fmaxf(x, 0.f) + e;
   }
+  static __device__ __forceinline__ uint32_t elu1(float a, float b) { return pack(elu1_f(a), elu1_f(b)); }
 };
+
+// fp32 -> tf32 with round-to-nearest (ties away), returned in an fp32 container.  tcgen05.mma kind::tf32 reads 32-bit operands
+// and IGNORES the low 13 mantissa bits (truncation: error up to 2^-10 relative, biased towards zero); operands that are
+// pre-rounded here carry half that error and no bias.  Used by the encoder kernels for every activation they write as a
+// pure MMA operand (the weights are pre-rounded on the host: kernels.py tf32_image).
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 tf32_rna4(float4 v) { return make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w)); }
 
 // warp-uniform helpers: values produced through these are known to be warp-uniform by the compiler, so descriptor
 // arithmetic and tcgen05.mma operands stay on the uniform datapath (no per-MMA R2UR moves)

@@ -79,7 +79,7 @@ def _weight_image(w):
         if len(_W_IMAGES) >= 256:
             _W_IMAGES.clear()
         Kd, CO = w.shape
-        ent = (w, w.detach().reshape(Kd // 4, 4, CO).permute(0, 2, 1).contiguous())
+        ent = (w, round_tf32(w).reshape(Kd // 4, 4, CO).permute(0, 2, 1).contiguous())
         _W_IMAGES[key] = ent
     return ent[1]
 
@@ -341,10 +341,17 @@ def sa_edge_mlp(p1, cc, idx, w2, b2, w3, b3):
     return out
 
 
+def round_tf32(w):
+    """fp32 -> nearest tf32 value (ties away from zero), kept in fp32 storage.  tcgen05 kind::tf32 ignores the low 13 mantissa
+    bits of its operands (truncation); weights that are pre-rounded here carry half the error and no bias towards zero."""
+    bits = w.detach().float().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1fff).view(torch.float32)
+
+
 def tf32_image(w):
-    """(C_out, C_in) fp32 weight -> tcgen05 K-major operand image [k/4][n][4] (fp32 bits, read as tf32)."""
+    """(C_out, C_in) fp32 weight -> tcgen05 K-major operand image [k/4][n][4] (tf32-rounded values in fp32 storage)."""
     n, kd = w.shape
-    return w.detach().float().reshape(n, kd // 4, 4).permute(1, 0, 2).contiguous()
+    return round_tf32(w).reshape(n, kd // 4, 4).permute(1, 0, 2).contiguous()
 
 
 def tf32_image_padded(w, k_pad):

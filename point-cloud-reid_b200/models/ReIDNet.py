@@ -93,6 +93,7 @@ class ReIDNet(nn.Module):
         # 'parity': fp32 kernels (logits within 1e-4 of the reference); 'parity_tc' / 'fast': fused tcgen05 matcher with
         # fp16 / bf16 operands where the configuration allows it (d_model 64, 2 heads, point-cat + both pooling)
         self.match_mode = 'parity'
+        self.parity_tc_fp_blocks = False   # True: FP_SA blocks also run as tf32 tcgen05 kernels in 'parity_tc' mode (see set_mode)
         self.tc_encoder = True      # in the tensor-core modes the encoder's 1x1 convs / Linears run as tf32 tcgen05 GEMMs
         self._fused = {}
         # encode() replays a captured CUDA graph per (shape, mode, weights version): the ~90 launches of one encoder pass
@@ -107,15 +108,19 @@ class ReIDNet(nn.Module):
 
     def set_mode(self, mode):
         """'parity': fp32 FFMA kernels everywhere (|dlogit| <= 1e-4).
-        'parity_tc': every contraction on the tensor cores at an 11-bit significand -- tcgen05 kind::tf32 shared MLPs /
-        attention blocks in the encoder, fused tcgen05 matcher with fp16 operands -- fp32 accumulation and norms
-        (|dlogit| <= 5e-3, the tf32 gate of SURVEY.md 8d).
-        'fast': the same kernels with bf16 matcher operands (|dlogit| <= 3e-2)."""
+        'parity_tc': the contractions on the tensor cores at an 11-bit significand -- tcgen05 kind::tf32 SA shared MLPs and
+        Self_Attention blocks in the encoder (operands pre-rounded to tf32), fused tcgen05 matcher with fp16 operands -- fp32
+        accumulation and norms (|dlogit| <= 5e-3, the tf32 gate of SURVEY.md 8d).  The three feature-propagation blocks
+        (FP_SA), whose output IS the embedding, stay on the fp32 kernels in this mode unless `parity_tc_fp_blocks` is set:
+        measured (scripts/encoder_error_probe.py, profiles/r02_parity_error_budget.md) they alone cost ~1 % of raw top-1
+        agreement on the random-init logits (top-2 gap median 5e-3) for 3 % of the step time.
+        'fast': every block on the tensor cores, bf16 matcher operands (|dlogit| <= 3e-2)."""
         assert mode in ('parity',) + self.TC_MODES
+        from .pointnet2_utils import FP_SA
         self.match_mode = mode
         for m in self.modules():
             if hasattr(m, 'tc_mode'):
-                m.tc_mode = mode in self.TC_MODES
+                m.tc_mode = mode in self.TC_MODES and not (mode == 'parity_tc' and isinstance(m, FP_SA) and not self.parity_tc_fp_blocks)
         return self
 
     def invalidate_packed(self):

@@ -9,7 +9,7 @@ modes of ReIDNet.match_all_pairs / match_forward_inference:
               with it).  Conversions saturate instead of overflowing.
 
 Everything that depends on one object only is computed once per object with the fp32 kernels and packed to 16-bit
-operand images (stage-1 queries elu(Wq1 h)+1, U = W0a1 h, h, Wv2 pos2(xyz), and the stage-1 attention operand
+operand images (stage-1 queries elu(Wq1 h)+1, h + beta2, Wv2 pos2(xyz), and the stage-1 attention operand
 MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the three fused kernels then score pairs without writing any per-pair
 activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and the stage-2 attention operands (36 KB / pair).
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
@@ -58,7 +58,7 @@ def supported(model, n_points):
 
 class ObjectPack:
     """per-object operand images of a set of objects (tracks or detections)."""
-    __slots__ = ("n", "npts", "fmt", "QF1", "U", "H", "PV", "MK1")
+    __slots__ = ("n", "npts", "fmt", "QF1", "H", "PV", "MK1")
 
 
 class FusedXcorr:
@@ -80,11 +80,15 @@ class FusedXcorr:
                 # LN1 affine folded forward, centred merge / mlp[2], q_proj scaled for the exp2-based elu epilogue
                 f = lambda t: t.detach().float()
                 W0_1, W0_2 = f(X1.mlp[0].weight), f(X2.mlp[0].weight)
-                self._w1a2 = torch.cat([
-                    _w_image(W0_1[:, d:] * f(X1.norm1.weight)[None, :], dt), _w_image(_center_out(X1.mlp[2].weight), dt),
-                    _f32_bytes(X1.norm2.weight)]).contiguous()
-                self._c1 = (W0_1[:, d:] @ f(X1.norm1.bias)).contiguous()           # W0b.beta1 -> bias of the per-object term U
+                # stage 1, G2 operand [X' | h + beta2 | 1]: columns = W0b.diag(g1) | W0a | W0b.beta1 - W0a.beta2 (the residual image
+                # carries LayerNorm2's beta, so the constant it adds through W0a is taken back out in the bias column)
                 self._b2_1 = f(X1.norm2.bias).contiguous()                         # added to the residual image H
+                W0ext1 = torch.zeros((2 * d, 2 * d + 16), device=W0_1.device)
+                W0ext1[:, :d] = W0_1[:, d:] * f(X1.norm1.weight)[None, :]
+                W0ext1[:, d:2 * d] = W0_1[:, :d]
+                W0ext1[:, 2 * d] = W0_1[:, d:] @ f(X1.norm1.bias) - W0_1[:, :d] @ self._b2_1
+                self._w1a2 = torch.cat([
+                    _w_image(W0ext1, dt), _w_image(_center_out(X1.mlp[2].weight), dt), _f32_bytes(X1.norm2.weight)]).contiguous()
                 self._merge1c = kmajor(_center_out(X1.merge.weight))
                 self._w1b2 = torch.cat([
                     _w_image(torch.cat([X2.k_proj.weight, X2.v_proj.weight], 0), dt),
@@ -98,7 +102,7 @@ class FusedXcorr:
                     _w_image(f(X2.q_proj.weight) / ln2, dt), _w_image(W0ext, dt), _w_image(_center_out(X2.mlp[2].weight), dt),
                     _f32_bytes(X2.norm2.weight)]).contiguous()
                 self._b2_2 = f(X2.norm2.bias).contiguous()                         # added after the pooling
-                assert self._w1a2.numel() == 33024 and self._w2y.numel() == 61696 and self._w1b2.numel() == 24576
+                assert self._w1a2.numel() == 53504 and self._w2y.numel() == 61696 and self._w1b2.numel() == 24576
             self._key = key
 
     def _tick(self):
@@ -133,7 +137,6 @@ class FusedXcorr:
         o = ObjectPack()
         o.n, o.npts, o.fmt = B, N, self.fmt
         o.QF1 = self._pack_image(K.cn_linear(h, pk1["q"]), K.ACT_ELU1)
-        o.U = self._pack_image(K.cn_linear(h, pk1["mlp0a"], bias=self._c1))     # W0a h + W0b beta1
         o.H = torch.empty((B, (N + 127) // 128, C // 8, 128, 16), device=h.device, dtype=torch.uint8)
         _OPS.pack_image_bias(B, C, N, h, h.stride(0), h.stride(1), self._b2_1, self.fmt, o.H)   # h + beta2
         pos2 = X2.position_code(xyz)
@@ -185,7 +188,7 @@ class FusedXcorr:
                 order = torch.argsort(tmpl, stable=True)                    # runs of units share the template operand
                 us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
             e0 = self._tick()
-            _OPS.pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, us, ut, sl, ps.QF1, ps.U, ps.H, pm.MK1, self._w1a2, A, self.n_ctas)
+            _OPS.pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, us, ut, sl, ps.QF1, ps.H, pm.MK1, self._w1a2, A, self.n_ctas)
             self._tock("pair_p1a2_kernel", e0, P)
             e0 = self._tick()
             _OPS.pair_p1b_n(P, N, role, self.fmt, sc, us, ut, sl, ps.PV, self._w1b2, A, B7, self.n_ctas)
