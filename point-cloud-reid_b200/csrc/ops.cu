@@ -706,6 +706,65 @@ __global__ void __launch_bounds__(256) ball_query_kernel(int N, int M, int k, fl
     for (int l = lane; l < k; l += 32) o[l] = N;
 }
 
+// Thread-per-query variant (the default for >= 64 queries per object).  The warp-per-query kernel above spends a ballot +
+// popcount + dependent count update per 32-point chunk and keeps 31 of 32 lanes waiting on that chain; here every lane walks
+// its own query over the object's points, which are staged once per CTA in shared memory as float4 (x, y, z, |p|^2) and read
+// as warp-wide broadcasts (one wavefront per point and warp).  Hits go to a shared-memory staging tile [slot][query] (row
+// stride 129 words: conflict-free for the per-thread writes and for the transposed read-out), padded with the first hit as
+// the reference does, and leave as fully coalesced 128-byte rows.  Same distances, same predicate, same order as MODE 0 / 1.
+constexpr int BQ_T = 128;          // queries per CTA
+constexpr int BQ_TILE = 2048;      // points staged per pass (32 KB)
+template <int MODE>
+__global__ void __launch_bounds__(BQ_T) ball_query_tq_kernel(int N, int M, int k, float min_r2, float max_r2,
+                                                             const float* __restrict__ qxyz, const float* __restrict__ xyz,
+                                                             int* __restrict__ idx) {
+  extern __shared__ __align__(16) uint8_t bq_smem[];
+  float4* pts = reinterpret_cast<float4*>(bq_smem);
+  int* stage = reinterpret_cast<int*>(bq_smem + (size_t)min(N, BQ_TILE) * sizeof(float4));      // [k][BQ_T + 1]
+  const int t = threadIdx.x, b = blockIdx.y, q0 = blockIdx.x * BQ_T, q = q0 + t;
+  const bool live = q < M;
+  const float* P = xyz + (size_t)b * N * 3;
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  if (live) {
+    const float* Q = qxyz + ((size_t)b * M + q) * 3;
+    qx = Q[0]; qy = Q[1]; qz = Q[2];
+  }
+  const float qn = MODE == 1 ? sqnorm3(qx, qy, qz) : 0.f;
+  int cnt = 0, first = MODE == 1 ? N : 0;
+  int* col = stage + t;
+  for (int base = 0; base < N; base += BQ_TILE) {
+    const int nt = min(BQ_TILE, N - base);
+    __syncthreads();
+    for (int i = t; i < nt; i += BQ_T) {
+      const float x = __ldg(P + (size_t)(base + i) * 3), y = __ldg(P + (size_t)(base + i) * 3 + 1), z = __ldg(P + (size_t)(base + i) * 3 + 2);
+      pts[i] = make_float4(x, y, z, 0.f);
+    }
+    __syncthreads();
+    if (!live || cnt >= k) continue;
+    for (int i = 0; i < nt; ++i) {
+      const float4 p = pts[i];
+      bool hit;
+      if (MODE == 0) {
+        const float d2 = dist_direct(qx, qy, qz, p.x, p.y, p.z);
+        hit = (d2 == 0.f) || (d2 >= min_r2 && d2 < max_r2);
+      } else {
+        hit = !(dist_expand(qx, qy, qz, qn, p.x, p.y, p.z) > max_r2);
+      }
+      if (hit) {
+        if (cnt == 0) first = base + i;
+        col[cnt * (BQ_T + 1)] = base + i;
+        if (++cnt >= k) break;
+      }
+    }
+  }
+  // remaining slots: the first hit (MODE 0 without any hit: the caller's zeros; MODE 1 without any hit: N)
+  for (int s = cnt; s < k; ++s) col[s * (BQ_T + 1)] = first;
+  __syncthreads();
+  const int nq = min(BQ_T, M - q0);
+  int* o = idx + ((size_t)b * M + q0) * k;
+  for (int i = t; i < nq * k; i += BQ_T) o[i] = stage[(i % k) * (BQ_T + 1) + i / k];
+}
+
 // ------------------------------------------------------------------------------------------------
 // group_points / gather_points:  out[b, c, p] = points[b, c, idx[b, p]],  p in [0, P)  (P = S*k or M)
 // ------------------------------------------------------------------------------------------------
@@ -999,6 +1058,14 @@ int pcreid_ball_query(int b, int n, int m, float min_radius, float max_radius, i
                       const float* xyz, int* idx, void* stream) {
   if (b <= 0 || m <= 0 || nsample <= 0) return PCREID_OK;
   if (n <= 0 || !new_xyz || !xyz || !idx) return PCREID_ERR_ARG;
+  if (b > 65535) return PCREID_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(n < BQ_TILE ? n : BQ_TILE) * sizeof(float4) + (size_t)nsample * (BQ_T + 1) * sizeof(int);
+  if (m >= 64 && smem <= 96 * 1024) {
+    cudaFuncSetAttribute(ball_query_tq_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ball_query_tq_kernel<0><<<dim3(ceil_div(m, BQ_T), b), BQ_T, smem, (cudaStream_t)stream>>>(n, m, nsample, min_radius * min_radius,
+                                                                                          max_radius * max_radius, new_xyz, xyz, idx);
+    return pcreid_launch_status();
+  }
   dim3 grid(ceil_div(m, 8), b);
   ball_query_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(n, m, nsample, min_radius * min_radius,
                                                                max_radius * max_radius, new_xyz, xyz, idx);
@@ -1011,6 +1078,12 @@ int pcreid_query_ball_point(int b, int n, int m, float r2, int nsample, const fl
   if (b <= 0 || m <= 0 || nsample <= 0) return PCREID_OK;
   if (n <= 0 || !new_xyz || !xyz || !idx) return PCREID_ERR_ARG;
   if (b > 65535) return PCREID_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)(n < BQ_TILE ? n : BQ_TILE) * sizeof(float4) + (size_t)nsample * (BQ_T + 1) * sizeof(int);
+  if (m >= 64 && smem <= 96 * 1024) {
+    cudaFuncSetAttribute(ball_query_tq_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ball_query_tq_kernel<1><<<dim3(ceil_div(m, BQ_T), b), BQ_T, smem, (cudaStream_t)stream>>>(n, m, nsample, 0.f, r2, new_xyz, xyz, idx);
+    return pcreid_launch_status();
+  }
   ball_query_kernel<1><<<dim3(ceil_div(m, 8), b), 256, 0, (cudaStream_t)stream>>>(n, m, nsample, 0.f, r2, new_xyz, xyz, idx);
   return pcreid_launch_status();
 }

@@ -33,3 +33,23 @@ def point_transformer_cfg(backbone_list=(256, 128, 64)):
                             dict(type='Linear', in_features=128, out_features=1)],
                 downsample=None, cls_head=None, fp_head=None, shape_head=None, cross_stage1=dict(xa), cross_stage2=dict(xa),
                 local_stage1=dict(), local_stage2=dict())
+
+
+_DOWNSAMPLE = [dict(type='LinearRes', n_in=1024, n_out=512, norm='GN', ng=64), dict(type='LinearRes', n_in=512, n_out=128, norm='GN', ng=16),
+               dict(type='Linear', in_features=128, out_features=64)]
+
+
+def dgcnn_cfg(backbone_list=(256, 128, 64)):
+    """configs_reid/_base_/reidentifiers/reid_pts_dgcnn_point-cat.py: DGCNN (k = 20, emb_dims 1024) + per-point downsample to 64."""
+    c = point_transformer_cfg(backbone_list)
+    c.update(use_dgcnn=True, backbone=dict(type='dgcnn', dropout=0.5, emb_dims=1024, k=20, output_channels=40),
+             downsample=[dict(d) for d in _DOWNSAMPLE],
+             match_head=[dict(type='LinearRes', n_in=128, n_out=128, norm='GN', ng=16), dict(type='Linear', in_features=128, out_features=1)])
+    return c
+
+
+def pointnet_cfg(backbone_list=(128, 64, 32)):
+    """configs_reid/_base_/reidentifiers/reid_pts_pointnet_point-cat.py: PointNet (T-Nets, 1024-wide trunk) + downsample to 64."""
+    c = point_transformer_cfg(backbone_list)
+    c.update(use_dgcnn=True, backbone=dict(type='PointNet', k=40, normal_channel=False), downsample=[dict(d) for d in _DOWNSAMPLE])
+    return c
