@@ -160,6 +160,21 @@ int pcreid_cn_groupnorm(const pcreid_norm_args* args, void* stream);
  * (not per-object) weights, channel-major inputs, no object maps; else PCREID_ERR_UNSUPPORTED. */
 int pcreid_cn_linear_tc2(const pcreid_linear_args* args, const float* W1img, const float* W2img, int n_sms, void* stream);
 
+/* Third generation (csrc/cn_linear_tma.cu): the same contract with both operands staged by TMA tensor maps
+ * (cp.async.bulk.tensor, 128-byte swizzle) directly from the channel-major activations and the k-major weights as
+ * MN-major tcgen05 kind::tf32 operands -- no weight images, any K (zero-filled by the TMA unit), shared or per-object
+ * weights, object maps (x1_map / x2_map / w1_map / r_map) as the third box coordinate.  x*_objs / w1_objs: number of objects in
+ * the mapped source tensors (the bound of the tensor map's third extent; ignored without a map).
+ * flags: PCREID_TMA_TF32_MAPS  activation maps typed TFLOAT32 (the TMA unit rounds fp32 -> tf32 instead of the tensor
+ *                             core truncating), PCREID_TMA_ROUND_OUT  Y rounded to tf32 (feeds another tf32 GEMM).
+ * PCREID_ERR_UNSUPPORTED: point-major inputs or outputs, CO < 32, CO % 4, rows % 4, row / object strides that are not multiples of 4 floats,
+ * unaligned base pointers, no driver entry point for cuTensorMapEncodeTiled. */
+#define PCREID_TMA_TF32_MAPS 1
+#define PCREID_TMA_ROUND_OUT 2
+#define PCREID_TMA_TILE128 4     /* A/B knob: never use the 256-channel tiles chosen for K >= 256 and CO >= 256 */
+int pcreid_cn_linear_tma(const pcreid_linear_args* args, long long x1_objs, long long x2_objs, long long w1_objs, int flags, int n_sms,
+                         void* stream);
+
 /* LinearAttention (pointnet2_utils.py:14-47, attention.py:19-54), split in two kernels:
  * kv:    Wkv[b] (d x d, k-major, block diagonal per head) = sum_s (elu(k_s)+1) (x) (v_s / S);  ksum[b] (d)
  * scale: Qs[b,c,n] = (elu(q)+1) * S / ( (elu(q_h)+1) . ksum_h + 1e-6 )

@@ -14,23 +14,33 @@ from . import torch_ops as _T
 _OPS = _T.ops          # torch.ops.pcreid.*: one dispatcher op per compute entry point of include/pcreid.h
 
 ACT_NONE, ACT_RELU, ACT_LEAKY02, ACT_ELU1 = 0, 1, 2, 3
+TMA_TF32_MAPS, TMA_ROUND_OUT = 1, 2        # flags of pcreid_cn_linear_tma (include/pcreid.h)
 
 # fast mode switch for cn_linear: tcgen05 kind::tf32 GEMM where the shape allows it (set by ReIDNet.set_mode / tensor_core_linear)
 _TC_LINEAR = {"on": False}
 
 
 class tensor_core_linear:
-    """context manager: `with tensor_core_linear(True): ...` routes cn_linear through pcreid_cn_linear_tc."""
+    """context manager: `with tensor_core_linear(True): ...` routes cn_linear through the tcgen05 kind::tf32 GEMMs.
+    min_k: smallest K1 + K2 that goes to the TMA-staged kernel (pcreid_cn_linear_tma); the models pass 32 in 'fast' mode (every
+    contraction with CO >= 32) and 256 in 'parity_tc' mode (the large projections only: the error budget of that mode,
+    profiles/r02_parity_error_budget.md, was measured with exactly those on tf32)."""
 
-    def __init__(self, on):
-        self.on, self.prev = bool(on), None
+    def __init__(self, on, min_k=None):
+        self.on, self.min_k, self.prev = bool(on), min_k, None
 
     def __enter__(self):
-        self.prev = _TC_LINEAR["on"]
+        self.prev = (_TC_LINEAR["on"], _TC_LINEAR.get("tma_min_k"))
         _TC_LINEAR["on"] = self.on
+        if self.min_k is not None:
+            _TC_LINEAR["tma_min_k"] = self.min_k
 
     def __exit__(self, *exc):
-        _TC_LINEAR["on"] = self.prev
+        _TC_LINEAR["on"] = self.prev[0]
+        if self.prev[1] is None:
+            _TC_LINEAR.pop("tma_min_k", None)
+        else:
+            _TC_LINEAR["tma_min_k"] = self.prev[1]
 
 
 def _stream():
@@ -140,6 +150,16 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
             out = torch.empty((B, CO, rows), device=x1.device, dtype=torch.float32)
         a.y_bs, a.ldy = _cn(out, "out")
     a.Y = out
+    # gen 3 (cn_linear_tma.cu): both operands staged by TMA tensor maps; serves every channel-major shape with CO >= 32 incl.
+    # object maps and per-object weights ("tma": None = by measured threshold, True = always, False = never)
+    tma = _TC_LINEAR.get("tma")
+    if (_TC_LINEAR["on"] and tma is not False and not x1_pm and not x2_pm and not y_pm and CO >= 32 and CO % 4 == 0 and rows % 4 == 0
+            and (tma or K1 + a.K2 >= _TC_LINEAR.get("tma_min_k", 256))):
+        flags = (TMA_TF32_MAPS if _TC_LINEAR.get("tma_tf32_maps", True) else 0) | (TMA_ROUND_OUT if _TC_LINEAR.get("round_out") else 0) | (4 if _TC_LINEAR.get("tma_tile128") else 0)
+        n_sms = torch.cuda.get_device_properties(x1.device).multi_processor_count
+        if _OPS.cn_linear_tma(*a.astuple(), x1.shape[0], x2.shape[0] if x2 is not None else 0, w1.shape[0] if w1.dim() == 3 else 0,
+                              flags, n_sms) != 3:
+            return out
     # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernels win from K >= 256; below that the FFMA kernel
     # (up to 48 TFLOP/s) is faster
     if (_TC_LINEAR["on"] and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None

@@ -123,6 +123,19 @@ class ReIDNet(nn.Module):
                 m.tc_mode = mode in self.TC_MODES and not (mode == 'parity_tc' and isinstance(m, FP_SA) and not self.parity_tc_fp_blocks)
         return self
 
+    def _tc_linear(self):
+        """tf32 tcgen05 GEMMs for the 1x1 convs / Linears outside the fused kernels: every contraction in 'fast' mode, the large
+        projections (K >= 256) in 'parity_tc' mode, none in 'parity'."""
+        return K.tensor_core_linear(self.match_mode in self.TC_MODES and self.tc_encoder, min_k=32 if self.match_mode == 'fast' else 256)
+
+    def _tc_match(self, fused):
+        """the matcher's Linears outside the fused kernels (per-object preparation, match head; the whole cross-attention chain
+        for shapes the fused matcher does not cover: d_model = 128, 'xcorr'): tf32 tcgen05 GEMMs in 'fast' mode; in 'parity_tc'
+        mode only when the fused matcher is not in use (its head and preparation stay fp32: they are part of that mode's
+        measured error budget)."""
+        on = self.match_mode == 'fast' or (self.match_mode == 'parity_tc' and not fused)
+        return K.tensor_core_linear(on, min_k=32)
+
     def invalidate_packed(self):
         """forget every packed / BN-folded / operand-image weight copy and captured CUDA graph (see _packing.invalidate_packed:
         needed only after parameters were written through `.data`, which no version counter records)."""
@@ -163,7 +176,7 @@ class ReIDNet(nn.Module):
 
     def encode(self, pts):
         """public inference entry: pts (B, N, 3) -> (xyz (B, N, 3), per-point embedding (B, C, N))."""
-        with torch.no_grad(), K.tensor_core_linear(self.match_mode in self.TC_MODES and self.tc_encoder):
+        with torch.no_grad(), self._tc_linear():
             if self.cuda_graphs and pts.is_cuda and pts.shape[0] > 0:
                 return self._encode_graphed(pts)
             return self._encode(pts)
@@ -223,13 +236,17 @@ class ReIDNet(nn.Module):
     def _head_cn(self, pooled_cn):
         """match_head on channel-major pooled features (1, C, P) -> logits (P,)."""
         x = pooled_cn
-        for m in self.match_head:
-            if isinstance(m, LinearRes):
-                x = m.forward_cn(x)
-            elif isinstance(m, nn.Linear):
-                x = K.cn_linear(x, _kmajor_cached(m), bias=_bias_cached(m))
-            else:
-                raise NotImplementedError(type(m))
+        # always the fp32 kernels: the pairs are the ROW axis here, and which tensor-core kernel could serve a shape depends on the
+        # row count -- a pair's logit must not depend on how many other pairs share its chunk (row-sharded multi-GPU driver,
+        # pair-list vs dense driver); the head is ~2 % of the match
+        with K.tensor_core_linear(False):
+            for m in self.match_head:
+                if isinstance(m, LinearRes):
+                    x = m.forward_cn(x)
+                elif isinstance(m, nn.Linear):
+                    x = K.cn_linear(x, _kmajor_cached(m), bias=_bias_cached(m))
+                else:
+                    raise NotImplementedError(type(m))
         return x.reshape(-1)
 
     def xcorr_eff(self, o1, xyz1, o2, xyz2, combine='add'):
@@ -251,7 +268,7 @@ class ReIDNet(nn.Module):
 
     def match_forward_inference(self, h1, h2, xyz1, xyz2):
         """aligned pairs: h1/h2 (P, C, N), xyz1/xyz2 (P, N, 3) -> logits (P,)."""
-        with torch.no_grad():
+        with torch.no_grad(), self._tc_match(False):
             P = h1.shape[0]
             if self.match_type == 'xcorr_eff':
                 ar = torch.arange(P, device=h1.device, dtype=torch.int32)
@@ -324,7 +341,7 @@ class ReIDNet(nn.Module):
                'point-cat': lambda: torch.cat([o1, o2], 2)}[self.combine]()
         return self._head_cn(self.get_pooled_feats(out).t().contiguous().unsqueeze(0))
 
-    def match_all_pairs(self, h_t, xyz_t, h_d, xyz_d, pair_mask=None, chunk=8192):
+    def match_all_pairs(self, h_t, xyz_t, h_d, xyz_d, pair_mask=None, chunk=8192, _exact_chunk=False):
         """Dense (T, D) logit matrix; entries where ``pair_mask`` (bool (T, D), e.g. the tracker's class gate,
         tracking_point_reid.py:15-33) is False are 0, as in the reference cost matrix."""
         with torch.no_grad():
@@ -341,7 +358,8 @@ class ReIDNet(nn.Module):
                 if fused_pairs.supported(self, h_t.shape[2]) and h_t.shape[2] == h_d.shape[2]:
                     fused = self.fused_matcher()
                     pk_t, pk_d = fused.prepare(h_t, xyz_t), fused.prepare(h_d, xyz_d)
-                    chunk = max(chunk, 65536 * 256 // h_t.shape[2])
+                    if not _exact_chunk:
+                        chunk = max(chunk, 65536 * 256 // h_t.shape[2])
             if pair_mask is None:
                 pairs = None
                 total = T * D
@@ -349,26 +367,27 @@ class ReIDNet(nn.Module):
                 pairs = pair_mask.nonzero()
                 total = pairs.shape[0]
             flat = out.view(-1)
-            if pairs is None and fused is not None and D > 0:
-                rows_per_chunk = max(1, chunk // D)                          # dense all-pairs: whole rows per chunk
-                for r0 in range(0, T, rows_per_chunk):
-                    nrows = min(rows_per_chunk, T - r0)
-                    flat[r0 * D:(r0 + nrows) * D] = fused.match(pk_t, pk_d, None, None, dense=(r0, nrows, D))
-                return out
-            for s in range(0, total, chunk):
-                e = min(total, s + chunk)
-                if pairs is None:
-                    lin = torch.arange(s, e, device=dev)
-                    ti, dj = lin // D, lin % D
-                else:
-                    ti, dj = pairs[s:e, 0], pairs[s:e, 1]
-                    lin = ti * D + dj
-                if fused is not None:
-                    flat[lin] = fused.match(pk_t, pk_d, ti, dj)
-                elif self.match_type == 'xcorr_eff':
-                    flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
-                else:
-                    flat[lin] = self._xcorr_search_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
+            with self._tc_match(fused is not None):
+                if pairs is None and fused is not None and D > 0:
+                    rows_per_chunk = max(1, chunk // D)                          # dense all-pairs: whole rows per chunk
+                    for r0 in range(0, T, rows_per_chunk):
+                        nrows = min(rows_per_chunk, T - r0)
+                        flat[r0 * D:(r0 + nrows) * D] = fused.match(pk_t, pk_d, None, None, dense=(r0, nrows, D))
+                    return out
+                for s in range(0, total, chunk):
+                    e = min(total, s + chunk)
+                    if pairs is None:
+                        lin = torch.arange(s, e, device=dev)
+                        ti, dj = lin // D, lin % D
+                    else:
+                        ti, dj = pairs[s:e, 0], pairs[s:e, 1]
+                        lin = ti * D + dj
+                    if fused is not None:
+                        flat[lin] = fused.match(pk_t, pk_d, ti, dj)
+                    elif self.match_type == 'xcorr_eff':
+                        flat[lin] = self._xcorr_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
+                    else:
+                        flat[lin] = self._xcorr_search_pairs(h_t, xyz_t, h_d, xyz_d, _i32(ti), _i32(dj))
             return out
 
     def pooled_embedding(self, h):

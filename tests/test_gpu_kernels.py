@@ -63,13 +63,143 @@ def test_cn_linear_tensor_core(B, K1, CO, N, act, gen):
     x, w, b = rnd(B, K1, N, seed=1), rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
     K._TC_LINEAR["min_k"] = 8            # force the tensor-core kernel for every shape under test
     K._TC_LINEAR["gen"] = gen
+    K._TC_LINEAR["tma"] = False
     try:
         with K.tensor_core_linear(True):
             got = K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act)
     finally:
         K._TC_LINEAR.pop("min_k")
         K._TC_LINEAR.pop("gen")
+        K._TC_LINEAR.pop("tma")
     close(got, F.cn_linear(x, w, bias=b, act=act), 3e-3)
+
+
+@pytest.fixture
+def tma_only():
+    """cn_linear must be served by pcreid_cn_linear_tma: the older tensor-core generations and the FFMA kernel are made to fail"""
+    K._TC_LINEAR["tma"] = True
+    real_tc, real_tc2, real_ffma = K._OPS.cn_linear_tc, K._OPS.cn_linear_tc2, K._OPS.cn_linear
+    calls = {"n": 0}
+    real_tma = K._OPS.cn_linear_tma
+
+    class _Ops:
+        def __getattr__(self, name):
+            if name in ("cn_linear_tc", "cn_linear_tc2", "cn_linear"):
+                raise AssertionError(f"{name} used although the TMA kernel supports the shape")
+            if name == "cn_linear_tma":
+                def counted(*a):
+                    calls["n"] += 1
+                    return real_tma(*a)
+                return counted
+            return getattr(real_ops, name)
+    real_ops = K._OPS
+    K._OPS = _Ops()
+    try:
+        with K.tensor_core_linear(True):
+            yield calls
+    finally:
+        K._OPS = real_ops
+        K._TC_LINEAR.pop("tma")
+
+
+@pytest.mark.parametrize("B,K1,CO,N", [(3, 64, 64, 256), (2, 128, 192, 132), (2, 1024, 512, 256), (5, 72, 36, 36), (1, 512, 1024, 100),
+                                       (4, 3, 64, 128), (2, 6, 32, 20), (3, 40, 100, 260), (2, 96, 160, 1024)])
+@pytest.mark.parametrize("act", [0, 2])
+@pytest.mark.parametrize("tf32_maps", [True, False])
+def test_cn_linear_tma(B, K1, CO, N, act, tf32_maps, tma_only):
+    """TMA tensor-map staged tcgen05 kind::tf32 GEMM (cn_linear_tma.cu): K tails / K = 3 zero-filled by the TMA unit, ragged point
+    and channel tiles, against the fp32 specification."""
+    x, w, b = rnd(B, K1, N, seed=1), rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
+    K._TC_LINEAR["tma_tf32_maps"] = tf32_maps
+    try:
+        got = K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act)
+    finally:
+        K._TC_LINEAR.pop("tma_tf32_maps")
+    assert tma_only["n"] == 1
+    close(got, F.cn_linear(x, w, bias=b, act=act), 3e-3)
+
+
+def test_cn_linear_tma_options(tma_only):
+    """second input pair, residual before / after the activation, object maps on every operand, per-object weights, strided
+    channel views, rows < N, point-major output, output into a channel slice"""
+    N, B = 200, 6
+    x1, x2, res = rnd(4, 64, N, seed=1), rnd(5, 32, N, seed=2), rnd(3, 128, N, seed=5)
+    w1, w2 = rnd(64, 128, seed=3) / 8, rnd(32, 128, seed=4) / 6
+    m1 = torch.tensor([3, 0, 2, 2, 1, 0], dtype=torch.int32)
+    m2 = torch.tensor([4, 4, 0, 1, 3, 2], dtype=torch.int32)
+    mr = torch.tensor([0, 2, 1, 1, 2, 0], dtype=torch.int32)
+    for after in (False, True):
+        got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), act=1, res=res.to(DEV), res_after_act=after,
+                          x1_map=m1.to(DEV), x2_map=m2.to(DEV), r_map=mr.to(DEV), B=B)
+        close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, act=1, res=res, res_after_act=after, x1_map=m1, x2_map=m2, r_map=mr, B=B), 3e-3)
+    wk = rnd(4, 64, 64, seed=7) / 8                          # per-object weights
+    close(K.cn_linear(x1.to(DEV), wk.to(DEV)), F.cn_linear(x1, wk), 3e-3)
+    wm = torch.tensor([3, 0, 2], dtype=torch.int32)
+    qkv = rnd(3, 192, N, seed=6)
+    qd = qkv.to(DEV)
+    close(K.cn_linear(qd[:, 64:128], wk.to(DEV), w1_map=wm.to(DEV), rows=96), F.cn_linear(qkv[:, 64:128], wk, w1_map=wm, rows=96), 3e-3)
+    out = torch.zeros(3, 256, N, device=DEV)
+    K.cn_linear(qd[:, :64], wk[1].contiguous().to(DEV), out=out[:, 64:128])
+    close(out[:, 64:128], F.cn_linear(qkv[:, :64], wk[1]), 3e-3)
+    assert float(out[:, :64].abs().max()) == 0 and float(out[:, 128:].abs().max()) == 0
+    # ragged rows next to foreign data: the tensor store clips at `rows`, columns [rows, N) of the output keep their content
+    out = torch.full((3, 64, N), 7.0, device=DEV)
+    K.cn_linear(qd[:, :64], wk[1].contiguous().to(DEV), out=out, rows=92)
+    close(out[:, :, :92], F.cn_linear(qkv[:, :64], wk[1], rows=92), 3e-3)
+    assert bool((out[:, :, 92:] == 7.0).all())
+
+
+def test_cn_linear_tma_unsupported_shapes_fall_back():
+    """point-major outputs / inputs and CO < 32 are answered PCREID_ERR_UNSUPPORTED and served by the older kernels"""
+    N = 200
+    qkv, wk = rnd(3, 192, N, seed=6), rnd(64, 64, seed=7) / 8
+    K._TC_LINEAR["tma"] = True
+    try:
+        with K.tensor_core_linear(True):
+            close(K.cn_linear(qkv.to(DEV)[:, 128:], wk.to(DEV), y_pm=True), F.cn_linear(qkv[:, 128:], wk, y_pm=True), 3e-3)
+            x, w = rnd(2, 64, N, seed=1), rnd(64, 12, seed=2) / 8
+            close(K.cn_linear(x.to(DEV), w.to(DEV)), F.cn_linear(x, w), 3e-3)
+            # the TMA unit clips the innermost extent in 16-byte units: row counts that are not multiples of 4 stay on the older kernels
+            out = torch.full((3, 64, N), 7.0, device=DEV)
+            K.cn_linear(qkv.to(DEV)[:, :64], wk.to(DEV), out=out, rows=90)
+            close(out[:, :, :90], F.cn_linear(qkv[:, :64], wk, rows=90), 3e-3)
+            assert bool((out[:, :, 90:] == 7.0).all())
+    finally:
+        K._TC_LINEAR.pop("tma")
+
+
+def test_cn_linear_tma_many_tiles_per_cta(tma_only):
+    """persistent loop: several tiles per CTA, both accumulator buffers and every ring slot reused many times"""
+    B, K1, K2, CO, N = 700, 256, 64, 320, 200
+    x1, x2 = rnd(B, K1, N, seed=1), rnd(B, K2, N, seed=2)
+    w1, w2, b = rnd(K1, CO, seed=3) / 16, rnd(K2, CO, seed=4) / 8, rnd(CO, seed=5)
+    res = rnd(B, CO, N, seed=6)
+    got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), bias=b.to(DEV), act=1, res=res.to(DEV))
+    close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, bias=b, act=1, res=res), 3e-3)
+
+
+def test_cn_linear_tma_rounding():
+    """what the two tensor-map element types do with the 13 low mantissa bits of an fp32 activation: FLOAT32 maps leave them to the
+    tensor core (which ignores them: truncation), TFLOAT32 maps round to nearest in the TMA unit; ROUND_OUT rounds the result."""
+    N = 128
+    x = torch.full((1, 32, N), 1.0 + 2.0 ** -11 + 2.0 ** -13)            # tf32: truncates to 1, rounds to 1 + 2^-10
+    w = torch.zeros(32, 32)
+    w[0, 0] = 1.0
+    K._TC_LINEAR["tma"] = True
+    try:
+        with K.tensor_core_linear(True):
+            res = {}
+            for tf32_maps in (False, True):
+                K._TC_LINEAR["tma_tf32_maps"] = tf32_maps
+                res[tf32_maps] = float(K.cn_linear(x.to(DEV), w.to(DEV))[0, 0, 5])
+            K._TC_LINEAR["round_out"] = True
+            y = K.cn_linear((x * 3).to(DEV), w.to(DEV))
+    finally:
+        for k in ("tma", "tma_tf32_maps", "round_out"):
+            K._TC_LINEAR.pop(k, None)
+    assert res[False] == 1.0, res
+    assert res[True] == 1.0 + 2.0 ** -10, res
+    assert torch.equal(y.view(torch.int32) & 0x1fff, torch.zeros_like(y, dtype=torch.int32))
 
 
 def test_cn_linear_tc2_many_tiles_per_cta():
@@ -78,8 +208,12 @@ def test_cn_linear_tc2_many_tiles_per_cta():
     x1, x2 = rnd(B, K1, N, seed=1), rnd(B, K2, N, seed=2)
     w1, w2, b = rnd(K1, CO, seed=3) / 16, rnd(K2, CO, seed=4) / 8, rnd(CO, seed=5)
     res = rnd(B, CO, N, seed=6)
-    with K.tensor_core_linear(True):
-        got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), bias=b.to(DEV), act=1, res=res.to(DEV))
+    K._TC_LINEAR["tma"] = False
+    try:
+        with K.tensor_core_linear(True):
+            got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), bias=b.to(DEV), act=1, res=res.to(DEV))
+    finally:
+        K._TC_LINEAR.pop("tma")
     close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, bias=b, act=1, res=res), 3e-3)
 
 
@@ -90,6 +224,7 @@ def test_cn_linear_tensor_core_options():
     wk = rnd(4, 64, 64, seed=7) / 8                          # per-object weights
     qkv = rnd(3, 192, N, seed=6)
     K._TC_LINEAR["min_k"] = 8
+    K._TC_LINEAR["tma"] = False
     with K.tensor_core_linear(True):
         for after in (False, True):
             got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), act=1, res=res.to(DEV), res_after_act=after)
@@ -103,6 +238,7 @@ def test_cn_linear_tensor_core_options():
         w3 = rnd(3, 32, seed=10)
         close(K.cn_linear(xyz.to(DEV), w3.to(DEV), x1_pm=True), F.cn_linear(xyz, w3, x1_pm=True))
     K._TC_LINEAR.pop("min_k")
+    K._TC_LINEAR.pop("tma")
 
 
 @pytest.mark.parametrize("C,G,N", [(64, 1, 256), (128, 8, 100), (512, 64, 33), (32, 1, 7)])

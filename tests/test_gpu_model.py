@@ -7,6 +7,7 @@ import pytest
 import torch
 
 import helpers
+import pcreid_b200.kernels as K
 from oracle import reid_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -57,6 +58,50 @@ def test_model_vs_oracle(kind, N, blist, dup):
     mask = torch.rand(6, 7, generator=torch.Generator().manual_seed(5)) > 0.5
     Lm = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.to(DEV)).cpu()
     assert (Lm - Lo * mask).abs().max() < TOL
+
+
+@pytest.mark.parametrize("kind,N,blist", [("dgcnn", 256, (128, 64, 32)), ("pointnet", 128, (128, 64, 32)), ("pt15m", 128, (128, 64, 32)),
+                                          ("pt7m", 128, (128, 64, 32)), ("xcorr", 128, (128, 64, 32)),
+                                          ("xcorr-baseline", 256, (256, 128, 64))])
+@pytest.mark.parametrize("mode,tol", [("fast", 3e-2), ("parity_tc", 5e-3)])
+def test_tensor_core_modes_every_config(kind, N, blist, mode, tol):
+    """the tensor-core modes on the configs the fused xcorr_eff matcher does not cover: DGCNN EdgeConv / conv5 / downsample and the
+    PointNet shared MLPs as TMA-staged tcgen05 kind::tf32 GEMMs (cn_linear_tma.cu; every contraction in 'fast' mode, K >= 256 in
+    'parity_tc'), the unfused cross-attention chains of the d_model = 128 / 'xcorr' / 'xcorr-baseline' matchers on the same kernel
+    with the pair gather maps as tensor-map coordinates.  Gates: |dlogit| within the mode's tolerance, decisive rows keep their top-1."""
+    m, orc = helpers.build_pair(kind, blist, device=DEV)
+    m.set_mode(mode)
+    t, d = O.synth_objects(6, N, 0), O.synth_objects(7, N, 1)
+    used = {"tma": 0}
+    real = K._OPS.cn_linear_tma
+
+    class _Count:
+        def __getattr__(self, name):
+            if name == "cn_linear_tma":
+                def f(*a):
+                    rc = real(*a)
+                    used["tma"] += rc == 0
+                    return rc
+                return f
+            return getattr(ops, name)
+    ops = K._OPS
+    K._OPS = _Count()
+    try:
+        xt, ht = m.encode(t.to(DEV))
+        xd, hd = m.encode(d.to(DEV))
+        L = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    finally:
+        K._OPS = ops
+    assert used["tma"] > 0, "no GEMM of this configuration reached the TMA-staged tensor-core kernel"
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    scale = max(1.0, float(oht.abs().max()))
+    assert float((ht.cpu() - oht).abs().max()) < 2e-2 * scale
+    err = float((L - Lo).abs().max())
+    assert err < tol, err
+    ok, agree, n = helpers.margin_aware_top1(Lo, L, err)
+    assert ok, f"top-1 changed on a decisive row (raw agreement {agree}, {n} decisive rows)"
 
 
 def test_degenerate_clouds_all_points_identical():
