@@ -73,6 +73,11 @@ jobs += [
     ("image", lambda: run_image("image-token matcher 256x256 @198 tokens", 198, 256, 256, "parity")),
     ("image", lambda: run_image("image-token matcher 1024x1024 @198 tokens", 198, 1024, 1024, "fast")),
 ]
+# model variants the fused xcorr_eff matcher does not cover (d_model = 128 / widened SA: -7M / -1.5M configs; 'xcorr' with the local
+# attention stages; 'xcorr-baseline'): unfused chains, fp32 FFMA kernels in 'parity', TMA-staged tf32 tcgen05 GEMMs in 'fast'
+for kind in ("pt7m", "pt15m", "xcorr", "xcorr-baseline"):
+    for mode in ("parity", "fast"):
+        jobs.append(("variants", (lambda k=kind, mo=mode: run(f"variant {k} 256x256 @256", k, 256, (256, 128, 64), 256, 256, mo, check=6, reps=2))))
 for tag, job in jobs:
     if not only or tag in only.split(","):
         job()
