@@ -9,6 +9,8 @@ LIB = os.path.join(HERE, "libpcreid_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]
+if os.environ.get("PCREID_F16_PACKED") == "1":       # A/B build: packed f16x2 epilogue arithmetic in the fp16 matcher (see profiles/)
+    FLAGS.append("-DPCREID_F16_PACKED")
 
 
 def sources():

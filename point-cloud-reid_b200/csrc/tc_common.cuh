@@ -209,10 +209,22 @@ struct OpBF16 {
   // elu(x)+1 of plain accumulators -> packed
   static __device__ __forceinline__ uint32_t elu1(float a, float b) { return bf2_elu1(pack_bf16(a, b)); }
 };
+// packed f16x2 arithmetic (same instruction shapes as the bf16x2 helpers above)
+__device__ __forceinline__ uint32_t h2_add(uint32_t a, uint32_t b) { uint32_t r; asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_mul(uint32_t a, uint32_t b) { uint32_t r; asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_max(uint32_t a, uint32_t b) { uint32_t r; asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_min(uint32_t a, uint32_t b) { uint32_t r; asm("min.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t h2_ex2(uint32_t a) { uint32_t r; asm("ex2.approx.f16x2 %0, %1;" : "=r"(r) : "r"(a)); return r; }
+__device__ __forceinline__ uint32_t h2_fma(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+
 struct OpF16 {
   static constexpr int FMT = FMT_F16;
   static constexpr uint32_t ONE_LO = 0x00003c00u;
+#ifdef PCREID_F16_PACKED
+  static constexpr bool PACKED_MATH = true;
+#else
   static constexpr bool PACKED_MATH = false;
+#endif
   static __device__ __forceinline__ uint32_t pack(float lo, float hi) {
     uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo)); return r;
   }
@@ -226,20 +238,39 @@ struct OpF16 {
     float f; asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}\n" : "=f"(f) : "r"(w)); return f;
   }
   static __device__ __forceinline__ uint32_t add_relu(float a, float b, uint32_t side) { return pack_relu(a + lo(side), b + hi(side)); }
+#ifdef PCREID_F16_PACKED
+  static __device__ __forceinline__ uint32_t add(float a, float b, uint32_t side) { return h2_add(pack(a, b), side); }
+#else
   static __device__ __forceinline__ uint32_t add(float a, float b, uint32_t side) { return pack(a + lo(side), b + hi(side)); }
+#endif
   // weights pre-scaled by 1/ln 2 (fp32-exact constant here: the multiply happens in fp32)
   static __device__ __forceinline__ float elu1s_f(float x) {
     float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f)));
     return fmaf(fmaxf(x, 0.f), 0.69314718056f, e);
   }
+#ifdef PCREID_F16_PACKED
+  // weights pre-scaled by 1/f16(ln 2) on the host: max(x',0) * LN2H + 2^min(x',0)
+  static __device__ __forceinline__ uint32_t elu1_scaled(float a, float b) {
+    const uint32_t x = pack(a, b);
+    return h2_fma(h2_max(x, 0u), 0x398c398cu, h2_ex2(h2_min(x, 0u)));
+  }
+#else
   static __device__ __forceinline__ uint32_t elu1_scaled(float a, float b) { return pack(elu1s_f(a), elu1s_f(b)); }
+#endif
   // elu(x)+1 = max(x,0) + exp(min(x,0)), branch-free: 5 instructions per element (the select form `x > 0 ? x + 1 : __expf(x)`
   // compiled to divergent regions around a non-ftz exp with denormal scaling: 12+ instructions and BSSY/BSYNC pairs)
   static __device__ __forceinline__ float elu1_f(float x) {
     float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(x, 0.f) * 1.4426950408889634f));
     return fmaxf(x, 0.f) + e;
   }
+#ifdef PCREID_F16_PACKED
+  static __device__ __forceinline__ uint32_t elu1(float a, float b) {
+    const uint32_t x = pack(a, b);
+    return h2_add(h2_max(x, 0u), h2_ex2(h2_mul(h2_min(x, 0u), 0x3dc53dc5u)));
+  }
+#else
   static __device__ __forceinline__ uint32_t elu1(float a, float b) { return pack(elu1_f(a), elu1_f(b)); }
+#endif
 };
 
 // fp32 -> tf32 with round-to-nearest (ties away), returned in an fp32 container.  tcgen05.mma kind::tf32 reads 32-bit operands

@@ -15,6 +15,7 @@ activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and th
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
 """
 import math
+import os
 
 import torch
 
@@ -25,6 +26,7 @@ from ._packing import kmajor
 IMG = 16384
 B7_BYTES = 18432
 FMT_BF16, FMT_F16 = 0, 1
+LN2H = 0.693359375        # f16(ln 2): the same for the packed f16x2 A/B build (PCREID_F16_PACKED=1)
 LN2B = 0.69140625          # bf16(ln 2): the packed elu epilogue of the bf16 kernels multiplies by this constant
 ATT_EPS = 1e-6             # LinearAttention.eps (attention.py:21)
 
@@ -97,7 +99,7 @@ class FusedXcorr:
                 W0ext[:, :d] = W0_2[:, :d]
                 W0ext[:, d:2 * d] = W0_2[:, d:] * f(X2.norm1.weight)[None, :]
                 W0ext[:, 2 * d] = W0_2[:, d:] @ f(X2.norm1.bias)
-                ln2 = math.log(2.0) if self.fmt == FMT_F16 else LN2B
+                ln2 = (LN2H if os.environ.get("PCREID_F16_PACKED") == "1" else math.log(2.0)) if self.fmt == FMT_F16 else LN2B
                 self._w2y = torch.cat([
                     _w_image(f(X2.q_proj.weight) / ln2, dt), _w_image(W0ext, dt), _w_image(_center_out(X2.mlp[2].weight), dt),
                     _f32_bytes(X2.norm2.weight)]).contiguous()
