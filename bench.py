@@ -54,8 +54,10 @@ MODE_TEXT = {
                  "-- fp32 accumulate / norms; gate |dlogit| <= 5e-3, raw top-1 >= 0.97",
     "fast": "fast: the same kernels with bf16 matcher operands; gate |dlogit| <= 3e-2",
     "parity": "parity: fp32 FFMA kernels, logits within 1e-4 of the reference",
+    "parity_x3": "parity_x3: the parity path with its Linears / 1x1 convs on tcgen05 at fp32-grade accuracy (TMA-staged 3 x tf32 GEMM, "
+                 "cn_linear_tma.cu), logits within 1e-4 of the reference",
 }
-DTYPE = {"parity_tc": "f16", "fast": "bf16", "parity": "f32"}
+DTYPE = {"parity_tc": "f16", "fast": "bf16", "parity": "f32", "parity_x3": "tf32x3"}
 
 
 def peaks():
@@ -208,7 +210,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="parity_tc", choices=["parity", "parity_tc", "fast"])
+    ap.add_argument("--mode", default="parity_tc", choices=["parity", "parity_x3", "parity_tc", "fast"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="which named BASELINE.json configuration (default: the headline c2)")
     ap.add_argument("--tracks", type=int, default=None, help="tracks per GPU (weak configs) / in total (strong configs)")
     ap.add_argument("--dets", type=int, default=None)

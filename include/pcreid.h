@@ -174,6 +174,12 @@ int pcreid_cn_linear_tc2(const pcreid_linear_args* args, const float* W1img, con
 #define PCREID_TMA_TILE128 4     /* A/B knob: never use the 256-channel tiles chosen for K >= 256 and CO >= 256 */
 int pcreid_cn_linear_tma(const pcreid_linear_args* args, long long x1_objs, long long x2_objs, long long w1_objs, int flags, int n_sms,
                          void* stream);
+/* fp32-grade variant of the same kernel ("3 x tf32"): every operand is split hi + lo (hi = the 19 bits the tensor core reads of the
+ * raw fp32 word, lo = the exact remainder), three MMAs per K step (lo.hi + hi.lo + hi.hi) into the fp32 accumulator.  W*lo: the
+ * weights' lo parts (same shapes / strides as W1 / W2), `w - float(bits(w) & 0xffffe000)`; the activations' lo tiles are made in
+ * shared memory.  Matches pcreid_cn_linear to ~1e-6 relative.  Same shape restrictions as pcreid_cn_linear_tma. */
+int pcreid_cn_linear_tma_x3(const pcreid_linear_args* args, const float* W1lo, const float* W2lo, long long x1_objs, long long x2_objs,
+                            long long w1_objs, int n_sms, void* stream);
 
 /* LinearAttention (pointnet2_utils.py:14-47, attention.py:19-54), split in two kernels:
  * kv:    Wkv[b] (d x d, k-major, block diagonal per head) = sum_s (elu(k_s)+1) (x) (v_s / S);  ksum[b] (d)

@@ -32,6 +32,14 @@
 //                      output regardless of K (profiles/r02_cn_linear_tma.md).
 // The tensor core reads only the upper 19 bits of an fp32 operand (truncation); with `tf32_maps` the tensor maps are
 // encoded as TFLOAT32, which makes the TMA unit round the data to tf32 (nearest) on its way into shared memory.
+//
+// X3 variant (pcreid_cn_linear_tma_x3, the fp32-grade mode): every operand is split x = hi + lo with hi = the 19 bits the
+// tensor core reads anyway (so the raw fp32 tile IS the hi operand) and lo = x - hi (exact; 13 significant bits, of which the
+// tensor core keeps 11).  The weights' lo part comes from the host as a second tensor, the activations' lo tile is written by
+// four converter warps into a second shared-memory tile once the stage has landed, and each K = 8 step issues three MMAs
+// lo.hi + hi.lo + hi.hi into the same accumulator (small terms first).  Products of 11-bit significands are exact in the
+// fp32 accumulator; the dropped lo.lo term is 2^-20 relative: the result matches the fp32 FFMA kernel to ~1e-6 relative at a third of
+// the tf32 tensor rate -- still far above the HBM roofline of the K <= 256 contractions it is used for.
 #include <cuda.h>
 
 #include "../../include/pcreid.h"
@@ -50,6 +58,8 @@ constexpr int RING_BYTES = ST * STAGE_BYTES;
 constexpr int SLAB_BYTES = 32 * 128 * 4;  // epilogue staging tile: 32 channels x 128 points
 constexpr int SMEM_BYTES = RING_BYTES + 2 * SLAB_BYTES + 1024;
 constexpr int NTHR = 320;
+constexpr int NTHR_X3 = 448;               // + four converter warps
+constexpr int ST_X3 = 3;                  // X3 stages: A | A_lo | W | W_lo = 64 KB
 
 struct TmaLinArgs {
   pcreid_linear_args a;
@@ -111,19 +121,20 @@ __device__ __forceinline__ void slab_to_smem(uint32_t taddr, float* slab, int ro
   }
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(NTHR, 1)
+template <int ACT, bool X3>
+__global__ void __launch_bounds__(X3 ? NTHR_X3 : NTHR, 1)
 cn_linear_tma_kernel(const __grid_constant__ CUtensorMap mX1, const __grid_constant__ CUtensorMap mX2, const __grid_constant__ CUtensorMap mW1,
-                     const __grid_constant__ CUtensorMap mW2, const __grid_constant__ CUtensorMap mY, const __grid_constant__ TmaLinArgs p) {
+                     const __grid_constant__ CUtensorMap mW2, const __grid_constant__ CUtensorMap mW1lo, const __grid_constant__ CUtensorMap mW2lo,
+                     const __grid_constant__ CUtensorMap mY, const __grid_constant__ TmaLinArgs p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t full[ST], empty[ST], acc_full[NACC], acc_empty[NACC];
+  __shared__ uint64_t full[ST], empty[ST], conv[ST], acc_full[NACC], acc_empty[NACC];
   __shared__ uint32_t tmem_base_s;
   // the swizzle pattern is a function of the shared-memory address bits: the stages start on a 1 KB boundary
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const pcreid_linear_args& a = p.a;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int i = 0; i < ST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < ST; ++i) { tc::mbar_init(&full[i], 1); tc::mbar_init(&empty[i], 1); tc::mbar_init(&conv[i], 128); }
     for (int i = 0; i < NACC; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 256); }
     tc::fence_mbar_init();
   }
@@ -136,8 +147,10 @@ cn_linear_tma_kernel(const __grid_constant__ CUtensorMap mX1, const __grid_const
   const int per_obj = p.tiles_n * p.tiles_c;
   const int TN = p.TN;
   // 256-channel tiles (large K and CO: halves the activation re-reads from L2): 4 stages of 48 KB, 2 accumulators of 256 columns
-  const int nst = TN > 128 ? 4 : ST, nacc = TN > 128 ? 2 : NACC, acc_cols = TN > 128 ? 256 : 128;
-  const int stage_bytes = TN > 128 ? 3 * STAGE_A : STAGE_BYTES;
+  const int nst = X3 ? ST_X3 : (TN > 128 ? 4 : ST), nacc = TN > 128 ? 2 : NACC, acc_cols = TN > 128 ? 256 : 128;
+  const int stage_bytes = X3 ? 4 * STAGE_A : (TN > 128 ? 3 * STAGE_A : STAGE_BYTES);
+  // X3 stage: A at 0, A_lo at STAGE_A, W at 2 STAGE_A, W_lo at 3 STAGE_A; else A at 0, W at STAGE_A
+  const uint32_t off_b = X3 ? 2 * STAGE_A : STAGE_A;
 
   if (warp == 8) {
     // ============================================================ producer (one thread)
@@ -157,12 +170,16 @@ cn_linear_tma_kernel(const __grid_constant__ CUtensorMap mX1, const __grid_const
           const int k0 = (second ? c - nch1 : c) * KC;
           const int s = g % nst, use = g / nst;
           if (use > 0) tc::mbar_wait(&empty[s], (uint32_t)((use - 1) & 1));
-          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes), sb = sa + STAGE_A;
-          mbar_expect_tx(&full[s], (uint32_t)((nbox_a + nbox_b) * BOX_BYTES));
+          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes), sb = sa + off_b;
+          mbar_expect_tx(&full[s], (uint32_t)((nbox_a + (X3 ? 2 : 1) * nbox_b) * BOX_BYTES));
           const CUtensorMap* mx = second ? &mX2 : &mX1;
           const CUtensorMap* mw = second ? &mW2 : &mW1;
           for (int i = 0; i < nbox_a; ++i) tma_box3(sa + i * BOX_BYTES, mx, n0 + 32 * i, k0, second ? bx2 : bx1, &full[s]);
           for (int j = 0; j < nbox_b; ++j) tma_box3(sb + j * BOX_BYTES, mw, co0 + 32 * j, k0, second ? bw2 : bw1, &full[s]);
+          if (X3) {
+            const CUtensorMap* ml = second ? &mW2lo : &mW1lo;
+            for (int j = 0; j < nbox_b; ++j) tma_box3(sb + STAGE_A + j * BOX_BYTES, ml, co0 + 32 * j, k0, second ? bw2 : bw1, &full[s]);
+          }
         }
       }
     }
@@ -181,22 +198,55 @@ cn_linear_tma_kernel(const __grid_constant__ CUtensorMap mX1, const __grid_const
           const int K = second ? a.K2 : a.K1, k0 = (second ? c - nch1 : c) * KC;
           const int ksteps = (min(KC, K - k0) + 7) / 8;
           const int s = g % nst, use = g / nst;
-          tc::mbar_wait(&full[s], (uint32_t)(use & 1));
+          tc::mbar_wait(X3 ? &conv[s] : &full[s], (uint32_t)(use & 1));
           tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes), sb = sa + STAGE_A;
+          const uint32_t sa = tc::smem_u32(smem + s * stage_bytes), sb = sa + off_b;
           // MN-major SWIZZLE_128B_BASE32B: leading byte offset = distance between 32-element blocks along M / N (one box),
           // stride byte offset = distance between groups of 4 k-rows (one 512 B atom); a K = 8 step spans two atoms
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint64_t ad = tc::smem_desc(sa + ks * 1024, BOX_BYTES, 512, tc::LAYOUT_SW128_BASE32B);
             const uint64_t bd = tc::smem_desc(sb + ks * 1024, BOX_BYTES, 512, tc::LAYOUT_SW128_BASE32B);
-            tc::umma_tf32(d, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            if (X3) {   // lo.hi + hi.lo first, hi.hi last
+              const uint64_t ald = tc::smem_desc(sa + STAGE_A + ks * 1024, BOX_BYTES, 512, tc::LAYOUT_SW128_BASE32B);
+              const uint64_t bld = tc::smem_desc(sb + STAGE_A + ks * 1024, BOX_BYTES, 512, tc::LAYOUT_SW128_BASE32B);
+              tc::umma_tf32(d, ald, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+              tc::umma_tf32(d, ad, bld, idesc, 1u);
+              tc::umma_tf32(d, ad, bd, idesc, 1u);
+            } else {
+              tc::umma_tf32(d, ad, bd, idesc, (c > 0 || ks > 0) ? 1u : 0u);
+            }
           }
           tc::umma_commit(&empty[s]);
         }
         tc::umma_commit(&acc_full[buf]);
       }
     }
-  } else {
+  } else if (X3 && warp >= 10) {
+    // ============================================================ converters: A_lo = A - (the 19 bits the tensor core reads of A)
+    const int t = tid - NTHR;
+    int g = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int n0 = ((tile % per_obj) / p.tiles_c) * 128;
+      const int nvec = min(4, (a.rows - n0 + 31) / 32) * (BOX_BYTES / 16);
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int s = g % nst, use = g / nst;
+        tc::mbar_wait(&full[s], (uint32_t)(use & 1));
+        const float4* A = reinterpret_cast<const float4*>(smem + s * stage_bytes);
+        float4* Alo = reinterpret_cast<float4*>(smem + s * stage_bytes + STAGE_A);
+        for (int v = t; v < nvec; v += 128) {
+          const float4 x = A[v];
+          float4 l;
+          l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          Alo[v] = l;
+        }
+        tc::fence_async_smem();
+        mbar_arrive(&conv[s]);
+      }
+    }
+  } else if (warp < 8) {
     // ============================================================ epilogue: group = warp / 4 owns slabs group, group + 2
     const int grp = warp >> 2, row = tid & 127;
     float* slab = reinterpret_cast<float*>(smem + RING_BYTES + grp * SLAB_BYTES);
@@ -270,57 +320,75 @@ bool make_map(CUtensorMap* m, const float* base, long long inner, long long rows
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int ACT>
-int launch_tma(const CUtensorMap& mX1, const CUtensorMap& mX2, const CUtensorMap& mW1, const CUtensorMap& mW2, const CUtensorMap& mY,
-               const TmaLinArgs& p, int grid, cudaStream_t st) {
-  cudaFuncSetAttribute(cn_linear_tma_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  cn_linear_tma_kernel<ACT><<<grid, NTHR, SMEM_BYTES, st>>>(mX1, mX2, mW1, mW2, mY, p);
+template <int ACT, bool X3>
+int launch_tma(const CUtensorMap* m, const TmaLinArgs& p, int grid, cudaStream_t st) {
+  const int smem = X3 ? ST_X3 * 4 * STAGE_A + 2 * SLAB_BYTES + 1024 : SMEM_BYTES;
+  cudaFuncSetAttribute(cn_linear_tma_kernel<ACT, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cn_linear_tma_kernel<ACT, X3><<<grid, X3 ? NTHR_X3 : NTHR, smem, st>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], p);
   return pcreid_launch_status();
 }
 
-}  // namespace
-
-extern "C" int pcreid_cn_linear_tma(const pcreid_linear_args* pa, long long x1_objs, long long x2_objs, long long w1_objs, int flags,
-                                    int n_sms, void* stream) {
+template <bool X3>
+int run_tma(const pcreid_linear_args* pa, const float* W1lo, const float* W2lo, long long x1_objs, long long x2_objs, long long w1_objs,
+            int flags, int n_sms, void* stream) {
   if (!pa) return PCREID_ERR_ARG;
   const pcreid_linear_args& a = *pa;
   if (a.B <= 0 || a.rows <= 0 || a.CO <= 0) return PCREID_OK;
   if (a.K1 <= 0 || !a.X1 || !a.W1 || !a.Y) return PCREID_ERR_ARG;
   if (a.K2 > 0 && (!a.X2 || !a.W2)) return PCREID_ERR_ARG;
+  if (X3 && (!W1lo || (a.K2 > 0 && !W2lo))) return PCREID_ERR_ARG;
   // point-major inputs would be K-major operands (another descriptor family), point-major outputs another staging layout: they
   // stay on pcreid_cn_linear
   // (the TMA unit clips the innermost extent in 16-byte units: rows and CO must be multiples of 4)
   if (a.x1_pm || (a.K2 > 0 && a.x2_pm) || a.y_pm || a.CO < 32 || (a.CO & 3) || (a.rows & 3)) return PCREID_ERR_UNSUPPORTED;
   if (a.act < ACT_NONE || a.act > ACT_ELU1) return PCREID_ERR_ARG;
   if ((a.x1_map && x1_objs <= 0) || (a.K2 > 0 && a.x2_map && x2_objs <= 0) || (a.w1_map && w1_objs <= 0)) return PCREID_ERR_ARG;
-  const bool tf32 = flags & PCREID_TMA_TF32_MAPS;
+  const bool tf32 = !X3 && (flags & PCREID_TMA_TF32_MAPS);      // X3 needs the raw fp32 tile: its hi part is what the tensor core reads
   TmaLinArgs p;
   p.a = a;
-  p.round_out = (flags & PCREID_TMA_ROUND_OUT) ? 1 : 0;
-  p.TN = a.CO >= 128 ? ((a.CO >= 256 && a.K1 + a.K2 >= 256 && !(flags & PCREID_TMA_TILE128)) ? 256 : 128) : ((a.CO + 31) / 32) * 32;
+  p.round_out = (!X3 && (flags & PCREID_TMA_ROUND_OUT)) ? 1 : 0;
+  p.TN = a.CO >= 128 ? ((!X3 && a.CO >= 256 && a.K1 + a.K2 >= 256 && !(flags & PCREID_TMA_TILE128)) ? 256 : 128) : ((a.CO + 31) / 32) * 32;
   p.tiles_n = (a.rows + 127) / 128;
   p.tiles_c = (a.CO + p.TN - 1) / p.TN;
   const long long total = (long long)a.B * p.tiles_n * p.tiles_c;
   if (total > 0x7fffffffLL) return PCREID_ERR_UNSUPPORTED;
   p.total_tiles = (int)total;
-  alignas(64) CUtensorMap mX1, mX2, mW1, mW2, mY;
-  if (!make_map(&mX1, a.X1, a.rows, a.K1, a.ldx1, a.x1_map ? x1_objs : a.B, a.x1_bs, tf32, false)) return PCREID_ERR_UNSUPPORTED;
-  if (!make_map(&mW1, a.W1, a.CO, a.K1, a.CO, a.w1_map ? w1_objs : a.B, a.w1_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
+  alignas(64) CUtensorMap m[7];      // X1, X2, W1, W2, W1lo, W2lo, Y
+  const long long wobjs = a.w1_map ? w1_objs : a.B;
+  if (!make_map(&m[0], a.X1, a.rows, a.K1, a.ldx1, a.x1_map ? x1_objs : a.B, a.x1_bs, tf32, false)) return PCREID_ERR_UNSUPPORTED;
+  if (!make_map(&m[2], a.W1, a.CO, a.K1, a.CO, wobjs, a.w1_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
+  m[4] = m[2];
+  if (X3 && !make_map(&m[4], W1lo, a.CO, a.K1, a.CO, wobjs, a.w1_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
   if (a.K2 > 0) {
-    if (!make_map(&mX2, a.X2, a.rows, a.K2, a.ldx2, a.x2_map ? x2_objs : a.B, a.x2_bs, tf32, false)) return PCREID_ERR_UNSUPPORTED;
-    if (!make_map(&mW2, a.W2, a.CO, a.K2, a.CO, a.B, a.w2_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
+    if (!make_map(&m[1], a.X2, a.rows, a.K2, a.ldx2, a.x2_map ? x2_objs : a.B, a.x2_bs, tf32, false)) return PCREID_ERR_UNSUPPORTED;
+    if (!make_map(&m[3], a.W2, a.CO, a.K2, a.CO, a.B, a.w2_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
+    m[5] = m[3];
+    if (X3 && !make_map(&m[5], W2lo, a.CO, a.K2, a.CO, a.B, a.w2_bs, false, false)) return PCREID_ERR_UNSUPPORTED;
   } else {
-    mX2 = mX1;
-    mW2 = mW1;
+    m[1] = m[0];
+    m[3] = m[2];
+    m[5] = m[4];
   }
-  if (!make_map(&mY, a.Y, a.rows, a.CO, a.ldy, a.B, a.y_bs, false, true)) return PCREID_ERR_UNSUPPORTED;
+  if (!make_map(&m[6], a.Y, a.rows, a.CO, a.ldy, a.B, a.y_bs, false, true)) return PCREID_ERR_UNSUPPORTED;
   if (n_sms <= 0) n_sms = 148;
   const int grid = total < n_sms ? (int)total : n_sms;
   cudaStream_t st = (cudaStream_t)stream;
   switch (a.act) {
-    case ACT_RELU: return launch_tma<ACT_RELU>(mX1, mX2, mW1, mW2, mY, p, grid, st);
-    case ACT_LEAKY02: return launch_tma<ACT_LEAKY02>(mX1, mX2, mW1, mW2, mY, p, grid, st);
-    case ACT_ELU1: return launch_tma<ACT_ELU1>(mX1, mX2, mW1, mW2, mY, p, grid, st);
-    default: return launch_tma<ACT_NONE>(mX1, mX2, mW1, mW2, mY, p, grid, st);
+    case ACT_RELU: return launch_tma<ACT_RELU, X3>(m, p, grid, st);
+    case ACT_LEAKY02: return launch_tma<ACT_LEAKY02, X3>(m, p, grid, st);
+    case ACT_ELU1: return launch_tma<ACT_ELU1, X3>(m, p, grid, st);
+    default: return launch_tma<ACT_NONE, X3>(m, p, grid, st);
   }
+}
+
+}  // namespace
+
+extern "C" int pcreid_cn_linear_tma(const pcreid_linear_args* pa, long long x1_objs, long long x2_objs, long long w1_objs, int flags,
+                                    int n_sms, void* stream) {
+  return run_tma<false>(pa, nullptr, nullptr, x1_objs, x2_objs, w1_objs, flags, n_sms, stream);
+}
+
+extern "C" int pcreid_cn_linear_tma_x3(const pcreid_linear_args* pa, const float* W1lo, const float* W2lo, long long x1_objs,
+                                       long long x2_objs, long long w1_objs, int n_sms, void* stream) {
+  return run_tma<true>(pa, W1lo, W2lo, x1_objs, x2_objs, w1_objs, 0, n_sms, stream);
 }

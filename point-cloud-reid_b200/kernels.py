@@ -24,23 +24,34 @@ class tensor_core_linear:
     """context manager: `with tensor_core_linear(True): ...` routes cn_linear through the tcgen05 kind::tf32 GEMMs.
     min_k: smallest K1 + K2 that goes to the TMA-staged kernel (pcreid_cn_linear_tma); the models pass 32 in 'fast' mode (every
     contraction with CO >= 32) and 256 in 'parity_tc' mode (the large projections only: the error budget of that mode,
-    profiles/r02_parity_error_budget.md, was measured with exactly those on tf32)."""
+    profiles/r02_parity_error_budget.md, was measured with exactly those on tf32).
+    x3: contractions below min_k run on the fp32-grade 3 x tf32 variant (pcreid_cn_linear_tma_x3) instead of the FFMA kernel."""
 
-    def __init__(self, on, min_k=None):
-        self.on, self.min_k, self.prev = bool(on), min_k, None
+    def __init__(self, on, min_k=None, x3=None):
+        self.on, self.min_k, self.x3, self.prev = bool(on), min_k, x3, None
 
     def __enter__(self):
-        self.prev = (_TC_LINEAR["on"], _TC_LINEAR.get("tma_min_k"))
+        self.prev = (_TC_LINEAR["on"], _TC_LINEAR.get("tma_min_k"), _TC_LINEAR.get("x3"))
         _TC_LINEAR["on"] = self.on
         if self.min_k is not None:
             _TC_LINEAR["tma_min_k"] = self.min_k
+        if self.x3 is not None:
+            _TC_LINEAR["x3"] = bool(self.x3)
 
     def __exit__(self, *exc):
         _TC_LINEAR["on"] = self.prev[0]
-        if self.prev[1] is None:
-            _TC_LINEAR.pop("tma_min_k", None)
-        else:
-            _TC_LINEAR["tma_min_k"] = self.prev[1]
+        for key, val in (("tma_min_k", self.prev[1]), ("x3", self.prev[2])):
+            if val is None:
+                _TC_LINEAR.pop(key, None)
+            else:
+                _TC_LINEAR[key] = val
+
+
+def fp32_grade_only():
+    """True inside the 'parity_x3' regime (every tensor-core contraction is the fp32-grade 3 x tf32 kernel): callers whose outputs feed
+    a DISCRETE decision that the parity gate assumes unchanged (DGCNN's feature-space kNN) keep those contractions on the FFMA kernel,
+    whose accumulation order the oracle's arithmetic was matched to."""
+    return bool(_TC_LINEAR["on"] and _TC_LINEAR.get("x3") and _TC_LINEAR.get("tma_min_k", 256) >= (1 << 30))
 
 
 def _stream():
@@ -91,6 +102,30 @@ def _weight_image(w):
         Kd, CO = w.shape
         ent = (w, round_tf32(w).reshape(Kd // 4, 4, CO).permute(0, 2, 1).contiguous())
         _W_IMAGES[key] = ent
+    return ent[1]
+
+
+_W_LO = {}
+# 3 x tf32 matches the FFMA kernel's error (2e-6 of the output scale) up to K = 256; the tensor core's truncating fp32 accumulation
+# grows it to 8e-6 at K = 1024 (tests/test_gpu_kernels.py), too close to the 1e-4 parity gate for O(10) features: longer contractions
+# stay on the FFMA kernel in the fp32-grade regime
+X3_MAX_K = 256
+
+
+def _lo_part(w):
+    """w - hi(w), hi = the 19 bits a tcgen05 kind::tf32 MMA reads of an fp32 word (exact remainder): the second weight operand of
+    pcreid_cn_linear_tma_x3.  Cached for 2-D (parameter) weights like _weight_image; per-object weights are split per call."""
+    def split(t):
+        return t - (t.view(torch.int32) & -8192).view(torch.float32)
+    if w.dim() != 2:
+        return split(w)
+    key = (w.data_ptr(), w._version, tuple(w.shape), str(w.device))
+    ent = _W_LO.get(key)
+    if ent is None or ent[0] is not w:
+        if len(_W_LO) >= 256:
+            _W_LO.clear()
+        ent = (w, split(w))
+        _W_LO[key] = ent
     return ent[1]
 
 
@@ -151,18 +186,23 @@ def cn_linear(x1, w1, x2=None, w2=None, bias=None, act=ACT_NONE, res=None, res_a
         a.y_bs, a.ldy = _cn(out, "out")
     a.Y = out
     # gen 3 (cn_linear_tma.cu): both operands staged by TMA tensor maps; serves every channel-major shape with CO >= 32 incl.
-    # object maps and per-object weights ("tma": None = by measured threshold, True = always, False = never)
+    # object maps and per-object weights ("tma": None = by threshold, True = always, False = never).  Below the threshold, "x3"
+    # selects the fp32-grade 3 x tf32 variant of the same kernel instead of the FFMA kernel.
     tma = _TC_LINEAR.get("tma")
-    if (_TC_LINEAR["on"] and tma is not False and not x1_pm and not x2_pm and not y_pm and CO >= 32 and CO % 4 == 0 and rows % 4 == 0
-            and (tma or K1 + a.K2 >= _TC_LINEAR.get("tma_min_k", 256))):
-        flags = (TMA_TF32_MAPS if _TC_LINEAR.get("tma_tf32_maps", True) else 0) | (TMA_ROUND_OUT if _TC_LINEAR.get("round_out") else 0) | (4 if _TC_LINEAR.get("tma_tile128") else 0)
+    if (_TC_LINEAR["on"] and tma is not False and not x1_pm and not x2_pm and not y_pm and CO >= 32 and CO % 4 == 0 and rows % 4 == 0):
         n_sms = torch.cuda.get_device_properties(x1.device).multi_processor_count
-        if _OPS.cn_linear_tma(*a.astuple(), x1.shape[0], x2.shape[0] if x2 is not None else 0, w1.shape[0] if w1.dim() == 3 else 0,
-                              flags, n_sms) != 3:
-            return out
+        objs = (x1.shape[0], x2.shape[0] if x2 is not None else 0, w1.shape[0] if w1.dim() == 3 else 0)
+        if tma or K1 + a.K2 >= _TC_LINEAR.get("tma_min_k", 256):
+            flags = ((TMA_TF32_MAPS if _TC_LINEAR.get("tma_tf32_maps", True) else 0) | (TMA_ROUND_OUT if _TC_LINEAR.get("round_out") else 0)
+                     | (4 if _TC_LINEAR.get("tma_tile128") else 0))
+            if _OPS.cn_linear_tma(*a.astuple(), *objs, flags, n_sms) != 3:
+                return out
+        elif _TC_LINEAR.get("x3") and K1 + a.K2 <= X3_MAX_K:
+            if _OPS.cn_linear_tma_x3(*a.astuple(), _lo_part(w1), _lo_part(w2) if w2 is not None else None, *objs, n_sms) != 3:
+                return out
     # measured on B200 (scripts/bench_linear.py): the tf32 tensor-core kernels win from K >= 256; below that the FFMA kernel
     # (up to 48 TFLOP/s) is faster
-    if (_TC_LINEAR["on"] and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None
+    if (_TC_LINEAR["on"] and not fp32_grade_only() and K1 + a.K2 >= _TC_LINEAR.get("min_k", 256) and x1_map is None and x2_map is None and w1_map is None
             and r_map is None and not x1_pm and not x2_pm):
         # gen 2 (warp-specialised, cn_linear_tc2.cu) wins from K >= 512: 127-141 vs 100-107 TFLOP/s on the DGCNN / PointNet heads
         if (_TC_LINEAR.get("gen", 2 if K1 + a.K2 >= 512 else 1) == 2 and w1.dim() == 2 and (w2 is None or w2.dim() == 2) and K1 % 8 == 0 and a.K2 % 8 == 0):

@@ -108,6 +108,9 @@ class ReIDNet(nn.Module):
 
     def set_mode(self, mode):
         """'parity': fp32 FFMA kernels everywhere (|dlogit| <= 1e-4).
+        'parity_x3': the parity path with every Linear / 1x1 conv the TMA-staged GEMM can serve on the tensor cores at fp32-grade
+        accuracy (pcreid_cn_linear_tma_x3: operands split hi + lo, three kind::tf32 MMAs per K step; ~1e-6 relative to the FFMA
+        kernel, same 1e-4 gate) -- the strict-parity mode on tcgen05.
         'parity_tc': the contractions on the tensor cores at an 11-bit significand -- tcgen05 kind::tf32 SA shared MLPs and
         Self_Attention blocks in the encoder (operands pre-rounded to tf32), fused tcgen05 matcher with fp16 operands -- fp32
         accumulation and norms (|dlogit| <= 5e-3, the tf32 gate of SURVEY.md 8d).  The three feature-propagation blocks
@@ -115,7 +118,7 @@ class ReIDNet(nn.Module):
         measured (scripts/encoder_error_probe.py, profiles/r02_parity_error_budget.md) they alone cost ~1 % of raw top-1
         agreement on the random-init logits (top-2 gap median 5e-3) for 3 % of the step time.
         'fast': every block on the tensor cores, bf16 matcher operands (|dlogit| <= 3e-2)."""
-        assert mode in ('parity',) + self.TC_MODES
+        assert mode in ('parity', 'parity_x3') + self.TC_MODES
         from .pointnet2_utils import FP_SA
         self.match_mode = mode
         for m in self.modules():
@@ -124,17 +127,28 @@ class ReIDNet(nn.Module):
         return self
 
     def _tc_linear(self):
-        """tf32 tcgen05 GEMMs for the 1x1 convs / Linears outside the fused kernels: every contraction in 'fast' mode, the large
-        projections (K >= 256) in 'parity_tc' mode, none in 'parity'."""
-        return K.tensor_core_linear(self.match_mode in self.TC_MODES and self.tc_encoder, min_k=32 if self.match_mode == 'fast' else 256)
+        """tcgen05 GEMMs for the 1x1 convs / Linears outside the fused kernels: 'fast': every contraction single-pass tf32;
+        'parity_tc': K >= 256 single-pass tf32 (the set its error budget was measured with), the rest fp32-grade 3 x tf32;
+        'parity_x3': everything fp32-grade 3 x tf32; 'parity': none (FFMA kernels)."""
+        mode = self.match_mode
+        if mode == 'parity_x3':
+            # 'xcorr': the matcher's local stages run a feature-space kNN on (functions of) the embeddings; a 1e-6 difference flips
+            # near-tied neighbours, which the 1e-4 gate does not absorb -> that configuration stays on the FFMA kernels end to end
+            return K.tensor_core_linear(self.tc_encoder and self.match_type != 'xcorr', min_k=1 << 30, x3=True)
+        return K.tensor_core_linear(mode in self.TC_MODES and self.tc_encoder, min_k=32 if mode == 'fast' else 256, x3=mode == 'parity_tc')
 
     def _tc_match(self, fused):
-        """the matcher's Linears outside the fused kernels (per-object preparation, match head; the whole cross-attention chain
-        for shapes the fused matcher does not cover: d_model = 128, 'xcorr'): tf32 tcgen05 GEMMs in 'fast' mode; in 'parity_tc'
-        mode only when the fused matcher is not in use (its head and preparation stay fp32: they are part of that mode's
-        measured error budget)."""
-        on = self.match_mode == 'fast' or (self.match_mode == 'parity_tc' and not fused)
-        return K.tensor_core_linear(on, min_k=32)
+        """the matcher's Linears outside the fused kernels (per-object preparation; the whole cross-attention chain for shapes
+        the fused matcher does not cover: d_model = 128, 'xcorr'): single-pass tf32 in 'fast' mode and, when the fused matcher is
+        not in use, in 'parity_tc' mode; fp32-grade 3 x tf32 around the fused matcher in 'parity_tc' (its preparation is part of
+        that mode's measured error budget) and everywhere in 'parity_x3'.  The match head always runs on the fp32 kernels."""
+        mode = self.match_mode
+        if mode == 'parity_x3' and self.match_type == 'xcorr':
+            # the local stages run a feature-space kNN on the cross-attended features: a 1e-6 difference flips near-tied neighbours
+            return K.tensor_core_linear(False)
+        if mode == 'fast' or (mode == 'parity_tc' and not fused):
+            return K.tensor_core_linear(True, min_k=32)
+        return K.tensor_core_linear(mode in ('parity_tc', 'parity_x3'), min_k=1 << 30, x3=True)
 
     def invalidate_packed(self):
         """forget every packed / BN-folded / operand-image weight copy and captured CUDA graph (see _packing.invalidate_packed:

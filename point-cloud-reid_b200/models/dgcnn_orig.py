@@ -55,8 +55,11 @@ class DGCNN(PackedModule):
         cur, off = x, 0
         for i, co in enumerate(widths, 1):
             idx = K.knn_feature(cur, self.k)
-            p = K.cn_linear(cur, pk[f"p{i}"])
-            q = K.cn_linear(cur, pk[f"q{i}"], bias=pk[f"t{i}"])
+            # layers 1-3 feed the next layer's feature-space kNN: in the strict-parity tensor-core regime they stay on the FFMA
+            # kernel (a 1e-6 feature difference flips near-tied neighbours, which the 1e-4 gate does not absorb)
+            with K.tensor_core_linear(not (i < 4 and K.fp32_grade_only()) and K._TC_LINEAR["on"]):
+                p = K.cn_linear(cur, pk[f"p{i}"])
+                q = K.cn_linear(cur, pk[f"q{i}"], bias=pk[f"t{i}"])
             cur = K.edge_gather_max(p, q, idx, K.ACT_LEAKY02, out=cat[:, off:off + co])
             off += co
         feats = K.cn_linear(cat, pk["w5"], bias=pk["t5"], act=K.ACT_LEAKY02)

@@ -21,7 +21,7 @@ Registered per op: the CUDA implementation (ctypes call into the library; any ot
 there is no CPU kernel) and a fake / meta implementation (the ops return nothing: outputs are preallocated by the callers
 in ops/*.py, kernels.py and models/fused_pairs.py, so shape inference is theirs), which is what FakeTensorMode, opcheck and
 torch.compile need.  A non-zero return code raises; the three entry points that answer PCREID_ERR_UNSUPPORTED for shapes
-outside their tiles (`cn_linear_tc`, `cn_linear_tc2`, `cn_linear_tma`, `sa_edge_mlp_tc2`) return the code instead (`-> int`).
+outside their tiles (`cn_linear_tc`, `cn_linear_tc2`, `cn_linear_tma`, `cn_linear_tma_x3`, `sa_edge_mlp_tc2`) return the code instead (`-> int`).
 """
 import ctypes
 import os
@@ -34,7 +34,7 @@ from . import _lib
 NAMESPACE = "pcreid"
 _HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "pcreid.h")
-RC_OPS = ("cn_linear_tc", "cn_linear_tc2", "cn_linear_tma", "sa_edge_mlp_tc2")      # return the code (UNSUPPORTED is an answer, not an error)
+RC_OPS = ("cn_linear_tc", "cn_linear_tc2", "cn_linear_tma", "cn_linear_tma_x3", "sa_edge_mlp_tc2")      # return the code (UNSUPPORTED is an answer, not an error)
 
 _STRUCTS = {"pcreid_linear_args": _lib.LinearArgs, "pcreid_norm_args": _lib.NormArgs}
 

@@ -38,7 +38,7 @@ for (B, N, Kd, CO) in SHAPES:
         res["ffma"] = timeit(lambda: K.cn_linear(x, w, act=1, out=out))
     ref = out.clone()
     K._TC_LINEAR["min_k"] = 8
-    for name, cfg in (("tc1", dict(gen=1, tma=False)), ("tc2", dict(gen=2, tma=False)), ("tma", dict(tma=True)), ("tma128", dict(tma=True, tma_tile128=True))):
+    for name, cfg in (("tc1", dict(gen=1, tma=False)), ("tc2", dict(gen=2, tma=False)), ("tma", dict(tma=True)), ("tma128", dict(tma=True, tma_tile128=True)), ("x3", dict(x3=True, tma_min_k=1 << 30))):
         K._TC_LINEAR.update(cfg)
         with K.tensor_core_linear(True):
             res[name] = timeit(lambda: K.cn_linear(x, w, act=1, out=out))
@@ -49,5 +49,5 @@ for (B, N, Kd, CO) in SHAPES:
     by = 4.0 * (B * N * (Kd + CO) + Kd * CO)
     print(json.dumps({"B": B, "N": N, "K": Kd, "CO": CO,
                       **{k + "_ms": round(v, 4) for k, v in res.items() if not k.endswith("_err")},
-                      **{k + "_TFLOPs": round(fl / res[k] / 1e9, 1) for k in ("ffma", "tc1", "tc2", "tma", "tma128")},
-                      "tma_frac_hbm": round(by / res["tma"] / 1e6 / HBM, 3), "tma_max_err": res["tma_err"], "tc2_max_err": res["tc2_err"]}), flush=True)
+                      **{k + "_TFLOPs": round(fl / res[k] / 1e9, 1) for k in ("ffma", "tc1", "tc2", "tma", "tma128", "x3")},
+                      "tma_frac_hbm": round(by / res["tma"] / 1e6 / HBM, 3), "tma_max_err": res["tma_err"], "tc2_max_err": res["tc2_err"], "x3_max_err": res["x3_err"]}), flush=True)

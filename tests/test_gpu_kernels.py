@@ -178,6 +178,62 @@ def test_cn_linear_tma_many_tiles_per_cta(tma_only):
     close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, bias=b, act=1, res=res), 3e-3)
 
 
+@pytest.mark.parametrize("B,K1,CO,N", [(3, 64, 64, 256), (2, 128, 192, 132), (2, 1024, 512, 256), (4, 3, 64, 128), (3, 40, 100, 260)])
+@pytest.mark.parametrize("act", [0, 1])
+def test_cn_linear_tma_x3_is_fp32_grade(B, K1, CO, N, act, monkeypatch):
+    monkeypatch.setattr(K, "X3_MAX_K", 1 << 20)          # the dispatch keeps K > 256 on the FFMA kernel; the kernel itself is tested beyond
+    """3 x tf32 (hi + lo operand split, pcreid_cn_linear_tma_x3) against a float64 reference: within 1e-5 of the output scale up to
+    K = 1024 (measured 2e-6 at K <= 128, 8e-6 at K = 1024: the tensor core's fp32 accumulation truncates; the FFMA kernel sits at
+    1.5e-6, single-pass tf32 at 1.5e-4), operands with full 24-bit significands"""
+    x, w, b = rnd(B, K1, N, seed=1) * 3.7, rnd(K1, CO, seed=2) / K1 ** 0.5, rnd(CO, seed=3)
+    ref = torch.einsum("bkn,kc->bcn", x.double(), w.double()) + b.double()[None, :, None]
+    if act:
+        ref = ref.clamp_min(0)
+    calls = {"n": 0}
+    real = K._OPS.cn_linear_tma_x3
+
+    class _Ops:
+        def __getattr__(self, name):
+            if name == "cn_linear_tma_x3":
+                def f(*a):
+                    calls["n"] += 1
+                    return real(*a)
+                return f
+            if name in ("cn_linear", "cn_linear_tc", "cn_linear_tc2", "cn_linear_tma"):
+                raise AssertionError(f"{name} used instead of the 3 x tf32 kernel")
+            return getattr(ops, name)
+    ops = K._OPS
+    K._OPS = _Ops()
+    try:
+        with K.tensor_core_linear(True, min_k=1 << 30, x3=True):
+            got = K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act)
+    finally:
+        K._OPS = ops
+    assert calls["n"] == 1
+    err = float((got.cpu().double() - ref).abs().max())
+    ffma = float((K.cn_linear(x.to(DEV), w.to(DEV), bias=b.to(DEV), act=act).cpu().double() - ref).abs().max())
+    scale = max(1.0, float(ref.abs().max()))
+    assert err <= 1e-5 * scale, (err, ffma, scale)
+
+
+def test_cn_linear_tma_x3_options():
+    """second input pair, residual, object maps on every operand, per-object weights with a map (their lo part is split per call)"""
+    N, B = 200, 6
+    x1, x2, res = rnd(4, 64, N, seed=1), rnd(5, 32, N, seed=2), rnd(3, 128, N, seed=5)
+    w1, w2 = rnd(64, 128, seed=3) / 8, rnd(32, 128, seed=4) / 6
+    m1 = torch.tensor([3, 0, 2, 2, 1, 0], dtype=torch.int32)
+    m2 = torch.tensor([4, 4, 0, 1, 3, 2], dtype=torch.int32)
+    mr = torch.tensor([0, 2, 1, 1, 2, 0], dtype=torch.int32)
+    wk = rnd(4, 64, 64, seed=7) / 8
+    wm = torch.tensor([3, 0, 2], dtype=torch.int32)
+    qkv = rnd(3, 192, N, seed=6)
+    with K.tensor_core_linear(True, min_k=1 << 30, x3=True):
+        got = K.cn_linear(x1.to(DEV), w1.to(DEV), x2=x2.to(DEV), w2=w2.to(DEV), act=1, res=res.to(DEV), res_after_act=True,
+                          x1_map=m1.to(DEV), x2_map=m2.to(DEV), r_map=mr.to(DEV), B=B)
+        close(got, F.cn_linear(x1, w1, x2=x2, w2=w2, act=1, res=res, res_after_act=True, x1_map=m1, x2_map=m2, r_map=mr, B=B))
+        close(K.cn_linear(qkv.to(DEV)[:, 64:128], wk.to(DEV), w1_map=wm.to(DEV), rows=96), F.cn_linear(qkv[:, 64:128], wk, w1_map=wm, rows=96))
+
+
 def test_cn_linear_tma_rounding():
     """what the two tensor-map element types do with the 13 low mantissa bits of an fp32 activation: FLOAT32 maps leave them to the
     tensor core (which ignores them: truncation), TFLOAT32 maps round to nearest in the TMA unit; ROUND_OUT rounds the result."""

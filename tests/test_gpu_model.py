@@ -104,6 +104,25 @@ def test_tensor_core_modes_every_config(kind, N, blist, mode, tol):
     assert ok, f"top-1 changed on a decisive row (raw agreement {agree}, {n} decisive rows)"
 
 
+@pytest.mark.parametrize("kind,N,blist", [("pt", 256, (256, 128, 64)), ("dgcnn", 256, (128, 64, 32)), ("pointnet", 128, (128, 64, 32)),
+                                          ("pt7m", 128, (128, 64, 32)), ("xcorr", 128, (128, 64, 32))])
+def test_parity_x3_mode_meets_the_fp32_gate(kind, N, blist):
+    """set_mode('parity_x3'): the strict-parity path with its contractions on tcgen05 (3 x tf32) -- same 1e-4 gates as fp32 parity"""
+    m, orc = helpers.build_pair(kind, blist, device=DEV)
+    m.set_mode('parity_x3')
+    t, d = O.synth_objects(6, N, 0), O.synth_objects(7, N, 1)
+    xt, ht = m.encode(t.to(DEV))
+    xd, hd = m.encode(d.to(DEV))
+    oxt, oht = orc.encode(t)
+    oxd, ohd = orc.encode(d)
+    assert (ht.cpu() - oht).abs().max() < TOL and (hd.cpu() - ohd).abs().max() < TOL
+    L = m.match_all_pairs(ht, xt, hd, xd, chunk=16).cpu()
+    Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
+    assert (L - Lo).abs().max() < TOL
+    ok, agree, n = helpers.margin_aware_top1(Lo, L, TOL)
+    assert ok, f"top-1 changed on a decisive row (raw agreement {agree}, {n} decisive rows)"
+
+
 def test_degenerate_clouds_all_points_identical():
     """all-zero / single-point clouds (empty crops, pc_utils.py:84-89): every kNN distance ties; features must still
     match because tied neighbours are identical points."""
