@@ -359,9 +359,44 @@ class ReIDNet(nn.Module):
                'point-cat': lambda: torch.cat([o1, o2], 2)}[self.combine]()
         return self._head_cn(self.get_pooled_feats(out).t().contiguous().unsqueeze(0))
 
+    GRAPH_MAX_PAIRS = 16384     # per-frame matrices of a tracker (10 Hz replay): launch-bound sizes; scratch stays below 2 GB per graph
+
     def match_all_pairs(self, h_t, xyz_t, h_d, xyz_d, pair_mask=None, chunk=8192, _exact_chunk=False):
         """Dense (T, D) logit matrix; entries where ``pair_mask`` (bool (T, D), e.g. the tracker's class gate,
-        tracking_point_reid.py:15-33) is False are 0, as in the reference cost matrix."""
+        tracking_point_reid.py:15-33) is False are 0, as in the reference cost matrix.
+        With enable_cuda_graphs() a small dense matrix (no mask, T*D <= GRAPH_MAX_PAIRS) is replayed from a captured CUDA graph:
+        its ~60 launches (per-object preparation, unit lists, fused kernels, pooling, head) cost more to issue than to run."""
+        if (self.cuda_graphs and pair_mask is None and h_t.is_cuda and self.match_type != 'concat'
+                and 0 < h_t.shape[0] * h_d.shape[0] <= self.GRAPH_MAX_PAIRS and self.match_mode in self.TC_MODES):
+            return self._match_graphed(h_t, xyz_t, h_d, xyz_d)
+        return self._match_all_pairs(h_t, xyz_t, h_d, xyz_d, pair_mask, chunk, _exact_chunk)
+
+    def _match_graphed(self, h_t, xyz_t, h_d, xyz_d):
+        """CUDA-graph replay of the dense match for fixed (T, D, N); the graph owns its inputs, scratch and output."""
+        ver = tuple((p.data_ptr(), p._version) for p in self.parameters()) + tuple((b.data_ptr(), b._version) for b in self.buffers())
+        key = ("match", tuple(h_t.shape), tuple(h_d.shape), str(h_t.device), self.match_mode)
+        ent = self._graphs.get(key)
+        if ent is None or ent[0] != ver:
+            if len(self._graphs) >= 6:
+                self._graphs.pop(next(iter(self._graphs)))
+            static = [t.float().contiguous().clone() for t in (h_t, xyz_t, h_d, xyz_d)]
+            side = torch.cuda.Stream(device=h_t.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):           # warm-up outside the capture: weight images, kernel attributes
+                self._match_all_pairs(*static)
+            torch.cuda.current_stream().wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = self._match_all_pairs(*static)
+            ent = (ver, g, static, static_out)
+            self._graphs[key] = ent
+        _, g, static, static_out = ent
+        for dst, src in zip(static, (h_t, xyz_t, h_d, xyz_d)):
+            dst.copy_(src)
+        g.replay()
+        return static_out.clone()
+
+    def _match_all_pairs(self, h_t, xyz_t, h_d, xyz_d, pair_mask=None, chunk=8192, _exact_chunk=False):
         with torch.no_grad():
             h_t, h_d = _cn(h_t), _cn(h_d)
             xyz_t, xyz_d = xyz_t.float().contiguous(), xyz_d.float().contiguous()

@@ -20,6 +20,7 @@ from pcreid_b200.parallel import gathered_bytes, match_all_pairs_sharded, shard_
 ap = argparse.ArgumentParser()
 ap.add_argument("--sizes", default="256,1024,4096")
 ap.add_argument("--mode", default="parity_tc")
+ap.add_argument("--graphs", type=int, default=1)
 ap.add_argument("--max-seconds", type=float, default=40.0, help="per size: steps are chosen so that the timed region stays below this")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -30,6 +31,7 @@ if world > 1:
 torch.manual_seed(66)
 model = build_model(S.point_transformer_cfg((256, 128, 64))).eval().to(dev)
 model.set_mode(args.mode)
+model.enable_cuda_graphs(bool(args.graphs))      # encode per shape; the match of per-frame sized blocks (T*D <= 16384 per call)
 
 
 def barrier():
@@ -64,7 +66,7 @@ for T in [int(v) for v in args.sizes.split(",")]:
     assert out.shape == (T, D) and bool(torch.isfinite(out).all())
     if rank == 0:
         print(json.dumps({"workload": f"configs[4] sweep: PT encode of {T}+{D} objects x 256 pts + {T}x{D} all-pairs xcorr_eff, row-sharded",
-                          "n_gpus": world, "mode": args.mode, "scaling": "strong", "tracks": T, "dets": D, "steps": steps, "warmup": warm,
+                          "n_gpus": world, "mode": args.mode, "cuda_graphs": bool(args.graphs), "scaling": "strong", "tracks": T, "dets": D, "steps": steps, "warmup": warm,
                           "ms_per_step_max_over_ranks": ms, "pairs_per_s": T * D / (ms * 1e-3), "objects_per_s": (T + D) / (ms * 1e-3),
                           "bytes_received_per_rank": gathered_bytes(model, 256, dc, tc, gather_scores=True)}), flush=True)
     del tracks, dets, out

@@ -134,3 +134,29 @@ def test_full_size_config_properties():
     oxd, ohd = orc.encode(d[di])
     Lo = orc.match_all_pairs(oht, oxt, ohd, oxd)
     assert (L[ti][:, di].cpu() - Lo).abs().max() < TOL_FAST
+
+
+@pytest.mark.parametrize("mode", ["fast", "parity_tc"])
+def test_small_dense_match_replays_from_a_cuda_graph(mode):
+    """enable_cuda_graphs(): a per-frame sized dense matrix (T*D <= GRAPH_MAX_PAIRS, no mask) is replayed from a captured graph --
+    bit-identical to the eager launches, correct for new inputs of the same shape, masked / large calls stay eager"""
+    m, _ = helpers.build_pair("pt", (128, 64, 32), device=DEV)
+    m.set_mode(mode)
+    outs = []
+    for seed in (0, 5):
+        t, d = O.synth_objects(9, 128, seed).to(DEV), O.synth_objects(12, 128, seed + 1).to(DEV)
+        m.enable_cuda_graphs(False)
+        xt, ht = m.encode(t)
+        xd, hd = m.encode(d)
+        eager = m.match_all_pairs(ht, xt, hd, xd)
+        m.enable_cuda_graphs(True)
+        xt2, ht2 = m.encode(t)
+        xd2, hd2 = m.encode(d)
+        assert torch.equal(ht, ht2) and torch.equal(hd, hd2)
+        got = m.match_all_pairs(ht2, xt2, hd2, xd2)
+        assert torch.equal(got, eager)
+        outs.append(got)
+        mask = torch.rand(9, 12, generator=torch.Generator().manual_seed(3)) > 0.4
+        assert torch.equal(m.match_all_pairs(ht2, xt2, hd2, xd2, pair_mask=mask.to(DEV)), eager * mask.to(DEV))
+    assert any(k[0] == "match" for k in m._graphs if isinstance(k[0], str))
+    assert not torch.equal(outs[0], outs[1])
