@@ -620,12 +620,147 @@ __global__ void __launch_bounds__(MAXT) fps_kernel(int N, int M, int log2bs, con
   }
 }
 
+// Second FPS kernel (xyz inputs, modes 0 / 2): coordinates live in shared memory in TIE-PRIORITY order and only the running
+// min-distances stay in registers, so a 1024-point object costs ~70 registers of ONE warp (14+ objects resident per SM; the
+// register-resident kernel above needs 220 and runs 2048 objects in two waves).
+//   slot s = rev(k mod bs) * Q + k div bs   (Q = ceil(N / bs); slots whose k >= N are padding with t = -1: never selected)
+// ascends exactly with the reference's tie priority (fps_tie32), and a thread scans its slots 4 (T j + tid) + c in ascending
+// order with a strict '>', so the block winner is  min slot over { slots whose distance equals the block maximum } : one
+// REDUX.MAX over the value bits (distances are >= +0: the int order is the float order) and one REDUX.MIN over the slots --
+// no per-point tie key, no lexicographic compare.  The next centroid's coordinates are a shared-memory broadcast read.
+struct FpsSlots {
+  int log2bs, Q;
+  __device__ __forceinline__ int to_k(int s) const {
+    const int rv = s / Q, q = s - rv * Q;
+    return log2bs ? (q << log2bs) + (int)(__brev((uint32_t)rv) >> (32 - log2bs)) : q;
+  }
+  __device__ __forceinline__ bool valid(int s, int N) const { return (s / Q) < (1 << log2bs) && to_k(s) < N; }
+  __device__ __forceinline__ int to_slot(int k) const {
+    if (!log2bs) return k;
+    const uint32_t kmod = (uint32_t)k & ((1u << log2bs) - 1u);
+    return (int)(__brev(kmod) >> (32 - log2bs)) * Q + (k >> log2bs);
+  }
+};
+
+constexpr int fps_rank_maxt(int ppt) { return ppt >= 32 ? 256 : ppt >= 16 ? 512 : 1024; }   // keeps t[PPT] out of local memory
+
+template <int PPT, int MODE>
+__global__ void __launch_bounds__(fps_rank_maxt(PPT)) fps_rank_kernel(int N, int M, int nsl, FpsSlots sl, const float* __restrict__ data,
+                                                        float* __restrict__ temp, int* __restrict__ idxs,
+                                                        const int* __restrict__ start) {
+  extern __shared__ __align__(16) float fps_sm[];
+  __shared__ int s_val[2][32], s_slot[2][32];
+  const int T = blockDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = T >> 5;
+  const int b = blockIdx.x;
+  const float* ds = data + (size_t)b * N * 3;
+  float* tp = temp ? temp + (size_t)b * N : nullptr;
+  int* out = idxs + (size_t)b * M;
+  float *xs = fps_sm, *ys = fps_sm + nsl, *zs = fps_sm + 2 * nsl;
+  for (int s = tid; s < nsl; s += T) { xs[s] = 0.f; ys[s] = 0.f; zs[s] = 0.f; }
+  __syncthreads();
+  for (int i = tid; i < 3 * N; i += T) {                       // coalesced read, scattered into the slot order
+    const int k = i / 3, c = i - 3 * k;
+    fps_sm[c * nsl + sl.to_slot(k)] = ds[i];
+  }
+  float t[PPT];
+#pragma unroll
+  for (int j = 0; j < PPT / 4; ++j)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int s = 4 * (T * j + tid) + c;
+      t[4 * j + c] = sl.valid(s, N) ? (tp ? tp[sl.to_k(s)] : 1e10f) : -1.f;
+    }
+  int old_slot = sl.to_slot(start ? start[b] : 0);
+  if (tid == 0) out[0] = start ? start[b] : 0;
+  __syncthreads();
+  const float4 *x4 = reinterpret_cast<const float4*>(xs), *y4 = reinterpret_cast<const float4*>(ys),
+               *z4 = reinterpret_cast<const float4*>(zs);
+  for (int s = 1; s < M; ++s) {
+    const float x1 = xs[old_slot], y1 = ys[old_slot], z1 = zs[old_slot];
+    float best = -2.f;
+    int bslot = 0;
+#pragma unroll
+    for (int j = 0; j < PPT / 4; ++j) {
+      const int g = T * j + tid;
+      const float4 X = x4[g], Y = y4[g], Z = z4[g];
+      const float xx[4] = {X.x, X.y, X.z, X.w}, yy[4] = {Y.x, Y.y, Y.z, Y.w}, zz[4] = {Z.x, Z.y, Z.z, Z.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float d = MODE == 2 ? dist_sum_sq(xx[c], yy[c], zz[c], x1, y1, z1) : dist_direct(xx[c], yy[c], zz[c], x1, y1, z1);
+        const float d2 = fminf(d, t[4 * j + c]);
+        t[4 * j + c] = d2;
+        if (d2 > best) { best = d2; bslot = 4 * g + c; }
+      }
+    }
+    int wv = __reduce_max_sync(FULL_MASK, __float_as_int(best));
+    uint32_t ws = __reduce_min_sync(FULL_MASK, __float_as_int(best) == wv ? (uint32_t)bslot : 0xffffffffu);
+    if (nwarp > 1) {
+      const int buf = s & 1;
+      if (lane == 0) { s_val[buf][warp] = wv; s_slot[buf][warp] = (int)ws; }
+      __syncthreads();
+      const int v = lane < nwarp ? s_val[buf][lane] : (int)0x80000000;
+      const uint32_t l = lane < nwarp ? (uint32_t)s_slot[buf][lane] : 0xffffffffu;
+      wv = __reduce_max_sync(FULL_MASK, v);
+      ws = __reduce_min_sync(FULL_MASK, v == wv ? l : 0xffffffffu);
+    }
+    old_slot = (int)ws;
+    if (tid == 0) out[s] = sl.to_k(old_slot);
+  }
+  if (tp) {
+#pragma unroll
+    for (int j = 0; j < PPT / 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int s = 4 * (T * j + tid) + c;
+        if (sl.valid(s, N)) tp[sl.to_k(s)] = t[4 * j + c];
+      }
+  }
+}
+
 static int fps_block_size_ref(int n) {   // opt_n_threads, furthest_point_sample_cuda.cu:11-15
   int pow_2 = (int)(std::log(static_cast<double>(n)) / std::log(2.0));
   int t = 1 << pow_2;
   if (t > 1024) t = 1024;
   if (t < 1) t = 1;
   return t;
+}
+
+// shared-memory / rank-order kernel: returns false when the shape is outside its range (the register kernel serves it)
+static bool fps_rank_launch(int b, int n, int m, int log2bs, const float* data, float* temp, int* idxs, int with_dist,
+                            cudaStream_t st, const int* start) {
+  static const int knob = [] { const char* e = getenv("PCREID_FPS_PPT"); return e ? atoi(e) : 0; }();   // A/B: 0 = heuristic, -1 = off
+  if (knob < 0) return false;
+  const int bs = 1 << log2bs;                                 // 1 on the torch path: slots are the point indices
+  const int Q = ceil_div(n, bs);
+  const long long raw = (long long)bs * Q;
+  if (raw > 8192) return false;
+  // slots per thread: 32 (a warp per <= 1024-point object, no barriers; the fewest warps per large object -- the two-level
+  // arg-max chain, not the distance arithmetic, bounds a step) unless few small objects leave the SMs empty
+  // (profiles/r02_fps_sweep.jsonl)
+  int want = knob > 0 ? knob : ((b >= 296 || raw >= 4096) ? 32 : 8);
+  int W = 1;
+  while (W < 32 && (long long)W * 32 * want < raw) W <<= 1;
+  int ppt = 4;
+  while ((long long)W * 32 * ppt < raw) ppt <<= 1;
+  if (ppt > 32 || W * 32 > fps_rank_maxt(ppt)) return false;
+  const int T = 32 * W, nsl = T * ppt;
+  const size_t smem = (size_t)nsl * 12;
+  FpsSlots sl{log2bs, Q};
+#define FPS_RANK_CASE(P)                                                                                                   \
+  case P:                                                                                                                  \
+    if (with_dist == 2) {                                                                                                  \
+      cudaFuncSetAttribute(fps_rank_kernel<P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+      fps_rank_kernel<P, 2><<<b, T, smem, st>>>(n, m, nsl, sl, data, temp, idxs, start);                                   \
+    } else {                                                                                                               \
+      cudaFuncSetAttribute(fps_rank_kernel<P, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+      fps_rank_kernel<P, 0><<<b, T, smem, st>>>(n, m, nsl, sl, data, temp, idxs, start);                                   \
+    }                                                                                                                      \
+    break;
+  switch (ppt) {
+    FPS_RANK_CASE(4) FPS_RANK_CASE(8) FPS_RANK_CASE(16) FPS_RANK_CASE(32)
+  }
+#undef FPS_RANK_CASE
+  return true;
 }
 
 static int fps_launch(int b, int n, int m, const float* data, float* temp, int* idxs, int with_dist, cudaStream_t st,
@@ -635,6 +770,7 @@ static int fps_launch(int b, int n, int m, const float* data, float* temp, int* 
   int bs = fps_block_size_ref(n), log2bs = 0;
   while ((1 << log2bs) < bs) ++log2bs;
   if (with_dist == 2) log2bs = 0;                           // torch.max: the first index among tied maxima
+  if (with_dist != 1 && fps_rank_launch(b, n, m, log2bs, data, temp, idxs, with_dist, st, start)) return pcreid_launch_status();
   int T;
   if (b >= 592 && n <= 1024 && with_dist != 1) T = 32;      // many small objects: one warp each, no barriers
   else {

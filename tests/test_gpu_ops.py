@@ -48,6 +48,43 @@ def test_fps_many_small_objects_warp_path():
     assert torch.equal(furthest_point_sample(x.to(DEV), 64).cpu(), P.furthest_point_sample(x, 64))
 
 
+@pytest.mark.parametrize("B,N,M", [(320, 1024, 96), (300, 700, 50), (5, 3000, 40), (3, 8192, 24), (2, 9000, 12)])
+def test_fps_rank_kernel_shapes(B, N, M):
+    """the shared-memory rank-order FPS kernel: a warp per object with 32 slots per lane (B >= 296, N <= 1024), slot counts that
+    are not a power of two (N = 3000: 3 rows of 1024 slots), its largest shape (8192 slots) and the first shape beyond it
+    (register kernel); clouds with repeated points so that the tie priority decides"""
+    from pcreid_b200.ops import furthest_point_sample
+    x = O.synth_objects(B, N, 11, dup=True)
+    got = furthest_point_sample(x.to(DEV), M).cpu()
+    assert torch.equal(got, P.furthest_point_sample(x, M))
+    if P.ref_available() and B <= 8:
+        assert torch.equal(got, P.ref_furthest_point_sample(x.to(DEV), M).cpu())
+
+
+@pytest.mark.parametrize("N", [256, 1000, 3000])
+def test_fps_temp_written_back(N):
+    """the op's `temp` argument is in/out (furthest_point_sample_cuda.cu:44-70): it ends as the running minimum distance of
+    every point to the sample set -- compared with the C restatement's buffer, and a second call that starts from it"""
+    import ctypes
+    import numpy as np
+    from pcreid_b200.ops._common import OPS
+    x = O.synth_objects(3, N, 4, dup=True)
+    M = 20
+    temp = torch.full((3, N), 1e10, device=DEV)
+    idx = torch.empty(3, M, dtype=torch.int32, device=DEV)
+    OPS.fps(3, N, M, x.to(DEV), temp, idx)
+    xn = np.ascontiguousarray(x.numpy())
+    tn = np.full((3, N), 1e10, np.float32)
+    inn = np.zeros((3, M), np.int32)
+    fp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    P._cpu().oracle_fps(3, N, M, fp(xn), fp(tn), fp(inn))
+    assert torch.equal(idx.cpu(), torch.from_numpy(inn))
+    assert torch.equal(temp.cpu(), torch.from_numpy(tn))
+    OPS.fps(3, N, M, x.to(DEV), temp, idx)                # warm start from the buffer
+    P._cpu().oracle_fps(3, N, M, fp(xn), fp(tn), fp(inn))
+    assert torch.equal(idx.cpu(), torch.from_numpy(inn)) and torch.equal(temp.cpu(), torch.from_numpy(tn))
+
+
 @pytest.mark.parametrize("N,M", [(128, 32), (100, 100)])
 def test_fps_with_dist_bit_exact(N, M):
     from pcreid_b200.ops import furthest_point_sample_with_dist
