@@ -27,14 +27,20 @@
 // tcgen05.ld.  A CTA holds three independent groups that share one copy of the weights, so the tensor pipe of one group
 // overlaps the epilogues of the other two.
 #include "pair_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
 constexpr int P1B_WKV = 0, P1B_WM = 16384, P1B_WBYTES = 24576;
 constexpr int P1B_AIMG = 0, P1B_KFV = IMG, P1B_GBYTES = IMG + 2 * IMG + ONES_BYTES;          // 53248 B per group
 
-template <class F>
-__global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
+// CS = column split: CS threads share a tile row (= TMEM lane), each on 64 / CS of the accumulator columns, so a group is
+// 4 CS warps (warps w and w + 4 sit on the same TMEM lane quadrant).  The epilogues of this kernel are purely elementwise
+// (no row statistics), so the split needs no exchange between the threads of a row.
+template <class F, int CS>
+__global__ void __launch_bounds__(NGX * GX * CS, 1) pair_p1b_kernel(const P1Args a) {
+  constexpr int GT = GX * CS, NTHR = NGX * GT;                           // threads per group / per CTA
+  constexpr int QB = 4 / CS, CB = 8 / CS;                                // 16-column batches / 8-column chunks per thread
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[2 * NGX];
   __shared__ uint32_t tmem_base_s;
@@ -44,24 +50,33 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
     tc::fence_mbar_init();
   }
   if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
-  copy_to_smem(Wsm, a.W, P1B_WBYTES, threadIdx.x, NGX * GX);
+  copy_to_smem(Wsm, a.W, P1B_WBYTES, threadIdx.x, NTHR);
   cp_async_commit();
   cp_async_wait<0>();
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  GroupX g;
-  groupx_setup(g, bars, tmem_base_s);
-  uint64_t* bar2 = bars + NGX + g.gid;
+  const int warp_u = (int)tc::uniform(threadIdx.x >> 5);
+  const int gid = warp_u / (4 * CS), wg = warp_u % (4 * CS), gt = threadIdx.x % GT;
+  const int half = wg / 4;                                               // which part of the columns this thread owns
+  const int row = (wg % 4) * 32 + (threadIdx.x & 31);                    // tile row == TMEM lane
+  const bool issuer = wg == 0;
+  const uint32_t tmem = tc::uniform(tmem_base_s) + gid * 160;
+  const uint32_t tlane = tmem + ((uint32_t)((wg % 4) * 32) << 16);
+  uint64_t* bar = bars + gid;
+  uint32_t par = 0;
+  auto gsync = [&]() { tc::bar_sync(1 + gid, GT); };
+  auto publish = [&]() { tc::fence_async_smem(); tc::tc_fence_before(); gsync(); tc::tc_fence_after(); };
+  auto gwait = [&]() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); };
+  uint64_t* bar2 = bars + NGX + gid;
   uint32_t par2 = 0;
-  uint8_t* G = smem + P1B_WBYTES + g.gid * P1B_GBYTES;
+  uint8_t* G = smem + P1B_WBYTES + gid * P1B_GBYTES;
   uint8_t* Aimg = G + P1B_AIMG;
   uint8_t* KfV = G + P1B_KFV;
   {
     uint4* ones = reinterpret_cast<uint4*>(KfV + 2 * IMG);
-    ones[g.t] = make_uint4(F::ONE_LO, 0, 0, 0);
-    ones[128 + g.t] = make_uint4(0, 0, 0, 0);
+    for (int i = gt; i < 256; i += GT) ones[i] = i < 128 ? make_uint4(F::ONE_LO, 0, 0, 0) : make_uint4(0, 0, 0, 0);
   }
   const uint32_t sA = tc::smem_u32(Aimg), sKfV = tc::smem_u32(KfV), sW = tc::smem_u32(Wsm);
   const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
@@ -69,10 +84,9 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
   // Wkv image is [k/8][128 rows: Wk 0..63 | Wv 64..127][8]: an N=64 operand is the same image entered at row 0 / row 64
   const Opnd oA = A_IMG(sA), oWk = W_IMG(sW + P1B_WKV, 128), oWv = W_IMG(sW + P1B_WKV + 64 * 16, 128), oWm = W_IMG(sW + P1B_WM, 64),
              oKfV = opnd(sKfV, 128u, 2048u, 256u), oVones = opnd(sKfV + 8 * 2048, 128u, 2048u, 256u);
-  const int row = g.t;
   const uint32_t KVC = 64;                                                // TMEM columns [64, 144): KV / Ksum accumulator
 
-  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + g.gid;
+  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + gid;
   const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
   int so_next = u0 < u1 ? a.u_search[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
   bool prefetched = false;
@@ -81,25 +95,26 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
     if (u + 1 < u1) { so_next = a.u_search[u + 1]; slot_next = a.u_slot[u + 1]; }
     for (int tile = 0; tile < a.NT; ++tile) {
       const size_t ti = (size_t)so * a.NT + tile;
-      if (!prefetched) copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, g.t, GX);
+      if (!prefetched) copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile) * IMG, IMG, gt, GT);
       prefetched = false;
       cp_async_commit();
       {   // L2 prefetch of the image after this one (the shared-memory copy can only start once both projections have read Aimg)
         int ns = slot, nt = tile + 1;
         if (nt == a.NT) { ns = slot_next; nt = 0; }
-        if (nt != 0 || u + 1 < u1) prefetch_l2_16k(a.A_out + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG, g.t);
+        if ((nt != 0 || u + 1 < u1) && gt < 128) prefetch_l2_16k(a.A_out + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG, gt);
       }
       cp_async_wait<0>();
-      g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWk, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
-      g.wait();
+      publish();
+      if (issuer) { if (tc::elect_one()) { issue_gemm<4>(tmem, oA, oWk, id64, false); tc::umma_commit(bar); } __syncwarp(); }
+      gwait();
       if (tile > 0) { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }   // previous KV GEMM still reads KfV
       {   // Kf = elu(k)+1 -> chunks 0..7 ; zero for padding rows (point index >= npts): they must not enter KV / Ksum
         const bool keep = tile * 128 + row < a.npts;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int qq = 0; qq < QB; ++qq) {
+          const int q = half * QB + qq;
           uint32_t r[16];
-          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld16(tlane + 16 * q, r);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -112,26 +127,27 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
         }
       }
       tc::tc_fence_before();
-      g.sync();                                                           // everybody has read k before v overwrites the columns
+      gsync();                                                            // everybody has read k before v overwrites the columns
       tc::tc_fence_after();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWv, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      if (issuer) { if (tc::elect_one()) { issue_gemm<4>(tmem, oA, oWv, id64, false); tc::umma_commit(bar); } __syncwarp(); }
       {   // V = v + Wv pos -> chunks 8..15
-        uint4 sdPV[8];
-        load_side<8>(sdPV, a.PV + ti * IMG, 0, row);
-        g.wait();
+        uint4 sdPV[CB];
+        load_side<CB>(sdPV, a.PV + ti * IMG, half * CB, row);
+        gwait();
         if (tile + 1 < a.NT) {   // both projections have consumed `a`: stream the unit's next tile in behind the V epilogue + KV GEMM
-          copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile + 1) * IMG, IMG, g.t, GX);
+          copy_to_smem(Aimg, a.A_out + (((size_t)slot * 2 + a.role) * a.NT + tile + 1) * IMG, IMG, gt, GT);
           cp_async_commit();
           prefetched = true;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int qq = 0; qq < QB; ++qq) {
+          const int q = half * QB + qq;
           uint32_t r[16];
-          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld16(tlane + 16 * q, r);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
-            const uint4 s4 = sdPV[2 * q + c];
+            const uint4 s4 = sdPV[2 * qq + c];
             const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
             uint32_t w[4];
 #pragma unroll
@@ -141,9 +157,9 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
           }
         }
       }
-      g.publish();
-      if (g.issuer) {   // KV += [Kf|V]^T [V|1]
-        if (tc::elect_one()) { issue_gemm<8>(g.tmem + KVC, oKfV, oVones, idkv, tile > 0); tc::umma_commit(bar2); }
+      publish();
+      if (issuer) {   // KV += [Kf|V]^T [V|1]
+        if (tc::elect_one()) { issue_gemm<8>(tmem + KVC, oKfV, oVones, idkv, tile > 0); tc::umma_commit(bar2); }
         __syncwarp();
       }
     }
@@ -151,54 +167,57 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b_kernel(const P1Args a) {
     par2 ^= 1u;
     tc::tc_fence_after();
     {   // B7 = [head-split blockdiag(KV) Wm^T | Ksum dots] of this (pair, direction) as template
-      float kv[64];
+      float kv[64 / CS];
       float ksum = 0.f;
       if (row < 64) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int qq = 0; qq < QB; ++qq) {
           uint32_t r[16];
-          tc::tmem_ld16(g.tlane + KVC + 16 * q, r);
+          tc::tmem_ld16(tlane + KVC + 16 * (half * QB + qq), r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]) * a.kv_scale;
+          for (int j = 0; j < 16; ++j) kv[16 * qq + j] = __uint_as_float(r[j]) * a.kv_scale;
         }
         uint32_t r8[8];
-        tc::tmem_ld8(g.tlane + KVC + 64, r8);
+        tc::tmem_ld8(tlane + KVC + 64, r8);
         tc::tmem_ld_wait();
         ksum = __uint_as_float(r8[0]) * a.kv_scale;
         const int hd = row >> 5;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int cc = 0; cc < CB; ++cc) {
+          const int c = half * CB + cc;
           uint32_t w[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] = ((c >> 2) == hd) ? F::pack(kv[c * 8 + 2 * j], kv[c * 8 + 2 * j + 1]) : 0u;
+          for (int j = 0; j < 4; ++j) w[j] = ((c >> 2) == hd) ? F::pack(kv[cc * 8 + 2 * j], kv[cc * 8 + 2 * j + 1]) : 0u;
           *reinterpret_cast<uint4*>(Aimg + c * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(Aimg + c * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+        for (int cc = 0; cc < CB; ++cc) *reinterpret_cast<uint4*>(Aimg + (half * CB + cc) * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
       }
-      g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oA, oWm, id64, false); tc::umma_commit(g.bar); } __syncwarp(); }
-      g.wait();
+      publish();
+      if (issuer) { if (tc::elect_one()) { issue_gemm<4>(tmem, oA, oWm, id64, false); tc::umma_commit(bar); } __syncwarp(); }
+      gwait();
       if (u + 1 < u1) {   // G6 has consumed the operand buffer: the next unit's first tile streams in behind the B7 write-out
-        copy_to_smem(Aimg, a.A_out + ((size_t)slot_next * 2 + a.role) * a.NT * IMG, IMG, g.t, GX);
+        copy_to_smem(Aimg, a.A_out + ((size_t)slot_next * 2 + a.role) * a.NT * IMG, IMG, gt, GT);
         cp_async_commit();
         prefetched = true;
       }
       if (row < 64) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int qq = 0; qq < QB; ++qq) {
           uint32_t r[16];
-          tc::tmem_ld16(g.tlane + 16 * q, r);
+          tc::tmem_ld16(tlane + 16 * (half * QB + qq), r);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]);
+          for (int j = 0; j < 16; ++j) kv[16 * qq + j] = __uint_as_float(r[j]);
         }
-        write_b7_row<F>(kv, ksum, row, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
+        uint8_t* dst = a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES;
+        if constexpr (CS == 1) write_b7_row<F>(kv, ksum, row, dst);
+        else write_b7_part<F>(kv, 4 * half, ksum, half == 0, row, dst);
       }
       tc::tc_fence_before();
-      g.sync();
+      gsync();
     }
   }
   tc::tc_fence_before();
@@ -246,12 +265,18 @@ __global__ void __launch_bounds__(64) pack_b7_kernel(const float* __restrict__ M
 
 }  // namespace
 
+template <class F, int CS>
+static int launch_p1b_cs(const P1Args& a, int grid, cudaStream_t st) {
+  const int smem = P1B_WBYTES + NGX * P1B_GBYTES;
+  cudaFuncSetAttribute(pair_p1b_kernel<F, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p1b_kernel<F, CS><<<grid, NGX * GX * CS, smem, st>>>(a);
+  return pcreid_launch_status();
+}
 template <class F>
 static int launch_p1b(const P1Args& a, int grid, cudaStream_t st) {
-  const int smem = P1B_WBYTES + NGX * P1B_GBYTES;
-  cudaFuncSetAttribute(pair_p1b_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p1b_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
-  return pcreid_launch_status();
+  // A/B: PCREID_P1B_SPLIT=2 -> two threads per tile row (8-warp groups, column-split epilogues)
+  static const int cs = [] { const char* e = getenv("PCREID_P1B_SPLIT"); return e ? atoi(e) : 1; }();
+  return cs == 2 ? launch_p1b_cs<F, 2>(a, grid, st) : launch_p1b_cs<F, 1>(a, grid, st);
 }
 
 extern "C" {
