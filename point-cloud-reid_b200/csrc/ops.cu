@@ -6,8 +6,9 @@
 //                k rounds of warp arg-min (two REDUX per round), canonical (d, idx) ascending order;
 //                exact-tie queries of the mmdet3d op fall back to an in-warp emulation of the
 //                reference heap so indices stay bit-identical   (ref: ops/knn/src/knn_cuda.cu:58-94)
-//   fps          one CTA (or one warp) per object, coordinates and running min-distances in
-//                registers, block arg-max with the reference's tie rule
+//   fps          one warp / CTA per object, coordinates in shared memory in tie-priority order, running
+//                min-distances in registers, arg-max = REDUX.MAX over value bits + REDUX.MIN over slots
+//                (fps_rank_kernel; fps_kernel keeps everything in registers for the with-dist form)
 //                                                  (ref: ops/furthest_point_sample/src/furthest_point_sample_cuda.cu:25-141)
 //   ball_query   one warp per query, ballot + prefix popcount keeps index order
 //                                                  (ref: ops/ball_query/src/ball_query_cuda.cu:11-54)

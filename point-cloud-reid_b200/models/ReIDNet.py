@@ -221,7 +221,8 @@ class ReIDNet(nn.Module):
                 self._encode(static_in)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: other host threads (the NCCL watchdog of a multi-rank job) may touch the CUDA API during the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 static_out = self._encode(static_in)
             ent = (ver, g, static_in, static_out)
             self._graphs[key] = ent
@@ -386,7 +387,8 @@ class ReIDNet(nn.Module):
                 self._match_all_pairs(*static)
             torch.cuda.current_stream().wait_stream(side)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: other host threads (the NCCL watchdog of a multi-rank job) may touch the CUDA API during the capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 static_out = self._match_all_pairs(*static)
             ent = (ver, g, static, static_out)
             self._graphs[key] = ent
