@@ -19,6 +19,7 @@
 //     running partials in registers across the tiles of a unit;
 //   * accumulators are read with 32-column tcgen05.ld and one wait per batch.
 #include "pair_common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -39,7 +40,11 @@ __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 
 // Attention accumulator (columns [0,64) head 0, [64,128) head 1, 128/129 the two Q.Ksum dots) -> LayerNorm1-normalised
 // merged message WITHOUT affine (folded into the next GEMM), packed to bf16 into this thread's row of an operand image.
-template <class F>
+// XT: X' goes to tensor-memory columns [128, 160) of this thread's lane (the TMEM-sourced A operand of the next GEMM's X' K-steps)
+// instead of the shared-memory image: the attention accumulator's dot columns 128 / 129 are read before they are overwritten, and
+// a lane is only ever touched by its own thread.  Saves the 16 KB image store and the tensor core's 4 x 4 KB operand reads per
+// tile on the shared-memory pipe, the most loaded unit of these kernels.
+template <class F, bool XT = false>
 __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row, float att_eps) {
   uint32_t d8[8], a0[32], a1[32], b0[32], b1[32];
   tc::tmem_ld8(tl + 128, d8);
@@ -68,6 +73,17 @@ __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row, flo
     ss3 = fmaf(m1[j + 1], m1[j + 1], ss3);
   }
   const float rstd = rsqrtf(((ss0 + ss1) + (ss2 + ss3)) * (1.f / 64.f) + LN_EPS * d0 * d0);
+  if constexpr (XT) {
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      w[j] = F::pack(m0[2 * j] * rstd, m0[2 * j + 1] * rstd);
+      w[16 + j] = F::pack(m1[2 * j] * rstd, m1[2 * j + 1] * rstd);
+    }
+    tc::tmem_st32(tl + 128, w);
+    tc::tmem_st_wait();
+    return;
+  }
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t w[4], v[4];
@@ -100,7 +116,7 @@ __device__ __forceinline__ float ld64_sumsq(uint32_t tl, uint32_t (&x0)[32], uin
 // ---------------------------------------------------------------------------------------------------------------
 // phase 1a: G1 attention (Qf1_i x MK1_j) -> LN1 -> G2 = [X' | h + beta2 | 1] W0'^T, ReLU (TMEM-resident) -> G3 -> LN2 + (h + beta2) -> a
 // ---------------------------------------------------------------------------------------------------------------
-template <class F>
+template <class F, bool XT>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
@@ -163,11 +179,20 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
       const size_t ti = (size_t)so * a.NT + tile;
       if (u == u0 && tile == 0) start_tile(ti, te);                       // every later tile was started by its predecessor
       g.wait();
-      epi_attn_norm<F>(g.tlane, xrow, a.att_eps);                                       // X' over the query image
+      epi_attn_norm<F, XT>(g.tlane, xrow, a.att_eps);                                   // X' over the query image / into TMEM
       g.publish();
       if (g.issuer) {
         if (tc::elect_one()) {
-          issue_gemm<8>(g.tmem, oQXa, oW0, id128, false);                                            // [X' | h + beta2]
+          if constexpr (XT) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)                                                           // X' K-steps: A from tensor memory
+              tc::umma_f16_ts(g.tmem, g.tmem + 128 + 8 * ks, oW0.desc + (uint64_t)(ks * oW0.kstep), id128, ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int ks = 4; ks < 8; ++ks)                                                           // h + beta2 K-steps: shared memory
+              tc::umma_f16(g.tmem, oQXa.desc + (uint64_t)(ks * oQXa.kstep), oW0.desc + (uint64_t)(ks * oW0.kstep), id128, 1u);
+          } else {
+            issue_gemm<8>(g.tmem, oQXa, oW0, id128, false);                                          // [X' | h + beta2]
+          }
           tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);         // + W0b.beta1 - W0a.beta2
           tc::umma_commit(g.bar);
         }
@@ -248,7 +273,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
 // ---------------------------------------------------------------------------------------------------------------
 // phase 2: q projection -> attention against B7 -> LN1 -> [a | X' | 1] W0'^T, ReLU (TMEM-resident) -> W2 -> LN2 + a -> pooling
 // ---------------------------------------------------------------------------------------------------------------
-template <class F>
+template <class F, bool XT>
 __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NGX];
@@ -344,11 +369,18 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);
         cp_async_commit();
       }
-      epi_attn_norm<F>(g.tlane, arow + IMG, a.att_eps);                                 // X' next to a: [a | X' | 1] is the K = 144 operand
+      epi_attn_norm<F, XT>(g.tlane, arow + IMG, a.att_eps);                             // X' (XT: in tensor memory): [a | X' | 1] is the K = 144 operand
       g.publish();
       if (g.issuer) {
         if (tc::elect_one()) {
-          issue_gemm<8>(g.tmem, oR1, oW0, id128, false);
+          if constexpr (XT) {
+            issue_gemm<4>(g.tmem, oR1, oW0, id128, false);                                          // a K-steps: shared memory
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)                                                          // X' K-steps: A from tensor memory
+              tc::umma_f16_ts(g.tmem, g.tmem + 128 + 8 * ks, oW0.desc + (uint64_t)((4 + ks) * oW0.kstep), id128, 1u);
+          } else {
+            issue_gemm<8>(g.tmem, oR1, oW0, id128, false);
+          }
           tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);      // + W0b.beta1
           tc::umma_commit(g.bar);
         }
@@ -520,20 +552,37 @@ __global__ void __launch_bounds__(256) pack_image_bias_kernel(int B, int C, int 
 
 }  // namespace
 
-template <class F>
-static int launch_p1a2(const P1Args& a, int grid, cudaStream_t st) {
-  const int smem = Q1A_ONES + 4096 + NGX * Q1A_GBYTES;
-  cudaFuncSetAttribute(pair_p1a2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p1a2_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
-  return pcreid_launch_status();
+// The LayerNorm1 output X' of phase 1a (bit 0) / phase 2 (bit 1) goes to tensor memory instead of its shared-memory operand image:
+// bit-identical results, phase 1a -8 %, phase 2 -2 % (profiles/r02_x_tmem_ab.json).  A/B: PCREID_X_TMEM=0 restores the images.
+// (Tried on top and dropped: phase 2's queries in tensor memory as well, with the Q.Ksum dots as 64 SIMT FMAs per row -- the
+// extra issue slots cost more than the 32 KB per tile saved on the shared-memory pipe: +1-2 % on phase 2.)
+static int x_tmem_mask() {
+  static const int m = [] { const char* e = getenv("PCREID_X_TMEM"); return e ? atoi(e) : 3; }();
+  return m;
 }
 
+template <class F, bool XT>
+static int launch_p1a2_x(const P1Args& a, int grid, cudaStream_t st) {
+  const int smem = Q1A_ONES + 4096 + NGX * Q1A_GBYTES;
+  cudaFuncSetAttribute(pair_p1a2_kernel<F, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p1a2_kernel<F, XT><<<grid, NGX * GX, smem, st>>>(a);
+  return pcreid_launch_status();
+}
+template <class F>
+static int launch_p1a2(const P1Args& a, int grid, cudaStream_t st) {
+  return (x_tmem_mask() & 1) ? launch_p1a2_x<F, true>(a, grid, st) : launch_p1a2_x<F, false>(a, grid, st);
+}
+
+template <class F, bool XT>
+static int launch_p2y_x(const P2Args& a, int grid, cudaStream_t st) {
+  const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;
+  cudaFuncSetAttribute(pair_p2y_kernel<F, XT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  pair_p2y_kernel<F, XT><<<grid, NGX * GX, smem, st>>>(a);
+  return pcreid_launch_status();
+}
 template <class F>
 static int launch_p2y(const P2Args& a, int grid, cudaStream_t st) {
-  const int smem = Q2_ONES + 4096 + NGX * Q2_GBYTES;
-  cudaFuncSetAttribute(pair_p2y_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  pair_p2y_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
-  return pcreid_launch_status();
+  return (x_tmem_mask() & 2) ? launch_p2y_x<F, true>(a, grid, st) : launch_p2y_x<F, false>(a, grid, st);
 }
 
 extern "C" {
