@@ -262,7 +262,7 @@ int pcreid_pair_concat_head(int T, int D, int E, int G, const float* A, const fl
 int pcreid_pack_image(int B, int C, int N, const float* src, long long s_bs, int lds, int act, int fmt, void* dst, void* stream);
 int pcreid_pack_image_bias(int B, int C, int N, const float* src, long long s_bs, int lds, const float* bias, int fmt, void* dst,
                            void* stream);
-/* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 18432 bytes) */
+/* M (B,64,64) = blockdiag(KV) Wm^T rows + ksum (B,64) -> attention operand images (B, 10240 bytes: one [10][32][8] 16-bit image per head) */
 int pcreid_pack_b7(int B, const float* M, const float* ksum, int fmt, void* dst, void* stream);
 /* pool_part (P,2,128) -> pooled^T (128,P): max | mean over the 2*npts points of the point-cat pair tensor (+ beta2) */
 int pcreid_pool_finish2(int P, int npts, const float* part, const float* bias /* (64) or NULL */, float* out, void* stream);

@@ -10,8 +10,14 @@ namespace {
 
 
 constexpr int IMG = 16384;              // bytes of a 128 x 64 bf16 operand image  [k/8][row][8]
-constexpr int NB7 = 144;                // columns of the attention operand: 64 (head 0) | 64 (head 1) | 16 (2 dots + pad)
-constexpr int B7_BYTES = (NB7 / 8) * 64 * 16;   // [n/8][k][8] bf16 = 18432
+// Attention operand of a template (stage 1: MK1 per object, stage 2: B7 per (pair, direction)), one image PER HEAD:
+//   head h: [n/8 (10 chunks)][k - 32 h (32 rows)][8]   columns 0..63 = (blockdiag(KV) Wm^T)[k][:], column 64 = Ksum[k], 65..79 = 0
+// Head h's queries (A K-steps 2h, 2h+1) meet only their own 32 k-rows: two N = 80, K = 32 GEMMs into accumulator columns
+// [0, 80) and [80, 160) instead of one N = 144, K = 64 GEMM against an image that was half structural zeros (18 KB -> 10 KB
+// per operand in HBM and shared memory, 18.4 -> 10 KB of tensor-core operand reads per tile; the sums are bit-identical).
+constexpr int NB7H = 80;                // columns per head: 64 merged output channels | Q.Ksum dot | pad
+constexpr int B7_HEAD = (NB7H / 8) * 32 * 16;   // 5120 B per head
+constexpr int B7_BYTES = 2 * B7_HEAD;           // 10240
 constexpr int ONES_BYTES = 2 * 2048;    // two extra 8-column chunks appended to V: column 64 == 1 (Ksum), rest 0
 constexpr float LN_EPS = 1e-5f;
 
@@ -74,7 +80,7 @@ __device__ __forceinline__ Opnd opnd(uint32_t addr, uint32_t lbo, uint32_t sbo, 
 // operand geometry (bytes): K-major activation image (128 rows), K-major weight image (N rows), MN-major attention operand
 #define A_IMG(addr) opnd((addr), 2048u, 128u, 4096u)
 #define W_IMG(addr, N) opnd((addr), (uint32_t)((N)*16), 128u, (uint32_t)(2 * (N)*16))
-#define B7_IMG(addr) opnd((addr), 128u, 1024u, 256u)
+#define B7_IMG(addr) opnd((addr), 128u, 512u, 256u)      /* one head: MN-major, 32 k-rows per 8-column chunk */
 
 // one thread: D[tmem_d] (+)= A x B^T over KSTEPS K=16 steps
 template <int KSTEPS>
@@ -91,25 +97,21 @@ __device__ __forceinline__ void load_side(uint4 (&sd)[NCH], const uint8_t* __res
   for (int c = 0; c < NCH; ++c) sd[c] = __ldg(reinterpret_cast<const uint4*>(img + (chunk0 + c) * 2048 + row * 16));
 }
 
-// chunks [c_lo, c_hi) of row d of the stage operand B7 / MK1 = [ head0: M[d][:] | head1: M[d][:] | ksum dots | 0 ]
-// (MN-major image [n/8][k=d][8]); M32 holds M[d][8*c_lo .. 8*c_hi)
+// chunks [c_lo, c_lo + 4) of row d (= k) of the stage operand B7 / MK1: M32 holds M[d][8*c_lo .. 8*c_lo + 32); the row lives in
+// the image of head d >> 5 only
 template <class F>
 __device__ __forceinline__ void write_b7_part(const float (&M32)[32], int c_lo, float ksum, bool tail, int d, uint8_t* dst) {
-  const int hd = d >> 5;
-  const uint4 zero = make_uint4(0, 0, 0, 0);
+  uint8_t* base = dst + (d >> 5) * B7_HEAD + (d & 31) * 16;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) w[j] = F::pack(M32[c * 8 + 2 * j], M32[c * 8 + 2 * j + 1]);
-    const uint4 val = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(dst + (c_lo + c) * 1024 + d * 16) = hd == 0 ? val : zero;
-    *reinterpret_cast<uint4*>(dst + (8 + c_lo + c) * 1024 + d * 16) = hd == 1 ? val : zero;
+    *reinterpret_cast<uint4*>(base + (c_lo + c) * 512) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   if (tail) {
-    *reinterpret_cast<uint4*>(dst + 16 * 1024 + d * 16) =
-        make_uint4(hd == 0 ? F::pack(ksum, 0.f) : F::pack(0.f, ksum), 0, 0, 0);
-    *reinterpret_cast<uint4*>(dst + 17 * 1024 + d * 16) = zero;
+    *reinterpret_cast<uint4*>(base + 8 * 512) = make_uint4(F::pack(ksum, 0.f), 0, 0, 0);
+    *reinterpret_cast<uint4*>(base + 9 * 512) = make_uint4(0, 0, 0, 0);
   }
 }
 

@@ -29,31 +29,43 @@ namespace {
 // to read (32 KB) and add in the epilogue (the constant W0a.beta2 this adds is taken back out through the bias K step).
 constexpr int Q1A_W0 = 0, Q1A_W2 = 18 * 2048, Q1A_LN = Q1A_W2 + 16384, Q1A_WBYTES = Q1A_LN + 256;   // 53504
 constexpr int Q1A_ONES = Q1A_WBYTES;                                                         // 4 KB: A chunk pair, k = 0 is 1.0
-constexpr int Q1A_QXA = 0, Q1A_H = IMG, Q1A_MK1 = 2 * IMG, Q1A_GBYTES = 2 * IMG + B7_BYTES;  // 51200 B per group
+constexpr int Q1A_QXA = 0, Q1A_H = IMG, Q1A_MK1 = 2 * IMG, Q1A_GBYTES = 2 * IMG + B7_BYTES;  // 43008 B per group
 // weights blob of phase 2: Wq/bf16(ln2) image (N=64, K=64) | [W0a | W0b.diag(g1) | W0b.beta1 | 0] image (N=128, K=144) |
 // centred W2 image (N=64, K=128) | LN2 gamma (64 fp32)
 constexpr int Q2_WQ = 0, Q2_W0 = 8192, Q2_W2 = Q2_W0 + 18 * 2048, Q2_LN = Q2_W2 + 16384, Q2_WBYTES = Q2_LN + 256;   // 61696
 constexpr int Q2_ONES = Q2_WBYTES;                                                           // 4 KB: A chunk pair, k = 0 is 1.0
-constexpr int Q2_R1 = 0, Q2_B7 = 2 * IMG, Q2_GBYTES = Q2_B7 + B7_BYTES;                      // 51200 B per group
+constexpr int Q2_R1 = 0, Q2_B7 = 2 * IMG, Q2_GBYTES = Q2_B7 + B7_BYTES;                      // 43008 B per group
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 
-// Attention accumulator (columns [0,64) head 0, [64,128) head 1, 128/129 the two Q.Ksum dots) -> LayerNorm1-normalised
+// one thread: the attention GEMM of a tile -- head h's queries (A K-steps 2h, 2h + 1 of the query image) against head h's image
+// of the template operand (32 k-rows, N = 80) -> accumulator columns [80 h, 80 h + 80)
+__device__ __forceinline__ void issue_attn(uint32_t tmem_d, const Opnd& Q, const Opnd& T, uint32_t id80) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      tc::umma_f16(tmem_d + NB7H * h, Q.desc + (uint64_t)((2 * h + ks) * Q.kstep), T.desc + (uint64_t)((B7_HEAD >> 4) * h + ks * T.kstep),
+                   id80, ks > 0 ? 1u : 0u);
+}
+
+// Attention accumulator (columns [0,64) head 0 | 64 its Q.Ksum dot, [80,144) head 1 | 144 its dot) -> LayerNorm1-normalised
 // merged message WITHOUT affine (folded into the next GEMM), packed to bf16 into this thread's row of an operand image.
 // XT: X' goes to tensor-memory columns [128, 160) of this thread's lane (the TMEM-sourced A operand of the next GEMM's X' K-steps)
-// instead of the shared-memory image: the attention accumulator's dot columns 128 / 129 are read before they are overwritten, and
-// a lane is only ever touched by its own thread.  Saves the 16 KB image store and the tensor core's 4 x 4 KB operand reads per
+// instead of the shared-memory image: the attention accumulator's columns there (head 1's tail and dot) are read before they are
+// overwritten, and a lane is only ever touched by its own thread.  Saves the 16 KB image store and the tensor core's 4 x 4 KB operand reads per
 // tile on the shared-memory pipe, the most loaded unit of these kernels.
 template <class F, bool XT = false>
 __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row, float att_eps) {
-  uint32_t d8[8], a0[32], a1[32], b0[32], b1[32];
-  tc::tmem_ld8(tl + 128, d8);
+  uint32_t d8[8], e8[8], a0[32], a1[32], b0[32], b1[32];
+  tc::tmem_ld8(tl + 64, d8);
+  tc::tmem_ld8(tl + 144, e8);
   tc::tmem_ld32(tl, a0);
-  tc::tmem_ld32(tl + 64, a1);
+  tc::tmem_ld32(tl + 80, a1);
   tc::tmem_ld_wait();
   tc::tmem_ld32(tl + 32, b0);                                   // in flight while the first half is processed
-  tc::tmem_ld32(tl + 96, b1);
-  const float d0 = u2f(d8[0]) + att_eps, d1 = u2f(d8[1]) + att_eps;
+  tc::tmem_ld32(tl + 112, b1);
+  const float d0 = u2f(d8[0]) + att_eps, d1 = u2f(e8[0]) + att_eps;
   const float r = __fdividef(d0, d1);
   float ss0 = 0.f, ss1 = 0.f, ss2 = 0.f, ss3 = 0.f;
   float m0[32], m1[32];
@@ -82,18 +94,18 @@ __device__ __forceinline__ void epi_attn_norm(uint32_t tl, uint8_t* dst_row, flo
     }
     tc::tmem_st32(tl + 128, w);
     tc::tmem_st_wait();
-    return;
-  }
+  } else {
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint32_t w[4], v[4];
+    for (int c = 0; c < 4; ++c) {
+      uint32_t w[4], v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      w[j] = F::pack(m0[c * 8 + 2 * j] * rstd, m0[c * 8 + 2 * j + 1] * rstd);
-      v[j] = F::pack(m1[c * 8 + 2 * j] * rstd, m1[c * 8 + 2 * j + 1] * rstd);
+      for (int j = 0; j < 4; ++j) {
+        w[j] = F::pack(m0[c * 8 + 2 * j] * rstd, m0[c * 8 + 2 * j + 1] * rstd);
+        v[j] = F::pack(m1[c * 8 + 2 * j] * rstd, m1[c * 8 + 2 * j + 1] * rstd);
+      }
+      *reinterpret_cast<uint4*>(dst_row + c * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(dst_row + (4 + c) * 2048) = make_uint4(v[0], v[1], v[2], v[3]);
     }
-    *reinterpret_cast<uint4*>(dst_row + c * 2048) = make_uint4(w[0], w[1], w[2], w[3]);
-    *reinterpret_cast<uint4*>(dst_row + (4 + c) * 2048) = make_uint4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   uint8_t* Hs = G + Q1A_H;
   uint8_t* MK1 = G + Q1A_MK1;
   const uint32_t sQXa = tc::smem_u32(QXa), sW = tc::smem_u32(Wsm);
-  const uint32_t id144 = tc::instr_desc(128, NB7, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id80 = tc::instr_desc(128, NB7H, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
   const uint32_t id128 = tc::instr_desc(128, 128, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   // QXa and Hs are adjacent: one K-major A operand of 8 K steps [X' | h + beta2]
@@ -170,7 +182,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
     cp_async_commit();
     cp_async_wait<0>();
     g.publish();
-    if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQXa, oMK1, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+    if (g.issuer) { if (tc::elect_one()) { issue_attn(g.tmem, oQXa, oMK1, id80); tc::umma_commit(g.bar); } __syncwarp(); }
   };
   for (int u = u0; u < u1; ++u) {
     const int so = so_next, te = te_next, slot = slot_next;
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   uint8_t* R1 = G + Q2_R1;
   uint8_t* B7 = G + Q2_B7;
   const uint32_t sR1 = tc::smem_u32(R1), sW = tc::smem_u32(Wsm);
-  const uint32_t id144 = tc::instr_desc(128, NB7, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
+  const uint32_t id80 = tc::instr_desc(128, NB7H, F::FMT, tc::MAJOR_K, tc::MAJOR_MN);
   const uint32_t id128 = tc::instr_desc(128, 128, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
   const Opnd oR1 = A_IMG(sR1), oQf = A_IMG(sR1 + IMG), oOnes = A_IMG(tc::smem_u32(smem + Q2_ONES)), oWq = W_IMG(sW + Q2_WQ, 64),
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         int ns = slot, nt = tile + 1;
         if (nt == a.NT) { ns = slot_next; nt = 0; }
         if (nt != 0 || u + 1 < u1) prefetch_l2_16k(a.A_in + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG, g.t);
-        if (tile == 0 && u + 1 < u1) prefetch_l2_16k(a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, g.t);
+        if (tile == 0 && u + 1 < u1 && g.t < B7_BYTES / 128) prefetch_l2_16k(a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, g.t);
       }
       g.wait();
       {   // Qf = elu(q)+1 -> second half of R1
@@ -363,7 +375,7 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
         }
       }
       g.publish();
-      if (g.issuer) { if (tc::elect_one()) { issue_gemm<4>(g.tmem, oQf, oB7, id144, false); tc::umma_commit(g.bar); } __syncwarp(); }
+      if (g.issuer) { if (tc::elect_one()) { issue_attn(g.tmem, oQf, oB7, id80); tc::umma_commit(g.bar); } __syncwarp(); }
       g.wait();
       if (tile + 1 == a.NT && u + 1 < u1) {   // last attention GEMM of the unit is done: next unit's B7 streams in
         copy_to_smem(B7, a.B7_in + ((size_t)slot_next * 2 + (1 - a.role)) * B7_BYTES, B7_BYTES, g.t, GX);

@@ -11,7 +11,7 @@ modes of ReIDNet.match_all_pairs / match_forward_inference:
 Everything that depends on one object only is computed once per object with the fp32 kernels and packed to 16-bit
 operand images (stage-1 queries elu(Wq1 h)+1, h + beta2, Wv2 pos2(xyz), and the stage-1 attention operand
 MK1 = [head-split blockdiag(KV1) Wm1^T | Ksum1]); the three fused kernels then score pairs without writing any per-pair
-activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and the stage-2 attention operands (36 KB / pair).
+activation except the 16-bit stage-1 outputs (64 KB / pair at 256 points) and the stage-2 attention operands (20 KB / pair).
 Reference: ReIDNet.xcorr_eff + get_pooled_feats + match_head (mmdet3d/models/ReIDNet.py:231-247, 526-534, 444-453).
 """
 import math
@@ -24,7 +24,9 @@ from .. import torch_ops as _T
 from ._packing import kmajor
 
 IMG = 16384
-B7_BYTES = 18432
+# attention operand: one [10 n-chunks][32 k][8] 16-bit image per head (pair_common.cuh B7_BYTES; the override exists for A/B runs
+# against an older build of the library, scripts/gpu_prev_ab.sh)
+B7_BYTES = int(os.environ.get("PCREID_B7_BYTES", 10240))
 FMT_BF16, FMT_F16 = 0, 1
 LN2H = 0.693359375        # f16(ln 2): the same for the packed f16x2 A/B build (PCREID_F16_PACKED=1)
 LN2B = 0.69140625          # bf16(ln 2): the packed elu epilogue of the bf16 kernels multiplies by this constant
@@ -214,6 +216,8 @@ def decode_image(img, dtype=torch.bfloat16):
 
 
 def decode_b7(img, dtype=torch.bfloat16):
-    """(..., 18432) uint8 attention operand -> (..., 64 k, 144 n) fp32 (debug / tests)."""
-    x = img.contiguous().view(dtype).float().reshape(*img.shape[:-1], 18, 64, 8)   # [n/8][k][8]
-    return x.permute(*range(x.dim() - 3), x.dim() - 2, x.dim() - 3, x.dim() - 1).reshape(*img.shape[:-1], 64, 144)
+    """(..., 10240) uint8 attention operand -> (..., 2 heads, 32 k, 80 n) fp32 (debug / tests): n < 64 merged output channels,
+    n = 64 the head's Ksum entry."""
+    x = img.contiguous().view(dtype).float().reshape(*img.shape[:-1], 2, 10, 32, 8)   # [head][n/8][k][8]
+    nd = x.dim()
+    return x.permute(*range(nd - 3), nd - 2, nd - 3, nd - 1).reshape(*img.shape[:-1], 2, 32, 80)

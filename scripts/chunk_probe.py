@@ -43,6 +43,6 @@ for chunk in (65536, 16384, 4096, 2048, 1024, 512):
     fn()
     e3.record()
     torch.cuda.synchronize()
-    print(json.dumps({"chunk_pairs": chunk, "scratch_MB": chunk * (2 * 2 * 16384 + 2 * 18432 + 1024) / 1e6, "kernels_ms": k,
+    print(json.dumps({"chunk_pairs": chunk, "scratch_MB": chunk * (2 * 2 * 16384 + 2 * 10240 + 1024) / 1e6, "kernels_ms": k,
                       "kernels_sum_ms": sum(k.values()), "wall_ms_with_events": e0.elapsed_time(e1), "wall_ms": e2.elapsed_time(e3),
                       "bit_identical_to_first": same}), flush=True)
