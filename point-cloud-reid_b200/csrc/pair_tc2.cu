@@ -38,6 +38,22 @@ constexpr int Q2_R1 = 0, Q2_B7 = 2 * IMG, Q2_GBYTES = Q2_B7 + B7_BYTES;         
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 
+// The three groups use 3 x 160 of the CTA's 512 tensor-memory columns; columns [480, 512) hold ONE constant A operand for all of
+// them: element k = 0 of every row is 1.0 (the K = 16 step that adds the folded LayerNorm1 bias).  Written once by group 0
+// (thread == lane); the caller's __syncthreads publishes it.
+template <class F>
+__device__ __forceinline__ void tmem_ones(const GroupX& g) {
+  if (g.gid == 0) {
+    uint32_t w[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) w[j] = 0u;
+    w[0] = F::ONE_LO;
+    tc::tmem_st32(g.tlane + 480, w);
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+}
+
 // one thread: the attention GEMM of a tile -- head h's queries (A K-steps 2h, 2h + 1 of the query image) against head h's image
 // of the template operand (32 k-rows, N = 80) -> accumulator columns [80 h, 80 h + 80)
 __device__ __forceinline__ void issue_attn(uint32_t tmem_d, const Opnd& Q, const Opnd& T, uint32_t id80) {
@@ -151,6 +167,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
   tc::tc_fence_after();
   GroupX g;
   groupx_setup(g, bars, tmem_base_s);
+  const uint32_t t_ones = tc::uniform(tmem_base_s) + 480;        // XT: the bias K-step's constant A operand lives in the spare columns
+  if constexpr (XT) { tmem_ones<F>(g); __syncthreads(); tc::tc_fence_after(); }
   uint8_t* G = smem + Q1A_ONES + 4096 + g.gid * Q1A_GBYTES;
   uint8_t* QXa = G + Q1A_QXA;
   uint8_t* Hs = G + Q1A_H;
@@ -205,7 +223,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1a2_kernel(const P1Args a) 
           } else {
             issue_gemm<8>(g.tmem, oQXa, oW0, id128, false);                                          // [X' | h + beta2]
           }
-          tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);         // + W0b.beta1 - W0a.beta2
+          if constexpr (XT) tc::umma_f16_ts(g.tmem, t_ones, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);
+          else tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);    // + W0b.beta1 - W0a.beta2
           tc::umma_commit(g.bar);
         }
         __syncwarp();
@@ -309,6 +328,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
   tc::tc_fence_after();
   GroupX g;
   groupx_setup(g, bars, tmem_base_s);
+  const uint32_t t_ones = tc::uniform(tmem_base_s) + 480;        // XT: the bias K-step's constant A operand lives in the spare columns
+  if constexpr (XT) { tmem_ones<F>(g); __syncthreads(); tc::tc_fence_after(); }
   const int warp_in_group = (int)tc::uniform(threadIdx.x >> 5) % 4;
   uint8_t* G = smem + Q2_ONES + 4096 + g.gid * Q2_GBYTES;
   uint8_t* R1 = G + Q2_R1;
@@ -393,7 +414,8 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p2y_kernel(const P2Args a) {
           } else {
             issue_gemm<8>(g.tmem, oR1, oW0, id128, false);
           }
-          tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);      // + W0b.beta1
+          if constexpr (XT) tc::umma_f16_ts(g.tmem, t_ones, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);
+          else tc::umma_f16(g.tmem, oOnes.desc, oW0.desc + (uint64_t)(8 * oW0.kstep), id128, 1u);   // + W0b.beta1
           tc::umma_commit(g.bar);
         }
         __syncwarp();
