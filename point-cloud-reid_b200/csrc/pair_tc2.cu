@@ -602,6 +602,9 @@ static int launch_p1a2_x(const P1Args& a, int grid, cudaStream_t st) {
   pair_p1a2_kernel<F, XT><<<grid, NGX * GX, smem, st>>>(a);
   return pcreid_launch_status();
 }
+// Tried and dropped (profiles/r02_unit_order_ab.json): a phase-1a loop that keeps the SEARCH tile resident and streams the 10 KB
+// template operands past it through a double buffer (37 -> 10 KB of cp.async fill per tile): 8 % slower than this per-unit loop,
+// whose units run in order of equal TEMPLATE -- the fills are not what loads the shared-memory pipe.
 template <class F>
 static int launch_p1a2(const P1Args& a, int grid, cudaStream_t st) {
   return (x_tmem_mask() & 1) ? launch_p1a2_x<F, true>(a, grid, st) : launch_p1a2_x<F, false>(a, grid, st);

@@ -169,13 +169,22 @@ class FusedXcorr:
         dev = pt.H.device
         if self.n_ctas is None or self._n_ctas_dev != dev:          # SM count of the device the operands live on
             self.n_ctas, self._n_ctas_dev = torch.cuda.get_device_properties(dev).multi_processor_count, dev
+        # unit order: phase 1a keeps the TEMPLATE operand in shared memory across units -> runs of equal template; phase 1b reads
+        # per-pair images by slot and the search object's position term -> runs of equal search object, slots ascending
+        # (-3.5 ... -5 % on pair_p1b, profiles/r02_unit_order_ab.json; A/B: PCREID_P1B_ORDER=templ)
+        by_search = False
+        b_by_search = os.environ.get("PCREID_P1B_ORDER", "search") == "search"
         if dense is not None:
             r0, nrows, Dn = dense
             P = nrows * Dn
             u = torch.arange(P, device=dev, dtype=torch.int32)
-            t_of, d_of = r0 + u % nrows, u // nrows                          # role 0: runs of equal detection (template)
-            unit_lists = ((t_of, d_of, (t_of - r0) * Dn + d_of),             # (search, template, slot)
-                          (u % Dn, r0 + u // Dn, u))                          # role 1: row-major order is already sorted by track
+            t_of, d_of = r0 + u % nrows, u // nrows
+            lists_s = ((r0 + u // Dn, u % Dn, u),                                      # role 0 (search, template, slot): row-major
+                       (u // nrows, r0 + u % nrows, (u % nrows) * Dn + u // nrows))       # role 1: detection-major
+            lists_t = ((t_of, d_of, (t_of - r0) * Dn + d_of),                           # role 0: runs of equal detection (template)
+                       (u % Dn, r0 + u // Dn, u))                                       # role 1: row-major = sorted by track (template)
+            unit_lists = lists_s if by_search else lists_t
+            unit_lists_b = lists_s if b_by_search else lists_t
         else:
             P = ti.numel()
             ti, dj = ti.long(), dj.long()
@@ -188,14 +197,19 @@ class FusedXcorr:
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             if unit_lists is not None:
                 us, ut, sl = (x.contiguous() for x in unit_lists[role])
+                bs, bt, bl = (us, ut, sl) if unit_lists_b is unit_lists else tuple(x.contiguous() for x in unit_lists_b[role])
             else:
-                order = torch.argsort(tmpl, stable=True)                    # runs of units share the template operand
+                order = torch.argsort(tmpl, stable=True)                    # phase 1a: runs of units share the template operand
                 us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
+                bs, bt, bl = us, ut, sl
+                if b_by_search:                                             # phase 1b: runs of units share the search object
+                    order = torch.argsort(srch, stable=True)
+                    bs, bt, bl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
             e0 = self._tick()
             _OPS.pair_p1a2(P, N, role, self.fmt, ATT_EPS * sc, us, ut, sl, ps.QF1, ps.H, pm.MK1, self._w1a2, A, self.n_ctas)
             self._tock("pair_p1a2_kernel", e0, P)
             e0 = self._tick()
-            _OPS.pair_p1b_n(P, N, role, self.fmt, sc, us, ut, sl, ps.PV, self._w1b2, A, B7, self.n_ctas)
+            _OPS.pair_p1b_n(P, N, role, self.fmt, sc, bs, bt, bl, ps.PV, self._w1b2, A, B7, self.n_ctas)
             self._tock("pair_p1b_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
