@@ -226,6 +226,219 @@ __global__ void __launch_bounds__(NGX * GX * CS, 1) pair_p1b_kernel(const P1Args
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// phase 1b, second cut: the stage-1 output `a` never enters shared memory.  Each thread loads ITS row of the tile's image from
+// global memory (8 x 16 B, a whole tile ahead) and writes it into tensor-memory columns [136, 168) of its lane: the TS-mode A
+// operand of both projections (before: a cp.async image that the tensor core read twice).  The key/value reduction runs as an
+// M = 64 GEMM (A = the Kf half of the image only; the old M = 128 form also computed V^T V into lanes nobody read) with N = 72
+// accumulator columns, which is what makes room: 64 (k / v) + 72 (KV | Ksum) + 32 (`a`) = 168 columns per group (3 x 168 <= 512).
+// An M = 64 accumulator lives in lanes 0-15 / 32-47 / 64-79 / 96-111 (row i -> lane (i % 16) + 32 (i / 16)): the B7 build reads
+// it with the low 16 lanes of each warp.  Same sums in the same order as pair_p1b_kernel: bit-identical.
+// Per tile this takes 16 KB of cp.async fill, 2 x 16 KB of projection A-operand reads and 16 KB of key/value A-operand reads off
+// the shared-memory pipe (1366 -> ~850 wavefronts).
+// ---------------------------------------------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(NGX * GX, 1) pair_p1b2_kernel(const P1Args a) {
+  constexpr int TG = 168, KVC = 64, AC = 136;                            // TMEM columns per group; KV accumulator; `a` operand
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[2 * NGX];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float ksum_s[NGX][64];
+  uint8_t* Wsm = smem;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2 * NGX; ++i) tc::mbar_init(&bars[i], 1);
+    tc::fence_mbar_init();
+  }
+  if (threadIdx.x < 32) { tc::tmem_alloc(&tmem_base_s, 512); tc::tmem_relinquish(); }
+  copy_to_smem(Wsm, a.W, P1B_WBYTES, threadIdx.x, NGX * GX);
+  cp_async_commit();
+  cp_async_wait<0>();
+  tc::fence_async_smem();
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const int warp_u = (int)tc::uniform(threadIdx.x >> 5);
+  const int gid = warp_u / 4, wq = warp_u % 4, row = threadIdx.x % GX, lane = threadIdx.x & 31;
+  const bool issuer = wq == 0;
+  const uint32_t tmem = tc::uniform(tmem_base_s) + gid * TG;
+  const uint32_t tlane = tmem + ((uint32_t)(wq * 32) << 16);
+  uint64_t* bar = bars + gid;
+  uint32_t par = 0;
+  auto gsync = [&]() { tc::bar_sync(1 + gid, GX); };
+  auto publish = [&]() { tc::fence_async_smem(); tc::tc_fence_before(); gsync(); tc::tc_fence_after(); };
+  auto gwait = [&]() { tc::mbar_wait(bar, par); par ^= 1u; tc::tc_fence_after(); };
+  uint64_t* bar2 = bars + NGX + gid;
+  uint32_t par2 = 0;
+  uint8_t* G = smem + P1B_WBYTES + gid * P1B_GBYTES;
+  uint8_t* Aimg = G + P1B_AIMG;                                          // only the B7 build's blockdiag(KV) operand lives here now
+  uint8_t* KfV = G + P1B_KFV;
+  {
+    uint4* ones = reinterpret_cast<uint4*>(KfV + 2 * IMG);
+    ones[row] = make_uint4(F::ONE_LO, 0, 0, 0);
+    ones[128 + row] = make_uint4(0, 0, 0, 0);
+  }
+  const uint32_t sA = tc::smem_u32(Aimg), sKfV = tc::smem_u32(KfV), sW = tc::smem_u32(Wsm);
+  const uint32_t id64 = tc::instr_desc(128, 64, F::FMT, tc::MAJOR_K, tc::MAJOR_K);
+  const uint32_t idkv = tc::instr_desc(64, 72, F::FMT, tc::MAJOR_MN, tc::MAJOR_MN);
+  const Opnd oA = A_IMG(sA), oWk = W_IMG(sW + P1B_WKV, 128), oWv = W_IMG(sW + P1B_WKV + 64 * 16, 128), oWm = W_IMG(sW + P1B_WM, 64),
+             oKf = opnd(sKfV, 128u, 2048u, 256u), oVones = opnd(sKfV + 8 * 2048, 128u, 2048u, 256u);
+
+  const int ngroups = gridDim.x * NGX, gg = blockIdx.x * NGX + gid;
+  const int u0 = (int)((long long)a.n_units * gg / ngroups), u1 = (int)((long long)a.n_units * (gg + 1) / ngroups);
+  int so_next = u0 < u1 ? a.u_search[u0] : 0, slot_next = u0 < u1 ? a.u_slot[u0] : 0;
+  // this thread's row of an `a` tile image: chunk c (channels 8c .. 8c+7) = words 4c .. 4c+3 of the TMEM operand
+  uint32_t areg[32];
+  auto load_row = [&](const uint8_t* img) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const uint4 v = ldg_early(img + c * 2048 + row * 16);
+      areg[4 * c] = v.x; areg[4 * c + 1] = v.y; areg[4 * c + 2] = v.z; areg[4 * c + 3] = v.w;
+    }
+  };
+  if (u0 < u1) load_row(a.A_out + ((size_t)slot_next * 2 + a.role) * a.NT * IMG);
+  for (int u = u0; u < u1; ++u) {
+    const int so = so_next, slot = slot_next;
+    if (u + 1 < u1) { so_next = a.u_search[u + 1]; slot_next = a.u_slot[u + 1]; }
+    for (int tile = 0; tile < a.NT; ++tile) {
+      const size_t ti = (size_t)so * a.NT + tile;
+      // the previous tile's v projection (the last reader of the operand columns) was waited for: overwrite them
+      tc::tmem_st32(tlane + AC, areg);
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      gsync();
+      tc::tc_fence_after();
+      if (issuer) {
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::umma_f16_ts(tmem, tmem + AC + 8 * ks, oWk.desc + (uint64_t)(ks * oWk.kstep), id64, ks > 0 ? 1u : 0u);
+          tc::umma_commit(bar);
+        }
+        __syncwarp();
+      }
+      {   // the next tile's row -> registers now (consumed a whole tile later), the one after that -> L2
+        int ns = slot, nt = tile + 1;
+        if (nt == a.NT) { ns = slot_next; nt = 0; }
+        if (nt != 0 || u + 1 < u1) {
+          load_row(a.A_out + (((size_t)ns * 2 + a.role) * a.NT + nt) * IMG);
+          int ns2 = ns, nt2 = nt + 1;
+          if (nt2 == a.NT) { nt2 = 0; ns2 = -1; }                        // (the unit after next is not known yet: only within a unit)
+          if (ns2 >= 0) prefetch_l2_16k(a.A_out + (((size_t)ns2 * 2 + a.role) * a.NT + nt2) * IMG, row);
+        }
+      }
+      gwait();
+      if (tile > 0) { tc::mbar_wait(bar2, par2); par2 ^= 1u; tc::tc_fence_after(); }   // previous KV GEMM still reads KfV
+      {   // Kf = elu(k)+1 -> chunks 0..7 ; zero for padding rows (point index >= npts): they must not enter KV / Ksum
+        const bool keep = tile * 128 + row < a.npts;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = keep ? F::elu1(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1])) : 0u;
+            *reinterpret_cast<uint4*>(KfV + (2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      gsync();                                                            // everybody has read k before v overwrites the columns
+      tc::tc_fence_after();
+      if (issuer) {
+        if (tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::umma_f16_ts(tmem, tmem + AC + 8 * ks, oWv.desc + (uint64_t)(ks * oWv.kstep), id64, ks > 0 ? 1u : 0u);
+          tc::umma_commit(bar);
+        }
+        __syncwarp();
+      }
+      {   // V = v + Wv pos -> chunks 8..15
+        uint4 sdPV[8];
+        load_side<8>(sdPV, a.PV + ti * IMG, 0, row);
+        gwait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint4 s4 = sdPV[2 * q + c];
+            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              w[j] = F::add(__uint_as_float(r[c * 8 + 2 * j]), __uint_as_float(r[c * 8 + 2 * j + 1]), sw[j]);
+            *reinterpret_cast<uint4*>(KfV + (8 + 2 * q + c) * 2048 + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      publish();
+      if (issuer) {   // KV += Kf^T [V|1]   (M = 64: the Kf half of the image)
+        if (tc::elect_one()) { issue_gemm<8>(tmem + KVC, oKf, oVones, idkv, tile > 0); tc::umma_commit(bar2); }
+        __syncwarp();
+      }
+    }
+    tc::mbar_wait(bar2, par2);
+    par2 ^= 1u;
+    tc::tc_fence_after();
+    {   // B7 = [per-head blockdiag(KV) Wm^T | Ksum] of this (pair, direction) as template
+      {   // accumulator row i = 16 wq + l sits in lane 32 wq + l (l < 16): the low half of every warp turns it into operand row i
+        float kv[64];
+        uint32_t r8[8];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(tlane + KVC + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]) * a.kv_scale;
+        }
+        tc::tmem_ld8(tlane + KVC + 64, r8);
+        tc::tmem_ld_wait();
+        if (lane < 16) {
+          const int i = 16 * wq + lane, hd = i >> 5;
+          ksum_s[gid][i] = __uint_as_float(r8[0]) * a.kv_scale;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = ((c >> 2) == hd) ? F::pack(kv[c * 8 + 2 * j], kv[c * 8 + 2 * j + 1]) : 0u;
+            *reinterpret_cast<uint4*>(Aimg + c * 2048 + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      if (row >= 64) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(Aimg + c * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+      }
+      publish();
+      if (issuer) { if (tc::elect_one()) { issue_gemm<4>(tmem, oA, oWm, id64, false); tc::umma_commit(bar); } __syncwarp(); }
+      gwait();
+      if (row < 64) {
+        float kv[64];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(tlane + 16 * q, r);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) kv[16 * q + j] = __uint_as_float(r[j]);
+        }
+        write_b7_row<F>(kv, ksum_s[gid][row], row, a.B7_out + ((size_t)slot * 2 + a.role) * B7_BYTES);
+      }
+      tc::tc_fence_before();
+      gsync();
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // packing kernels (fp32 per-object tensors of the parity path -> bf16 operand images)
 // ---------------------------------------------------------------------------------------------------------------
 // src (B, C, N) channel-major fp32 -> dst [B][N/128][C/8][128][8] bf16, optional elu+1
@@ -274,8 +487,16 @@ static int launch_p1b_cs(const P1Args& a, int grid, cudaStream_t st) {
 }
 template <class F>
 static int launch_p1b(const P1Args& a, int grid, cudaStream_t st) {
-  // A/B: PCREID_P1B_SPLIT=2 -> two threads per tile row (8-warp groups, column-split epilogues)
+  // default: pair_p1b2_kernel (`a` in tensor memory, M = 64 key/value GEMM: -3 %, profiles/r02_p1b2_ab.json).
+  // A/B: PCREID_P1B=1 -> the shared-memory form (pair_p1b_kernel); with it PCREID_P1B_SPLIT=2 -> two threads per tile row
+  static const int gen = [] { const char* e = getenv("PCREID_P1B"); return e ? atoi(e) : 2; }();
   static const int cs = [] { const char* e = getenv("PCREID_P1B_SPLIT"); return e ? atoi(e) : 1; }();
+  if (gen == 2) {
+    const int smem = P1B_WBYTES + NGX * P1B_GBYTES;
+    cudaFuncSetAttribute(pair_p1b2_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    pair_p1b2_kernel<F><<<grid, NGX * GX, smem, st>>>(a);
+    return pcreid_launch_status();
+  }
   return cs == 2 ? launch_p1b_cs<F, 2>(a, grid, st) : launch_p1b_cs<F, 1>(a, grid, st);
 }
 
