@@ -438,6 +438,12 @@ __global__ void __launch_bounds__(NGX * GX, 1) pair_p1b2_kernel(const P1Args a) 
   if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
+// Tried on top of this kernel and dropped (profiles/r02_p1b2_ab.json): pipelining the projections BEHIND the epilogues -- read an
+// accumulator into registers, issue the next GEMM over its columns (v(n) after k(n) is in registers, k(n+1) after v(n) is, with the
+// Kf image double-buffered through Aimg and a(n+2) prefetched), then do the elu / add arithmetic while the tensor core works.
+// Bit-identical, 155-168 registers, and 14-17 % SLOWER (1.23-1.27 ms against 1.05-1.09): the tile chain of this kernel is not
+// what bounds it either.
+
 // ---------------------------------------------------------------------------------------------------------------
 // packing kernels (fp32 per-object tensors of the parity path -> bf16 operand images)
 // ---------------------------------------------------------------------------------------------------------------
