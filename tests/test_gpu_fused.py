@@ -160,3 +160,46 @@ def test_small_dense_match_replays_from_a_cuda_graph(mode):
         assert torch.equal(m.match_all_pairs(ht2, xt2, hd2, xd2, pair_mask=mask.to(DEV)), eager * mask.to(DEV))
     assert any(k[0] == "match" for k in m._graphs if isinstance(k[0], str))
     assert not torch.equal(outs[0], outs[1])
+
+
+_AB_SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import helpers
+from oracle import reid_oracle as O
+out = {}
+for mode in ("parity_tc", "fast"):
+    for N, T, D in ((256, 9, 7), (160, 4, 5), (128, 6, 3)):
+        m, _ = helpers.build_pair("pt", (N, N // 2, N // 4), device="cuda")
+        m.set_mode(mode)
+        xt, ht = m.encode(O.synth_objects(T, N, 0).cuda())
+        xd, hd = m.encode(O.synth_objects(D, N, 1).cuda())
+        out[f"{mode}_{N}"] = m.match_all_pairs(ht, xt, hd, xd).cpu()
+        mask = torch.rand(T, D, generator=torch.Generator().manual_seed(N)) > 0.4
+        out[f"{mode}_{N}_masked"] = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.cuda()).cpu()
+torch.save(out, sys.argv[2])
+'''
+
+
+def test_ab_kernel_variants_are_bit_identical(tmp_path):
+    """The kernels this library shipped before the shared-memory-pipe work stay selectable for A/B runs (PCREID_X_TMEM=0: X' and the
+    bias operand as shared-memory images; PCREID_P1B=1: phase 1b with `a` as a cp.async image and an M = 128 key/value GEMM;
+    PCREID_P1B_ORDER=templ: one unit order for both phase-1 kernels).  Every variant computes the same sums in the same order: the
+    logits must be bit-identical to the default build's, dense and pair-list drivers, full and ragged tiles, both operand formats."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "ab.py"
+    script.write_text(_AB_SCRIPT)
+    res = {}
+    for tag, env in (("default", {}), ("before", {"PCREID_X_TMEM": "0", "PCREID_P1B": "1", "PCREID_P1B_ORDER": "templ"}),
+                     ("split", {"PCREID_P1B": "1", "PCREID_P1B_SPLIT": "2"})):
+        out = tmp_path / f"{tag}.pt"
+        e = dict(os.environ)
+        e.update(env)
+        subprocess.run([sys.executable, str(script), root, str(out)], check=True, env=e, timeout=600)
+        res[tag] = torch.load(out)
+    for tag in ("before", "split"):
+        for k, v in res["default"].items():
+            assert torch.equal(v, res[tag][k]), f"{tag} variant differs from the default kernels on {k}"
