@@ -210,7 +210,7 @@ class FusedXcorr:
             self._tock("pair_p1a2_kernel", e0, P)
             e0 = self._tick()
             _OPS.pair_p1b_n(P, N, role, self.fmt, sc, bs, bt, bl, ps.PV, self._w1b2, A, B7, self.n_ctas)
-            self._tock("pair_p1b_kernel", e0, P)
+            self._tock("pair_p1b_kernel" if os.environ.get("PCREID_P1B") == "1" else "pair_p1b2_kernel", e0, P)
         slots = torch.arange(P, device=dev, dtype=torch.int32)
         pooled = torch.empty((1, 128, P), device=dev, dtype=torch.float32)
         for role in (0, 1):
