@@ -9,6 +9,8 @@ key/value summaries, position codes) is computed once per object and gathered th
 """
 import copy
 
+import os
+
 import torch
 from torch import nn
 
@@ -96,6 +98,7 @@ class ReIDNet(nn.Module):
         self.parity_tc_fp_blocks = False   # True: FP_SA blocks also run as tf32 tcgen05 kernels in 'parity_tc' mode (see set_mode)
         self.parity_tc_x3 = False   # 'parity_tc': K < 256 contractions on the 3 x tf32 kernel instead of the FFMA kernel (see _tc_linear)
         self.tc_encoder = True      # in the tensor-core modes the encoder's 1x1 convs / Linears run as tf32 tcgen05 GEMMs
+        self.head_x3 = os.environ.get("PCREID_HEAD_X3", "1") != "0"   # tensor-core modes: match head on the 3 x tf32 GEMM (see _head_cn)
         self._fused = {}
         # encode() replays a captured CUDA graph per (shape, mode, weights version): the ~90 launches of one encoder pass
         # are issued by the GPU front-end instead of by ~90 Python -> ctypes -> cudaLaunchKernel round trips
@@ -255,10 +258,16 @@ class ReIDNet(nn.Module):
     def _head_cn(self, pooled_cn):
         """match_head on channel-major pooled features (1, C, P) -> logits (P,)."""
         x = pooled_cn
-        # always the fp32 kernels: the pairs are the ROW axis here, and which tensor-core kernel could serve a shape depends on the
-        # row count -- a pair's logit must not depend on how many other pairs share its chunk (row-sharded multi-GPU driver,
-        # pair-list vs dense driver); the head is ~2 % of the match
-        with K.tensor_core_linear(False):
+        P = x.shape[2]
+        # The pairs are the ROW axis here, and a pair's logit must not depend on how many other pairs share its chunk (row-sharded
+        # multi-GPU driver, pair-list vs dense driver, CUDA-graph replay): ONE kernel family serves every row count of a mode.
+        # Tensor-core modes: the fp32-grade 3 x tf32 TMA GEMM (pcreid_cn_linear_tma_x3; per-row sums in a fixed K order whatever the
+        # row count) with the row count padded to the multiple of 4 its tensor maps need -- 0.15 -> 0.05 ms per 65 536 pairs;
+        # 'parity': the FFMA kernels.  The final Linear (one output channel) is FFMA in every mode.
+        x3 = self.match_mode in self.TC_MODES + ('parity_x3',) and self.head_x3 and x.is_cuda and P > 0
+        if x3 and P % 4:
+            x = torch.nn.functional.pad(x, (0, 4 - P % 4))
+        with (K.tensor_core_linear(True, min_k=1 << 30, x3=True) if x3 else K.tensor_core_linear(False)):
             for m in self.match_head:
                 if isinstance(m, LinearRes):
                     x = m.forward_cn(x)
@@ -266,7 +275,7 @@ class ReIDNet(nn.Module):
                     x = K.cn_linear(x, _kmajor_cached(m), bias=_bias_cached(m))
                 else:
                     raise NotImplementedError(type(m))
-        return x.reshape(-1)
+        return x.reshape(-1)[:P]
 
     def xcorr_eff(self, o1, xyz1, o2, xyz2, combine='add'):
         o1__ = self.cross_stage1(o1, xyz1, o2, xyz2)

@@ -20,7 +20,7 @@ xt, ht = model.encode(t)
 xd, hd = model.encode(d)
 fm = model.fused_matcher()
 ref = None
-for chunk in (65536, 16384, 4096, 2048, 1024, 512):
+for chunk in [int(c) for c in os.environ.get("CHUNKS", "65536,16384,4096,2048,1024,512").split(",")]:
     import pcreid_b200.models.ReIDNet as R
     fn = lambda: model.match_all_pairs(ht, xt, hd, xd, chunk=chunk, _exact_chunk=True)
     out = fn()
