@@ -154,6 +154,15 @@ typedef struct pcreid_norm_args {
 } pcreid_norm_args;
 int pcreid_cn_groupnorm(const pcreid_norm_args* args, void* stream);
 
+/* Tail of the match head in one pass over the pairs (the second GroupNorm + identity shortcut + ReLU of LinearRes followed by
+ * the final Linear(C, 1): mmdet3d/models/lanegcn_nets.py:228-241 `LinearRes.forward`, head configs
+ * configs_reid/.../reid_pts_point-transformer_point-cat.py:24-25):
+ *   y[:, p] = relu(GroupNorm_G(X[:, p]) * gamma + beta + R[:, p]),   out[p] = w . y[:, p] + bias
+ * X, R: (C, rows) channel-major with channel strides ldx / ldr; the same GroupNorm arithmetic as pcreid_cn_groupnorm (eps 1e-5,
+ * biased variance).  y is never written. */
+int pcreid_gn_res_relu_dot(int rows, int C, int G, const float* X, int ldx, const float* gamma, const float* beta,
+                           const float* R, int ldr, const float* w, float bias, float* out, void* stream);
+
 /* Second generation of pcreid_cn_linear_tc (csrc/cn_linear_tc2.cu): warp-specialised persistent tf32 GEMM (activation
  * loader warps, bulk-TMA weight loader, MMA issuer, epilogue warps over a double-buffered TMEM accumulator).  Same
  * contract; the weights are ALSO passed as operand images W*img[(k/4)][co][k%4] (fp32, K a multiple of 8).  Shared

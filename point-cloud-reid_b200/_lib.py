@@ -68,6 +68,7 @@ _SIGS = {
     "pcreid_cn_linear_tma": [ctypes.POINTER(LinearArgs), c_ll, c_ll, c_ll, c_int, c_int, c_vp],
     "pcreid_cn_linear_tma_x3": [ctypes.POINTER(LinearArgs), c_vp, c_vp, c_ll, c_ll, c_ll, c_int, c_vp],
     "pcreid_cn_groupnorm": [ctypes.POINTER(NormArgs), c_vp],
+    "pcreid_gn_res_relu_dot": [c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_float, c_vp, c_vp],
     "pcreid_attn_front_blob_bytes": [c_int, c_int, c_int, c_int],
     "pcreid_attn_front": [c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, c_int,
                           c_vp],

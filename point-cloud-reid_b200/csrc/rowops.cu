@@ -351,6 +351,52 @@ __global__ void __launch_bounds__(128) cn_groupnorm_kernel(const pcreid_norm_arg
   }
 }
 
+// Tail of the match head: GroupNorm + shortcut + ReLU + dot with the final Linear's weight row, one thread per pair (column);
+// the same operations in the same order as cn_groupnorm_kernel followed by a sequential fma chain over the channels.
+template <int CG>
+__global__ void __launch_bounds__(128) gn_res_relu_dot_kernel(int rows, int C, int G, const float* __restrict__ X, int ldx,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              const float* __restrict__ R, int ldr, const float* __restrict__ w,
+                                                              float bias, float* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  const int cg = CG > 0 ? CG : C / G;
+  float acc = 0.f;
+  for (int g = 0; g < G; ++g) {
+    if (CG > 0) {
+      float x[CG > 0 ? CG : 1];
+#pragma unroll
+      for (int i = 0; i < CG; ++i) x[i] = X[(size_t)(g * CG + i) * ldx + n];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < CG; ++i) s += x[i];
+      const float mean = s / (float)CG;
+      float v = 0.f;
+#pragma unroll
+      for (int i = 0; i < CG; ++i) { const float d = x[i] - mean; v = fmaf(d, d, v); }
+      const float rstd = rsqrtf(v / (float)CG + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < CG; ++i) {
+        const int c = g * CG + i;
+        const float y = (x[i] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) + R[(size_t)c * ldr + n];
+        acc = fmaf(fmaxf(y, 0.f), __ldg(w + c), acc);
+      }
+      continue;
+    }
+    float s = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) s += X[(size_t)c * ldx + n];
+    const float mean = s / (float)cg;
+    float v = 0.f;
+    for (int c = g * cg; c < (g + 1) * cg; ++c) { const float d = X[(size_t)c * ldx + n] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(v / (float)cg + 1e-5f);
+    for (int c = g * cg; c < (g + 1) * cg; ++c) {
+      const float y = (X[(size_t)c * ldx + n] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c) + R[(size_t)c * ldr + n];
+      acc = fmaf(fmaxf(y, 0.f), __ldg(w + c), acc);
+    }
+  }
+  out[n] = acc + bias;
+}
+
 // ------------------------------------------------------------------------------------------------
 // linear attention reductions
 // ------------------------------------------------------------------------------------------------
@@ -812,6 +858,21 @@ int pcreid_cn_groupnorm(const pcreid_norm_args* p, void* stream) {
       case 128: cn_groupnorm_kernel<128><<<grid, 128, 0, st>>>(s); break;
       default: cn_groupnorm_kernel<0><<<grid, 128, 0, st>>>(s); break;
     }
+  }
+  return pcreid_launch_status();
+}
+
+int pcreid_gn_res_relu_dot(int rows, int C, int G, const float* X, int ldx, const float* gamma, const float* beta, const float* R,
+                           int ldr, const float* w, float bias, float* out, void* stream) {
+  if (rows <= 0) return PCREID_OK;
+  if (!X || !gamma || !beta || !R || !w || !out || C <= 0 || G <= 0 || C % G) return PCREID_ERR_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((rows + 127) / 128);
+  switch (C / G) {
+    case 8: gn_res_relu_dot_kernel<8><<<grid, 128, 0, st>>>(rows, C, G, X, ldx, gamma, beta, R, ldr, w, bias, out); break;
+    case 16: gn_res_relu_dot_kernel<16><<<grid, 128, 0, st>>>(rows, C, G, X, ldx, gamma, beta, R, ldr, w, bias, out); break;
+    case 32: gn_res_relu_dot_kernel<32><<<grid, 128, 0, st>>>(rows, C, G, X, ldx, gamma, beta, R, ldr, w, bias, out); break;
+    default: gn_res_relu_dot_kernel<0><<<grid, 128, 0, st>>>(rows, C, G, X, ldx, gamma, beta, R, ldr, w, bias, out); break;
   }
   return pcreid_launch_status();
 }

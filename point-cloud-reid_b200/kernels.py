@@ -234,6 +234,18 @@ def cn_groupnorm(x, gamma, beta, groups=1, res=None, r_map=None, act=ACT_NONE, o
     return out
 
 
+def gn_res_relu_dot(x, gamma, beta, groups, res, w, bias):
+    """tail of the match head: relu(GroupNorm_G(x) * gamma + beta + res) . w + bias per column; x, res (1, C, P) channel-major,
+    w (C,) on the device, bias a host float -> (P,)   (pcreid_gn_res_relu_dot)."""
+    _need_cuda(x, gamma, beta, res, w)
+    assert x.shape[0] == 1 and res.shape == x.shape
+    _, ldx = _cn(x, "x")
+    _, ldr = _cn(res, "res")
+    out = torch.empty((x.shape[2],), device=x.device, dtype=torch.float32)
+    _OPS.gn_res_relu_dot(x.shape[2], x.shape[1], groups, x, ldx, gamma, beta, res, ldr, w, float(bias), out)
+    return out
+
+
 def linattn_kv(k, v, nhead):
     """-> (Wkv (B, d, d) k-major block-diagonal, ksum (B, d)) from pre-activation keys / values (B, d, S)."""
     _need_cuda(k, v)

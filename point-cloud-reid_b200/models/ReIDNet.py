@@ -268,6 +268,16 @@ class ReIDNet(nn.Module):
         if x3 and P % 4:
             x = torch.nn.functional.pad(x, (0, 4 - P % 4))
         with (K.tensor_core_linear(True, min_k=1 << 30, x3=True) if x3 else K.tensor_core_linear(False)):
+            mh = self.match_head
+            if (x3 and len(mh) == 2 and isinstance(mh[0], LinearRes) and mh[0].transform is None and isinstance(mh[1], nn.Linear)
+                    and mh[1].out_features == 1 and mh[1].bias is not None):
+                # LinearRes + Linear(C, 1): the second GroupNorm + shortcut + ReLU and the final dot in one pass (no (C, P) round trip,
+                # and not a 128 x 64-tile GEMM for ONE output channel)
+                pk = mh[0].packed()
+                h = K.cn_groupnorm(K.cn_linear(x, pk["w1"]), pk["g1"], pk["b1"], mh[0].groups, act=K.ACT_RELU)
+                h = K.cn_linear(h, pk["w2"])
+                fw, fb = _final_cached(mh[1])
+                return K.gn_res_relu_dot(h, pk["g2"], pk["b2"], mh[0].groups, x, fw, fb)[:P]
             for m in self.match_head:
                 if isinstance(m, LinearRes):
                     x = m.forward_cn(x)

@@ -373,3 +373,20 @@ def test_pair_concat_head(T, D):
     dv = lambda *ts: [t.to(DEV) for t in ts]
     got = K.pair_concat_head(*dv(a, bv, et, ed, w2, g1, b1, g2, b2, w), 0.25, G, mask.to(DEV))
     close(got, F.pair_concat_head(a, bv, et, ed, w2, g1, b1, g2, b2, w, 0.25, G, mask), 1e-4)
+
+
+@pytest.mark.parametrize("C,G,P", [(128, 8, 1000), (128, 16, 65), (256, 32, 300), (96, 8, 17)])
+def test_gn_res_relu_dot_matches_the_unfused_head_tail(C, G, P):
+    """pcreid_gn_res_relu_dot = cn_groupnorm(.., res, ReLU) followed by the Linear(C, 1): same GroupNorm arithmetic, the dot as one
+    fma chain over the channels (the unfused GEMM sums in the same order: 1e-6 of the scale)."""
+    x, r = rnd(1, C, P, seed=1), rnd(1, C, P, seed=2)
+    g, b, w = rnd(C, seed=3), rnd(C, seed=4), rnd(C, seed=5) / C ** 0.5
+    got = K.gn_res_relu_dot(x.to(DEV), g.to(DEV), b.to(DEV), G, r.to(DEV), w.to(DEV), 0.25)
+    y = K.cn_groupnorm(x.to(DEV), g.to(DEV), b.to(DEV), G, res=r.to(DEV), act=K.ACT_RELU)
+    want = (y[0] * w.to(DEV)[:, None]).sum(0) + 0.25
+    assert got.shape == (P,)
+    close(got, want, 1e-5)
+    xg = x.view(1, G, C // G, P)
+    ref = ((xg - xg.mean(2, keepdim=True)) / torch.sqrt(xg.var(2, unbiased=False, keepdim=True) + 1e-5)).view(1, C, P)
+    ref = torch.relu(ref * g[None, :, None] + b[None, :, None] + r)[0]
+    close(got, (ref * w[:, None]).sum(0) + 0.25, 1e-4)
