@@ -74,6 +74,7 @@ class FusedXcorr:
         self.n_ctas = None
         self._n_ctas_dev = None
         self.timing = None      # set to a list to collect (name, start_event, end_event) per fused kernel launch
+        self._units = {}        # dense-block unit lists by geometry (see _dense_units)
 
     def _weights(self):
         X1, X2 = self.model.cross_stage1, self.model.cross_stage2
@@ -159,6 +160,31 @@ class FusedXcorr:
         _OPS.pack_b7(B, M, ksum, self.fmt, o.MK1)
         return o
 
+    def _dense_units(self, dev, r0, nrows, Dn, by_search, b_by_search):
+        """(search, template, slot) int32 lists of the row block [r0, r0 + nrows) x [0, Dn), per role, in the orders phase 1a and
+        phase 1b want.  They depend on the block's geometry only, so a steady stream of equal-shaped matches (the chunks of a large
+        matrix, a tracker's frames) reuses them instead of re-running ~25 index kernels per chunk; never cached while a CUDA graph
+        is being captured (the tensors would live in the graph's private pool)."""
+        key = (str(dev), r0, nrows, Dn, by_search, b_by_search)
+        capturing = torch.cuda.is_current_stream_capturing()      # a graph must own every buffer its kernels read: no cache either way
+        hit = None if capturing else self._units.get(key)
+        if hit is not None:
+            return hit
+        P = nrows * Dn
+        u = torch.arange(P, device=dev, dtype=torch.int32)
+        t_of, d_of = r0 + u % nrows, u // nrows
+        c = lambda *xs: tuple(x.contiguous() for x in xs)
+        lists_s = (c(r0 + u // Dn, u % Dn, u),                                        # role 0 (search, template, slot): row-major
+                   c(u // nrows, r0 + u % nrows, (u % nrows) * Dn + u // nrows))       # role 1: detection-major
+        lists_t = (c(t_of, d_of, (t_of - r0) * Dn + d_of),                             # role 0: runs of equal detection (template)
+                   c(u % Dn, r0 + u // Dn, u))                                        # role 1: row-major = sorted by track (template)
+        out = (lists_s if by_search else lists_t, lists_s if b_by_search else lists_t)
+        if not capturing:
+            if len(self._units) >= 64:                      # a few MB per entry: keep the working set of one large matrix
+                self._units.pop(next(iter(self._units)))
+            self._units[key] = out
+        return out
+
     def match(self, pt, pd, ti, dj, debug=None, dense=None):
         """logits (P,) for the pairs (ti[p], dj[p]); ti / dj int64 or int32 index tensors on the device.
         dense=(r0, nrows, D): the pairs are the full row block [r0, r0+nrows) x [0, D) in row-major order (ti, dj may be
@@ -177,14 +203,7 @@ class FusedXcorr:
         if dense is not None:
             r0, nrows, Dn = dense
             P = nrows * Dn
-            u = torch.arange(P, device=dev, dtype=torch.int32)
-            t_of, d_of = r0 + u % nrows, u // nrows
-            lists_s = ((r0 + u // Dn, u % Dn, u),                                      # role 0 (search, template, slot): row-major
-                       (u // nrows, r0 + u % nrows, (u % nrows) * Dn + u // nrows))       # role 1: detection-major
-            lists_t = ((t_of, d_of, (t_of - r0) * Dn + d_of),                           # role 0: runs of equal detection (template)
-                       (u % Dn, r0 + u // Dn, u))                                       # role 1: row-major = sorted by track (template)
-            unit_lists = lists_s if by_search else lists_t
-            unit_lists_b = lists_s if b_by_search else lists_t
+            unit_lists, unit_lists_b = self._dense_units(dev, r0, nrows, Dn, by_search, b_by_search)
         else:
             P = ti.numel()
             ti, dj = ti.long(), dj.long()
@@ -196,8 +215,8 @@ class FusedXcorr:
         sc = self.kv_scale(N)
         for role, (srch, tmpl, ps, pm) in enumerate(((ti, dj, pt, pd), (dj, ti, pd, pt))):
             if unit_lists is not None:
-                us, ut, sl = (x.contiguous() for x in unit_lists[role])
-                bs, bt, bl = (us, ut, sl) if unit_lists_b is unit_lists else tuple(x.contiguous() for x in unit_lists_b[role])
+                us, ut, sl = unit_lists[role]
+                bs, bt, bl = unit_lists_b[role]
             else:
                 order = torch.argsort(tmpl, stable=True)                    # phase 1a: runs of units share the template operand
                 us, ut, sl = srch[order].int().contiguous(), tmpl[order].int().contiguous(), order.int().contiguous()
