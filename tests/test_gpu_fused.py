@@ -203,3 +203,21 @@ def test_ab_kernel_variants_are_bit_identical(tmp_path):
     for tag in ("before", "split"):
         for k, v in res["default"].items():
             assert torch.equal(v, res[tag][k]), f"{tag} variant differs from the default kernels on {k}"
+
+
+@pytest.mark.parametrize("mode", ["parity_tc", "fast"])
+@pytest.mark.parametrize("N,T,D", [(1024, 3, 4), (640, 3, 3), (96, 5, 6)])
+def test_fused_long_and_short_objects(N, T, D, mode):
+    """tile counts beyond the headline's two: 8 tiles per object (the 1024-point Waymo config), 5 tiles, and a single ragged tile --
+    the row prefetch of phase 1b runs two tiles ahead across unit boundaries, the key/value GEMM accumulates over all of them;
+    dense driver and pair-list driver must agree bit for bit on the pairs they share"""
+    m, _ = helpers.build_pair("pt", (N, N // 2, N // 4), device=DEV)
+    xt, ht = m.encode(O.synth_objects(T, N, 0).to(DEV))
+    xd, hd = m.encode(O.synth_objects(D, N, 1).to(DEV))
+    Lp = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    m.match_mode = mode
+    Lf = m.match_all_pairs(ht, xt, hd, xd).cpu()
+    assert (Lf - Lp).abs().max() < TOL[mode]
+    mask = torch.rand(T, D, generator=torch.Generator().manual_seed(1)) > 0.3
+    Lm = m.match_all_pairs(ht, xt, hd, xd, pair_mask=mask.to(DEV)).cpu()
+    assert torch.equal(Lm[mask], Lf[mask]) and float(Lm[~mask].abs().max()) == 0.0
