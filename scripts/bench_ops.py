@@ -19,6 +19,7 @@ from pcreid_b200.ops import (ball_query, furthest_point_sample, gather_points, g
 dev = "cuda"
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+ALU_EVALS_PER_S = 148 * 128 * 1.965e9 / 6.0      # distance evaluations / s if the fp32 pipes did nothing else (6.2e12)
 
 
 def timeit(fn, iters=10, warm=3):
@@ -45,6 +46,9 @@ def add(name, ms, bytes_algo, evals=None, ref_ms=None, shape=""):
          "frac_of_measured_hbm": bytes_algo / ms / 1e6 / peak}
     if evals:
         r["distance_evals_per_s"] = evals / (ms * 1e-3)
+        # ALU roofline of the distance arithmetic alone: 6 fp32-pipe instructions per evaluation (3 subtractions, 1 multiply,
+        # 2 fused multiply-adds; selection / bookkeeping not counted) on 148 SMs x 128 fp32 lanes at the maximum SM clock
+        r["frac_of_fp32_alu_roofline"] = r["distance_evals_per_s"] / ALU_EVALS_PER_S
     if ref_ms:
         r["reference_cu_ms"] = ref_ms
         r["speedup_vs_reference_cu"] = ref_ms / ms
