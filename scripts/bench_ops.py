@@ -100,4 +100,6 @@ xf = torch.randn(B, 64, 256, device=dev)
 ms = timeit(lambda: K.knn_feature(xf, 20))
 add("knn_feature (DGCNN)", ms, B * (4 * 64 * 256 + 4 * 256 * 20), B * 256 * 256, None, f"B={B} C=64 N=256 k=20")
 print(json.dumps({"hbm_peak_GBps": peak, "peak_source": "MEASURED_PEAKS.json", "l2_flush": "256 MB zero-fill between iterations",
+                  "alu_roofline": {"distance_evals_per_s": ALU_EVALS_PER_S, "how": "6 fp32-pipe instructions per distance evaluation (3 sub, "
+                                   "1 mul, 2 fma; selection / bookkeeping not counted) x 148 SMs x 128 fp32 lanes x 1.965 GHz"},
                   "reference_cu": "oracle/_ref (reference .cu unmodified, sm_100a)" if have_ref else "unavailable", "rows": rows}, indent=1))
